@@ -1,0 +1,145 @@
+/*
+ * b200dit -- C ABI of the B200-native Wan2.1 DiT / WanVAE engine (libb200dit.so).
+ *
+ * The reference (johndpope/OmniHuman-1-hack) has no FFI layer: its hot path is entered through three
+ * Python signatures.  Each entry point below names the reference call it replaces; the Python
+ * host side (omnihuman-1-hack_b200/wan_shim.py) binds these with ctypes and is installed over the
+ * reference objects the same way the reference installs its own USP variant
+ * (seaweed_apt/wan/text2video.py:95-98, types.MethodType).
+ *
+ * Conventions
+ *   - plain C types only; every tensor argument is a raw pointer + explicit sizes, no framework types;
+ *   - tensor pointers handed to *_forward / *_decode are DEVICE pointers borrowed for the call
+ *     (weights may be host or device pointers; they are copied and repacked at load time);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream)
+ *     and the call returns without synchronising;
+ *   - return value 0 = ok, non-zero = error; b200_last_error() returns the message (thread-local).
+ *     Error conditions mirror the reference's asserts (model.py:485,521; attention.py:53-54).
+ *   - a handle is not thread-safe; one handle per CUDA device per thread, like the reference's
+ *     one-process-per-GPU callers (text2video.py:61, distilled_trainer.py:384-385).
+ */
+#ifndef B200DIT_H_
+#define B200DIT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#define B200_DTYPE_F32 0
+#define B200_DTYPE_F16 1
+#define B200_DTYPE_BF16 2
+
+#define B200_MAX_ITEMS 16 /* items (samples x CFG branches) co-batched by one forward call */
+
+typedef struct b200dit_engine b200dit_engine;
+typedef struct b200vae_engine b200vae_engine;
+
+/* Mirrors the constructor arguments of WanModel (seaweed_apt/wan/modules/model.py:388-404). */
+typedef struct b200dit_config {
+  int32_t dim;        /* 1536 */
+  int32_t ffn_dim;    /* 8960 */
+  int32_t num_heads;  /* 12; dim / num_heads must be 128 */
+  int32_t num_layers; /* 30 */
+  int32_t in_dim;     /* 16 (+ channels of the optional `y` stack, model.py:511-512) */
+  int32_t out_dim;    /* 16 */
+  int32_t text_dim;   /* 4096 */
+  int32_t text_len;   /* 512 */
+  int32_t freq_dim;   /* 256 */
+  int32_t i2v;        /* 1 = model_type 'i2v': img_emb MLP + second K/V stream (model.py:189-230,494-495) */
+  float eps;          /* 1e-6 */
+} b200dit_config;
+
+/* WanModel.__init__ (model.py:388-498): allocates packed-weight storage for the given architecture. */
+B200_API int b200dit_create(const b200dit_config* cfg, b200dit_engine** out);
+B200_API void b200dit_destroy(b200dit_engine* e);
+
+/* WanModel.load_state_dict: one call per state_dict entry, reference key names (model.py:463-498):
+ * patch_embedding.{weight,bias}, text_embedding.{0,2}.*, time_embedding.{0,2}.*, time_projection.1.*,
+ * blocks.N.{modulation,norm3.*,self_attn.{q,k,v,o}.*,self_attn.norm_{q,k}.weight,cross_attn.{q,k,v,o}.*,
+ * cross_attn.norm_{q,k}.weight[,cross_attn.{k_img,v_img}.*,cross_attn.norm_k_img.weight],ffn.{0,2}.*},
+ * head.{modulation,head.weight,head.bias}[, img_emb.proj.{0,1,3,4}.*].
+ * `data` may live on the host or the device; GEMM weights are repacked to fp16. */
+B200_API int b200dit_load_weight(b200dit_engine* e, const char* name, const void* data, int32_t dtype, int32_t ndim,
+                        const int64_t* shape);
+/* Fails (naming the first missing key) unless every parameter of the architecture was loaded. */
+B200_API int b200dit_finalize(b200dit_engine* e);
+
+/* WanModel.forward(x, t, context, seq_len, clip_fea=None, y=None) (model.py:502-563) for n_items
+ * items that share one latent grid [C, F, H, W]:
+ *   x[i]        fp32 [in_dim - y_channels, F, H, W]
+ *   y[i]        fp32 [y_channels, F, H, W] or y == NULL            (channel stack, model.py:511-512)
+ *   t           fp32 [n_items] on the device
+ *   context[i]  [context_rows[i], text_dim] of context_dtype, context_rows[i] <= text_len
+ *   clip_fea[i] fp32 [257, 1280] or clip_fea == NULL                (i2v engines only, model.py:534-537)
+ *   seq_len     only validated: F*(H/2)*(W/2) <= seq_len           (model.py:521)
+ *   out[i]      fp32 [out_dim, F, H, W]
+ */
+B200_API int b200dit_forward(b200dit_engine* e, int32_t n_items, const float* const* x, const float* const* y,
+                    int32_t y_channels, const float* t, const void* const* context, const int32_t* context_rows,
+                    int32_t context_dtype, const float* const* clip_fea, int32_t F, int32_t H, int32_t W,
+                    int32_t seq_len, float* const* out, void* stream);
+
+/* One classifier-free-guidance denoise evaluation for n_samples samples
+ * (text2video.py:238-244, generate.py:227-229): cond and uncond forwards co-batched as 2*n_samples
+ * items, combine  uncond + guide_scale * (cond - uncond)  fused into the head projection.
+ * out[i] fp32 [out_dim, F, H, W]. */
+B200_API int b200dit_forward_cfg(b200dit_engine* e, int32_t n_samples, const float* const* x, const float* const* y,
+                        int32_t y_channels, const float* t, const void* const* context_cond,
+                        const int32_t* rows_cond, const void* const* context_uncond, const int32_t* rows_uncond,
+                        int32_t context_dtype, const float* const* clip_fea, int32_t F, int32_t H, int32_t W,
+                        int32_t seq_len, float guide_scale, float* const* out, void* stream);
+
+/* Residual-stream taps (the APT discriminator reads block outputs through forward hooks,
+ * seaweed_apt/model.py:150-155): after the next forward, copy the fp32 stream [n_items*L, dim] that
+ * left block `block_idx` into dst (device).  block_idx < 0 disables. */
+B200_API int b200dit_set_tap(b200dit_engine* e, int32_t block_idx, float* dst);
+
+/* Capture each distinct (n_items, grid, mode) forward into a CUDA graph and replay it (default on). */
+B200_API int b200dit_set_graphs(b200dit_engine* e, int32_t enabled);
+
+/* ---- WanVAE decode (seaweed_apt/wan/modules/vae.py:619-663) ---- */
+/* WanVAE.__init__ -> _video_vae (vae.py:592-616): decoder of width `dim` (96), z_dim 16. */
+B200_API int b200vae_create(int32_t dim, int32_t z_dim, b200vae_engine** out);
+B200_API void b200vae_destroy(b200vae_engine* e);
+/* state_dict entries `conv2.*` and `decoder.*` (encoder keys are accepted and ignored). */
+B200_API int b200vae_load_weight(b200vae_engine* e, const char* name, const void* data, int32_t dtype, int32_t ndim,
+                        const int64_t* shape);
+B200_API int b200vae_finalize(b200vae_engine* e);
+/* WanVAE.decode for one latent (vae.py:657-663 -> 544-568): z fp32 [z_dim, T, h, w] (device) ->
+ * out fp32 [3, 1 + 4 (T-1), 8h, 8w], clamped to [-1, 1]. */
+B200_API int b200vae_decode(b200vae_engine* e, const float* z, int32_t T, int32_t h, int32_t w, float* out, void* stream);
+
+/* ---- operator seam (attention.py:24-130) and its GEMM sibling, exposed for unit parity tests,
+ *      micro-benchmarks and for patching `wan.modules.model.flash_attention` directly ---- */
+/* flash_attention(q, k, v, k_lens=...) with head_dim 128, non-causal: q [B, Lq, H, 128], k / v
+ * [B, Lk, H, 128], out [B, Lq, H, 128], all fp16 on the device; k_lens host int32 [B] or NULL (= Lk).
+ * softmax_scale <= 0 selects 1/sqrt(128). */
+B200_API int b200_flash_attention(const void* q, const void* k, const void* v, const int32_t* k_lens, int32_t B,
+                                  int32_t Lq, int32_t Lk, int32_t H, float softmax_scale, void* out, void* stream);
+/* nn.Linear: out[M,N] = epilogue(A[M,K] W[N,K]^T + bias).  A, W fp16 device (row-major, leading
+ * dimensions lda / ldw in elements), bias fp32 or NULL.  epilogue 0: fp16 store, 1: GELU(tanh) + fp16
+ * store, 4: fp32 store.  block_n 0 = automatic, else 128 or 256. */
+B200_API int b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int32_t M,
+                         int32_t N, int32_t K, int32_t epilogue, void* out, int64_t ldo, int32_t block_n,
+                         void* stream);
+
+/* ---- library-wide ---- */
+B200_API const char* b200_last_error(void);
+/* kernels launched by this library in this process so far */
+B200_API int64_t b200_kernel_launches(void);
+/* algorithmic FLOPs of the most recent forward / decode (SURVEY.md section 8d formulas) */
+B200_API double b200dit_last_flops(const b200dit_engine* e);
+B200_API const char* b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DIT_H_ */

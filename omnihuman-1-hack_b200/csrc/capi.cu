@@ -1,0 +1,170 @@
+// extern "C" surface of libb200dit.so (declared in include/b200dit.h).  Every entry point converts
+// C++ exceptions into a status code + thread-local message, the convention SURVEY.md section 8b
+// adopts for the reference's Python asserts.
+#include <string>
+
+#include "../../include/b200dit.h"
+#include "dit_engine.h"
+#include "vae_engine.h"
+
+struct b200dit_engine {
+  b2::DitEngine impl;
+  explicit b200dit_engine(const b200dit_config& c) : impl(c) {}
+};
+struct b200vae_engine {
+  b2::VaeEngine impl;
+  b200vae_engine(int dim, int z) : impl(dim, z) {}
+};
+
+static thread_local std::string g_err;
+
+template <class Fn>
+static int guarded(Fn&& fn) {
+  try {
+    fn();
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    cudaGetLastError();   // clear a sticky-free launch error so later calls report their own
+    return 1;
+  } catch (...) {
+    g_err = "unknown error";
+    return 1;
+  }
+}
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_err.c_str(); }
+int64_t b200_kernel_launches(void) { return b2::launches_total(); }
+const char* b200_version(void) { return "b200dit 0.1 (sm_100a; tcgen05 GEMM + attention, TMA, CUDA graphs)"; }
+
+int b200dit_create(const b200dit_config* cfg, b200dit_engine** out) {
+  return guarded([&] {
+    B2_CHECK(cfg != nullptr && out != nullptr, "null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    B2_CHECK(e == cudaSuccess && ndev > 0, "no CUDA device available: the B200 engine has no CPU fallback");
+    *out = new b200dit_engine(*cfg);
+  });
+}
+void b200dit_destroy(b200dit_engine* e) { delete e; }
+
+int b200dit_load_weight(b200dit_engine* e, const char* name, const void* data, int32_t dtype, int32_t ndim,
+                        const int64_t* shape) {
+  return guarded([&] {
+    B2_CHECK(e && name && data && shape, "null argument");
+    e->impl.load_weight(name, data, dtype, ndim, shape);
+  });
+}
+int b200dit_finalize(b200dit_engine* e) {
+  return guarded([&] { B2_CHECK(e, "null engine"); e->impl.finalize(); });
+}
+
+int b200dit_forward(b200dit_engine* e, int32_t n_items, const float* const* x, const float* const* y,
+                    int32_t y_channels, const float* t, const void* const* context, const int32_t* context_rows,
+                    int32_t context_dtype, const float* const* clip_fea, int32_t F, int32_t H, int32_t W,
+                    int32_t seq_len, float* const* out, void* stream) {
+  return guarded([&] {
+    B2_CHECK(e && x && t && context && context_rows && out, "null argument");
+    e->impl.forward(n_items, x, y, y_channels, t, context, context_rows, nullptr, nullptr, context_dtype, clip_fea, F, H,
+                    W, seq_len, false, 0.f, out, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int b200dit_forward_cfg(b200dit_engine* e, int32_t n_samples, const float* const* x, const float* const* y,
+                        int32_t y_channels, const float* t, const void* const* context_cond,
+                        const int32_t* rows_cond, const void* const* context_uncond, const int32_t* rows_uncond,
+                        int32_t context_dtype, const float* const* clip_fea, int32_t F, int32_t H, int32_t W,
+                        int32_t seq_len, float guide_scale, float* const* out, void* stream) {
+  return guarded([&] {
+    B2_CHECK(e && x && t && context_cond && rows_cond && context_uncond && rows_uncond && out, "null argument");
+    e->impl.forward(n_samples, x, y, y_channels, t, context_cond, rows_cond, context_uncond, rows_uncond, context_dtype,
+                    clip_fea, F, H, W, seq_len, true, guide_scale, out, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int b200dit_set_tap(b200dit_engine* e, int32_t block_idx, float* dst) {
+  return guarded([&] {
+    B2_CHECK(e, "null engine");
+    B2_CHECK(block_idx < e->impl.cfg.num_layers, "tap block %d out of range", block_idx);
+    e->impl.tap_block = block_idx < 0 ? -1 : block_idx;
+    e->impl.tap_dst = block_idx < 0 ? nullptr : dst;
+  });
+}
+int b200dit_set_graphs(b200dit_engine* e, int32_t enabled) {
+  return guarded([&] { B2_CHECK(e, "null engine"); e->impl.use_graphs = enabled != 0; });
+}
+double b200dit_last_flops(const b200dit_engine* e) { return e ? e->impl.last_flops : 0.0; }
+
+int b200vae_create(int32_t dim, int32_t z_dim, b200vae_engine** out) {
+  return guarded([&] {
+    B2_CHECK(out != nullptr, "null argument");
+    int ndev = 0;
+    cudaError_t er = cudaGetDeviceCount(&ndev);
+    B2_CHECK(er == cudaSuccess && ndev > 0, "no CUDA device available: the B200 engine has no CPU fallback");
+    *out = new b200vae_engine(dim, z_dim);
+  });
+}
+void b200vae_destroy(b200vae_engine* e) { delete e; }
+int b200vae_load_weight(b200vae_engine* e, const char* name, const void* data, int32_t dtype, int32_t ndim,
+                        const int64_t* shape) {
+  return guarded([&] {
+    B2_CHECK(e && name && data && shape, "null argument");
+    e->impl.load_weight(name, data, dtype, ndim, shape);
+  });
+}
+int b200vae_finalize(b200vae_engine* e) {
+  return guarded([&] { B2_CHECK(e, "null engine"); e->impl.finalize(); });
+}
+int b200vae_decode(b200vae_engine* e, const float* z, int32_t T, int32_t h, int32_t w, float* out, void* stream) {
+  return guarded([&] {
+    B2_CHECK(e && z && out, "null argument");
+    e->impl.decode(z, T, h, w, out, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int b200_flash_attention(const void* q, const void* k, const void* v, const int32_t* k_lens, int32_t B, int32_t Lq,
+                         int32_t Lk, int32_t H, float softmax_scale, void* out, void* stream) {
+  return guarded([&] {
+    B2_CHECK(q && k && v && out, "null argument");
+    B2_CHECK(B >= 1 && B <= b2::MAX_ITEMS && Lq >= 1 && Lk >= 1 && H >= 1, "bad attention shape");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int Lp = (Lk + 7) & ~7;
+    void* vt = nullptr;
+    const size_t bytes = (size_t)B * H * 128 * Lp * 2;
+    B2_CUDA(cudaMallocAsync(&vt, bytes, s));
+    B2_CUDA(cudaMemsetAsync(vt, 0, bytes, s));
+    b2::launch_transpose_v(static_cast<const __half*>(v), static_cast<__half*>(vt), B, Lk, H, Lp, s);
+    b2::AttnParams p{};
+    p.q = static_cast<const __half*>(q); p.ldq = (long long)H * 128;
+    p.k = static_cast<const __half*>(k); p.ldk = (long long)H * 128;
+    p.vt = static_cast<const __half*>(vt); p.ldvt = Lp;
+    p.out = static_cast<__half*>(out); p.ldo = (long long)H * 128;
+    p.items = B; p.heads = H; p.Lq = Lq; p.Lk_rows = Lk;
+    p.scale = softmax_scale > 0.f ? softmax_scale : 0.08838834764831845f;
+    for (int i = 0; i < B; ++i) p.klen[i] = k_lens ? (k_lens[i] < Lk ? k_lens[i] : Lk) : Lk;
+    b2::launch_attention(p, s);
+    B2_CUDA(cudaFreeAsync(vt, s));
+  });
+}
+
+int b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int32_t M, int32_t N,
+                int32_t K, int32_t epilogue, void* out, int64_t ldo, int32_t block_n, void* stream) {
+  return guarded([&] {
+    B2_CHECK(A && W && out, "null argument");
+    B2_CHECK(epilogue == b2::EPI_F16 || epilogue == b2::EPI_GELU_F16 || epilogue == b2::EPI_F32,
+             "b200_linear: epilogue %d not exposed", epilogue);
+    int dev = 0, sms = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    b2::GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.bias = bias;
+    if (epilogue == b2::EPI_F32) { p.out_f = static_cast<float*>(out); p.ld_f = ldo; }
+    else { p.out_h = static_cast<__half*>(out); p.ld_h = ldo; }
+    b2::gemm_linear(epilogue, static_cast<const __half*>(A), lda, static_cast<const __half*>(W), ldw, p, sms,
+                    static_cast<cudaStream_t>(stream), block_n);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// DitEngine: see dit_engine.cu.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/b200dit.h"
+#include "host_util.h"
+#include "kernels.h"
+
+namespace b2 {
+
+struct Slot {
+  void* dst; int dst_dtype; long long numel; bool loaded;
+  int tr_rows, tr_cols;     // > 0: source is [tr_rows, tr_cols], stored transposed (fp32)
+};
+void load_into_slot(Slot& s, const char* name, const void* data, int dtype, int ndim, const int64_t* shape);
+void launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t s);
+
+struct BlockWeights {
+  float *norm3_w, *norm3_b;
+  __half* qkv_w; float* qkv_b; float *norm_q, *norm_k; __half* o_w; float* o_b;
+  __half* cq_w; float* cq_b; float *cnorm_q, *cnorm_k; __half* ckv_w; float* ckv_b; __half* co_w; float* co_b;
+  __half* ckv_img_w = nullptr; float* ckv_img_b = nullptr; float* cnorm_k_img = nullptr;
+  __half* ffn0_w; float* ffn0_b; __half* ffn2_w; float* ffn2_b;
+};
+
+struct DitWeights {
+  __half* patch_w; float* patch_b;
+  __half* text0_w; float* text0_b; __half* text2_w; float* text2_b;
+  float *time0_w, *time0_b, *time2_w, *time2_b, *timep_w, *timep_b;
+  float* modulation;                     // [layers, 6, dim]
+  std::vector<BlockWeights> blocks;
+  float *head_mod, *head_wt, *head_b;    // head weight stored transposed [dim, P]
+  float *img_ln0_w, *img_ln0_b; __half* img_fc1_w; float* img_fc1_b; __half* img_fc3_w; float* img_fc3_b;
+  float *img_ln4_w, *img_ln4_b;
+};
+
+struct DitWorkspace {
+  float* x_res; __half *u, *qk, *vt, *att, *hid; float* ssq; __half* patch;
+  __half *ctx16, *ctx_h, *ctx_e, *kc, *vtc; float* ssq_c;
+  float *e, *e0, *modtab, *tscratch, *t_items;
+  __half* clip16; float* clip_f; __half* clip_g; float* img_f; __half *ctx_img, *ki, *vti; float* ssq_i;
+};
+
+struct FwdInputs {
+  int B = 0, F = 0, H = 0, W = 0, y_channels = 0;
+  ItemPtrs x{}, y{}, ctx{};
+  int ctx_rows[MAX_ITEMS] = {0};
+  int ctx_dtype = DT_F32;
+  const float* t = nullptr;              // device [B]
+  bool has_clip = false;
+  const float* clip_packed = nullptr;    // device fp32 [B*257, 1280]
+  ItemPtrsMut out{};
+  int cfg_pairs = 0;                     // > 0: items [0,cfg_pairs) cond, [cfg_pairs, 2 cfg_pairs) uncond
+  const float* cfg_scale = nullptr;      // device scalar
+};
+
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  int uses = 0;
+  int launches = 0;      // kernels per replay
+};
+
+class DitEngine {
+ public:
+  explicit DitEngine(const b200dit_config& c);
+  ~DitEngine();
+  void load_weight(const char* name, const void* data, int dtype, int ndim, const int64_t* shape);
+  void finalize();
+  // user-facing forward (pointers as in the C ABI); cfg: n samples -> 2n items
+  void forward(int n, const float* const* x, const float* const* y, int y_channels, const float* t,
+               const void* const* ctx_a, const int* rows_a, const void* const* ctx_b, const int* rows_b, int ctx_dtype,
+               const float* const* clip, int F, int H, int W, int seq_len, bool cfg, float guide_scale,
+               float* const* out, cudaStream_t stream);
+  double flops(int B, int L) const;
+
+  b200dit_config cfg;
+  int num_sms = 148;
+  bool finalized = false;
+  bool use_graphs = true;
+  int tap_block = -1;
+  float* tap_dst = nullptr;
+  double last_flops = 0.0;
+
+ private:
+  void alloc_weights();
+  void add_slot(const std::string& name, void* dst, int dt, long long numel, int tr_rows = 0, int tr_cols = 0);
+  void ensure_workspace(int B, int L);
+  void ensure_static_io(int B, int F, int H, int W);
+  const float* rope_table(int F, int Hp, int Wp);
+  void enqueue(const FwdInputs& in, cudaStream_t s);
+
+  std::unordered_map<std::string, Slot> slots;
+  DevBuf w16, w32, ws, sio;
+  DitWeights wt{};
+  DitWorkspace w{};
+  int ws_B = 0, ws_L = 0;
+  std::map<long long, std::unique_ptr<DevBuf>> rope_cache;
+  // static I/O staging for graph replay
+  size_t sio_item_x = 0, sio_item_ctx = 0, sio_item_out = 0;
+  int sio_B = 0;
+  float* s_x = nullptr; float* s_y = nullptr; uint8_t* s_ctx = nullptr; float* s_clip = nullptr; float* s_out = nullptr;
+  float* s_t = nullptr; float* s_scale = nullptr;
+  std::map<std::vector<int>, GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;
+};
+
+}  // namespace b2

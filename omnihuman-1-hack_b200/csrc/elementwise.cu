@@ -1,0 +1,462 @@
+// HBM-bound passes of the DiT forward: LayerNorm+AdaLN modulate+cast, q/k RMSNorm+3-D RoPE,
+// timestep embedding MLPs, patchify, context pad/cast, head (+unpatchify, +CFG combine).
+// All 128-bit vectorised, fp32 statistics, one pass over the data each.
+#include <cuda_bf16.h>
+
+#include "host_util.h"
+#include "kernels.h"
+
+namespace b2 {
+
+static long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+long long launches_total() { return g_launches; }
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ LayerNorm * a + b -> fp16
+// model.py:91-104 (+ :293,:315 modulation, :313 affine norm3).  One warp per row, row kept in registers.
+template <int NV>
+__global__ void __launch_bounds__(256) ln_affine_kernel(const float* __restrict__ x, __half* __restrict__ out,
+                                                        const float* __restrict__ a, const float* __restrict__ b,
+                                                        long long item_stride, int M, int rows_per_item, float eps) {
+  constexpr int DIM = NV * 128;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * DIM);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { v[i] = xr[i * 32 + lane]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
+  const float mean = warp_sum(s) * (1.0f / DIM);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += dx * dx + dy * dy + dz * dz + dw * dw;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / DIM) + eps);
+  const long long ioff = (long long)(rows_per_item > 0 ? row / rows_per_item : 0) * item_stride;
+  const float4* ar = reinterpret_cast<const float4*>(a + ioff);
+  const float4* br = reinterpret_cast<const float4*>(b + ioff);
+  uint2* orow = reinterpret_cast<uint2*>(out + (long long)row * DIM);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 aa = __ldg(ar + i * 32 + lane), bb = __ldg(br + i * 32 + lane);
+    const float y0 = (v[i].x - mean) * rstd * aa.x + bb.x, y1 = (v[i].y - mean) * rstd * aa.y + bb.y;
+    const float y2 = (v[i].z - mean) * rstd * aa.z + bb.z, y3 = (v[i].w - mean) * rstd * aa.w + bb.w;
+    orow[i * 32 + lane] = make_uint2(pack_h2(y0, y1), pack_h2(y2, y3));
+  }
+}
+
+// ------------------------------------------------------------------ q/k RMSNorm (+ RoPE), in place on fp16
+// model.py:85-88 over all `dim` channels (sum of squares arrives as per-N-tile partials from the
+// producing GEMM), then model.py:42-69: lanes (2j,2j+1) of each head rotate by the token's angle.
+struct RmsRopeParams {
+  __half* x; long long ld; int dim;
+  const float* ssq; int ssq_ld; int ssq_n;            // slice s uses partials [s*ssq_n, (s+1)*ssq_n)
+  const float* gamma[2];
+  const float2* cs;                                    // [rows_per_item, 64] (cos, sin) or nullptr
+  int M, rows_per_item; float eps;
+};
+
+__global__ void __launch_bounds__(192) rms_rope_kernel(const RmsRopeParams p) {
+  const int row = blockIdx.x, slice = blockIdx.y;
+  float tot = 0.f;
+  for (int i = 0; i < p.ssq_n; ++i) tot += p.ssq[(long long)row * p.ssq_ld + slice * p.ssq_n + i];
+  const float inv = rsqrtf(tot / (float)p.dim + p.eps);
+  __half* xr = p.x + (long long)row * p.ld + (long long)slice * p.dim;
+  const float* g = p.gamma[slice];
+  const int tok = row % p.rows_per_item;
+  for (int ci = threadIdx.x; ci < p.dim / 8; ci += blockDim.x) {
+    const int col = ci * 8;
+    uint4 raw = *reinterpret_cast<const uint4*>(xr + col);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + col));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + col + 4));
+    float v[8];
+    float2 f;
+    f = __half22float2(h[0]); v[0] = f.x * inv * g0.x; v[1] = f.y * inv * g0.y;
+    f = __half22float2(h[1]); v[2] = f.x * inv * g0.z; v[3] = f.y * inv * g0.w;
+    f = __half22float2(h[2]); v[4] = f.x * inv * g1.x; v[5] = f.y * inv * g1.y;
+    f = __half22float2(h[3]); v[6] = f.x * inv * g1.z; v[7] = f.y * inv * g1.w;
+    if (p.cs != nullptr) {
+      const int j0 = (col & 127) >> 1;                 // first complex pair of this chunk within its head
+      const float4* cs4 = reinterpret_cast<const float4*>(p.cs + (long long)tok * 64 + j0);
+      const float4 c01 = __ldg(cs4), c23 = __ldg(cs4 + 1);
+      float a, b;
+      a = v[0]; b = v[1]; v[0] = a * c01.x - b * c01.y; v[1] = a * c01.y + b * c01.x;
+      a = v[2]; b = v[3]; v[2] = a * c01.z - b * c01.w; v[3] = a * c01.w + b * c01.z;
+      a = v[4]; b = v[5]; v[4] = a * c23.x - b * c23.y; v[5] = a * c23.y + b * c23.x;
+      a = v[6]; b = v[7]; v[6] = a * c23.z - b * c23.w; v[7] = a * c23.w + b * c23.z;
+    }
+    *reinterpret_cast<uint4*>(xr + col) =
+        make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+  }
+}
+
+// ------------------------------------------------------------------ timestep embedding (model.py:17-27,526-528)
+__global__ void sinusoid_kernel(const float* __restrict__ t, int B, int freq_dim, float* __restrict__ out) {
+  const int half = freq_dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, k = i % half;
+  const double w = pow(10000.0, -(double)k / (double)half);
+  const double ang = (double)t[b] * w;
+  out[b * freq_dim + k] = (float)cos(ang);
+  out[b * freq_dim + half + k] = (float)sin(ang);
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// out[b, n] = act_out( sum_k act_in(in[b,k]) * W[n,k] + bias[n] ), fp32, one warp per output feature
+template <bool SILU_IN, bool SILU_OUT>
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                                                           const float* __restrict__ bias, float* __restrict__ out,
+                                                           int B, int K, int N) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float acc[MAX_ITEMS];
+#pragma unroll
+  for (int b = 0; b < MAX_ITEMS; ++b) acc[b] = 0.f;
+  const float* wr = W + (long long)n * K;
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+    for (int b = 0; b < MAX_ITEMS; ++b) {
+      if (b < B) {
+        float4 x4 = *reinterpret_cast<const float4*>(in + (long long)b * K + k);
+        if (SILU_IN) { x4.x = silu_f(x4.x); x4.y = silu_f(x4.y); x4.z = silu_f(x4.z); x4.w = silu_f(x4.w); }
+        acc[b] += x4.x * w4.x + x4.y * w4.y + x4.z * w4.z + x4.w * w4.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < MAX_ITEMS; ++b) {
+    if (b < B) {
+      float v = warp_sum(acc[b]);
+      if (lane == 0) {
+        v += bias ? bias[n] : 0.f;
+        out[(long long)b * N + n] = SILU_OUT ? silu_f(v) : v;
+      }
+    }
+  }
+}
+
+// mod[layer][item][6][dim] = modulation[layer][6][dim] + e0[item][6][dim]; rows 1 and 4 (scales) get +1
+__global__ void mod_table_kernel(const float* __restrict__ modulation, const float* __restrict__ e0,
+                                 float* __restrict__ out, int layers, int B, int dim) {
+  const long long n = (long long)layers * B * 6 * dim;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = i % dim;
+    const int k = (i / dim) % 6;
+    const int b = (i / (6LL * dim)) % B;
+    const int l = i / (6LL * dim * B);
+    float v = modulation[((long long)l * 6 + k) * dim + c] + e0[((long long)b * 6 + k) * dim + c];
+    if (k == 1 || k == 4) v += 1.0f;
+    out[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------ patchify (model.py:515-518, patch (1,2,2))
+__global__ void patchify_kernel(ItemPtrs x, ItemPtrs y, int C, int Cy, int F, int H, int W, int B,
+                                __half* __restrict__ out, long long ld) {
+  const int Hp = H / 2, Wp = W / 2, L = F * Hp * Wp, Ct = C + Cy;
+  const long long n = (long long)B * L * Ct * 2;                // one thread per (token, c, q) -> 2 outputs
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int q = i & 1;
+    const int c = (i >> 1) % Ct;
+    const long long tokg = (i >> 1) / Ct;
+    const int b = tokg / L, tok = tokg % L;
+    const int w = tok % Wp, h = (tok / Wp) % Hp, f = tok / (Wp * Hp);
+    const float* src = (c < C) ? x.p[b] + (long long)c * F * H * W : y.p[b] + (long long)(c - C) * F * H * W;
+    const float2 v = *reinterpret_cast<const float2*>(src + ((long long)f * H + 2 * h + q) * W + 2 * w);
+    *reinterpret_cast<__half2*>(out + tokg * ld + c * 4 + q * 2) = __floats2half2_rn(v.x, v.y);
+  }
+}
+
+struct RowCounts { int n[MAX_ITEMS]; };
+
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// context rows -> fp16, zero padded to rows_out per item (model.py:532)
+template <typename T>
+__global__ void pad_cast_rows_kernel(ItemPtrs src, RowCounts rows_in, int B, int rows_out, int cols,
+                                     __half* __restrict__ out) {
+  const long long n = (long long)B * rows_out * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = i % cols;
+    const int r = (i / cols) % rows_out;
+    const int b = i / ((long long)cols * rows_out);
+    float v = 0.f;
+    if (r < rows_in.n[b]) v = to_f<T>(reinterpret_cast<const T*>(src.p[b])[(long long)r * cols + c]);
+    out[i] = __float2half_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------ head + unpatchify (+ CFG)
+// model.py:349-359 in fp32: y = Linear(LN(x) * (1 + m1) + m0), (m0, m1) = head.modulation + e;
+// model.py:565-588: out[c, f, 2h+q, 2w+r] = y[token(f,h,w), (2q+r)*out_dim + c].
+// With cfg_pairs > 0 item b (cond) and item b+cfg_pairs (uncond) are combined as
+// uncond + s (cond - uncond)  (text2video.py:243-244) before the store.
+constexpr int HEAD_ROWS = 8;
+
+__global__ void __launch_bounds__(256)
+head_kernel(const float* __restrict__ x, const float* __restrict__ e, const float* __restrict__ head_mod,
+            const float* __restrict__ w_t, const float* __restrict__ bias, int L, int Hp, int Wp, int F, int dim,
+            int out_dim, float eps, ItemPtrsMut out, int cfg_pairs, const float* __restrict__ cfg_scale_p) {
+  extern __shared__ float sm[];
+  float* u = sm;                          // [HEAD_ROWS][dim]
+  float* yv = sm + HEAD_ROWS * dim;       // [HEAD_ROWS][64]
+  const int P = out_dim * 4;
+  const int toks_per_block = cfg_pairs > 0 ? HEAD_ROWS / 2 : HEAD_ROWS;
+  const int tok0 = blockIdx.x * toks_per_block;
+  const int oitem = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  {  // LayerNorm + modulation of row `warp`
+    const int tl = cfg_pairs > 0 ? (warp & 3) : warp;
+    const int item = cfg_pairs > 0 ? (warp < 4 ? oitem : oitem + cfg_pairs) : oitem;
+    const int tok = tok0 + tl;
+    float* ur = u + warp * dim;
+    if (tok < L) {
+      const float* xr = x + ((long long)item * L + tok) * dim;
+      float s = 0.f;
+      for (int k = lane; k < dim; k += 32) s += xr[k];
+      const float mean = warp_sum(s) / dim;
+      float q = 0.f;
+      for (int k = lane; k < dim; k += 32) { const float d = xr[k] - mean; q += d * d; }
+      const float rstd = rsqrtf(warp_sum(q) / dim + eps);
+      const float* er = e + (long long)item * dim;
+      for (int k = lane; k < dim; k += 32)
+        ur[k] = (xr[k] - mean) * rstd * (1.0f + head_mod[dim + k] + er[k]) + (head_mod[k] + er[k]);
+    } else {
+      for (int k = lane; k < dim; k += 32) ur[k] = 0.f;
+    }
+  }
+  __syncthreads();
+  {
+    const int o = threadIdx.x & 63, g = threadIdx.x >> 6;      // rows 2g, 2g+1
+    float a0 = 0.f, a1 = 0.f;
+    if (o < P) {
+      const float* u0 = u + (2 * g) * dim;
+      const float* u1 = u0 + dim;
+#pragma unroll 4
+      for (int k = 0; k < dim; ++k) {
+        const float w = __ldg(w_t + (long long)k * P + o);
+        a0 = fmaf(u0[k], w, a0);
+        a1 = fmaf(u1[k], w, a1);
+      }
+      a0 += bias[o]; a1 += bias[o];
+    }
+    yv[(2 * g) * 64 + o] = a0;
+    yv[(2 * g + 1) * 64 + o] = a1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < toks_per_block * P; i += blockDim.x) {
+    const int tl = i / P, o = i % P;
+    const int tok = tok0 + tl;
+    if (tok >= L) continue;
+    float v = yv[tl * 64 + o];
+    if (cfg_pairs > 0) { const float un = yv[(tl + 4) * 64 + o]; v = un + __ldg(cfg_scale_p) * (v - un); }
+    const int w = tok % Wp, h = (tok / Wp) % Hp, f = tok / (Wp * Hp);
+    const int c = o % out_dim, qr = o / out_dim, q = qr >> 1, r = qr & 1;
+    out.p[oitem][(((long long)c * F + f) * (2 * Hp) + 2 * h + q) * (2 * Wp) + 2 * w + r] = v;
+  }
+}
+
+template <typename S, typename D>
+__global__ void convert_kernel(const S* __restrict__ s, D* __restrict__ d, long long n);
+
+template <typename D>
+__device__ __forceinline__ D from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+template <typename S, typename D>
+__global__ void convert_kernel(const S* __restrict__ s, D* __restrict__ d, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = from_f<D>(to_f<S>(s[i]));
+}
+
+__global__ void transpose_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  const long long n = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = i / cols, c = i % cols;
+    dst[(long long)c * rows + r] = src[i];
+  }
+}
+
+// 32x32 smem tile transpose of V: [B, Lk, C] -> [B, C, Lp]
+__global__ void transpose_v_kernel(const __half* __restrict__ v, __half* __restrict__ vt, int Lk, int C, int Lp) {
+  __shared__ __half tile[32][33];
+  const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int l = l0 + i;
+    tile[i][tx] = (l < Lk) ? v[((long long)b * Lk + l) * C + c0 + tx] : __float2half(0.f);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int l = l0 + tx;
+    if (l < Lp) vt[((long long)b * C + c0 + i) * Lp + l] = tile[tx][i];
+  }
+}
+
+__global__ void gelu_erf_cast_kernel(const float* __restrict__ x, __half* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    out[i] = __float2half_rn(0.5f * v * (1.0f + erff(v * 0.7071067811865476f)));
+  }
+}
+
+inline int grid_for(long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+}  // namespace
+
+void launch_ln_affine(const float* x, __half* out, const float* a, const float* b, long long item_stride, int M,
+                      int rows_per_item, int dim, float eps, cudaStream_t s) {
+  B2_CHECK(dim % 128 == 0, "LayerNorm width %d must be a multiple of 128", dim);
+  const int grid = (M + 7) / 8;
+#define B2_LN_CASE(NV) \
+  case NV: ln_affine_kernel<NV><<<grid, 256, 0, s>>>(x, out, a, b, item_stride, M, rows_per_item, eps); break;
+  switch (dim / 128) {
+    B2_LN_CASE(1) B2_LN_CASE(2) B2_LN_CASE(3) B2_LN_CASE(4) B2_LN_CASE(8) B2_LN_CASE(10) B2_LN_CASE(12)
+    B2_LN_CASE(16) B2_LN_CASE(40)
+    default: fail("LayerNorm width %d not instantiated", dim);
+  }
+#undef B2_LN_CASE
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void launch_rms_rope(__half* x, long long ld, int dim, int nslices, const float* ssq, int ssq_ld, int ssq_n,
+                     const float* gamma0, const float* gamma1, const float* cs_table, int M, int rows_per_item,
+                     float eps, cudaStream_t s) {
+  RmsRopeParams p;
+  p.x = x; p.ld = ld; p.dim = dim; p.ssq = ssq; p.ssq_ld = ssq_ld; p.ssq_n = ssq_n;
+  p.gamma[0] = gamma0; p.gamma[1] = gamma1;
+  p.cs = reinterpret_cast<const float2*>(cs_table);
+  p.M = M; p.rows_per_item = rows_per_item; p.eps = eps;
+  rms_rope_kernel<<<dim3(M, nslices), 192, 0, s>>>(p);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void launch_time_embed(const float* t, int B, int freq_dim, int dim, const float* w0, const float* b0, const float* w2,
+                       const float* b2, const float* wp, const float* bp, float* scratch, float* e, float* e0,
+                       cudaStream_t s) {
+  B2_CHECK(B <= MAX_ITEMS, "at most %d items per launch", MAX_ITEMS);
+  B2_CHECK(freq_dim % 4 == 0 && dim % 4 == 0, "time embedding widths must be multiples of 4");
+  float* sin_buf = scratch;                       // [B, freq_dim]
+  float* h1 = scratch + (long long)B * freq_dim;  // [B, dim]
+  sinusoid_kernel<<<(B * freq_dim / 2 + 127) / 128, 128, 0, s>>>(t, B, freq_dim, sin_buf);
+  small_linear_kernel<false, true><<<(dim + 7) / 8, 256, 0, s>>>(sin_buf, w0, b0, h1, B, freq_dim, dim);
+  small_linear_kernel<false, false><<<(dim + 7) / 8, 256, 0, s>>>(h1, w2, b2, e, B, dim, dim);
+  small_linear_kernel<true, false><<<(6 * dim + 7) / 8, 256, 0, s>>>(e, wp, bp, e0, B, dim, 6 * dim);
+  B2_CUDA(cudaGetLastError());
+  count_launch(4);
+}
+
+void launch_mod_table(const float* modulation, const float* e0, float* out, int layers, int B, int dim,
+                      cudaStream_t s) {
+  mod_table_kernel<<<grid_for((long long)layers * B * 6 * dim), 256, 0, s>>>(modulation, e0, out, layers, B, dim);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void launch_patchify(ItemPtrs x, ItemPtrs y, int C, int Cy, int F, int H, int W, int B, __half* out, long long ld,
+                     cudaStream_t s) {
+  B2_CHECK(H % 2 == 0 && W % 2 == 0, "latent H, W must be even for the (1,2,2) patch");
+  const long long n = (long long)B * F * (H / 2) * (W / 2) * (C + Cy) * 2;
+  patchify_kernel<<<grid_for(n), 256, 0, s>>>(x, y, C, Cy, F, H, W, B, out, ld);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void launch_pad_cast_rows(ItemPtrs src, int src_dtype, const int* rows_in, int B, int rows_out, int cols, __half* out,
+                          cudaStream_t s) {
+  RowCounts rc;
+  for (int i = 0; i < MAX_ITEMS; ++i) rc.n[i] = i < B ? rows_in[i] : 0;
+  const int g = grid_for((long long)B * rows_out * cols);
+  if (src_dtype == DT_F32) pad_cast_rows_kernel<float><<<g, 256, 0, s>>>(src, rc, B, rows_out, cols, out);
+  else if (src_dtype == DT_F16) pad_cast_rows_kernel<__half><<<g, 256, 0, s>>>(src, rc, B, rows_out, cols, out);
+  else if (src_dtype == DT_BF16) pad_cast_rows_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(src, rc, B, rows_out, cols, out);
+  else fail("unsupported context dtype %d", src_dtype);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void launch_head(const float* x, const float* e, const float* head_mod, const float* w_t, const float* bias, int B,
+                 int F, int Hp, int Wp, int dim, int out_dim, float eps, ItemPtrsMut out, int cfg_pairs,
+                 const float* cfg_scale, cudaStream_t s) {
+  B2_CHECK(out_dim * 4 <= 64, "head output width %d > 64", out_dim * 4);
+  const int L = F * Hp * Wp;
+  const size_t smem = (size_t)(HEAD_ROWS * dim + HEAD_ROWS * 64) * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    B2_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int tpb = cfg_pairs > 0 ? HEAD_ROWS / 2 : HEAD_ROWS;
+  const int n_out = cfg_pairs > 0 ? cfg_pairs : B;
+  head_kernel<<<dim3((L + tpb - 1) / tpb, n_out), 256, smem, s>>>(x, e, head_mod, w_t, bias, L, Hp, Wp, F, dim, out_dim,
+                                                                  eps, out, cfg_pairs, cfg_scale);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void launch_convert(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, cudaStream_t s) {
+  const int g = grid_for(n);
+#define B2_CVT(ST, DT) convert_kernel<ST, DT><<<g, 256, 0, s>>>(reinterpret_cast<const ST*>(src), reinterpret_cast<DT*>(dst), n)
+  if (dst_dtype == DT_F16) {
+    if (src_dtype == DT_F32) B2_CVT(float, __half);
+    else if (src_dtype == DT_F16) B2_CVT(__half, __half);
+    else if (src_dtype == DT_BF16) B2_CVT(__nv_bfloat16, __half);
+    else fail("unsupported source dtype %d", src_dtype);
+  } else if (dst_dtype == DT_F32) {
+    if (src_dtype == DT_F32) B2_CVT(float, float);
+    else if (src_dtype == DT_F16) B2_CVT(__half, float);
+    else if (src_dtype == DT_BF16) B2_CVT(__nv_bfloat16, float);
+    else fail("unsupported source dtype %d", src_dtype);
+  } else {
+    fail("unsupported destination dtype %d", dst_dtype);
+  }
+#undef B2_CVT
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void launch_transpose_v(const __half* v, __half* vt, int B, int Lk, int H, int Lp, cudaStream_t s) {
+  const int C = H * 128;
+  transpose_v_kernel<<<dim3((Lp + 31) / 32, C / 32, B), 256, 0, s>>>(v, vt, Lk, C, Lp);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t s) {
+  transpose_f32_kernel<<<grid_for((long long)rows * cols), 256, 0, s>>>(src, dst, rows, cols);
+  B2_CUDA(cudaGetLastError());
+}
+
+void launch_gelu_erf_cast(const float* x, __half* out, long long n, cudaStream_t s) {
+  gelu_erf_cast_kernel<<<grid_for(n), 256, 0, s>>>(x, out, n);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+}  // namespace b2

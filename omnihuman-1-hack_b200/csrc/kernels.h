@@ -1,0 +1,80 @@
+// Launcher declarations for every kernel in the library (definitions in the .cu files named
+// beside each group).  All launchers enqueue on `stream` and never synchronise.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_tc.cuh"
+
+namespace b2 {
+
+constexpr int MAX_ITEMS = 16;   // items co-batched in one launch (per-item scalars ride in kernel params)
+
+// number of kernels launched by this library since load (reported as bench.py's gpu_launches)
+void count_launch(int n = 1);
+long long launches_total();
+
+// ---- gemm_tc.cu
+void launch_gemm(int epi, int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
+                 cudaStream_t stream);
+void gemm_linear(int epi, const __half* A, long long lda, const __half* W, long long ldw, GemmParams p, int num_sms,
+                 cudaStream_t stream, int force_bn = 0);
+inline int pick_bn(long long M, long long N, int num_sms) {
+  const long long t256 = ((M + 127) / 128) * ((N + 255) / 256);
+  return (N % 256 == 0 && t256 >= num_sms) ? 256 : 128;
+}
+
+// ---- attn_tc.cu : softmax(Q K^T / sqrt(128)) V, head_dim 128, non-causal, keys >= klen masked
+struct AttnParams {
+  const __half* q; long long ldq;      // [items*Lq, ldq], head h at columns h*128
+  const __half* k; long long ldk;      // [items*Lk_rows, ldk]
+  const __half* vt; long long ldvt;    // [items*heads*128, ldvt]   V transposed per (item, head)
+  __half* out; long long ldo;          // [items*Lq, ldo]
+  int items, heads;
+  int Lq;                              // query rows per item
+  int Lk_rows;                         // key rows per item in the k buffer
+  int klen[MAX_ITEMS];                 // valid keys per item (<= Lk_rows)
+  float scale;                         // 1/sqrt(head_dim)
+  int accumulate;                      // 1: out += result (fp16 add; i2v second K/V stream)
+};
+void launch_attention(const AttnParams& p, cudaStream_t stream);
+
+// ---- elementwise.cu
+struct ItemPtrs { const float* p[MAX_ITEMS]; };
+struct ItemPtrsMut { float* p[MAX_ITEMS]; };
+
+// LayerNorm(x) * a + b  ->  fp16.  a/b are [dim] vectors, per item when item_stride != 0.
+void launch_ln_affine(const float* x, __half* out, const float* a, const float* b, long long item_stride, int M,
+                      int rows_per_item, int dim, float eps, cudaStream_t s);
+// in-place on fp16 [M, ld]: per slice (q at column 0, k at column dim) x * rsqrt(mean(x^2)+eps) * gamma,
+// then optional 3-D RoPE (cos/sin table [rows_per_item, 64] float2).  ssq holds per-N-tile partial sums.
+void launch_rms_rope(__half* x, long long ld, int dim, int nslices, const float* ssq, int ssq_ld, int ssq_n,
+                     const float* gamma0, const float* gamma1, const float* cs_table, int M, int rows_per_item,
+                     float eps, cudaStream_t s);
+// sinusoid(t) -> time MLP -> e [B, dim], e0 [B, 6*dim]  (all fp32, model.py:526-528)
+void launch_time_embed(const float* t, int B, int freq_dim, int dim, const float* w0, const float* b0, const float* w2,
+                       const float* b2, const float* wp, const float* bp, float* scratch, float* e, float* e0,
+                       cudaStream_t s);
+// per-layer AdaLN table: mod[layer][item][6][dim] = modulation[layer] + e0[item], with +1 folded into the scales
+void launch_mod_table(const float* modulation, const float* e0, float* out, int layers, int B, int dim, cudaStream_t s);
+// latent [C,F,H,W] fp32 (+ optional y channel stack) -> fp16 patch rows [B*L, K = (C+Cy)*4], K index c*4+q*2+r
+void launch_patchify(ItemPtrs x, ItemPtrs y, int C, int Cy, int F, int H, int W, int B, __half* out, long long ld,
+                     cudaStream_t s);
+// fp32/bf16/fp16 rows -> fp16 matrix, zero-padded to rows_out rows per item
+void launch_pad_cast_rows(ItemPtrs src, int src_dtype, const int* rows_in, int B, int rows_out, int cols, __half* out,
+                          cudaStream_t s);
+// head: LN + modulation + Linear(dim -> P) in fp32, unpatchify scatter, optional fused CFG combine
+void launch_head(const float* x, const float* e, const float* head_mod, const float* w_t, const float* bias, int B,
+                 int F, int Hp, int Wp, int dim, int out_dim, float eps, ItemPtrsMut out, int cfg_pairs,
+                 const float* cfg_scale, cudaStream_t s);
+// v [B, Lk, H*128] fp16 -> vt [B*H*128, Lp]
+void launch_transpose_v(const __half* v, __half* vt, int B, int Lk, int H, int Lp, cudaStream_t s);
+void launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t s);
+void launch_convert(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, cudaStream_t s);
+void launch_gelu_erf_cast(const float* x, __half* out, long long n, cudaStream_t s);
+
+enum DType : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
+
+}  // namespace b2

@@ -1,0 +1,24 @@
+// VaeEngine: WanVAE decode on the tcgen05 implicit-GEMM convolution path (see vae_engine.cu).
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "dit_engine.h"
+
+namespace b2 {
+
+class VaeEngine {
+ public:
+  VaeEngine(int dim, int z_dim);
+  ~VaeEngine();
+  void load_weight(const char* name, const void* data, int dtype, int ndim, const int64_t* shape);
+  void finalize();
+  void decode(const float* z, int T, int h, int w, float* out, cudaStream_t stream);
+
+ private:
+  struct Impl;
+  Impl* impl = nullptr;
+};
+
+}  // namespace b2

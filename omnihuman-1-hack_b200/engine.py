@@ -1,0 +1,293 @@
+"""Host side of the B200 engine: torch tensors in, raw device pointers across the C ABI.
+
+PyTorch is used for device memory, streams and (in parallel.py) torch.distributed only; all
+arithmetic of the hot path runs in libb200dit.so.  `DitEngine.forward` has the exact argument
+meaning of the reference `WanModel.forward` (seaweed_apt/wan/modules/model.py:502-563),
+`VaeEngine.decode` of `WanVAE.decode` (seaweed_apt/wan/modules/vae.py:657-663).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import B200Error, DitConfig, check, int_array, lib, ptr_array
+
+_DT = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _load_state(load_fn, handle, sd, accept):
+    for name, tensor in sd.items():
+        if not accept(name):
+            continue
+        t = tensor.detach()
+        if t.dtype not in _DT:
+            t = t.float()
+        t = t.contiguous()
+        shape = (C.c_int64 * max(t.dim(), 1))(*(list(t.shape) or [1]))
+        check(load_fn(handle, name.encode(), C.c_void_p(t.data_ptr()), _DT[t.dtype], max(t.dim(), 1), shape))
+
+
+class DitEngine:
+    """B200 replacement for the arithmetic of one `WanModel` instance."""
+
+    def __init__(self, dim=1536, ffn_dim=8960, num_heads=12, num_layers=30, in_dim=16, out_dim=16, text_dim=4096,
+                 text_len=512, freq_dim=256, i2v=False, eps=1e-6, device=None):
+        if not torch.cuda.is_available():
+            raise B200Error("no CUDA device: the B200 engine has no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.cfg = dict(dim=dim, ffn_dim=ffn_dim, num_heads=num_heads, num_layers=num_layers, in_dim=in_dim,
+                        out_dim=out_dim, text_dim=text_dim, text_len=text_len, freq_dim=freq_dim, i2v=int(bool(i2v)),
+                        eps=eps)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().b200dit_create(C.byref(DitConfig(**self.cfg)), C.byref(self._h)))
+        self._tap = None
+
+    # ------------------------------------------------------------------ construction helpers
+    @classmethod
+    def from_state_dict(cls, sd, num_heads, text_len=512, eps=1e-6, device=None):
+        """Infers the architecture from reference state_dict shapes (key names: model.py:463-498)."""
+        dim = sd["patch_embedding.weight"].shape[0]
+        layers = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("blocks."))
+        eng = cls(dim=dim, ffn_dim=sd["blocks.0.ffn.0.weight"].shape[0], num_heads=num_heads, num_layers=layers,
+                  in_dim=sd["patch_embedding.weight"].shape[1], out_dim=sd["head.head.weight"].shape[0] // 4,
+                  text_dim=sd["text_embedding.0.weight"].shape[1], text_len=text_len,
+                  freq_dim=sd["time_embedding.0.weight"].shape[1], i2v="img_emb.proj.0.weight" in sd, eps=eps,
+                  device=device)
+        eng.load_state_dict(sd)
+        return eng
+
+    @classmethod
+    def from_module(cls, model, device=None):
+        """Builds an engine from a reference `WanModel` instance (attributes set at model.py:445-460)."""
+        eng = cls(dim=model.dim, ffn_dim=model.ffn_dim, num_heads=model.num_heads, num_layers=model.num_layers,
+                  in_dim=model.in_dim, out_dim=model.out_dim, text_dim=model.text_dim, text_len=model.text_len,
+                  freq_dim=model.freq_dim, i2v=(model.model_type == "i2v"), eps=model.eps, device=device)
+        eng.load_state_dict(model.state_dict())
+        return eng
+
+    def load_state_dict(self, sd):
+        with torch.cuda.device(self.device):
+            _load_state(lib().b200dit_load_weight, self._h, sd, lambda n: n != "freqs")
+            check(lib().b200dit_finalize(self._h))
+
+    def set_graphs(self, enabled):
+        check(lib().b200dit_set_graphs(self._h, int(bool(enabled))))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().b200dit_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ forward
+    def _prep_items(self, x, context, clip_fea, y):
+        xs = [u for u in x] if not isinstance(x, (list, tuple)) else list(x)
+        xs = [u.to(self.device, torch.float32, non_blocking=True).contiguous() for u in xs]
+        ys = None
+        if y is not None:
+            ys = [v.to(self.device, torch.float32, non_blocking=True).contiguous() for v in y]
+        ctx = []
+        for c in context:
+            c = c if c.dtype in _DT else c.float()
+            ctx.append(c.to(self.device, non_blocking=True).contiguous())
+        dts = {c.dtype for c in ctx}
+        if len(dts) > 1:
+            ctx = [c.float() for c in ctx]
+        clips = None
+        if clip_fea is not None:
+            clips = [c.to(self.device, torch.float32, non_blocking=True).contiguous() for c in clip_fea]
+        return xs, ys, ctx, clips
+
+    def _t_tensor(self, t, n):
+        if not torch.is_tensor(t):
+            t = torch.tensor(t, dtype=torch.float32)
+        t = t.reshape(-1).to(self.device, torch.float32, non_blocking=True)
+        if t.numel() == 1 and n > 1:
+            t = t.expand(n)
+        assert t.numel() == n, f"t has {t.numel()} entries for {n} items"
+        return t.contiguous()
+
+    def forward(self, x, t, context, seq_len, clip_fea=None, y=None):
+        """WanModel.forward (model.py:502): list (or batched tensor) of [C,F,H,W] -> list of fp32 [16,F,H,W]."""
+        xs, ys, ctx, clips = self._prep_items(x, context, clip_fea, y)
+        n = len(xs)
+        tt = self._t_tensor(t, n)
+        outs = [None] * n
+        groups = {}
+        for i, u in enumerate(xs):
+            groups.setdefault(tuple(u.shape[1:]), []).append(i)
+        with torch.cuda.device(self.device):
+            for (F, H, W), idx in groups.items():
+                for s in range(0, len(idx), _lib.MAX_ITEMS):
+                    part = idx[s:s + _lib.MAX_ITEMS]
+                    o = [torch.empty((self.cfg["out_dim"], F, H, W), dtype=torch.float32, device=self.device)
+                         for _ in part]
+                    t_part = tt[part].contiguous() if len(part) != n else tt
+                    ych = ys[part[0]].shape[0] if ys is not None else 0
+                    check(lib().b200dit_forward(
+                        self._h, len(part), ptr_array([xs[i].data_ptr() for i in part]),
+                        ptr_array([ys[i].data_ptr() for i in part]) if ys is not None else None, ych,
+                        C.c_void_p(t_part.data_ptr()), ptr_array([ctx[i].data_ptr() for i in part]),
+                        int_array([ctx[i].shape[0] for i in part]), _DT[ctx[part[0]].dtype],
+                        ptr_array([clips[i].data_ptr() for i in part]) if clips is not None else None,
+                        F, H, W, int(seq_len) if seq_len is not None else 0,
+                        ptr_array([q.data_ptr() for q in o]), _stream_ptr()))
+                    for i, q in zip(part, o):
+                        outs[i] = q
+        return outs
+
+    __call__ = forward
+
+    def forward_cfg(self, x, t, context, context_null, seq_len, guide_scale, clip_fea=None, y=None):
+        """cond + uncond forwards and `uncond + s (cond - uncond)` (text2video.py:238-244) in one call."""
+        xs, ys, ctx, clips = self._prep_items(x, context, clip_fea, y)
+        _, _, ctx_n, _ = self._prep_items([], context_null, None, None)
+        n = len(xs)
+        if len(ctx_n) == 1 and n > 1:
+            ctx_n = ctx_n * n
+        if ctx and ctx_n and ctx[0].dtype != ctx_n[0].dtype:
+            ctx, ctx_n = [c.float() for c in ctx], [c.float() for c in ctx_n]
+        tt = self._t_tensor(t, n)
+        outs = [None] * n
+        groups = {}
+        for i, u in enumerate(xs):
+            groups.setdefault(tuple(u.shape[1:]), []).append(i)
+        half = _lib.MAX_ITEMS // 2
+        with torch.cuda.device(self.device):
+            for (F, H, W), idx in groups.items():
+                for s in range(0, len(idx), half):
+                    part = idx[s:s + half]
+                    o = [torch.empty((self.cfg["out_dim"], F, H, W), dtype=torch.float32, device=self.device)
+                         for _ in part]
+                    t_part = tt[part].contiguous() if len(part) != n else tt
+                    ych = ys[part[0]].shape[0] if ys is not None else 0
+                    check(lib().b200dit_forward_cfg(
+                        self._h, len(part), ptr_array([xs[i].data_ptr() for i in part]),
+                        ptr_array([ys[i].data_ptr() for i in part]) if ys is not None else None, ych,
+                        C.c_void_p(t_part.data_ptr()),
+                        ptr_array([ctx[i].data_ptr() for i in part]), int_array([ctx[i].shape[0] for i in part]),
+                        ptr_array([ctx_n[i].data_ptr() for i in part]), int_array([ctx_n[i].shape[0] for i in part]),
+                        _DT[ctx[part[0]].dtype],
+                        ptr_array([clips[i].data_ptr() for i in part]) if clips is not None else None,
+                        F, H, W, int(seq_len) if seq_len is not None else 0, float(guide_scale),
+                        ptr_array([q.data_ptr() for q in o]), _stream_ptr()))
+                    for i, q in zip(part, o):
+                        outs[i] = q
+        return outs
+
+    def set_tap(self, block_idx, n_rows=None):
+        """Residual stream after block `block_idx` (APT discriminator taps, seaweed_apt/model.py:150-155)."""
+        if block_idx is None or block_idx < 0:
+            check(lib().b200dit_set_tap(self._h, -1, None))
+            self._tap = None
+            return None
+        self._tap = torch.empty((n_rows, self.cfg["dim"]), dtype=torch.float32, device=self.device)
+        check(lib().b200dit_set_tap(self._h, int(block_idx), C.c_void_p(self._tap.data_ptr())))
+        return self._tap
+
+    @property
+    def last_flops(self):
+        return float(lib().b200dit_last_flops(self._h))
+
+
+class VaeEngine:
+    """B200 replacement for `WanVAE.decode` (vae.py:657-663)."""
+
+    def __init__(self, dim=96, z_dim=16, device=None):
+        if not torch.cuda.is_available():
+            raise B200Error("no CUDA device: the B200 engine has no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.dim, self.z_dim = dim, z_dim
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().b200vae_create(dim, z_dim, C.byref(self._h)))
+
+    @classmethod
+    def from_state_dict(cls, sd, device=None):
+        dim = sd["decoder.head.2.weight"].shape[1]
+        eng = cls(dim=dim, z_dim=sd["conv2.weight"].shape[0], device=device)
+        eng.load_state_dict(sd)
+        return eng
+
+    def load_state_dict(self, sd):
+        with torch.cuda.device(self.device):
+            _load_state(lib().b200vae_load_weight, self._h, sd,
+                        lambda n: n.startswith("decoder.") or n.startswith("conv2."))
+            check(lib().b200vae_finalize(self._h))
+
+    def decode(self, zs):
+        """List of [16,T,h,w] latents -> list of fp32 [3, 1+4(T-1), 8h, 8w] in [-1, 1]."""
+        outs = []
+        with torch.cuda.device(self.device):
+            for z in zs:
+                z = z.to(self.device, torch.float32, non_blocking=True).contiguous()
+                _, T, h, w = z.shape
+                o = torch.empty((3, 1 + 4 * (T - 1), 8 * h, 8 * w), dtype=torch.float32, device=self.device)
+                check(lib().b200vae_decode(self._h, C.c_void_p(z.data_ptr()), T, h, w, C.c_void_p(o.data_ptr()),
+                                           _stream_ptr()))
+                outs.append(o)
+        return outs
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().b200vae_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def flash_attention(q, k, v, q_lens=None, k_lens=None, dropout_p=0., softmax_scale=None, q_scale=None, causal=False,
+                    window_size=(-1, -1), deterministic=False, dtype=torch.bfloat16, version=None):
+    """Drop-in for the reference operator seam `flash_attention` (attention.py:24-38): same signature,
+    q [B,Lq,N,128], k/v [B,Lk,N,128]; returns q's dtype.  Operands run in fp16 (model.py:540 autocast)."""
+    assert q.is_cuda and q.size(-1) == 128, "B200 flash_attention needs CUDA tensors with head_dim 128"
+    assert not causal and q_lens is None and dropout_p == 0. and tuple(window_size) == (-1, -1)
+    b, lq, n, _ = q.shape
+    lk = k.shape[1]
+    out_dtype = q.dtype
+    if q_scale is not None:
+        q = q * q_scale
+    qh, kh, vh = (u.to(torch.float16).contiguous() for u in (q, k, v))
+    out = torch.empty_like(qh)
+    kl = None
+    if k_lens is not None:
+        kl = int_array([int(u) for u in (k_lens.tolist() if torch.is_tensor(k_lens) else k_lens)])
+    with torch.cuda.device(q.device):
+        check(lib().b200_flash_attention(C.c_void_p(qh.data_ptr()), C.c_void_p(kh.data_ptr()), C.c_void_p(vh.data_ptr()),
+                                         kl, b, lq, lk, n, float(softmax_scale or 0.0), C.c_void_p(out.data_ptr()),
+                                         _stream_ptr()))
+    return out.to(out_dtype)
+
+
+def linear(a, w, bias=None, epilogue="f16", block_n=0):
+    """nn.Linear on the tcgen05 GEMM: a [M,K] fp16, w [N,K] fp16 -> [M,N] (fp16, gelu fp16 or fp32)."""
+    epi = {"f16": 0, "gelu": 1, "f32": 4}[epilogue]
+    a, w = a.contiguous(), w.contiguous()
+    assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.is_cuda
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32 if epi == 4 else torch.float16, device=a.device)
+    b = bias.float().contiguous() if bias is not None else None
+    with torch.cuda.device(a.device):
+        check(lib().b200_linear(C.c_void_p(a.data_ptr()), K, C.c_void_p(w.data_ptr()), K,
+                                C.c_void_p(b.data_ptr()) if b is not None else None, M, N, K, epi,
+                                C.c_void_p(out.data_ptr()), N, block_n, _stream_ptr()))
+    return out
+
+
+def kernel_launches():
+    return int(lib().b200_kernel_launches())

@@ -1,0 +1,85 @@
+"""Generates tests/golden/*.pt by running the UNMODIFIED reference modules (oracle/ref_loader.py)
+on seeded synthetic weights/inputs.  Container-only (needs /root/reference); the outputs are the
+committed known-answer vectors that pin oracle/ and the CUDA engine on the GPU box.
+
+    python oracle/make_golden.py
+
+Fixtures (all small enough to commit; weights stored as fp16 = exactly the values used):
+  dit_t2v_tiny.pt   WanModel t2v, dim 128 / 1 head / ffn 256 / 2 layers / text_dim 32, two items with
+                    different grids, t and context lengths, seq_len padding  (model.py:502-563)
+  dit_i2v_tiny.pt   same with model_type='i2v', in_dim 32 (y channel stack) and clip_fea (config 3 hooks)
+  dit_block_1p3b.pt outputs only (weights by seed): ONE 1.3B-shaped block + head on [16,1,60,104]
+                    (BASELINE.json configs[0]); weights regenerate from make_synthetic_weights(seed)
+  vae_tiny.pt       WanVAE_ decoder, dim 8, z [16,3,6,8] -> [3,9,48,64]  (vae.py:544-568)
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import dit_oracle as O, ref_loader, vae_oracle as VO  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def half(sd):
+    return {k: v.half() for k, v in sd.items()}
+
+
+def run_ref_dit(M, cfg, sd, x, t, ctx, seq_len, clip=None, y=None):
+    m = M.WanModel(model_type="i2v" if cfg["i2v"] else "t2v", in_dim=cfg["in_dim"], dim=cfg["dim"],
+                   ffn_dim=cfg["ffn_dim"], num_heads=cfg["num_heads"], num_layers=cfg["num_layers"],
+                   text_dim=cfg["text_dim"], use_checkpoint=False).eval()
+    m.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        return [o.clone() for o in m(x, t, ctx, seq_len=seq_len, clip_fea=clip, y=y)]
+
+
+def main():
+    M, V = ref_loader.load_reference_modules()
+    os.makedirs(OUT, exist_ok=True)
+    g = torch.Generator().manual_seed(1234)
+    rn = lambda *s: torch.randn(*s, generator=g)
+
+    for name, i2v in (("dit_t2v_tiny", False), ("dit_i2v_tiny", True)):
+        cfg = dict(dim=128, ffn_dim=256, num_heads=1, num_layers=2, text_dim=32, in_dim=32 if i2v else 16, i2v=i2v)
+        sd = O.make_synthetic_weights(cfg["dim"], cfg["ffn_dim"], cfg["num_heads"], cfg["num_layers"],
+                                      in_dim=cfg["in_dim"], text_dim=cfg["text_dim"], i2v=i2v, seed=7)
+        x = [rn(16, 2, 8, 12), rn(16, 1, 6, 10)]
+        y = [rn(16, 2, 8, 12), rn(16, 1, 6, 10)] if i2v else None
+        clip = rn(2, 257, 1280) if i2v else None
+        t = torch.tensor([999.0, 417.0])
+        ctx = [rn(100, 32), rn(37, 32)]
+        out = run_ref_dit(M, cfg, sd, x, t, ctx, 60, clip, y)
+        torch.save(dict(cfg=cfg, sd=half(sd), x=x, y=y, clip_fea=clip, t=t, context=ctx, seq_len=60, out=out),
+                   os.path.join(OUT, name + ".pt"))
+        print(name, [tuple(o.shape) for o in out], float(out[0].std()))
+
+    # one 1.3B-shaped block (configs[0]); weights regenerate from the seed, only I/O is stored
+    cfg = dict(dim=1536, ffn_dim=8960, num_heads=12, num_layers=1, text_dim=4096, in_dim=16, i2v=False, seed=11)
+    sd = O.make_synthetic_weights(1536, 8960, 12, 1, seed=11)
+    x = [rn(16, 1, 60, 104)]
+    t = torch.tensor([999.0])
+    ctx = [rn(77, 4096)]
+    # inputs are stored as fp16, so the reference is run on the rounded inputs: the vector is exact
+    xh, ch = x[0].half(), ctx[0].half()
+    out = run_ref_dit(M, cfg, sd, [xh.float()], t, [ch.float()], 1560)
+    torch.save(dict(cfg=cfg, x=[xh], t=t, context=[ch], seq_len=1560, out=out),
+               os.path.join(OUT, "dit_block_1p3b.pt"))
+    print("dit_block_1p3b", tuple(out[0].shape), float(out[0].std()))
+
+    vsd = VO.make_synthetic_vae_weights(dim=8, seed=5)
+    vae = V.WanVAE_(dim=8, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2, attn_scales=[],
+                    temperal_downsample=[False, True, True]).eval()
+    vae.load_state_dict(vsd, strict=False)
+    z = rn(16, 3, 6, 8)
+    mean, std = torch.tensor(VO.VAE_MEAN), torch.tensor(VO.VAE_STD)
+    with torch.no_grad():
+        pix = vae.decode(z[None], [mean, 1.0 / std]).float().clamp_(-1, 1)[0]
+    torch.save(dict(dim=8, sd=half(vsd), z=z, out=pix), os.path.join(OUT, "vae_tiny.pt"))
+    print("vae_tiny", tuple(pix.shape), float(pix.std()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,110 @@
+"""TEST INFRASTRUCTURE ONLY -- loads the *unmodified* reference modules by file path.
+
+Used in the authoring container (where /root/reference is mounted) to
+  (a) validate the in-repo restatements in oracle/dit_oracle.py / oracle/vae_oracle.py, and
+  (b) generate the committed golden fixtures under tests/golden/ (oracle/make_golden.py).
+The GPU box has no /root/reference: nothing under tests -m gpu, smoke() or bench.py calls this.
+
+Shims:
+  * `diffusers.configuration_utils.{ConfigMixin, register_to_config}` and
+    `diffusers.models.modeling_utils.ModelMixin` stubs (model.py:7-8 import them; diffusers is
+    not installed here),
+  * a `logger` module with a `.logger` attribute (model.py:10),
+  * `model.flash_attention` rebound to an exact masked softmax attention on CPU, because
+    attention.py:54 asserts CUDA. Key j of item b is valid iff j < k_lens[b] (attention.py:72-80).
+No reference source is copied; the files are executed from where they lie.
+"""
+import importlib.util
+import logging
+import os
+import sys
+import types
+
+import torch
+
+REF_ROOTS = [os.environ.get("B200DIT_REF", ""), "/root/reference"]
+
+
+def find_reference():
+    for r in REF_ROOTS:
+        if r and os.path.isfile(os.path.join(r, "seaweed_apt/wan/modules/model.py")):
+            return r
+    return None
+
+
+def _masked_attention(q, k, v, q_lens=None, k_lens=None, dropout_p=0., softmax_scale=None,
+                      q_scale=None, causal=False, window_size=(-1, -1), deterministic=False,
+                      dtype=torch.bfloat16, version=None):
+    """CPU stand-in for attention.py:24-130 (exact softmax attention, fp32)."""
+    assert not causal and q_lens is None
+    b, lq, n, d = q.shape
+    lk = k.shape[1]
+    out_dtype = q.dtype
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    if q_scale is not None:
+        qf = qf * q_scale
+    scale = softmax_scale if softmax_scale is not None else d ** -0.5
+    s = torch.matmul(qf, kf.transpose(-1, -2)) * scale
+    if k_lens is not None:
+        kl = torch.as_tensor(k_lens).view(b, 1, 1, 1).clamp(max=lk)
+        mask = torch.arange(lk).view(1, 1, 1, lk) >= kl
+        s = s.masked_fill(mask, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    o = torch.matmul(p, vf).permute(0, 2, 1, 3).contiguous()
+    return o.to(out_dtype)
+
+
+def _install_stubs():
+    if "diffusers" not in sys.modules:
+        d = types.ModuleType("diffusers")
+        cu = types.ModuleType("diffusers.configuration_utils")
+        mo = types.ModuleType("diffusers.models")
+        mu = types.ModuleType("diffusers.models.modeling_utils")
+
+        class ConfigMixin:
+            pass
+
+        def register_to_config(f):
+            return f
+
+        class ModelMixin(torch.nn.Module):
+            pass
+
+        cu.ConfigMixin, cu.register_to_config = ConfigMixin, register_to_config
+        mu.ModelMixin = ModelMixin
+        d.configuration_utils, d.models = cu, mo
+        mo.modeling_utils = mu
+        sys.modules.update({"diffusers": d, "diffusers.configuration_utils": cu,
+                            "diffusers.models": mo, "diffusers.models.modeling_utils": mu})
+    if "logger" not in sys.modules:
+        lg = types.ModuleType("logger")
+        lg.logger = logging.getLogger("ref")
+        sys.modules["logger"] = lg
+
+
+def load_reference_modules(root=None):
+    """Returns (model_module, vae_module) of the reference, executed in place."""
+    root = root or find_reference()
+    if root is None:
+        raise FileNotFoundError("reference tree not available (container-only tool)")
+    _install_stubs()
+    pkg_name = "_refwan_modules"
+    if pkg_name + ".model" in sys.modules:
+        return sys.modules[pkg_name + ".model"], sys.modules[pkg_name + ".vae"]
+    mdir = os.path.join(root, "seaweed_apt/wan/modules")
+    pkg = types.ModuleType(pkg_name)
+    pkg.__path__ = [mdir]
+    sys.modules[pkg_name] = pkg
+    mods = {}
+    for name in ("attention", "model", "vae"):
+        spec = importlib.util.spec_from_file_location(f"{pkg_name}.{name}", os.path.join(mdir, f"{name}.py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[f"{pkg_name}.{name}"] = m
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            spec.loader.exec_module(m)
+        mods[name] = m
+    mods["model"].flash_attention = _masked_attention
+    # model.py:503 calls torch.cuda.empty_cache(); harmless without CUDA.
+    return mods["model"], mods["vae"]

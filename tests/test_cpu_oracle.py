@@ -1,0 +1,92 @@
+"""CPU suite: the oracle against the committed golden vectors (produced by the unmodified reference
+modules, oracle/make_golden.py) and, when /root/reference is mounted, against the reference itself."""
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_l2
+from oracle import dit_oracle as O, ref_loader, vae_oracle as VO
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=True)
+
+
+@pytest.mark.parametrize("name", ["dit_t2v_tiny.pt", "dit_i2v_tiny.pt"])
+def test_dit_oracle_vs_golden(name):
+    g = _load(name)
+    sd = {k: v.float() for k, v in g["sd"].items()}
+    out = O.dit_forward(sd, g["x"], g["t"], g["context"], g["seq_len"], clip_fea=g["clip_fea"], y=g["y"],
+                        num_heads=g["cfg"]["num_heads"])
+    for o, r in zip(out, g["out"]):
+        assert o.shape == r.shape and o.dtype == torch.float32
+        assert rel_l2(o, r) < 1e-5
+
+
+def test_dit_oracle_block_1p3b_vs_golden():
+    g = _load("dit_block_1p3b.pt")
+    sd = O.make_synthetic_weights(1536, 8960, 12, 1, seed=g["cfg"]["seed"])
+    out = O.dit_forward(sd, [g["x"][0].float()], g["t"], [g["context"][0].float()], g["seq_len"])
+    assert rel_l2(out[0], g["out"][0]) < 1e-5
+
+
+def test_vae_oracle_vs_golden_and_two_pass():
+    g = _load("vae_tiny.pt")
+    sd = {k: v.float() for k, v in g["sd"].items()}
+    a = VO.vae_decode(sd, g["z"])
+    assert a.shape == g["out"].shape
+    assert float((a - g["out"]).abs().max()) < 1e-5
+    b = VO.vae_decode(sd, g["z"], chunks=[1, g["z"].shape[1] - 1])     # the engine's two-pass schedule
+    assert float((b - g["out"]).abs().max()) < 1e-5
+
+
+def test_seq_len_overflow_raises():
+    g = _load("dit_t2v_tiny.pt")
+    sd = {k: v.float() for k, v in g["sd"].items()}
+    with pytest.raises(AssertionError):
+        O.dit_forward(sd, g["x"][:1], g["t"][:1], g["context"][:1], seq_len=10, num_heads=1)
+
+
+def test_rope_and_sinusoid_layouts():
+    """SURVEY App. E identities: pair split (22,21,21), [cos | sin] layout."""
+    ang = O.rope_angles(128, (3, 4, 5))
+    assert ang.shape == (60, 64)
+    tok = (2 * 4 + 3) * 5 + 1                            # (f,h,w) = (2,3,1)
+    assert abs(float(ang[tok, 1]) - 2 * 10000 ** (-2 / 44)) < 1e-12
+    assert abs(float(ang[tok, 22 + 2]) - 3 * 10000 ** (-4 / 42)) < 1e-12
+    assert abs(float(ang[tok, 43 + 5]) - 1 * 10000 ** (-10 / 42)) < 1e-12
+    s = O.sinusoid_256(256, torch.tensor([10.0]))
+    assert abs(float(s[0, 0]) - float(torch.cos(torch.tensor(10.0, dtype=torch.float64)))) < 1e-12
+    assert abs(float(s[0, 128]) - float(torch.sin(torch.tensor(10.0, dtype=torch.float64)))) < 1e-12
+
+
+def test_flop_formulas_match_survey():
+    assert abs(O.dit_flops(1560) / 1e12 - 4.652) < 0.01
+    assert abs(O.dit_flops(32760) / 1e12 - 283.0) < 0.5
+    assert abs(VO.vae_decode_flops(1) / 1e12 - 4.35) < 0.05
+
+
+@pytest.mark.skipif(ref_loader.find_reference() is None, reason="reference tree not mounted (container-only check)")
+def test_oracle_vs_live_reference():
+    M, V = ref_loader.load_reference_modules()
+    sd = O.make_synthetic_weights(256, 512, 2, 2, text_dim=64, seed=9)
+    m = M.WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, use_checkpoint=False).eval()
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(2)
+    x = [torch.randn(16, 2, 8, 12, generator=g), torch.randn(16, 1, 6, 10, generator=g)]
+    ctx = [torch.randn(100, 64, generator=g), torch.randn(37, 64, generator=g)]
+    t = torch.tensor([999.0, 3.0])
+    with torch.no_grad():
+        ref = m(x, t, ctx, seq_len=60)
+    mine = O.dit_forward(sd, x, t, ctx, seq_len=60, num_heads=2)
+    for a, b in zip(mine, ref):
+        assert rel_l2(a, b) < 1e-5
+    vsd = VO.make_synthetic_vae_weights(dim=8, seed=4)
+    vae = V.WanVAE_(dim=8, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2, attn_scales=[],
+                    temperal_downsample=[False, True, True]).eval()
+    vae.load_state_dict(vsd, strict=False)
+    z = torch.randn(16, 3, 4, 6, generator=g)
+    with torch.no_grad():
+        pix = vae.decode(z[None], [torch.tensor(VO.VAE_MEAN), 1.0 / torch.tensor(VO.VAE_STD)])[0].clamp(-1, 1)
+    assert float((VO.vae_decode(vsd, z) - pix).abs().max()) < 1e-5
