@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Headline benchmark: DiT denoise-steps/sec, Wan2.1-T2V-1.3B, 480x832 latent [16,1,60,104]
+(BASELINE.json configs[1]): one step = cond forward + uncond forward + CFG combine + solver update
+for one sample; every rank (GPU) denoises its own independent sample(s) (weak scaling), one NCCL
+all_gather of the final latents closes the timed region.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--samples-per-gpu S] [--frames T]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Prints ONE JSON line (rank 0).  Keys: see the task contract; `value` is device-resident throughput,
+`e2e` the same metric through the public Python API with pinned-host inputs copied in and the
+result copied out every step, `roofline` the tensor-core GEMM family timed with CUDA events inside
+real (eager) steps, `cpu_baseline` the CPU oracle port on a bounded sample.
+Weights are random-init (reference init, model.py:590-612) because no checkpoint is reachable
+offline; data is synthetic of the reference's shapes.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG_13B = dict(dim=1536, ffn_dim=8960, num_heads=12, num_layers=30, in_dim=16, out_dim=16, text_dim=4096,
+               text_len=512, freq_dim=256)
+GUIDE = 5.0          # text2video.py:118
+SHIFT = 5.0          # text2video.py:115
+NUM_STEPS = 50
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+def sigmas_flow(n, shift):
+    """Flow-matching sigma schedule (fm_solvers_unipc.py:182-211): shift*s/(1+(shift-1)s) on linspace(1, 1/1000)."""
+    out = []
+    for i in range(n):
+        s = 1.0 + (1.0 / 1000.0 - 1.0) * i / n            # linspace(1, 1/1000, n + 1)[:-1]
+        out.append(shift * s / (1.0 + (shift - 1.0) * s))
+    return out + [0.0]
+
+
+class ClockSampler:
+    """nvidia-smi samples during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        busy = [v for v in sm if mx and v > 0.3 * mx] or sm
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def make_device_weights(cfg, seed, device):
+    """Reference init (model.py:590-612; head re-initialised as SURVEY 8c), generated on the GPU in fp16."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    d, f = cfg["dim"], cfg["ffn_dim"]
+
+    def xavier(o, i):
+        a = math.sqrt(6.0 / (i + o))
+        return ((torch.rand(o, i, generator=g, device=device) * 2 - 1) * a).half()
+
+    def normal(*s, std=1.0):
+        return (torch.randn(*s, generator=g, device=device) * std).half()
+
+    sd = {"patch_embedding.weight": xavier(d, cfg["in_dim"] * 4).view(d, cfg["in_dim"], 1, 2, 2),
+          "patch_embedding.bias": normal(d, std=0.02),
+          "text_embedding.0.weight": normal(d, cfg["text_dim"], std=0.02), "text_embedding.0.bias": normal(d, std=0.02),
+          "text_embedding.2.weight": normal(d, d, std=0.02), "text_embedding.2.bias": normal(d, std=0.02),
+          "time_embedding.0.weight": normal(d, cfg["freq_dim"], std=0.02), "time_embedding.0.bias": normal(d, std=0.02),
+          "time_embedding.2.weight": normal(d, d, std=0.02), "time_embedding.2.bias": normal(d, std=0.02),
+          "time_projection.1.weight": xavier(6 * d, d), "time_projection.1.bias": normal(6 * d, std=0.02),
+          "head.modulation": normal(1, 2, d) / math.sqrt(d), "head.head.weight": normal(64, d, std=0.02),
+          "head.head.bias": normal(64, std=0.02)}
+    for i in range(cfg["num_layers"]):
+        p = f"blocks.{i}."
+        sd[p + "modulation"] = normal(1, 6, d) / math.sqrt(d)
+        sd[p + "norm3.weight"] = 1.0 + normal(d, std=0.05)
+        sd[p + "norm3.bias"] = normal(d, std=0.02)
+        for att in ("self_attn", "cross_attn"):
+            for n in "qkvo":
+                sd[p + f"{att}.{n}.weight"] = xavier(d, d)
+                sd[p + f"{att}.{n}.bias"] = normal(d, std=0.02)
+            sd[p + f"{att}.norm_q.weight"] = 1.0 + normal(d, std=0.05)
+            sd[p + f"{att}.norm_k.weight"] = 1.0 + normal(d, std=0.05)
+        sd[p + "ffn.0.weight"] = xavier(f, d); sd[p + "ffn.0.bias"] = normal(f, std=0.02)
+        sd[p + "ffn.2.weight"] = xavier(d, f); sd[p + "ffn.2.bias"] = normal(d, std=0.02)
+    return sd
+
+
+def cpu_baseline(frames, budget_layers=2):
+    """CPU oracle port (oracle/dit_oracle.py, fp32, all host threads) on a bounded sample of the same
+    workload: `budget_layers` of the 30 blocks for both CFG branches + embeddings + head, scaled to 30."""
+    import torch
+    from oracle import dit_oracle as O
+    cores = torch.get_num_threads()
+    sd = O.make_synthetic_weights(num_layers=budget_layers, seed=0)
+    g = torch.Generator().manual_seed(42)
+    x = [torch.randn(16, frames, 60, 104, generator=g)]
+    ctx = [torch.randn(512, 4096, generator=g)]
+    ctx0 = [torch.randn(512, 4096, generator=g)]
+    t = torch.tensor([999.0])
+    L = 1560 * frames
+
+    def one(nl):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            c = O.dit_forward(sd, x, t, ctx, L, num_layers=nl)[0]
+            u = O.dit_forward(sd, x, t, ctx0, L, num_layers=nl)[0]
+            O.cfg_combine(c, u, GUIDE)
+        return time.perf_counter() - t0
+
+    one(1)                                               # warm-up (thread pool, allocator)
+    t_full = one(budget_layers)
+    t_one = one(1)
+    per_block = max((t_full - t_one) / max(budget_layers - 1, 1), 1e-9)
+    step_s = t_one + per_block * (CFG_13B["num_layers"] - 1)
+    return {"value": 1.0 / step_s, "unit": "denoise-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{budget_layers} of 30 blocks x 2 CFG branches + embeddings/head at L={L}, fp32 oracle, "
+                      f"block cost scaled to 30 layers ({t_full + t_one:.1f}s of CPU work)"}, step_s
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU implementation (oracle port; the Python reference
+    itself cannot travel to the GPU box) with all host threads; each step is a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    vals = []
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_baseline(args.frames, 2)
+    info = None
+    for _ in range(max(1, min(args.steps, 3))):
+        info, step_s = cpu_baseline(args.frames, 2)
+        vals.append(step_s)
+    vals.sort()
+    step_s = vals[len(vals) // 2]
+    v = 1.0 / step_s
+    info["value"] = v
+    line = {"impl": "reference", "metric": "DiT denoise-steps/sec (Wan2.1-T2V-1.3B, CFG, 480x832)", "value": v,
+            "unit": "denoise-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"Wan2.1-T2V-1.3B CFG denoise step, latent [16,{args.frames},60,104], 1 sample"},
+            "cpu_baseline": info,
+            "e2e": {"value": v, "unit": "denoise-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "host_threads": torch.get_num_threads()}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--samples-per-gpu", type=int, default=1)
+    ap.add_argument("--frames", type=int, default=1, help="latent frames T (1 = configs[1]; 21 = 81-frame video)")
+    ap.add_argument("--layers", type=int, default=CFG_13B["num_layers"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import b200dit
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+    S = args.samples_per_gpu
+    T = args.frames
+    cfg = dict(CFG_13B, num_layers=args.layers)
+    L = 1560 * T
+
+    eng = b200dit.DitEngine(**cfg, device=dev)
+    eng.load_state_dict(make_device_weights(cfg, 0, dev))
+    eng.set_graphs(not args.no_graphs)
+    torch.cuda.synchronize()
+
+    # ---- synthetic inputs: noise seed 42+rank, N(0,1) contexts as the T5 stage emits (bf16)
+    g = torch.Generator().manual_seed(42 + rank)
+    host_x = [torch.randn(16, T, 60, 104, generator=g).pin_memory() for _ in range(S)]
+    host_ctx = [torch.randn(512, 4096, generator=g).bfloat16().pin_memory() for _ in range(S)]
+    host_ctx0 = [torch.randn(512, 4096, generator=g).bfloat16().pin_memory() for _ in range(S)]
+    sig = sigmas_flow(NUM_STEPS, SHIFT)
+    lat = [h.to(dev) for h in host_x]
+    ctx = [h.to(dev) for h in host_ctx]
+    ctx0 = [h.to(dev) for h in host_ctx0]
+    t_dev = [torch.full((S,), sig[i % NUM_STEPS] * 1000.0, device=dev) for i in range(NUM_STEPS)]
+
+    def step_device(i, x):
+        """one denoise step with everything resident in HBM: fused cond/uncond/CFG forward + Euler flow update"""
+        k = i % NUM_STEPS
+        v = eng.forward_cfg(x, t_dev[k], ctx, ctx0, L, GUIDE)
+        dt = sig[k + 1] - sig[k]
+        return [xi + dt * vi for xi, vi in zip(x, v)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    x = lat
+    for i in range(W):
+        x = step_device(i, x)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = b200dit.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    x = lat
+    for i in range(K):
+        x = step_device(i, x)
+    if world > 1:                                         # the single collective of the path: gather final latents
+        mine = torch.stack(x)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = b200dit.kernel_launches() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    ms_step = ms / K
+    value = world * S / (ms_step / 1e3)
+
+    # ---- e2e: public API, pinned-host inputs in, result out, every step
+    def step_e2e(i, hx):
+        k = i % NUM_STEPS
+        xs = [h.to(dev, non_blocking=True) for h in hx]
+        cs = [h.to(dev, non_blocking=True) for h in host_ctx]
+        c0 = [h.to(dev, non_blocking=True) for h in host_ctx0]
+        tt = torch.full((S,), sig[k] * 1000.0).pin_memory().to(dev, non_blocking=True)
+        v = eng.forward_cfg(xs, tt, cs, c0, L, GUIDE)
+        out = [(xi + (sig[k + 1] - sig[k]) * vi).to("cpu", non_blocking=False) for xi, vi in zip(xs, v)]
+        return out
+
+    hx = host_x
+    for i in range(2):
+        step_e2e(i, hx)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        hx_out = step_e2e(i, hx)
+        hx = hx_out
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_val = world * S / (e2e_s / K)
+    h2d = S * (16 * T * 60 * 104 * 4 + 2 * 512 * 4096 * 2 + 4)
+    d2h = S * 16 * T * 60 * 104 * 4
+
+    # ---- roofline of the dominant kernel family (tcgen05 GEMM), CUDA events around every launch of real steps
+    roof = None
+    if rank == 0:
+        eng.set_graphs(False)
+        b200dit.profile_enable(True)
+        xs = lat
+        for i in range(2):
+            xs = step_device(i, xs)
+        torch.cuda.synchronize()
+        prof = b200dit.profile_collect()
+        b200dit.profile_enable(False)
+        eng.set_graphs(not args.no_graphs)
+        burst, sustained, hbm, src = peaks()
+        gm = prof["gemm"]
+        tot_ms = sum(p["ms"] for p in prof.values())
+        ach = gm["flops"] / (gm["ms"] / 1e3) / 1e12 if gm["ms"] > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 128xN tiles, fused epilogues)",
+                "achieved": ach, "peak": sustained, "peak_burst": burst, "unit": "TFLOP/s", "frac": ach / sustained,
+                "frac_of_burst": ach / burst, "peak_source": src + " (sustained: kernel timed inside a long step)",
+                "traffic": None, "launches_per_step": gm["launches"] // 2,
+                "avg_launch_us": 1e3 * gm["ms"] / max(gm["launches"], 1),
+                "flops_per_launch": gm["flops"] / max(gm["launches"], 1),
+                "share_of_step": gm["ms"] / tot_ms if tot_ms else None,
+                "by_category_ms_per_step": {k: v["ms"] / 2 for k, v in prof.items()},
+                "attention_tflops": (prof["attention"]["flops"] / (prof["attention"]["ms"] / 1e3) / 1e12)
+                if prof["attention"]["ms"] > 0 else None}
+
+    if rank == 0:
+        from oracle import dit_oracle as O
+        flops_step = 2 * S * O.dit_flops(L, layers=cfg["num_layers"])
+        burst, sustained, hbm, src = peaks()
+        line = {"metric": "DiT denoise-steps/sec (Wan2.1-T2V-1.3B, CFG, 480x832)", "value": value,
+                "unit": "denoise-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+                "data": "synthetic",
+                "config": {"workload": f"Wan2.1-T2V-1.3B ({cfg['num_layers']} blocks, dim 1536, ffn 8960, 12 heads) "
+                                       f"CFG denoise step on latent [16,{T},60,104] (L={L} tokens), guide {GUIDE}, "
+                                       f"flow shift {SHIFT}, {S} sample(s) per GPU, cond+uncond co-batched",
+                           "samples_per_gpu": S, "parallelism": f"replicas x{world} (independent samples, one all_gather)",
+                           "l2_policy": "weights 2.84 GB per forward exceed the 126 MB L2 (no flush needed)",
+                           "cuda_graphs": not args.no_graphs, "operands": "fp16 x fp16 -> fp32 accumulate (model.py:540)"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": "denoise-steps/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / K},
+                "gpu_launches": int(launches),
+                "step_tflops": flops_step / (ms_step / 1e3) / 1e12,
+                "step_frac_of_peak": flops_step / (ms_step / 1e3) / 1e12 / sustained,
+                "roofline": roof}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"], _ = cpu_baseline(T)
+        elif world > 1:
+            line["cpu_baseline"] = {"value": None, "unit": "denoise-steps/s", "cores": 0, "kind": "port",
+                                    "sample": "measured at N=1 only"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

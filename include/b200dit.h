@@ -138,6 +138,13 @@ B200_API int64_t b200_kernel_launches(void);
 /* algorithmic FLOPs of the most recent forward / decode (SURVEY.md section 8d formulas) */
 B200_API double b200dit_last_flops(const b200dit_engine* e);
 B200_API const char* b200_version(void);
+/* Opt-in per-launch timing with CUDA events on the launching stream, by kernel category
+ * (0 tensor-core GEMM, 1 attention, 2 norm / RoPE passes, 3 other, 4 implicit-GEMM convolution).
+ * collect() synchronises, fills four arrays of B200_PROFILE_CATEGORIES entries (milliseconds,
+ * algorithmic FLOPs, algorithmic bytes, launches) and resets the counters. */
+#define B200_PROFILE_CATEGORIES 5
+B200_API int b200_profile_enable(int32_t enabled);
+B200_API int b200_profile_collect(double* ms, double* flops, double* bytes, int64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -8,5 +8,6 @@ the `b200dit` alias module at the repository root:
     eng = b200dit.DitEngine.from_module(wan_model)      # or b200dit.install(wan_model)
 """
 from ._lib import B200Error, LIB_PATH, MAX_ITEMS  # noqa: F401
-from .engine import DitEngine, VaeEngine, flash_attention, kernel_launches, linear  # noqa: F401
+from .engine import (DitEngine, VaeEngine, flash_attention, kernel_launches, linear, profile_collect,  # noqa: F401
+                     profile_enable)
 from .wan_shim import install, install_vae, uninstall  # noqa: F401

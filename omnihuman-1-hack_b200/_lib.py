@@ -48,6 +48,9 @@ SIGNATURES = {
     "b200_last_error": (C.c_char_p, []),
     "b200_kernel_launches": (C.c_int64, []),
     "b200_version": (C.c_char_p, []),
+    "b200_profile_enable": (_I, [_I]),
+    "b200_profile_collect": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_int64)]),
 }
 
 _lib = None

@@ -275,6 +275,9 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
   CUtensorMap tk = make_tmap_2d(p.k, (uint64_t)p.items * p.Lk_rows, dim, p.ldk, 128);
   CUtensorMap tv = make_tmap_2d(p.vt, (uint64_t)p.items * p.heads * 128, p.ldvt, p.ldvt, 128);
   dim3 grid((p.Lq + TILE - 1) / TILE, p.heads, p.items);
+  double keys = 0;
+  for (int i = 0; i < p.items; ++i) keys += p.klen[i];
+  ProfScope prof(PC_ATTN, 4.0 * p.Lq * keys * 128.0 * p.heads, 0.0, stream);
   attn_fwd_kernel<<<grid, 192, ATTN_SMEM, stream>>>(tq, tk, tv, p);
   B2_CUDA(cudaGetLastError());
   count_launch();

@@ -167,4 +167,16 @@ int b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const fl
   });
 }
 
+int b200_profile_enable(int32_t enabled) {
+  return guarded([&] { b2::prof_enable(enabled != 0); });
+}
+int b200_profile_collect(double* ms, double* flops, double* bytes, int64_t* launches) {
+  return guarded([&] {
+    B2_CHECK(ms && flops && bytes && launches, "null argument");
+    long long l[b2::PC_COUNT];
+    b2::prof_collect(ms, flops, bytes, l);
+    for (int i = 0; i < b2::PC_COUNT; ++i) launches[i] = l[i];
+  });
+}
+
 }  // extern "C"

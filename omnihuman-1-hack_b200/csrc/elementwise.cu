@@ -332,6 +332,7 @@ void launch_ln_affine(const float* x, __half* out, const float* a, const float* 
                       int rows_per_item, int dim, float eps, cudaStream_t s) {
   B2_CHECK(dim % 128 == 0, "LayerNorm width %d must be a multiple of 128", dim);
   const int grid = (M + 7) / 8;
+  ProfScope prof(PC_NORM, 0.0, 6.0 * M * dim, s);
 #define B2_LN_CASE(NV) \
   case NV: ln_affine_kernel<NV><<<grid, 256, 0, s>>>(x, out, a, b, item_stride, M, rows_per_item, eps); break;
   switch (dim / 128) {
@@ -352,6 +353,7 @@ void launch_rms_rope(__half* x, long long ld, int dim, int nslices, const float*
   p.gamma[0] = gamma0; p.gamma[1] = gamma1;
   p.cs = reinterpret_cast<const float2*>(cs_table);
   p.M = M; p.rows_per_item = rows_per_item; p.eps = eps;
+  ProfScope prof(PC_NORM, 0.0, 4.0 * M * dim * nslices, s);
   rms_rope_kernel<<<dim3(M, nslices), 192, 0, s>>>(p);
   B2_CUDA(cudaGetLastError());
   count_launch();
@@ -362,6 +364,7 @@ void launch_time_embed(const float* t, int B, int freq_dim, int dim, const float
                        cudaStream_t s) {
   B2_CHECK(B <= MAX_ITEMS, "at most %d items per launch", MAX_ITEMS);
   B2_CHECK(freq_dim % 4 == 0 && dim % 4 == 0, "time embedding widths must be multiples of 4");
+  ProfScope prof(PC_OTHER, 0.0, 4.0 * dim * (freq_dim + 7.0 * dim), s);
   float* sin_buf = scratch;                       // [B, freq_dim]
   float* h1 = scratch + (long long)B * freq_dim;  // [B, dim]
   sinusoid_kernel<<<(B * freq_dim / 2 + 127) / 128, 128, 0, s>>>(t, B, freq_dim, sin_buf);
@@ -412,6 +415,7 @@ void launch_head(const float* x, const float* e, const float* head_mod, const fl
     B2_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  ProfScope prof(PC_OTHER, 2.0 * B * L * dim * out_dim * 4, 4.0 * B * L * dim, s);
   const int tpb = cfg_pairs > 0 ? HEAD_ROWS / 2 : HEAD_ROWS;
   const int n_out = cfg_pairs > 0 ? cfg_pairs : B;
   head_kernel<<<dim3((L + tpb - 1) / tpb, n_out), 256, smem, s>>>(x, e, head_mod, w_t, bias, L, Hp, Wp, F, dim, out_dim,

@@ -18,6 +18,8 @@ static void launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   const int tiles = ((p.M + 127) / 128) * ((p.N + BN - 1) / BN);
   if (tiles <= 0) return;
   const int grid = tiles < num_sms ? tiles : num_sms;
+  const double rows = p.cv.enabled ? (double)p.cv.T * p.cv.H * p.cv.W : (double)p.M;
+  ProfScope prof(p.cv.enabled ? PC_CONV : PC_GEMM, 2.0 * rows * p.N * p.K, 0.0, stream);
   kern<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
   B2_CUDA(cudaGetLastError());
   count_launch();

@@ -16,6 +16,18 @@ constexpr int MAX_ITEMS = 16;   // items co-batched in one launch (per-item scal
 void count_launch(int n = 1);
 long long launches_total();
 
+// ---- profile.cu : opt-in per-launch CUDA-event timing by kernel category
+enum ProfCat : int { PC_GEMM = 0, PC_ATTN = 1, PC_NORM = 2, PC_OTHER = 3, PC_CONV = 4, PC_COUNT = 5 };
+void prof_enable(bool on);
+bool prof_enabled();
+void prof_collect(double* ms, double* flops, double* bytes, long long* launches);   // synchronises, then resets
+struct ProfScope {
+  ProfScope(int cat, double flops, double bytes, cudaStream_t s);
+  ~ProfScope();
+  cudaStream_t stream;
+  int idx;
+};
+
 // ---- gemm_tc.cu
 void launch_gemm(int epi, int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
                  cudaStream_t stream);

@@ -291,3 +291,19 @@ def linear(a, w, bias=None, epilogue="f16", block_n=0):
 
 def kernel_launches():
     return int(lib().b200_kernel_launches())
+
+
+PROFILE_CATEGORIES = ("gemm", "attention", "norm", "other", "conv")
+
+
+def profile_enable(on=True):
+    """Per-launch CUDA-event timing by kernel category (disables nothing; graphs simply are not timed)."""
+    check(lib().b200_profile_enable(int(bool(on))))
+
+
+def profile_collect():
+    n = len(PROFILE_CATEGORIES)
+    ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    check(lib().b200_profile_collect(ms, fl, by, cnt))
+    return {c: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=int(cnt[i])) for i, c in enumerate(PROFILE_CATEGORIES)}
