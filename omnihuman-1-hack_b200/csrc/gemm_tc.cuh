@@ -52,8 +52,11 @@ struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : 2 * BLOCK_N;   // two accumulators
+  static constexpr int STAGES_FIT = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  // two accumulators; TMEM allocations are powers of two >= 32 columns
+  static constexpr int TMEM_COLS = 2 * BLOCK_N <= 32 ? 32 : 2 * BLOCK_N <= 64 ? 64 : 2 * BLOCK_N <= 128 ? 128
+                                   : 2 * BLOCK_N <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int THREADS = 192;
 };

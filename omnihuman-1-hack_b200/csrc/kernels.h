@@ -33,6 +33,30 @@ void launch_gemm(int epi, int block_n, const CUtensorMap& ta, const CUtensorMap&
                  cudaStream_t stream);
 void gemm_linear(int epi, const __half* A, long long lda, const __half* W, long long ldw, GemmParams p, int num_sms,
                  cudaStream_t stream, int force_bn = 0);
+void conv_gemm(int epi, const __half* in, int Tbuf, int H, int W, int Cin, const __half* w, int Cout, int kt, int kh,
+               int kw, int T_out, GemmParams p, int num_sms, cudaStream_t stream);
+
+// ---- vae_kernels.cu : HBM-bound passes of the VAE decode (channels-last volumes [T, H, W, C])
+// z fp32 [C, T, h, w] -> (z * std + mean) -> fp16 [T*h*w, C]               (vae.py:547-551)
+void launch_vae_prep_latent(const float* z, const float* mean, const float* stdv, __half* out, int C, int T, int hw,
+                            cudaStream_t s);
+// RMS_norm over channels (F.normalize * sqrt(C) * gamma, vae.py:51-54) (+ SiLU) : fp32 [P, C] -> fp16 [P, C]
+void launch_vae_norm(const float* x, const float* gamma, __half* out, long long P, int C, int silu, cudaStream_t s);
+void launch_vae_cast(const float* x, __half* out, long long n, cudaStream_t s);
+// nearest-exact 2x spatial upsample (vae.py:57-63,76-83) of fp32 [T, H, W, Cs] -> fp16 [To, 2H, 2W, C].
+// interleave = 1: the source holds 2C channels per pixel from time_conv; output frame f takes source
+// frame f/2, channels [(f&1)*C, (f&1)*C + C)  (vae.py:128-137), To = 2T.  interleave = 0: To = T, Cs = C.
+void launch_vae_upsample(const float* x, __half* out, int T, int H, int W, int C, int interleave, cudaStream_t s);
+// row softmax of fp32 scores [R, ld_in] * scale -> fp16 probabilities [R, ld_out] (cols >= n zero-filled)
+void launch_vae_softmax(const float* sc, long long ld_in, __half* out, long long ld_out, int R, int n, float scale,
+                        cudaStream_t s);
+// fp16 [R, C] (leading dimension ld) -> fp16 [C, ldo] transposed
+void launch_transpose_h(const __half* in, long long ld, __half* out, long long ldo, int R, int C, cudaStream_t s);
+// fp32 [T, HW, 3] -> clamp(-1,1) -> out[c, t0 + t, hw] of a [3, T_total, HW] tensor    (vae.py:661)
+void launch_vae_store_rgb(const float* x, float* out, int T, long long HW, int t0, int T_total, cudaStream_t s);
+// conv weight [Cout, Cin, taps] (any float dtype staged as fp32) -> fp16 [Cout, taps, cpad], zero padded
+void launch_repack_conv_weight(const float* src, __half* dst, int Cout, int Cin, int taps, int cpad, cudaStream_t s);
+
 inline int pick_bn(long long M, long long N, int num_sms) {
   const long long t256 = ((M + 127) / 128) * ((N + 255) / 256);
   return (N % 256 == 0 && t256 >= num_sms) ? 256 : 128;

@@ -1,10 +1,357 @@
+// WanVAE decode (seaweed_apt/wan/modules/vae.py:544-568, Decoder3d :369-472) on the tcgen05
+// implicit-GEMM convolution path.
+//
+// Layout: every activation is a channels-last volume [T, H, W, C]; the residual stream is fp32, the
+// operand of each convolution (RMS_norm+SiLU output, or a plain cast) is fp16.  A causal 3x3x3
+// conv reads [2 history frames | chunk] from one buffer, so the reference's per-conv two-frame cache
+// (vae.py:14,207-217) is two frames of fp16 kept per conv between chunks; chunk 0 is latent frame 0
+// on its own (its upsample3d stages skip time_conv, vae.py:106-108), later chunks carry up to
+// `chunk_frames` latent frames each (equivalent to the reference's one-frame loop).
 #include "vae_engine.h"
 
+#include <cmath>
+#include <memory>
+
 namespace b2 {
-struct VaeEngine::Impl {};
-VaeEngine::VaeEngine(int, int) {}
+
+namespace {
+struct ConvW {
+  std::unique_ptr<DevBuf> w, b;
+  int cin = 0, cout = 0, kt = 1, kh = 1, kw = 1, cpad = 0;
+  bool w_loaded = false, b_loaded = false;
+};
+struct PlanItem { int kind; int cin, cout; };   // kind 0 res, 1 up3d, 2 up2d
+const float kMean[16] = {-0.7571f, -0.7089f, -0.9113f, 0.1075f, -0.1745f, 0.9653f, -0.1517f, 1.5508f,
+                         0.4134f, -0.0715f, 0.5517f, -0.3632f, -0.1922f, -0.9497f, 0.2503f, -0.2921f};   // vae.py:629-632
+const float kStd[16] = {2.8184f, 1.4541f, 2.3275f, 2.6558f, 1.2196f, 1.7708f, 2.6052f, 2.0743f,
+                        3.2687f, 2.1526f, 2.8652f, 1.5579f, 1.6382f, 1.1253f, 2.8251f, 1.9160f};       // vae.py:633-636
+}  // namespace
+
+struct VaeEngine::Impl {
+  int dim, zdim, c0, num_sms = 148;
+  int chunk_frames = 4;
+  std::vector<PlanItem> plan;
+  std::unordered_map<std::string, ConvW> convs;
+  std::unordered_map<std::string, std::unique_ptr<DevBuf>> gammas;
+  std::unordered_map<std::string, bool> gamma_loaded;
+  std::unordered_map<std::string, std::unique_ptr<DevBuf>> hist;
+  DevBuf F[3], A0, A1, Z16, X0, attn_ws, consts;
+  bool finalized = false;
+  cudaStream_t s = nullptr;
+
+  void add_conv(const std::string& name, int cin, int cout, int kt, int kh, int kw) {
+    ConvW c;
+    c.cin = cin; c.cout = cout; c.kt = kt; c.kh = kh; c.kw = kw;
+    const int taps = kt * kh * kw;
+    c.cpad = taps == 1 ? cin : ((cin + 63) / 64) * 64;
+    c.w = std::make_unique<DevBuf>(); c.b = std::make_unique<DevBuf>();
+    c.w->ensure((size_t)cout * taps * c.cpad * 2, true);
+    c.b->ensure((size_t)cout * 4, true);
+    convs.emplace(name, std::move(c));
+  }
+  void add_gamma(const std::string& name, int c) {
+    auto b = std::make_unique<DevBuf>();
+    b->ensure((size_t)c * 4);
+    gammas[name] = std::move(b);
+    gamma_loaded[name] = false;
+  }
+  void add_res(const std::string& p, int cin, int cout) {
+    add_gamma(p + "residual.0.gamma", cin);
+    add_conv(p + "residual.2", cin, cout, 3, 3, 3);
+    add_gamma(p + "residual.3.gamma", cout);
+    add_conv(p + "residual.6", cout, cout, 3, 3, 3);
+    if (cin != cout) add_conv(p + "shortcut", cin, cout, 1, 1, 1);
+  }
+
+  Impl(int dim_, int z) : dim(dim_), zdim(z) {
+    B2_CHECK(dim % 8 == 0 && z % 8 == 0 && z <= 16, "unsupported VAE widths dim=%d z=%d", dim, z);
+    int dev = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    // Decoder3d plan (vae.py:388-416): dims [4d,4d,4d,2d,d], 3 res blocks per stage, up3d,up3d,up2d
+    const int dims[5] = {dim * 4, dim * 4, dim * 4, dim * 2, dim};
+    c0 = dims[0];
+    for (int i = 0; i < 4; ++i) {
+      int cin = dims[i], cout = dims[i + 1];
+      if (i >= 1) cin /= 2;
+      for (int r = 0; r < 3; ++r) { plan.push_back({0, cin, cout}); cin = cout; }
+      if (i != 3) plan.push_back({i < 2 ? 1 : 2, cout, cout / 2});
+    }
+    add_conv("conv2", z, z, 1, 1, 1);
+    add_conv("decoder.conv1", z, c0, 3, 3, 3);
+    add_res("decoder.middle.0.", c0, c0);
+    add_gamma("decoder.middle.1.norm.gamma", c0);
+    add_conv("decoder.middle.1.to_qkv", c0, 3 * c0, 1, 1, 1);
+    add_conv("decoder.middle.1.proj", c0, c0, 1, 1, 1);
+    add_res("decoder.middle.2.", c0, c0);
+    for (size_t i = 0; i < plan.size(); ++i) {
+      const std::string p = "decoder.upsamples." + std::to_string(i) + ".";
+      if (plan[i].kind == 0) add_res(p, plan[i].cin, plan[i].cout);
+      else {
+        add_conv(p + "resample.1", plan[i].cin, plan[i].cout, 1, 3, 3);
+        if (plan[i].kind == 1) add_conv(p + "time_conv", plan[i].cin, 2 * plan[i].cin, 3, 1, 1);
+      }
+    }
+    add_gamma("decoder.head.0.gamma", dim);
+    add_conv("decoder.head.2", dim, 3, 3, 3, 3);
+    consts.ensure(32 * 4);
+    B2_CUDA(cudaMemcpy(consts.p, kMean, 16 * 4, cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpy(consts.as<float>() + 16, kStd, 16 * 4, cudaMemcpyHostToDevice));
+  }
+
+  void load(const char* name, const void* data, int dtype, int ndim, const int64_t* shape) {
+    std::string n(name);
+    long long numel = 1;
+    for (int i = 0; i < ndim; ++i) numel *= shape[i];
+    const size_t esz = dtype == DT_F32 ? 4 : 2;
+    auto stage_f32 = [&](DevBuf& tmp) {
+      DevBuf st;
+      st.ensure(numel * esz);
+      B2_CUDA(cudaMemcpy(st.p, data, numel * esz, cudaMemcpyDefault));
+      tmp.ensure(numel * 4);
+      launch_convert(st.p, dtype, tmp.p, DT_F32, numel, 0);
+      B2_CUDA(cudaDeviceSynchronize());
+    };
+    auto g = gammas.find(n);
+    if (g != gammas.end()) {
+      B2_CHECK(numel * 4 == (long long)g->second->bytes, "gamma %s has %lld elements", name, numel);
+      DevBuf tmp;
+      stage_f32(tmp);
+      B2_CUDA(cudaMemcpy(g->second->p, tmp.p, numel * 4, cudaMemcpyDeviceToDevice));
+      gamma_loaded[n] = true;
+      return;
+    }
+    const bool is_w = n.size() > 7 && n.compare(n.size() - 7, 7, ".weight") == 0;
+    const bool is_b = n.size() > 5 && n.compare(n.size() - 5, 5, ".bias") == 0;
+    B2_CHECK(is_w || is_b, "unexpected VAE parameter '%s'", name);
+    const std::string base = n.substr(0, n.size() - (is_w ? 7 : 5));
+    auto c = convs.find(base);
+    B2_CHECK(c != convs.end(), "unexpected VAE parameter '%s'", name);
+    ConvW& cw = c->second;
+    DevBuf tmp;
+    if (is_b) {
+      B2_CHECK(numel == cw.cout, "bias %s has %lld elements, expected %d", name, numel, cw.cout);
+      stage_f32(tmp);
+      B2_CUDA(cudaMemcpy(cw.b->p, tmp.p, numel * 4, cudaMemcpyDeviceToDevice));
+      cw.b_loaded = true;
+    } else {
+      const int taps = cw.kt * cw.kh * cw.kw;
+      B2_CHECK(numel == (long long)cw.cout * cw.cin * taps, "weight %s has %lld elements, expected %lld", name, numel,
+               (long long)cw.cout * cw.cin * taps);
+      stage_f32(tmp);
+      launch_repack_conv_weight(tmp.as<float>(), cw.w->as<__half>(), cw.cout, cw.cin, taps, cw.cpad, 0);
+      B2_CUDA(cudaDeviceSynchronize());
+      cw.w_loaded = true;
+    }
+    finalized = false;
+  }
+
+  void finalize() {
+    for (auto& kv : convs)
+      B2_CHECK(kv.second.w_loaded && kv.second.b_loaded, "VAE parameter '%s.{weight,bias}' was never loaded",
+               kv.first.c_str());
+    for (auto& kv : gamma_loaded) B2_CHECK(kv.second, "VAE parameter '%s' was never loaded", kv.first.c_str());
+    finalized = true;
+  }
+
+  // ---- conv plumbing --------------------------------------------------------------------------
+  // Returns where the producer must write the chunk's Tc frames; history (2 frames) is placed in front.
+  __half* begin_causal(const std::string& name, int Tc, int H, int W, int C) {
+    const size_t frame = (size_t)H * W * C;
+    auto& hb = hist[name];
+    if (!hb) {
+      hb = std::make_unique<DevBuf>();
+      hb->ensure(2 * frame * 2, true);
+      hist_frame[name] = frame;
+    } else if (hist_frame[name] != frame) {
+      hb->release();
+      hb->ensure(2 * frame * 2, true);
+      hist_frame[name] = frame;
+    }
+    if (hist_fresh.count(name) == 0) {            // first use in this decode: the causal zero padding
+      B2_CUDA(cudaMemsetAsync(hb->p, 0, 2 * frame * 2, s));
+      hist_fresh[name] = true;
+    }
+    B2_CUDA(cudaMemcpyAsync(A0.p, hb->p, 2 * frame * 2, cudaMemcpyDeviceToDevice, s));
+    return A0.as<__half>() + 2 * frame;
+  }
+  void end_causal(const std::string& name, int Tc, int H, int W, int C) {
+    const size_t frame = (size_t)H * W * C;
+    B2_CUDA(cudaMemcpyAsync(hist[name]->p, A0.as<__half>() + (size_t)Tc * frame, 2 * frame * 2,
+                            cudaMemcpyDeviceToDevice, s));
+  }
+  void run_conv(const std::string& name, const __half* in, int Tc, int H, int W, float* out, const float* add) {
+    const ConvW& c = convs.at(name);
+    GemmParams p{};
+    p.bias = c.b->as<float>(); p.out_f = out; p.ld_f = c.cout; p.add_f = add;
+    conv_gemm(EPI_F32, in, Tc + c.kt - 1, H, W, c.cin, c.w->as<__half>(), c.cout, c.kt, c.kh, c.kw, Tc, p, num_sms, s);
+  }
+  void linear_1x1(const std::string& name, const __half* in, long long rows, int epi, void* out, const float* add) {
+    const ConvW& c = convs.at(name);
+    GemmParams p{};
+    p.M = (int)rows; p.N = c.cout; p.K = c.cin; p.bias = c.b->as<float>();
+    if (epi == EPI_F32) { p.out_f = static_cast<float*>(out); p.ld_f = c.cout; p.add_f = add; }
+    else { p.out_h = static_cast<__half*>(out); p.ld_h = c.cout; }
+    gemm_linear(epi, in, c.cin, c.w->as<__half>(), c.cin, p, num_sms, s);
+  }
+
+  // ResidualBlock (vae.py:186-220): x (fp32, buffer xi) -> returns index of the buffer holding the result
+  int res_block(const std::string& p, int xi, int Tc, int H, int W, int cin, int cout) {
+    const long long P = (long long)Tc * H * W;
+    const int yi = (xi + 1) % 3, si = (xi + 2) % 3;
+    __half* a = begin_causal(p + "residual.2", Tc, H, W, cin);
+    launch_vae_norm(F[xi].as<float>(), gammas.at(p + "residual.0.gamma")->as<float>(), a, P, cin, 1, s);
+    end_causal(p + "residual.2", Tc, H, W, cin);
+    run_conv(p + "residual.2", A0.as<__half>(), Tc, H, W, F[yi].as<float>(), nullptr);
+    int out = xi;
+    if (cin != cout) {
+      launch_vae_cast(F[xi].as<float>(), A1.as<__half>(), P * cin, s);
+      linear_1x1(p + "shortcut", A1.as<__half>(), P, EPI_F32, F[si].as<float>(), nullptr);
+      out = si;
+    }
+    a = begin_causal(p + "residual.6", Tc, H, W, cout);
+    launch_vae_norm(F[yi].as<float>(), gammas.at(p + "residual.3.gamma")->as<float>(), a, P, cout, 1, s);
+    end_causal(p + "residual.6", Tc, H, W, cout);
+    run_conv(p + "residual.6", A0.as<__half>(), Tc, H, W, F[out].as<float>(), F[out].as<float>());   // + shortcut, in place
+    return out;
+  }
+
+  // AttentionBlock (vae.py:223-262): per frame, single head over H*W positions; in place on buffer xi
+  void attn_block(const std::string& p, int xi, int Tc, int H, int W, int C) {
+    const int hw = H * W, hwp = (hw + 7) & ~7;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+    const size_t o_qkv = take((size_t)hw * 3 * C * 2), o_s = take((size_t)hw * hwp * 4), o_p = take((size_t)hw * hwp * 2);
+    const size_t o_vt = take((size_t)C * hwp * 2), o_o = take((size_t)hw * C * 2), o_n = take((size_t)hw * C * 2);
+    attn_ws.ensure(off);
+    uint8_t* base = attn_ws.as<uint8_t>();
+    __half* qkv = reinterpret_cast<__half*>(base + o_qkv);
+    float* S = reinterpret_cast<float*>(base + o_s);
+    __half* Pm = reinterpret_cast<__half*>(base + o_p);
+    __half* vt = reinterpret_cast<__half*>(base + o_vt);
+    __half* O = reinterpret_cast<__half*>(base + o_o);
+    __half* xn = reinterpret_cast<__half*>(base + o_n);
+    const float* gamma = gammas.at(p + "norm.gamma")->as<float>();
+    for (int f = 0; f < Tc; ++f) {
+      float* xf = F[xi].as<float>() + (size_t)f * hw * C;
+      launch_vae_norm(xf, gamma, xn, hw, C, 0, s);
+      linear_1x1(p + "to_qkv", xn, hw, EPI_F16, qkv, nullptr);
+      {
+        GemmParams g{}; g.M = hw; g.N = hw; g.K = C; g.out_f = S; g.ld_f = hwp;
+        gemm_linear(EPI_F32, qkv, 3 * C, qkv + C, 3 * C, g, num_sms, s);
+      }
+      launch_vae_softmax(S, hwp, Pm, hwp, hw, hw, 1.0f / std::sqrt((float)C), s);
+      launch_transpose_h(qkv + 2 * C, 3 * C, vt, hwp, hw, C, s);
+      {
+        GemmParams g{}; g.M = hw; g.N = C; g.K = hwp; g.out_h = O; g.ld_h = C;
+        gemm_linear(EPI_F16, Pm, hwp, vt, hwp, g, num_sms, s);
+      }
+      linear_1x1(p + "proj", O, hw, EPI_F32, xf, xf);
+    }
+  }
+
+  // Resample upsample2d / upsample3d (vae.py:101-141)
+  int up_block(const std::string& p, int xi, int& Tc, int& H, int& W, int cin, int cout, bool temporal, bool first) {
+    const int yi = (xi + 1) % 3;
+    int src = xi, interleave = 0;
+    if (temporal && !first) {
+      const long long P = (long long)Tc * H * W;
+      __half* a = begin_causal(p + "time_conv", Tc, H, W, cin);
+      launch_vae_cast(F[xi].as<float>(), a, P * cin, s);
+      end_causal(p + "time_conv", Tc, H, W, cin);
+      run_conv(p + "time_conv", A0.as<__half>(), Tc, H, W, F[yi].as<float>(), nullptr);      // [Tc,H,W,2cin]
+      src = yi; interleave = 1;
+    }
+    launch_vae_upsample(F[src].as<float>(), A1.as<__half>(), Tc, H, W, cin, interleave, s);
+    if (interleave) Tc *= 2;
+    H *= 2; W *= 2;
+    const int oi = (src + 1) % 3;
+    run_conv(p + "resample.1", A1.as<__half>(), Tc, H, W, F[oi].as<float>(), nullptr);
+    return oi;
+  }
+
+  void ensure_buffers(int T, int Tc_max, int h, int w) {
+    // worst-case element counts over the decoder for a chunk of Tc_max latent frames
+    size_t f32_max = 0, a0_max = 0, a1_max = 0;
+    int Tc = Tc_max, H = h, W = w;
+    auto upd = [&](size_t& m, size_t v) { if (v > m) m = v; };
+    upd(f32_max, (size_t)Tc * H * W * c0);
+    upd(a0_max, (size_t)(Tc + 2) * H * W * c0);
+    upd(a1_max, (size_t)H * W * c0);
+    for (auto& it : plan) {
+      if (it.kind == 0) {
+        upd(f32_max, (size_t)Tc * H * W * it.cout);
+        upd(a0_max, (size_t)(Tc + 2) * H * W * (it.cin > it.cout ? it.cin : it.cout));
+        upd(a1_max, (size_t)Tc * H * W * it.cin);
+      } else {
+        if (it.kind == 1) { upd(f32_max, (size_t)Tc * H * W * 2 * it.cin); upd(a0_max, (size_t)(Tc + 2) * H * W * it.cin); Tc *= 2; }
+        H *= 2; W *= 2;
+        upd(a1_max, (size_t)Tc * H * W * it.cin);
+        upd(f32_max, (size_t)Tc * H * W * it.cout);
+      }
+    }
+    upd(a0_max, (size_t)(Tc + 2) * H * W * dim);
+    for (int i = 0; i < 3; ++i) F[i].ensure(f32_max * 4 + 256);
+    A0.ensure(a0_max * 2 + 256);
+    A1.ensure(a1_max * 2 + 256);
+    Z16.ensure((size_t)T * h * w * zdim * 2 + 256);
+    X0.ensure((size_t)T * h * w * zdim * 4 + 256);
+  }
+
+  void decode(const float* z, int T, int h, int w, float* out, cudaStream_t stream) {
+    B2_CHECK(finalized, "b200vae_finalize() has not been called");
+    B2_CHECK(T >= 1 && h >= 1 && w >= 1, "bad latent shape");
+    s = stream;
+    hist_fresh.clear();
+    const int Tc_max = T > 1 ? (T - 1 < chunk_frames ? T - 1 : chunk_frames) : 1;
+    ensure_buffers(T, Tc_max, h, w);
+    const int hw = h * w, T_total = 1 + 4 * (T - 1);
+    // de-normalise + conv2 over the whole sequence (vae.py:547-553)
+    launch_vae_prep_latent(z, consts.as<float>(), consts.as<float>() + 16, Z16.as<__half>(), zdim, T, hw, s);
+    linear_1x1("conv2", Z16.as<__half>(), (long long)T * hw, EPI_F32, X0.p, nullptr);
+    int t0 = 0, f_out = 0;
+    while (t0 < T) {
+      const bool first = t0 == 0;
+      int Tc = first ? 1 : (T - t0 < chunk_frames ? T - t0 : chunk_frames);
+      const int Tl = Tc;
+      int H = h, W = w;
+      // conv1 (vae.py:424-439)
+      __half* a = begin_causal("decoder.conv1", Tc, H, W, zdim);
+      launch_vae_cast(X0.as<float>() + (size_t)t0 * hw * zdim, a, (long long)Tc * hw * zdim, s);
+      end_causal("decoder.conv1", Tc, H, W, zdim);
+      run_conv("decoder.conv1", A0.as<__half>(), Tc, H, W, F[0].as<float>(), nullptr);
+      int xi = res_block("decoder.middle.0.", 0, Tc, H, W, c0, c0);
+      attn_block("decoder.middle.1.", xi, Tc, H, W, c0);
+      xi = res_block("decoder.middle.2.", xi, Tc, H, W, c0, c0);
+      for (size_t i = 0; i < plan.size(); ++i) {
+        const std::string p = "decoder.upsamples." + std::to_string(i) + ".";
+        if (plan[i].kind == 0) xi = res_block(p, xi, Tc, H, W, plan[i].cin, plan[i].cout);
+        else xi = up_block(p, xi, Tc, H, W, plan[i].cin, plan[i].cout, plan[i].kind == 1, first);
+      }
+      // head (vae.py:455-471)
+      a = begin_causal("decoder.head.2", Tc, H, W, dim);
+      launch_vae_norm(F[xi].as<float>(), gammas.at("decoder.head.0.gamma")->as<float>(), a, (long long)Tc * H * W, dim, 1, s);
+      end_causal("decoder.head.2", Tc, H, W, dim);
+      const int oi = (xi + 1) % 3;
+      run_conv("decoder.head.2", A0.as<__half>(), Tc, H, W, F[oi].as<float>(), nullptr);
+      launch_vae_store_rgb(F[oi].as<float>(), out, Tc, (long long)H * W, f_out, T_total, s);
+      f_out += Tc;
+      t0 += Tl;
+    }
+  }
+
+  std::unordered_map<std::string, size_t> hist_frame;
+  std::unordered_map<std::string, bool> hist_fresh;
+};
+
+VaeEngine::VaeEngine(int dim, int z_dim) : impl(new Impl(dim, z_dim)) {}
 VaeEngine::~VaeEngine() { delete impl; }
-void VaeEngine::load_weight(const char*, const void*, int, int, const int64_t*) { fail("VAE engine not built yet"); }
-void VaeEngine::finalize() { fail("VAE engine not built yet"); }
-void VaeEngine::decode(const float*, int, int, int, float*, cudaStream_t) { fail("VAE engine not built yet"); }
+void VaeEngine::load_weight(const char* name, const void* data, int dtype, int ndim, const int64_t* shape) {
+  impl->load(name, data, dtype, ndim, shape);
+}
+void VaeEngine::finalize() { impl->finalize(); }
+void VaeEngine::decode(const float* z, int T, int h, int w, float* out, cudaStream_t stream) {
+  impl->decode(z, T, h, w, out, stream);
+}
+
 }  // namespace b2
