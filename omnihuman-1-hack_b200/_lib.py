@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200dit.so")
+# B200DIT_LIB selects another build of the same ABI (developer A/B runs); the default is the in-tree build
+LIB_PATH = os.environ.get("B200DIT_LIB") or os.path.join(_HERE, "libb200dit.so")
 
 DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 MAX_ITEMS = 16

@@ -26,6 +26,9 @@ constexpr int OFF_P = OFF_V + 2 * TILE_BYTES;
 constexpr int OFF_BAR = OFF_P + TILE_BYTES;
 constexpr int ATTN_SMEM = OFF_BAR + 256 + 1024;
 constexpr float RESCALE_THRESHOLD = 8.0f;          // log2 units: P stays below 2^8, exact after normalisation
+// warps 0..3: softmax (TMEM lane quadrant = warp id); the single-lane TMA / MMA roles take the
+// highest ids so the sub-partition arbiter (highest warp id first) never queues them behind softmax
+constexpr int WARP_TMA = 4, WARP_MMA = 5;
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -55,7 +58,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int klen = p.klen[item];
   const int n_kv = (klen + TILE - 1) / TILE;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_vt);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -67,14 +70,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == WARP_MMA) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 256;
 
-  if (warp == 0) {
+  if (warp == WARP_TMA) {
     if (lane == 0) {
       const int q_row0 = item * p.Lq + qt * TILE;
       mbar_expect_tx(q_full, TILE_BYTES);
@@ -89,12 +92,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tma_load_2d(smem + OFF_K + st * TILE_BYTES + SUB_BYTES, &tmap_k, &k_full[st], head * 128 + 64, k_row0);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_expect_tx(&v_full[st], TILE_BYTES);
-        const int v_row0 = (item * p.heads + head) * 128;
-        tma_load_2d(smem + OFF_V + st * TILE_BYTES, &tmap_vt, &v_full[st], j * TILE, v_row0);
-        tma_load_2d(smem + OFF_V + st * TILE_BYTES + SUB_BYTES, &tmap_vt, &v_full[st], j * TILE + 64, v_row0);
+        const int v_row0 = head * 128, v_col0 = item * p.Lk_rows + j * TILE;   // V^T [heads*128, global key]
+        tma_load_2d(smem + OFF_V + st * TILE_BYTES, &tmap_vt, &v_full[st], v_col0, v_row0);
+        tma_load_2d(smem + OFF_V + st * TILE_BYTES + SUB_BYTES, &tmap_vt, &v_full[st], v_col0 + 64, v_row0);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == WARP_MMA) {
     constexpr uint32_t idesc = umma_idesc_f16(128, 128);
     const uint32_t sq = smem_u32(smem + OFF_Q), sp = smem_u32(smem + OFF_P);
     auto issue_qk = [&](int i) {
@@ -252,7 +255,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 
   __syncthreads();
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -273,7 +276,7 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
   const uint64_t dim = (uint64_t)p.heads * 128;
   CUtensorMap tq = make_tmap_2d(p.q, (uint64_t)p.items * p.Lq, dim, p.ldq, 128);
   CUtensorMap tk = make_tmap_2d(p.k, (uint64_t)p.items * p.Lk_rows, dim, p.ldk, 128);
-  CUtensorMap tv = make_tmap_2d(p.vt, (uint64_t)p.items * p.heads * 128, p.ldvt, p.ldvt, 128);
+  CUtensorMap tv = make_tmap_2d(p.vt, (uint64_t)p.heads * 128, (uint64_t)p.items * p.Lk_rows, p.ldvt, 128);
   dim3 grid((p.Lq + TILE - 1) / TILE, p.heads, p.items);
   double keys = 0;
   for (int i = 0; i < p.items; ++i) keys += p.klen[i];

@@ -130,12 +130,12 @@ int b200_flash_attention(const void* q, const void* k, const void* v, const int3
     B2_CHECK(q && k && v && out, "null argument");
     B2_CHECK(B >= 1 && B <= b2::MAX_ITEMS && Lq >= 1 && Lk >= 1 && H >= 1, "bad attention shape");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int Lp = (Lk + 7) & ~7;
+    const int Lp = (B * Lk + 7) & ~7;                 // V^T [H*128, B*Lk] with the leading dimension padded to 8
     void* vt = nullptr;
-    const size_t bytes = (size_t)B * H * 128 * Lp * 2;
+    const size_t bytes = (size_t)H * 128 * Lp * 2;
     B2_CUDA(cudaMallocAsync(&vt, bytes, s));
-    B2_CUDA(cudaMemsetAsync(vt, 0, bytes, s));
-    b2::launch_transpose_v(static_cast<const __half*>(v), static_cast<__half*>(vt), B, Lk, H, Lp, s);
+    b2::launch_transpose_h(static_cast<const __half*>(v), (long long)H * 128, static_cast<__half*>(vt), Lp, B * Lk,
+                           H * 128, s);
     b2::AttnParams p{};
     p.q = static_cast<const __half*>(q); p.ldq = (long long)H * 128;
     p.k = static_cast<const __half*>(k); p.ldk = (long long)H * 128;
@@ -153,6 +153,8 @@ int b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const fl
                 int32_t K, int32_t epilogue, void* out, int64_t ldo, int32_t block_n, void* stream) {
   return guarded([&] {
     B2_CHECK(A && W && out, "null argument");
+    B2_CHECK(ldo % (epilogue == b2::EPI_F32 ? 4 : 8) == 0 && lda % 8 == 0 && ldw % 8 == 0,
+             "leading dimensions must be multiples of 16 bytes (TMA)");
     B2_CHECK(epilogue == b2::EPI_F16 || epilogue == b2::EPI_GELU_F16 || epilogue == b2::EPI_F32,
              "b200_linear: epilogue %d not exposed", epilogue);
     int dev = 0, sms = 0;

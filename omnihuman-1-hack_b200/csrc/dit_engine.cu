@@ -5,7 +5,8 @@
 //   x_res   fp32 [M, d]        residual stream (model.py: fp32 after the first gated add)
 //   u       fp16 [M, d]        LayerNorm+modulation output = A operand of the next GEMM
 //   qk      fp16 [M, 2d]       q | k of self-attention (normalised + rotated in place); cross q reuses it as [M, d]
-//   vt      fp16 [items*H*128, Lp]   V transposed per (item, head) so P.V is a K-major x K-major MMA
+//   vt      fp16 [H*128, Mp]         V transposed (row = head*128 + d, column = global token) so P.V is a
+//                                  K-major x K-major MMA; Mp = M rounded up to 8, padding columns stay zero
 //   att     fp16 [M, d]        attention output = A operand of the o projection
 //   hid     fp16 [M, f]        GELU(ffn.0) output
 //   ctx_e   fp16 [items*TL, d] text embedding;  kc fp16 [items*TL, d];  vtc fp16 [items*H*128, TL]
@@ -243,14 +244,14 @@ void DitEngine::ensure_workspace(int B, int L) {
   size_t bytes = 0;
   auto add = [&](size_t n, size_t esz) { bytes += padded(n * esz); };
   add(Mx * d, 4); add(Mx * d, 2); add(Mx * 2 * d, 2); add(nB * Hn * 128 * Lpx, 2); add(Mx * d, 2); add(Mx * f, 2);
-  add(Mx * (2 * d / 128), 4); add(Mx * cfg.in_dim * 4, 2);
+  add(Mx * (4 * d / 128), 4); add(Mx * cfg.in_dim * 4, 2);
   add(nB * TL * cfg.text_dim, 2); add(nB * TL * d, 2); add(nB * TL * d, 2); add(nB * TL * d, 2);
-  add(nB * Hn * 128 * TL, 2); add(nB * TL * (d / 128), 4);
+  add(nB * Hn * 128 * TL, 2); add(nB * TL * (2 * d / 128), 4);
   add(nB * d, 4); add(nB * 6 * d, 4); add((size_t)cfg.num_layers * nB * 6 * d, 4); add(nB * (cfg.freq_dim + d), 4);
   add(MAX_ITEMS, 4);
   if (cfg.i2v) {
     add(nB * 257 * 1280, 2); add(nB * 257 * 1280, 4); add(nB * 257 * 1280, 2); add(nB * 257 * d, 4);
-    add(nB * 257 * d, 2); add(nB * 257 * d, 2); add(nB * Hn * 128 * 264, 2); add(nB * 257 * (d / 128), 4);
+    add(nB * 257 * d, 2); add(nB * 257 * d, 2); add(nB * Hn * 128 * 264, 2); add(nB * 257 * (2 * d / 128), 4);
   }
   ws.release();
   ws.ensure(bytes + 4096, /*zero=*/true);       // zero: V^T padding columns must stay finite
@@ -258,17 +259,17 @@ void DitEngine::ensure_workspace(int B, int L) {
   w.x_res = carve<float>(p, Mx * d);
   w.u = carve<__half>(p, Mx * d);
   w.qk = carve<__half>(p, Mx * 2 * d);
-  w.vt = carve<__half>(p, nB * Hn * 128 * Lpx);
+  w.vt = carve<__half>(p, Hn * 128 * (((size_t)nB * nL + 7) & ~size_t(7)));
   w.att = carve<__half>(p, Mx * d);
   w.hid = carve<__half>(p, Mx * f);
-  w.ssq = carve<float>(p, Mx * (2 * d / 128));
+  w.ssq = carve<float>(p, Mx * (4 * d / 128));      // 2 partial sums per (row, N tile)
   w.patch = carve<__half>(p, Mx * cfg.in_dim * 4);
   w.ctx16 = carve<__half>(p, nB * TL * cfg.text_dim);
   w.ctx_h = carve<__half>(p, nB * TL * d);
   w.ctx_e = carve<__half>(p, nB * TL * d);
   w.kc = carve<__half>(p, nB * TL * d);
   w.vtc = carve<__half>(p, nB * Hn * 128 * TL);
-  w.ssq_c = carve<float>(p, nB * TL * (d / 128));
+  w.ssq_c = carve<float>(p, nB * TL * (2 * d / 128));
   w.e = carve<float>(p, nB * d);
   w.e0 = carve<float>(p, nB * 6 * d);
   w.modtab = carve<float>(p, (size_t)cfg.num_layers * nB * 6 * d);
@@ -282,7 +283,7 @@ void DitEngine::ensure_workspace(int B, int L) {
     w.ctx_img = carve<__half>(p, nB * 257 * d);
     w.ki = carve<__half>(p, nB * 257 * d);
     w.vti = carve<__half>(p, nB * Hn * 128 * 264);
-    w.ssq_i = carve<float>(p, nB * 257 * (d / 128));
+    w.ssq_i = carve<float>(p, nB * 257 * (2 * d / 128));
   }
   ws_B = nB; ws_L = nL;
   // workspaces moved: every captured graph holds stale pointers
@@ -305,7 +306,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   const int B = in.B, F = in.F, Hl = in.H, Wl = in.W;
   const int Hp = Hl / 2, Wp = Wl / 2, L = F * Hp * Wp, M = B * L;
   const int d = cfg.dim, f = cfg.ffn_dim, TL = cfg.text_len, Hn = cfg.num_heads;
-  const int Lp = (L + 7) & ~7;
+  const int Mp = (M + 7) & ~7;                 // leading dimension of the transposed V
   const int Kp = cfg.in_dim * 4;
   const float eps = cfg.eps;
   const float* cs = rope_table(F, Hp, Wp);
@@ -339,18 +340,18 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   }
 
   AttnParams self{};
-  self.q = w.qk; self.ldq = 2 * d; self.k = w.qk + d; self.ldk = 2 * d; self.vt = w.vt; self.ldvt = Lp;
+  self.q = w.qk; self.ldq = 2 * d; self.k = w.qk + d; self.ldk = 2 * d; self.vt = w.vt; self.ldvt = Mp;
   self.out = w.att; self.ldo = d; self.items = B; self.heads = Hn; self.Lq = L; self.Lk_rows = L;
   self.scale = 1.0f / std::sqrt(128.0f);
   for (int i = 0; i < B; ++i) self.klen[i] = L;
   AttnParams cross = self;
-  cross.ldq = d; cross.k = w.kc; cross.ldk = d; cross.vt = w.vtc; cross.ldvt = TL; cross.Lk_rows = TL;
+  cross.ldq = d; cross.k = w.kc; cross.ldk = d; cross.vt = w.vtc; cross.ldvt = B * TL; cross.Lk_rows = TL;
   for (int i = 0; i < B; ++i) {
     int kl = in.ctx_rows[i] + (img ? 257 : 0);      // model.py:531,537 (+ App. A.12 clamp)
     cross.klen[i] = kl < TL ? kl : TL;
   }
   AttnParams cimg = cross;
-  cimg.k = w.ki; cimg.vt = w.vti; cimg.ldvt = 264; cimg.Lk_rows = 257; cimg.accumulate = 1;
+  cimg.k = w.ki; cimg.vt = w.vti; cimg.ldvt = (B * 257 + 7) & ~7; cimg.Lk_rows = 257; cimg.accumulate = 1;
   for (int i = 0; i < B; ++i) cimg.klen[i] = 257;
 
   const int bn_qkv = (d % 256 == 0 && pick_bn(M, 3 * d, num_sms) == 256) ? 256 : 128;
@@ -364,11 +365,11 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
     launch_ln_affine(w.x_res, w.u, mod + d, mod, 6 * d, M, L, d, eps, s);
     {
       GemmParams p{}; p.M = M; p.N = 3 * d; p.K = d; p.bias = b.qkv_b; p.out_h = w.qk; p.ld_h = 2 * d;
-      p.ssq = w.ssq; p.ssq_cols = 2 * d; p.ssq_ld = 2 * d / bn_qkv; p.vt = w.vt; p.vt_col0 = 2 * d; p.vt_ld = Lp;
-      p.heads = Hn; p.rows_per_item = L;
+      p.ssq = w.ssq; p.ssq_cols = 2 * d; p.ssq_ld = 4 * d / bn_qkv; p.vt = w.vt; p.vt_col0 = 2 * d; p.vt_ld = Mp;
+      p.vt_rows = d; p.rows_per_item = L;
       gemm_linear(EPI_QKV, w.u, d, b.qkv_w, d, p, num_sms, s, bn_qkv);
     }
-    launch_rms_rope(w.qk, 2 * d, d, 2, w.ssq, 2 * d / bn_qkv, d / bn_qkv, b.norm_q, b.norm_k, cs, M, L, eps, s);
+    launch_rms_rope(w.qk, 2 * d, d, 2, w.ssq, 4 * d / bn_qkv, 2 * d / bn_qkv, b.norm_q, b.norm_k, cs, M, L, eps, s);
     launch_attention(self, s);
     {
       GemmParams p{}; p.M = M; p.N = d; p.K = d; p.bias = b.o_b; p.out_f = w.x_res; p.ld_f = d;
@@ -379,24 +380,24 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
     launch_ln_affine(w.x_res, w.u, b.norm3_w, b.norm3_b, 0, M, L, d, eps, s);
     {
       GemmParams p{}; p.M = M; p.N = d; p.K = d; p.bias = b.cq_b; p.out_h = w.qk; p.ld_h = d;
-      p.ssq = w.ssq; p.ssq_cols = d; p.ssq_ld = d / bn_cq; p.vt_col0 = d; p.rows_per_item = L; p.heads = Hn;
+      p.ssq = w.ssq; p.ssq_cols = d; p.ssq_ld = 2 * d / bn_cq; p.vt_col0 = d; p.rows_per_item = L;
       gemm_linear(EPI_QKV, w.u, d, b.cq_w, d, p, num_sms, s, bn_cq);
     }
-    launch_rms_rope(w.qk, d, d, 1, w.ssq, d / bn_cq, d / bn_cq, b.cnorm_q, nullptr, nullptr, M, L, eps, s);
+    launch_rms_rope(w.qk, d, d, 1, w.ssq, 2 * d / bn_cq, 2 * d / bn_cq, b.cnorm_q, nullptr, nullptr, M, L, eps, s);
     {
       GemmParams p{}; p.M = B * TL; p.N = 2 * d; p.K = d; p.bias = b.ckv_b; p.out_h = w.kc; p.ld_h = d;
-      p.ssq = w.ssq_c; p.ssq_cols = d; p.ssq_ld = d / bn_ckv; p.vt = w.vtc; p.vt_col0 = d; p.vt_ld = TL;
-      p.heads = Hn; p.rows_per_item = TL;
+      p.ssq = w.ssq_c; p.ssq_cols = d; p.ssq_ld = 2 * d / bn_ckv; p.vt = w.vtc; p.vt_col0 = d; p.vt_ld = B * TL;
+      p.vt_rows = d; p.rows_per_item = TL;
       gemm_linear(EPI_QKV, w.ctx_e, d, b.ckv_w, d, p, num_sms, s, bn_ckv);
     }
-    launch_rms_rope(w.kc, d, d, 1, w.ssq_c, d / bn_ckv, d / bn_ckv, b.cnorm_k, nullptr, nullptr, B * TL, TL, eps, s);
+    launch_rms_rope(w.kc, d, d, 1, w.ssq_c, 2 * d / bn_ckv, 2 * d / bn_ckv, b.cnorm_k, nullptr, nullptr, B * TL, TL, eps, s);
     launch_attention(cross, s);
     if (img) {
       GemmParams p{}; p.M = B * 257; p.N = 2 * d; p.K = d; p.bias = b.ckv_img_b; p.out_h = w.ki; p.ld_h = d;
-      p.ssq = w.ssq_i; p.ssq_cols = d; p.ssq_ld = d / 128; p.vt = w.vti; p.vt_col0 = d; p.vt_ld = 264;
-      p.heads = Hn; p.rows_per_item = 257;
+      p.ssq = w.ssq_i; p.ssq_cols = d; p.ssq_ld = 2 * d / 128; p.vt = w.vti; p.vt_col0 = d; p.vt_ld = (B * 257 + 7) & ~7;
+      p.vt_rows = d; p.rows_per_item = 257;
       gemm_linear(EPI_QKV, w.ctx_img, d, b.ckv_img_w, d, p, num_sms, s, 128);
-      launch_rms_rope(w.ki, d, d, 1, w.ssq_i, d / 128, d / 128, b.cnorm_k_img, nullptr, nullptr, B * 257, 257, eps, s);
+      launch_rms_rope(w.ki, d, d, 1, w.ssq_i, 2 * d / 128, 2 * d / 128, b.cnorm_k_img, nullptr, nullptr, B * 257, 257, eps, s);
       launch_attention(cimg, s);
     }
     {

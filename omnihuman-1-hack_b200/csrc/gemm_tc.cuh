@@ -2,11 +2,22 @@
 //
 //   D[M,N] = A[M,K] * W[N,K]^T        A, W fp16 (K-major), fp32 accumulation in TMEM
 //
-// One CTA per SM loops over 128 x BLOCK_N output tiles.  Roles:
-//   warp 0      TMA producer     (A and W tiles, 64-wide K slices, 128B swizzle, STAGES-deep ring)
-//   warp 1      MMA issuer       (one elected lane: tcgen05.mma 128 x BLOCK_N x 16, 4 per K slice)
-//   warps 2..5  epilogue         (tcgen05.ld of a finished accumulator while the next tile's MMAs
-//                                 run into the other half of TMEM)
+// One CTA per SM.  Roles (10 warps):
+//   warps 0..7  epilogue: TMEM -> registers -> (bias / GELU / gate) -> swizzled shared-memory staging
+//               -> TMA bulk store (or TMA reduce-add for the fp32 residual update), 32 rows x 32
+//               columns per step.  Every TMEM lane quadrant is served by two warps (w, w+4), each
+//               taking half of the tile's columns, so two instruction streams per sub-partition hide
+//               each other's latencies.  Stores go through TMA because per-thread row stores
+//               (one 64-byte piece of 32 different rows per instruction) measured 30 % of the kernel.
+//   warp 8      TMA producer: A and W tiles, 64-wide K slices, 128B swizzle, STAGES-deep ring
+//   warp 9      MMA issuer: one lane issues tcgen05.mma 128 x BLOCK_N x 16 (4 per K slice) into one of
+//               two TMEM accumulators, so the epilogue of tile i overlaps the main loop of tile i+1
+// Scheduling: whole tiles wave by wave; the left-over tiles of the last wave can be split along K
+// across the otherwise idle CTAs.  A split tile is finished by the CTA that owns its first K slice:
+// the others dump fp32 partial accumulators to a workspace, raise a flag per epilogue warp, and the
+// finisher adds the partials in CTA order -- deterministic, no atomics on the data.
+// Clusters (CL = 2): the two CTAs of a cluster work on vertically adjacent M tiles of the same N
+// tile; each loads half of the W tile and multicasts it into both CTAs' shared memory.
 // The A operand is either a plain row-major matrix (2-D TMA) or an NDHWC activation volume read
 // through a 4-D TMA window per filter tap (implicit-GEMM causal convolution, used by the VAE).
 #pragma once
@@ -15,13 +26,12 @@
 namespace b2 {
 
 enum EpiMode : int {
-  EPI_F16 = 0,       // out_h = acc + bias
-  EPI_GELU_F16 = 1,  // out_h = gelu_tanh(acc + bias)
-  EPI_RESID_F32 = 2, // out_f += gate[item, col] * (acc + bias)            (fp32 residual stream, in place)
-  EPI_QKV = 3,       // cols < vt_col0 -> out_h (+ per-row sum of squares for cols < ssq_cols);
-                     // cols >= vt_col0 -> transposed V store  vt[item][head][d][token]
-  EPI_F32 = 4,       // out_f = acc + bias (+ add_f)                       (fp32 store)
-  EPI_F16_ADD = 5,   // out_h = acc + bias, and out_f = add_f + acc + bias (VAE: raw fp32 + fp16 copy)
+  EPI_F16 = 0,       // out (fp16) = acc + bias
+  EPI_GELU_F16 = 1,  // out (fp16) = gelu_tanh(acc + bias)
+  EPI_RESID_F32 = 2, // out (fp32) += gate[item, col] * (acc + bias)       (TMA reduce-add, gate optional)
+  EPI_QKV = 3,       // cols < vt_col0 -> out (fp16) (+ per-row sum of squares for cols < ssq_cols);
+                     // cols >= vt_col0 -> transposed V store  vt[head*128 + d][global row]
+  EPI_F32 = 4,       // out (fp32) = acc + bias
 };
 
 struct ConvGeom {
@@ -37,14 +47,23 @@ struct ConvGeom {
 struct GemmParams {
   int M, N, K;            // conv: M = T*tiles_h*tiles_w*128 (tile-padded), K = taps*cblocks*64
   const float* bias;      // [N] or nullptr
+  // outputs (host side: used to build the store tensor maps; the kernel stores through TMA)
   __half* out_h; long long ld_h;
   float* out_f; long long ld_f;
-  const float* add_f;     // optional fp32 addend with out_f's layout (EPI_F32 / EPI_F16_ADD)
+  __half* vt; long long vt_ld; int vt_rows;    // EPI_QKV: V^T [vt_rows = heads*128, vt_ld >= M]
   const float* gate; int gate_stride; int rows_per_item;
   float* ssq; int ssq_ld; int ssq_cols;
-  __half* vt; int vt_col0; int vt_ld; int heads;
+  int vt_col0;
   ConvGeom cv;
+  int sk;                 // K-split factor S of the last (partial) wave's tiles, <= 1: no split
+  float* sk_ws;           // [gridDim.x][BLOCK_N][128] fp32 partial accumulators
+  int* sk_flags;          // [gridDim.x][8], zero between launches
+  int dbg;                // diagnosis only (B200_GEMM_DBG): bit 0 = skip the epilogue's global stores
 };
+
+constexpr int WARP_TMA = 8, WARP_MMA = 9;
+constexpr int EPI_WARPS = 8;
+constexpr int STAGING_BYTES = EPI_WARPS * 4096;          // 32 rows x 128 B per epilogue warp
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -52,21 +71,22 @@ struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_FIT = (196 * 1024) / STAGE_BYTES;
+  static constexpr int BIAS_BYTES = 2 * 2 * 128 * 4;     // [column half][accumulator parity][<= 128 values]
+  static constexpr int TAIL_BYTES = STAGING_BYTES + 256 /*barriers*/ + BIAS_BYTES;
+  static constexpr int STAGES_FIT = (227 * 1024 - TAIL_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   // two accumulators; TMEM allocations are powers of two >= 32 columns
   static constexpr int TMEM_COLS = 2 * BLOCK_N <= 32 ? 32 : 2 * BLOCK_N <= 64 ? 64 : 2 * BLOCK_N <= 128 ? 128
                                    : 2 * BLOCK_N <= 256 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int THREADS = 192;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TAIL_BYTES;      // dynamic smem is 1024-aligned
+  static constexpr int THREADS = 320;
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
-  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))),  tanh(u) = 1 - 2 / (exp(2u) + 1)
-  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-  const float e = __expf(2.0f * u);
-  const float th = 1.0f - __fdividef(2.0f, e + 1.0f);
-  return 0.5f * x * (1.0f + th);
+  // 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3)   ==   x * sigmoid(2u) = x / (1 + exp(-2u))
+  const float x2 = x * x;
+  const float t = x * fmaf(x2, -2.0f * 0.7978845608028654f * 0.044715f, -2.0f * 0.7978845608028654f);   // -2u
+  return __fdividef(x, 1.0f + __expf(t));
 }
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -74,47 +94,87 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(192, 1)
+// Work distribution shared by the three roles of a CTA (all compute the same sequence):
+// W full waves of whole tiles (unit = wave * G + c), then the R = units % G left-over tiles are
+// each cut into S K-slices handled by S consecutive CTAs, so the last wave costs 1/S of a tile
+// instead of a whole one.  Slice 0 finishes the tile; slices 1..S-1 contribute partials.
+struct TileSched {
+  int KB, G, c, S, W, R, w;
+  bool tail_done;
+  __device__ TileSched(int units, int KB_, int G_, int c_, int S_) : KB(KB_), G(G_), c(c_), S(S_ < 1 ? 1 : S_) {
+    W = units / G;
+    R = units - W * G;
+    w = 0;
+    tail_done = false;
+  }
+  __device__ bool next(int& unit, int& kb0, int& kb1, int& n_contrib) {
+    n_contrib = 0;
+    if (w < W) { unit = w * G + c; kb0 = 0; kb1 = KB; ++w; return true; }
+    if (tail_done || R == 0) return false;
+    tail_done = true;
+    if (S == 1) {
+      if (c >= R) return false;
+      unit = W * G + c; kb0 = 0; kb1 = KB;
+      return true;
+    }
+    if (c >= R * S) return false;
+    const int j = c % S;
+    unit = W * G + c / S;
+    kb0 = KB * j / S;
+    kb1 = KB * (j + 1) / S;
+    if (j == 0) n_contrib = S - 1;
+    return true;
+  }
+};
+
+template <int BLOCK_N, int EPI, int CL>
+__global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_vt,
                const GemmParams p) {
   using C = GemmCfg<BLOCK_N>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;                 // [8][4096], 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint64_t* full = bars;                       // [STAGES]   TMA -> MMA
-  uint64_t* empty = bars + C::STAGES;          // [STAGES]   MMA -> TMA
+  uint64_t* empty = bars + C::STAGES;          // [STAGES]   MMA (of every CTA in the cluster) -> TMA
   uint64_t* acc_full = bars + 2 * C::STAGES;   // [2]        MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;          // [2]        epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* bias_all = reinterpret_cast<float*>(staging + STAGING_BYTES + 256);
 
   const int warp = warp_id();
   const int lane = lane_id();
+  const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
 
   const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles_m = (p.M + C::BLOCK_M - 1) / C::BLOCK_M;
-  const int num_tiles = tiles_m * tiles_n;
+  const int units = ((tiles_m + CL - 1) / CL) * tiles_n;       // one unit = CL vertically adjacent tiles
   const int num_kb = (p.K + C::BLOCK_K - 1) / C::BLOCK_K;
+  const int G = gridDim.x / CL, cid = blockIdx.x / CL;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    tma_prefetch_desc(&tmap_o);
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == WARP_MMA) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == WARP_TMA) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+      TileSched sched(units, num_kb, G, cid, p.sk);
+      int unit, kb0, kb1, n_contrib;
+      while (sched.next(unit, kb0, kb1, n_contrib)) {
+        const int m_blk = (unit / tiles_n) * CL + rank, n_blk = unit % tiles_n;
         int ct = 0, ch0 = 0, cw0 = 0;
         if (p.cv.enabled) {
           const int per_frame = p.cv.tiles_h * p.cv.tiles_w;
@@ -123,7 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           ch0 = (r / p.cv.tiles_w) * p.cv.TH - p.cv.pad_h;
           cw0 = (r % p.cv.tiles_w) * p.cv.TW - p.cv.pad_w;
         }
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
@@ -135,23 +195,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           } else {
             tma_load_2d(sa, &tmap_a, &full[stage], kb * C::BLOCK_K, m_blk * C::BLOCK_M);
           }
-          tma_load_2d(sb, &tmap_b, &full[stage], kb * C::BLOCK_K, n_blk * BLOCK_N);
+          if (CL == 1) {
+            tma_load_2d(sb, &tmap_b, &full[stage], kb * C::BLOCK_K, n_blk * BLOCK_N);
+          } else {
+            // this CTA fetches rows [rank*BN/CL, (rank+1)*BN/CL) of the W tile for every CTA of the cluster
+            constexpr int ROWS = BLOCK_N / CL;
+            tma_load_2d_mc(sb + rank * ROWS * 128, &tmap_b, &full[stage], kb * C::BLOCK_K,
+                           n_blk * BLOCK_N + rank * ROWS, (uint16_t)((1u << CL) - 1));
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == WARP_MMA) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_f16(C::BLOCK_M, BLOCK_N);
     int stage = 0; uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+    int seg = 0;
+    TileSched sched(units, num_kb, G, cid, p.sk);
+    int unit, kb0, kb1, n_contrib;
+    while (sched.next(unit, kb0, kb1, n_contrib)) {
+      const int acc = seg & 1;
+      const uint32_t acc_phase = (seg >> 1) & 1;
+      ++seg;
       mbar_wait(&acc_empty[acc], acc_phase ^ 1);       // epilogue drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (lane == 0) {
@@ -160,159 +230,215 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < C::BLOCK_K / C::UMMA_K; ++k) {
             umma_f16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc,
-                     (kb > 0 || k > 0) ? 1u : 0u);
+                     (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);                    // smem slot reusable once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&acc_full[acc]);
+          // the smem slot is reusable once these MMAs retire; with clusters the peer writes into it too
+          if (CL == 1) umma_commit(&empty[stage]);
+          else umma_commit_mc(&empty[stage], (uint16_t)((1u << CL) - 1));
+          if (kb == kb1 - 1) umma_commit(&acc_full[acc]);
         }
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 0..7)
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may access
+    const int half = warp >> 2;                          // which half of the tile's 32-column chunks
+    constexpr int NCH = BLOCK_N / 32;
+    constexpr int C_SPLIT = (NCH + 1) / 2;               // half 0: [0, C_SPLIT), half 1: [C_SPLIT, NCH)
+    const int c_begin = half ? C_SPLIT : 0, c_end = half ? NCH : C_SPLIT;
     const int r_in_tile = quad * 32 + lane;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+    uint8_t* stg_base = staging + warp * 4096;           // this warp's private staging area
+    constexpr bool OUT_F32 = (EPI == EPI_RESID_F32 || EPI == EPI_F32);
+    int n_store = 0;                                     // fp16 boxes are 2 KB: two of them alternate
+    int seg = 0;
+    TileSched sched(units, num_kb, G, cid, p.sk);
+    int unit, kb0, kb1, n_contrib;
+    while (sched.next(unit, kb0, kb1, n_contrib)) {
+      const int acc = seg & 1;
+      const uint32_t acc_phase = (seg >> 1) & 1;
+      ++seg;
+      const int m_blk = (unit / tiles_n) * CL + rank, n_blk = unit % tiles_n;
+      const uint32_t t_acc = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N;
 
-      // global row (token / pixel) owned by this thread, -1 when outside the problem
-      long long grow;
+      if (kb0 > 0) {
+        // ---- contributor: this CTA holds a later K range of the tile; hand the partial to the finisher
+        float* ws = p.sk_ws + (size_t)blockIdx.x * (BLOCK_N * 128);
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_acc + c * 32, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ws[(c * 32 + j) * 128 + r_in_tile] = __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&acc_empty[acc]);
+          st_release_gpu(p.sk_flags + blockIdx.x * EPI_WARPS + warp, 1);
+        }
+        continue;
+      }
+
+      // ---- finisher (or sole owner) of the tile: the next n_contrib CTAs hold the later K slices
+      // (warp w of a contributor wrote exactly the rows / columns warp w of the finisher reads)
+      if (n_contrib > 0) {
+        if (lane == 0)
+          for (int q = 0; q < n_contrib; ++q)
+            wait_flag_gpu(p.sk_flags + ((cid + 1 + q) * CL + rank) * EPI_WARPS + warp);
+        __syncwarp();
+      }
+
+      // bias values of this warp's chunks (lane l <-> column l of each chunk): fetched before the wait
+      // on the accumulator so the global latency is hidden, published to shared memory after it
+      float bv[C_SPLIT];
+#pragma unroll
+      for (int ci = 0; ci < C_SPLIT; ++ci) {
+        const int col = n_blk * BLOCK_N + (c_begin + ci) * 32 + lane;
+        bv[ci] = (p.bias != nullptr && c_begin + ci < c_end && col < p.N) ? __ldg(p.bias + col) : 0.f;
+      }
+
+      // output coordinates of this warp's 32 rows
+      const int row0 = m_blk * C::BLOCK_M + quad * 32;   // matrix mode: first global row
+      int ct = 0, ch = 0, cw = 0;                         // conv mode: frame / first pixel row / first pixel col
       if (p.cv.enabled) {
         const int per_frame = p.cv.tiles_h * p.cv.tiles_w;
-        const int ct = m_blk / per_frame, r = m_blk % per_frame;
-        const int hh = (r / p.cv.tiles_w) * p.cv.TH + r_in_tile / p.cv.TW;
-        const int ww = (r % p.cv.tiles_w) * p.cv.TW + r_in_tile % p.cv.TW;
-        grow = (hh < p.cv.H && ww < p.cv.W) ? ((long long)ct * p.cv.H + hh) * p.cv.W + ww : -1;
-      } else {
-        const int row = m_blk * C::BLOCK_M + r_in_tile;
-        grow = row < p.M ? row : -1;
+        ct = m_blk / per_frame;
+        const int r = m_blk % per_frame;
+        const int p0 = quad * 32;                         // first tile pixel of this warp (row-major TH x TW)
+        ch = (r / p.cv.tiles_w) * p.cv.TH + p0 / p.cv.TW;
+        cw = (r % p.cv.tiles_w) * p.cv.TW + p0 % p.cv.TW;
       }
-      const bool row_ok = grow >= 0;
+      const long long grow = (long long)row0 + lane;      // matrix mode only (gate / ssq / item)
+      const bool row_ok = !p.cv.enabled && grow < p.M;
       const int item = (p.rows_per_item > 0 && row_ok) ? (int)(grow / p.rows_per_item) : 0;
 
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
+      // acc_full of this segment implies every epilogue warp is done with the segment two back, the
+      // previous user of this parity's bias slot; the 4 warps of a column half write identical values
+      float* bias_w = bias_all + (half * 2 + acc) * 128;
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int ci = 0; ci < C_SPLIT; ++ci) bias_w[ci * 32 + lane] = bv[ci];
+        __syncwarp();
+      }
       float ssq_acc = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         const int col0 = n_blk * BLOCK_N + c * 32;
         if (col0 >= p.N) break;                           // warp-uniform
         uint32_t r[32];
-        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + c * 32, r);
+        tmem_ld32(t_acc + c * 32, r);
         tmem_wait_ld();
         float v[32];
-        const bool full_chunk = col0 + 32 <= p.N;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float b = 0.f;
-          if (p.bias != nullptr && (full_chunk || col0 + j < p.N)) b = __ldg(p.bias + col0 + j);
-          v[j] = __uint_as_float(r[j]) + b;
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+#pragma unroll 1
+        for (int q = 0; q < n_contrib; ++q) {             // partials in CTA order: deterministic sum
+          const float* ws = p.sk_ws + (size_t)((cid + 1 + q) * CL + rank) * (BLOCK_N * 128) + (c * 32) * 128 + r_in_tile;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldcg(ws + j * 128);
         }
-        if (!row_ok) continue;
-
-        if constexpr (EPI == EPI_F16 || EPI == EPI_GELU_F16 || EPI == EPI_F16_ADD) {
-          if constexpr (EPI == EPI_F16_ADD) {
-            float* of = p.out_f + grow * p.ld_f + col0;
-            const float* af = p.add_f ? p.add_f + grow * p.ld_f + col0 : nullptr;
-            if (full_chunk) {
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias_w + (c - c_begin) * 32);     // broadcast LDS.128
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (af) {
-                  const float4 a4 = *reinterpret_cast<const float4*>(af + j);
-                  v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
-                }
-                *reinterpret_cast<float4*>(of + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j];
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (p.dbg & 1) continue;
+
+        // the bulk store that last used this staging box must have finished reading it
+        uint8_t* stg = stg_base + (OUT_F32 ? 0 : (n_store & 1) * 2048);
+        ++n_store;
+        if (lane == 0) { if (OUT_F32) tma_store_wait_read0(); else tma_store_wait_read1(); }
+        __syncwarp();
+
+        bool to_vt = false;
+        if constexpr (EPI == EPI_QKV) to_vt = col0 >= p.vt_col0;
+        if constexpr (OUT_F32) {
+          if constexpr (EPI == EPI_RESID_F32) {
+            if (p.gate != nullptr) {
+              const float4* g4 = reinterpret_cast<const float4*>(p.gate + (long long)item * p.gate_stride + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 g = __ldg(g4 + j);
+                v[4 * j] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
               }
-            } else {
-              for (int j = 0; j < 32 && col0 + j < p.N; ++j) { if (af) v[j] += af[j]; of[j] = v[j]; }
             }
           }
+          // 32 rows x 128 B, 128-byte swizzle: 16-byte piece k of row r lives at piece k ^ (r & 7)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        } else if (!to_vt) {
           if constexpr (EPI == EPI_GELU_F16) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
           }
-          if (p.out_h != nullptr) {
-            __half* o = p.out_h + grow * p.ld_h + col0;
-            if (full_chunk) {
+          uint32_t h[16];
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 q4 = make_uint4(pack_h2(v[j], v[j + 1]), pack_h2(v[j + 2], v[j + 3]),
-                                      pack_h2(v[j + 4], v[j + 5]), pack_h2(v[j + 6], v[j + 7]));
-                *reinterpret_cast<uint4*>(o + j) = q4;
+          for (int j = 0; j < 16; ++j) h[j] = pack_h2(v[2 * j], v[2 * j + 1]);
+          if constexpr (EPI == EPI_QKV) {
+            if (col0 < p.ssq_cols) {                      // sum of squares of exactly what attention will read
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 f = __half22float2(*reinterpret_cast<__half2*>(&h[j]));
+                ssq_acc = fmaf(f.x, f.x, fmaf(f.y, f.y, ssq_acc));
               }
-            } else {
-              for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = __float2half_rn(v[j]);
             }
           }
-        } else if constexpr (EPI == EPI_RESID_F32) {
-          float* o = p.out_f + grow * p.ld_f + col0;
-          const float* g = p.gate ? p.gate + (long long)item * p.gate_stride + col0 : nullptr;
-          if (full_chunk) {
+          // 32 rows x 64 B, 64-byte swizzle: piece k of row r lives at piece k ^ ((r >> 1) & 3)
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 x4 = *reinterpret_cast<const float4*>(o + j);
-              float4 g4 = g ? __ldg(reinterpret_cast<const float4*>(g + j)) : make_float4(1.f, 1.f, 1.f, 1.f);
-              x4.x += g4.x * v[j]; x4.y += g4.y * v[j + 1]; x4.z += g4.z * v[j + 2]; x4.w += g4.w * v[j + 3];
-              *reinterpret_cast<float4*>(o + j) = x4;
-            }
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+        } else {
+          // transposed V: staging holds [32 d][32 rows] fp16 (64 B per d, no swizzle)
+          __half* sv = reinterpret_cast<__half*>(stg);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sv[j * 32 + lane] = __float2half_rn(v[j]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (to_vt) {
+            tma_store_2d(&tmap_vt, stg, row0, col0 - p.vt_col0);        // (global row, head*128 + d)
+          } else if (p.cv.enabled) {
+            if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_4d(&tmap_o, stg, col0, cw, ch, ct);
+            else tma_store_4d(&tmap_o, stg, col0, cw, ch, ct);
           } else {
-            for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] += (g ? g[j] : 1.f) * v[j];
+            if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_2d(&tmap_o, stg, col0, row0);
+            else tma_store_2d(&tmap_o, stg, col0, row0);
           }
-        } else if constexpr (EPI == EPI_F32) {
-          float* o = p.out_f + grow * p.ld_f + col0;
-          const float* af = p.add_f ? p.add_f + grow * p.ld_f + col0 : nullptr;
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (af) {
-                const float4 a4 = *reinterpret_cast<const float4*>(af + j);
-                v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
-              }
-              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-          } else {
-            for (int j = 0; j < 32 && col0 + j < p.N; ++j) o[j] = v[j] + (af ? af[j] : 0.f);
-          }
-        } else if constexpr (EPI == EPI_QKV) {
-          if (col0 < p.vt_col0) {
-            // round to fp16 first: the norm that follows sees exactly what attention will see
-            __half* o = p.out_h + grow * p.ld_h + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q4 = make_uint4(pack_h2(v[j], v[j + 1]), pack_h2(v[j + 2], v[j + 3]),
-                                    pack_h2(v[j + 4], v[j + 5]), pack_h2(v[j + 6], v[j + 7]));
-              *reinterpret_cast<uint4*>(o + j) = q4;
-            }
-            if (col0 < p.ssq_cols) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) { const float h = __half2float(__float2half_rn(v[j])); ssq_acc += h * h; }
-            }
-          } else {
-            const int cc = col0 - p.vt_col0;               // 32 consecutive d of one head
-            const int head = cc >> 7, d0 = cc & 127;
-            const long long tok = grow - (long long)item * p.rows_per_item;
-            __half* o = p.vt + (((long long)item * p.heads + head) * 128 + d0) * p.vt_ld + tok;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[(long long)j * p.vt_ld] = __float2half_rn(v[j]);
-          }
+          tma_store_commit();
         }
       }
       if constexpr (EPI == EPI_QKV) {
-        if (row_ok && n_blk * BLOCK_N < p.ssq_cols) p.ssq[grow * p.ssq_ld + n_blk] = ssq_acc;
+        // two partial sums per (row, N tile): one from each of the two warps that share the quadrant
+        if (row_ok && n_blk * BLOCK_N < p.ssq_cols) p.ssq[grow * p.ssq_ld + n_blk * 2 + half] = ssq_acc;
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) {
+        mbar_arrive(&acc_empty[acc]);
+        for (int q = 0; q < n_contrib; ++q) p.sk_flags[((cid + 1 + q) * CL + rank) * EPI_WARPS + warp] = 0;   // re-arm
+      }
     }
+    if (lane == 0) tma_store_wait_all();                 // bulk stores read shared memory asynchronously
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
+  if (CL > 1) cluster_sync(); else __syncthreads();
+  if (warp == WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }

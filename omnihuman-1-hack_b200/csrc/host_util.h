@@ -55,9 +55,10 @@ inline PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-// fp16 tensor, up to 4 dims (dim 0 innermost / contiguous), 128-byte swizzle, zero OOB fill.
-inline CUtensorMap make_tmap_f16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                 const uint32_t* box) {
+// Tensor map of up to 4 dims (dim 0 innermost / contiguous), zero OOB fill.
+// swizzle_bytes: 0 (none), 64 or 128 -- must match how the kernel lays the box out in shared memory.
+inline CUtensorMap make_tmap(const void* base, bool f32, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                             const uint32_t* box, int swizzle_bytes) {
   CUtensorMap m;
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bdim[5], estr[5];
@@ -66,12 +67,18 @@ inline CUtensorMap make_tmap_f16(const void* base, int rank, const uint64_t* dim
   B2_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
   for (int i = 0; i + 1 < rank; ++i)
     B2_CHECK(gstr[i] % 16 == 0, "TMA stride %d = %llu bytes is not a multiple of 16", i, (unsigned long long)gstr[i]);
-  CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim,
-                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = get_encode_tiled()(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
+                                  const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B2_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d (rank %d, dims %llu x %llu)", (int)r, rank,
            (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0));
   return m;
+}
+inline CUtensorMap make_tmap_f16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                 const uint32_t* box) {
+  return make_tmap(base, false, rank, dims, strides_bytes, box, 128);
 }
 
 // row-major [rows, cols] fp16 matrix with leading dimension ld (elements); box = [box_rows, 64]

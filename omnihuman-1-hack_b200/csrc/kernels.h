@@ -29,8 +29,9 @@ struct ProfScope {
 };
 
 // ---- gemm_tc.cu
-void launch_gemm(int epi, int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
-                 cudaStream_t stream);
+void launch_gemm(int epi, int block_n, int cluster, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                 int num_sms, cudaStream_t stream);
+int gemm_cluster_size(int block_n, long long M, bool conv);
 void gemm_linear(int epi, const __half* A, long long lda, const __half* W, long long ldw, GemmParams p, int num_sms,
                  cudaStream_t stream, int force_bn = 0);
 void conv_gemm(int epi, const __half* in, int Tbuf, int H, int W, int Cin, const __half* w, int Cout, int kt, int kh,
@@ -58,15 +59,16 @@ void launch_vae_store_rgb(const float* x, float* out, int T, long long HW, int t
 void launch_repack_conv_weight(const float* src, __half* dst, int Cout, int Cin, int taps, int cpad, cudaStream_t s);
 
 inline int pick_bn(long long M, long long N, int num_sms) {
-  const long long t256 = ((M + 127) / 128) * ((N + 255) / 256);
-  return (N % 256 == 0 && t256 >= num_sms) ? 256 : 128;
+  // stream-K balances any tile count, so take the widest tile the problem supports (fewest A re-reads)
+  (void)num_sms;
+  return (N % 256 == 0 && M > 128) ? 256 : 128;
 }
 
 // ---- attn_tc.cu : softmax(Q K^T / sqrt(128)) V, head_dim 128, non-causal, keys >= klen masked
 struct AttnParams {
   const __half* q; long long ldq;      // [items*Lq, ldq], head h at columns h*128
   const __half* k; long long ldk;      // [items*Lk_rows, ldk]
-  const __half* vt; long long ldvt;    // [items*heads*128, ldvt]   V transposed per (item, head)
+  const __half* vt; long long ldvt;    // [heads*128, ldvt >= items*Lk_rows]  V transposed, column = item*Lk_rows + key
   __half* out; long long ldo;          // [items*Lq, ldo]
   int items, heads;
   int Lq;                              // query rows per item

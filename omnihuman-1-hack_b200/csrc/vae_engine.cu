@@ -180,17 +180,19 @@ struct VaeEngine::Impl {
     B2_CUDA(cudaMemcpyAsync(hist[name]->p, A0.as<__half>() + (size_t)Tc * frame, 2 * frame * 2,
                             cudaMemcpyDeviceToDevice, s));
   }
-  void run_conv(const std::string& name, const __half* in, int Tc, int H, int W, float* out, const float* add) {
+  // out = conv(in) + bias, or out += conv(in) + bias when `accumulate` (the residual add, in place)
+  void run_conv(const std::string& name, const __half* in, int Tc, int H, int W, float* out, bool accumulate) {
     const ConvW& c = convs.at(name);
     GemmParams p{};
-    p.bias = c.b->as<float>(); p.out_f = out; p.ld_f = c.cout; p.add_f = add;
-    conv_gemm(EPI_F32, in, Tc + c.kt - 1, H, W, c.cin, c.w->as<__half>(), c.cout, c.kt, c.kh, c.kw, Tc, p, num_sms, s);
+    p.bias = c.b->as<float>(); p.out_f = out; p.ld_f = (c.cout + 3) & ~3;      // TMA rows are 16-byte multiples
+    conv_gemm(accumulate ? EPI_RESID_F32 : EPI_F32, in, Tc + c.kt - 1, H, W, c.cin, c.w->as<__half>(), c.cout, c.kt,
+              c.kh, c.kw, Tc, p, num_sms, s);
   }
-  void linear_1x1(const std::string& name, const __half* in, long long rows, int epi, void* out, const float* add) {
+  void linear_1x1(const std::string& name, const __half* in, long long rows, int epi, void* out, bool accumulate) {
     const ConvW& c = convs.at(name);
     GemmParams p{};
     p.M = (int)rows; p.N = c.cout; p.K = c.cin; p.bias = c.b->as<float>();
-    if (epi == EPI_F32) { p.out_f = static_cast<float*>(out); p.ld_f = c.cout; p.add_f = add; }
+    if (epi == EPI_F32) { p.out_f = static_cast<float*>(out); p.ld_f = c.cout; if (accumulate) epi = EPI_RESID_F32; }
     else { p.out_h = static_cast<__half*>(out); p.ld_h = c.cout; }
     gemm_linear(epi, in, c.cin, c.w->as<__half>(), c.cin, p, num_sms, s);
   }
@@ -202,17 +204,17 @@ struct VaeEngine::Impl {
     __half* a = begin_causal(p + "residual.2", Tc, H, W, cin);
     launch_vae_norm(F[xi].as<float>(), gammas.at(p + "residual.0.gamma")->as<float>(), a, P, cin, 1, s);
     end_causal(p + "residual.2", Tc, H, W, cin);
-    run_conv(p + "residual.2", A0.as<__half>(), Tc, H, W, F[yi].as<float>(), nullptr);
+    run_conv(p + "residual.2", A0.as<__half>(), Tc, H, W, F[yi].as<float>(), false);
     int out = xi;
     if (cin != cout) {
       launch_vae_cast(F[xi].as<float>(), A1.as<__half>(), P * cin, s);
-      linear_1x1(p + "shortcut", A1.as<__half>(), P, EPI_F32, F[si].as<float>(), nullptr);
+      linear_1x1(p + "shortcut", A1.as<__half>(), P, EPI_F32, F[si].as<float>(), false);
       out = si;
     }
     a = begin_causal(p + "residual.6", Tc, H, W, cout);
     launch_vae_norm(F[yi].as<float>(), gammas.at(p + "residual.3.gamma")->as<float>(), a, P, cout, 1, s);
     end_causal(p + "residual.6", Tc, H, W, cout);
-    run_conv(p + "residual.6", A0.as<__half>(), Tc, H, W, F[out].as<float>(), F[out].as<float>());   // + shortcut, in place
+    run_conv(p + "residual.6", A0.as<__half>(), Tc, H, W, F[out].as<float>(), true);   // += onto the shortcut, in place
     return out;
   }
 
@@ -235,7 +237,7 @@ struct VaeEngine::Impl {
     for (int f = 0; f < Tc; ++f) {
       float* xf = F[xi].as<float>() + (size_t)f * hw * C;
       launch_vae_norm(xf, gamma, xn, hw, C, 0, s);
-      linear_1x1(p + "to_qkv", xn, hw, EPI_F16, qkv, nullptr);
+      linear_1x1(p + "to_qkv", xn, hw, EPI_F16, qkv, false);
       {
         GemmParams g{}; g.M = hw; g.N = hw; g.K = C; g.out_f = S; g.ld_f = hwp;
         gemm_linear(EPI_F32, qkv, 3 * C, qkv + C, 3 * C, g, num_sms, s);
@@ -246,7 +248,7 @@ struct VaeEngine::Impl {
         GemmParams g{}; g.M = hw; g.N = C; g.K = hwp; g.out_h = O; g.ld_h = C;
         gemm_linear(EPI_F16, Pm, hwp, vt, hwp, g, num_sms, s);
       }
-      linear_1x1(p + "proj", O, hw, EPI_F32, xf, xf);
+      linear_1x1(p + "proj", O, hw, EPI_F32, xf, true);        // x += proj(attn)
     }
   }
 
@@ -259,14 +261,14 @@ struct VaeEngine::Impl {
       __half* a = begin_causal(p + "time_conv", Tc, H, W, cin);
       launch_vae_cast(F[xi].as<float>(), a, P * cin, s);
       end_causal(p + "time_conv", Tc, H, W, cin);
-      run_conv(p + "time_conv", A0.as<__half>(), Tc, H, W, F[yi].as<float>(), nullptr);      // [Tc,H,W,2cin]
+      run_conv(p + "time_conv", A0.as<__half>(), Tc, H, W, F[yi].as<float>(), false);      // [Tc,H,W,2cin]
       src = yi; interleave = 1;
     }
     launch_vae_upsample(F[src].as<float>(), A1.as<__half>(), Tc, H, W, cin, interleave, s);
     if (interleave) Tc *= 2;
     H *= 2; W *= 2;
     const int oi = (src + 1) % 3;
-    run_conv(p + "resample.1", A1.as<__half>(), Tc, H, W, F[oi].as<float>(), nullptr);
+    run_conv(p + "resample.1", A1.as<__half>(), Tc, H, W, F[oi].as<float>(), false);
     return oi;
   }
 
@@ -308,7 +310,7 @@ struct VaeEngine::Impl {
     const int hw = h * w, T_total = 1 + 4 * (T - 1);
     // de-normalise + conv2 over the whole sequence (vae.py:547-553)
     launch_vae_prep_latent(z, consts.as<float>(), consts.as<float>() + 16, Z16.as<__half>(), zdim, T, hw, s);
-    linear_1x1("conv2", Z16.as<__half>(), (long long)T * hw, EPI_F32, X0.p, nullptr);
+    linear_1x1("conv2", Z16.as<__half>(), (long long)T * hw, EPI_F32, X0.p, false);
     int t0 = 0, f_out = 0;
     while (t0 < T) {
       const bool first = t0 == 0;
@@ -319,7 +321,7 @@ struct VaeEngine::Impl {
       __half* a = begin_causal("decoder.conv1", Tc, H, W, zdim);
       launch_vae_cast(X0.as<float>() + (size_t)t0 * hw * zdim, a, (long long)Tc * hw * zdim, s);
       end_causal("decoder.conv1", Tc, H, W, zdim);
-      run_conv("decoder.conv1", A0.as<__half>(), Tc, H, W, F[0].as<float>(), nullptr);
+      run_conv("decoder.conv1", A0.as<__half>(), Tc, H, W, F[0].as<float>(), false);
       int xi = res_block("decoder.middle.0.", 0, Tc, H, W, c0, c0);
       attn_block("decoder.middle.1.", xi, Tc, H, W, c0);
       xi = res_block("decoder.middle.2.", xi, Tc, H, W, c0, c0);
@@ -333,7 +335,7 @@ struct VaeEngine::Impl {
       launch_vae_norm(F[xi].as<float>(), gammas.at("decoder.head.0.gamma")->as<float>(), a, (long long)Tc * H * W, dim, 1, s);
       end_causal("decoder.head.2", Tc, H, W, dim);
       const int oi = (xi + 1) % 3;
-      run_conv("decoder.head.2", A0.as<__half>(), Tc, H, W, F[oi].as<float>(), nullptr);
+      run_conv("decoder.head.2", A0.as<__half>(), Tc, H, W, F[oi].as<float>(), false);     // [.., 4]: 3 channels, pitch 4
       launch_vae_store_rgb(F[oi].as<float>(), out, Tc, (long long)H * W, f_out, T_total, s);
       f_out += Tc;
       t0 += Tl;

@@ -147,7 +147,7 @@ __global__ void store_rgb_kernel(const float* __restrict__ x, float* __restrict_
     const int t = i / HW;
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-      out[((long long)c * T_total + t0 + t) * HW + hw] = fminf(fmaxf(x[i * 3 + c], -1.f), 1.f);
+      out[((long long)c * T_total + t0 + t) * HW + hw] = fminf(fmaxf(x[i * 4 + c], -1.f), 1.f);   // pixel pitch 4
   }
 }
 

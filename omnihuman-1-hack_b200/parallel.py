@@ -1,0 +1,89 @@
+"""Multi-GPU layer: one process per GPU (torchrun), independent items sharded across ranks, ONE
+collective -- an all_gather of the finished latents -- at the end.
+
+The path has no exchange step: `WanModel.forward` never mixes batch items (model.py:515-527 take a
+per-item `t`; probed co-batching equivalence), the teacher sweep iterates independent
+seeds (generate.py:209-232) and cond/uncond share inputs but no state (text2video.py:238-241).  So
+items `i % world == rank` run on a full weight replica and nothing crosses NVLink until the gather.
+Results are bit-identical to a single-GPU run as long as the per-call co-batch size is the same
+(every output row's reduction order is fixed by the tile schedule, not by the world size).
+
+Everything here is host logic over torch.distributed and works on CPU tensors with the gloo
+backend (tests/test_cpu_parallel.py); on the B200 box the backend is NCCL over NVLink 5/NVSwitch.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init(backend=None):
+    """Initialise torch.distributed from the torchrun environment (no-op for a single process)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 or dist.is_initialized():
+        return rank(), max(world, world_size())
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    kw = {}
+    if backend == "nccl":
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        kw["device_id"] = torch.device("cuda", local)
+    dist.init_process_group(backend, **kw)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def rank():
+    return dist.get_rank() if dist.is_initialized() else 0
+
+
+def world_size():
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+def shard_indices(n_items, rank_=None, world=None):
+    """Round-robin ownership: item i belongs to rank i % world."""
+    r = rank() if rank_ is None else rank_
+    w = world_size() if world is None else world
+    return list(range(r, n_items, w))
+
+
+def gather_items(local, n_items, group=None):
+    """The single collective of the path.  `local` holds this rank's results in shard_indices order
+    (tensors of identical shape); returns all n_items results in original order on every rank."""
+    w = world_size()
+    if w == 1:
+        return list(local)
+    per_rank = (n_items + w - 1) // w
+    proto = local[0] if local else None
+    if proto is None:
+        raise ValueError("every rank needs at least one item (n_items >= world size)")
+    buf = torch.zeros((per_rank,) + tuple(proto.shape), dtype=proto.dtype, device=proto.device)
+    for j, t in enumerate(local):
+        buf[j].copy_(t)
+    out = [torch.empty_like(buf) for _ in range(w)]
+    dist.all_gather(out, buf, group=group)
+    res = [None] * n_items
+    for r in range(w):
+        for j, i in enumerate(range(r, n_items, w)):
+            res[i] = out[r][j]
+    return res
+
+
+def sharded_map(fn, items, group=None):
+    """Runs fn(item) for the items this rank owns and gathers every result (one all_gather)."""
+    idx = shard_indices(len(items))
+    local = [fn(items[i]) for i in idx]
+    return gather_items(local, len(items), group=group)
+
+
+def max_over_ranks(value, device=None):
+    """Timing reduction used by bench.py: every multi-GPU number is the max over ranks."""
+    if world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64,
+                     device=device or ("cuda" if dist.get_backend() == "nccl" else "cpu"))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

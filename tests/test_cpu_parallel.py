@@ -1,0 +1,48 @@
+"""N>1 host path on CPU: world_size-2 gloo processes shard items round-robin, run a stand-in for the
+per-item computation, and gather with the single all_gather (omnihuman-1-hack_b200/parallel.py)."""
+import os
+import socket
+import subprocess
+import sys
+
+from conftest import ROOT
+
+WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, os.environ["B200_ROOT"])
+import importlib.util
+spec = importlib.util.spec_from_file_location("b200par", os.path.join(os.environ["B200_ROOT"], "omnihuman-1-hack_b200", "parallel.py"))
+par = importlib.util.module_from_spec(spec); spec.loader.exec_module(par)
+rank, world = par.init("gloo")
+assert world == 2
+items = [torch.full((16, 1, 4, 6), float(i)) for i in range(5)]
+calls = []
+def fn(x):
+    calls.append(int(x[0, 0, 0, 0]))
+    return x * 2 + 1
+res = par.sharded_map(fn, items)
+assert calls == list(range(rank, 5, 2)), calls                       # ownership i % world == rank
+for i, r in enumerate(res):
+    assert torch.equal(r, items[i] * 2 + 1), i                        # original order, every rank
+assert par.max_over_ranks(1.0 + rank) == 2.0
+assert par.shard_indices(7, 1, 4) == [1, 5]
+print("ok", rank)
+'''
+
+
+def test_gloo_world2_shard_and_gather(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), B200_ROOT=ROOT, CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for r, p in enumerate(procs):
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
+        assert f"ok {r}" in out
