@@ -3,10 +3,10 @@
 // for both self-attention (Lk = L) and text/extra-stream cross-attention (Lk <= 512).
 //
 // One CTA = one 128-query tile of one (item, head).  Roles:
-//   warp 0      TMA: Q once, then K_j and V^T_j tiles (128 keys) through 2-deep rings
-//   warp 1      MMA: S_j = Q K_j^T into TMEM (double buffered), O += P_j V_j
-//   warps 2..5  softmax: one query row per thread; S row -> registers, online softmax with lazy
-//               (thresholded) rescaling of O, P_j written to shared memory as the fp16 A operand
+//   warp 8      TMA: Q once, then K_j and V^T_j tiles (128 keys) through 2-deep rings
+//   warp 9      MMA: S_j = Q K_j^T into TMEM (double buffered), O += P_j V_j
+//   warps 0..7  softmax: two threads per query row (64 keys each); S -> registers, online softmax with
+//               lazy (thresholded) rescaling of O, P_j written to shared memory as the fp16 A operand
 // TMEM columns: S0 [0,128) S1 [128,256) O [256,384).
 #include "host_util.h"
 #include "kernels.h"
@@ -24,11 +24,12 @@ constexpr int OFF_K = OFF_Q + TILE_BYTES;          // 2 stages
 constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;      // 2 stages
 constexpr int OFF_P = OFF_V + 2 * TILE_BYTES;
 constexpr int OFF_BAR = OFF_P + TILE_BYTES;
-constexpr int ATTN_SMEM = OFF_BAR + 256 + 1024;
+constexpr int OFF_XCH = OFF_BAR + 256;                // row-max / row-sum exchange between the two column halves
+constexpr int ATTN_SMEM = OFF_XCH + 2 * 2 * 128 * 4 + 1024;
 constexpr float RESCALE_THRESHOLD = 8.0f;          // log2 units: P stays below 2^8, exact after normalisation
-// warps 0..3: softmax (TMEM lane quadrant = warp id); the single-lane TMA / MMA roles take the
+// warps 0..7: softmax (TMEM lane quadrant = warp id & 3); the single-lane TMA / MMA roles take the
 // highest ids so the sub-partition arbiter (highest warp id first) never queues them behind softmax
-constexpr int WARP_TMA = 4, WARP_MMA = 5;
+constexpr int WARP_TMA = 8, WARP_MMA = 9;
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -36,7 +37,7 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -64,9 +65,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
     }
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -138,22 +139,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       __syncwarp();
     }
   } else {
-    const int quad = warp & 3;
+    // ---- softmax: two threads per query row (warps w and w+4), each owning 64 of the tile's 128 keys
+    // and 64 of O's 128 columns; the row maximum is exchanged through shared memory once per tile
+    const int quad = warp & 3, half = warp >> 2;
     const int r = quad * 32 + lane;                         // query row within the tile
     const uint32_t lane_sel = uint32_t(quad * 32) << 16;
     const float c = p.scale * 1.4426950408889634f;
     float m_ref = -INFINITY, l_sum = 0.f;
-    uint8_t* p_row = smem + OFF_P;
+    uint8_t* p_row = smem + OFF_P + half * SUB_BYTES;       // keys [64 half, 64 half + 64) = one SW128 sub-tile
+    float* xch = reinterpret_cast<float*>(smem + OFF_XCH);  // [2 parity][2 half][128 rows]
 
     for (int j = 0; j < n_kv; ++j) {
       const int sb = j & 1; const uint32_t ph = (j >> 1) & 1;
       mbar_wait(&s_full[sb], ph);
       tc_fence_after();
-      float s[128];
+      float s[64];
 #pragma unroll
-      for (int cidx = 0; cidx < 4; ++cidx) {
+      for (int cidx = 0; cidx < 2; ++cidx) {
         uint32_t t[32];
-        tmem_ld32(tmem_base + lane_sel + sb * 128 + cidx * 32, t);
+        tmem_ld32(tmem_base + lane_sel + sb * 128 + half * 64 + cidx * 32, t);
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) s[cidx * 32 + i] = __uint_as_float(t[i]);
@@ -162,14 +166,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
 
-      const int valid = klen - j * TILE;                    // >= 1
-      if (valid < TILE) {
+      const int valid = klen - j * TILE - half * 64;        // may be <= 0 for the upper half of the last tile
+      if (valid < 64) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) if (i >= valid) s[i] = -INFINITY;
+        for (int i = 0; i < 64; ++i) if (i >= valid) s[i] = -INFINITY;
       }
       float tmax = s[0];
 #pragma unroll
-      for (int i = 1; i < 128; ++i) tmax = fmaxf(tmax, s[i]);
+      for (int i = 1; i < 64; ++i) tmax = fmaxf(tmax, s[i]);
+      xch[(sb * 2 + half) * 128 + r] = tmax;
+      asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 softmax warps
+      tmax = fmaxf(tmax, xch[(sb * 2 + (half ^ 1)) * 128 + r]);
 
       float alpha = 1.f;
       bool rescale = false;
@@ -183,9 +190,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       const float mc = m_ref * c;
       float psum = 0.f;
-      uint32_t pk[64];
+      uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 128; i += 2) {
+      for (int i = 0; i < 64; i += 2) {
         const float p0 = ex2(fmaf(s[i], c, -mc)), p1 = ex2(fmaf(s[i + 1], c, -mc));
         // accumulate what the tensor core will see (fp16-rounded P)
         __half2 h = __floats2half2_rn(p0, p1);
@@ -200,36 +207,41 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tc_fence_after();
         if (__any_sync(0xffffffffu, rescale)) {
 #pragma unroll
-          for (int cidx = 0; cidx < 4; ++cidx) {
+          for (int cidx = 0; cidx < 2; ++cidx) {
             uint32_t t[32];
-            tmem_ld32(tmem_o + lane_sel + cidx * 32, t);
+            tmem_ld32(tmem_o + lane_sel + half * 64 + cidx * 32, t);
             tmem_wait_ld();
 #pragma unroll
             for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
-            tmem_st32(tmem_o + lane_sel + cidx * 32, t);
+            tmem_st32(tmem_o + lane_sel + half * 64 + cidx * 32, t);
           }
           tmem_wait_st();
         }
       }
 #pragma unroll
-      for (int ch = 0; ch < 16; ++ch) {
+      for (int ch = 0; ch < 8; ++ch) {
         const uint4 v4 = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-        *reinterpret_cast<uint4*>(p_row + (ch >> 3) * SUB_BYTES + sw128_offset(r, ch & 7)) = v4;
+        *reinterpret_cast<uint4*>(p_row + sw128_offset(r, ch)) = v4;
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
 
+    // total row sum = both halves
+    xch[half * 128 + r] = l_sum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l_sum += xch[(half ^ 1) * 128 + r];
+
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
     const int q_in_item = qt * TILE + r;
     const float inv_l = 1.0f / l_sum;
-    __half* o = p.out + ((long long)item * p.Lq + q_in_item) * p.ldo + head * 128;
+    __half* o = p.out + ((long long)item * p.Lq + q_in_item) * p.ldo + head * 128 + half * 64;
 #pragma unroll
-    for (int cidx = 0; cidx < 4; ++cidx) {
+    for (int cidx = 0; cidx < 2; ++cidx) {
       uint32_t t[32];
-      tmem_ld32(tmem_o + lane_sel + cidx * 32, t);
+      tmem_ld32(tmem_o + lane_sel + half * 64 + cidx * 32, t);
       tmem_wait_ld();
       if (q_in_item < p.Lq) {
 #pragma unroll
@@ -281,7 +293,7 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
   double keys = 0;
   for (int i = 0; i < p.items; ++i) keys += p.klen[i];
   ProfScope prof(PC_ATTN, 4.0 * p.Lq * keys * 128.0 * p.heads, 0.0, stream);
-  attn_fwd_kernel<<<grid, 192, ATTN_SMEM, stream>>>(tq, tk, tv, p);
+  attn_fwd_kernel<<<grid, 320, ATTN_SMEM, stream>>>(tq, tk, tv, p);
   B2_CUDA(cudaGetLastError());
   count_launch();
 }

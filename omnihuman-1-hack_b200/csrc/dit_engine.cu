@@ -77,7 +77,7 @@ void DitEngine::alloc_weights() {
     if (i2v) { H(2 * d * d); Fp(2 * d); Fp(d); }
     H(f * d); Fp(f); H(d * f); Fp(d);
   }
-  Fp(2 * d); Fp(d * P); Fp(P);
+  Fp(2 * d); Fp(d * P); Fp(P); H(3 * d * P);
   if (i2v) { Fp(1280); Fp(1280); H(1280 * 1280); Fp(1280); H(d * 1280); Fp(d); Fp(d); Fp(d); }
   w16.ensure(h16 * 2 + 4096);
   w32.ensure(f32 * 4 + 4096);
@@ -149,9 +149,9 @@ void DitEngine::alloc_weights() {
     add_slot(p + "ffn.2.weight", b.ffn2_w, DT_F16, d * f);
     add_slot(p + "ffn.2.bias", b.ffn2_b, DT_F32, d);
   }
-  wt.head_mod = W32(2 * d); wt.head_wt = W32(d * P); wt.head_b = W32(P);
+  wt.head_mod = W32(2 * d); wt.head_w32 = W32(d * P); wt.head_b = W32(P); wt.head_w3 = W16(3 * d * P);
   add_slot("head.modulation", wt.head_mod, DT_F32, 2 * d);
-  add_slot("head.head.weight", wt.head_wt, DT_F32, d * P, (int)P, (int)d);   // stored transposed [d, P]
+  add_slot("head.head.weight", wt.head_w32, DT_F32, d * P);   // split into fp16 [hi | lo | hi] at finalize()
   add_slot("head.head.bias", wt.head_b, DT_F32, P);
   if (i2v) {
     wt.img_ln0_w = W32(1280); wt.img_ln0_b = W32(1280); wt.img_fc1_w = W16(1280 * 1280); wt.img_fc1_b = W32(1280);
@@ -198,6 +198,8 @@ void DitEngine::load_weight(const char* name, const void* data, int dtype, int n
 
 void DitEngine::finalize() {
   for (auto& kv : slots) B2_CHECK(kv.second.loaded, "weight '%s' was never loaded", kv.first.c_str());
+  launch_split_weight(wt.head_w32, wt.head_w3, cfg.out_dim * 4, cfg.dim, 0);
+  B2_CUDA(cudaDeviceSynchronize());
   finalized = true;
 }
 
@@ -243,7 +245,7 @@ void DitEngine::ensure_workspace(int B, int L) {
   (void)M; (void)Lp;
   size_t bytes = 0;
   auto add = [&](size_t n, size_t esz) { bytes += padded(n * esz); };
-  add(Mx * d, 4); add(Mx * d, 2); add(Mx * 2 * d, 2); add(nB * Hn * 128 * Lpx, 2); add(Mx * d, 2); add(Mx * f, 2);
+  add(Mx * d, 4); add(Mx * 3 * d, 2); add(Mx * 64, 4); add(nB * 2 * d, 4); add(Mx * d, 2); add(Mx * 2 * d, 2); add(nB * Hn * 128 * Lpx, 2); add(Mx * d, 2); add(Mx * f, 2);
   add(Mx * (4 * d / 128), 4); add(Mx * cfg.in_dim * 4, 2);
   add(nB * TL * cfg.text_dim, 2); add(nB * TL * d, 2); add(nB * TL * d, 2); add(nB * TL * d, 2);
   add(nB * Hn * 128 * TL, 2); add(nB * TL * (2 * d / 128), 4);
@@ -258,6 +260,9 @@ void DitEngine::ensure_workspace(int B, int L) {
   uint8_t* p = ws.as<uint8_t>();
   w.x_res = carve<float>(p, Mx * d);
   w.u = carve<__half>(p, Mx * d);
+  w.u3 = carve<__half>(p, Mx * 3 * d);
+  w.y = carve<float>(p, Mx * 64);
+  w.headtab = carve<float>(p, nB * 2 * d);
   w.qk = carve<__half>(p, Mx * 2 * d);
   w.vt = carve<__half>(p, Hn * 128 * (((size_t)nB * nL + 7) & ~size_t(7)));
   w.att = carve<__half>(p, Mx * d);
@@ -354,9 +359,13 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   cimg.k = w.ki; cimg.vt = w.vti; cimg.ldvt = (B * 257 + 7) & ~7; cimg.Lk_rows = 257; cimg.accumulate = 1;
   for (int i = 0; i < B; ++i) cimg.klen[i] = 257;
 
-  const int bn_qkv = (d % 256 == 0 && pick_bn(M, 3 * d, num_sms) == 256) ? 256 : 128;
-  const int bn_cq = (d % 256 == 0 && pick_bn(M, d, num_sms) == 256) ? 256 : 128;
-  const int bn_ckv = (d % 256 == 0 && pick_bn(B * TL, 2 * d, num_sms) == 256) ? 256 : 128;
+  // tile widths of the GEMMs whose epilogue slices columns at multiples of d (q | k | v boundaries)
+  auto bn_for = [&](long long rows, long long cols) {
+    int bn = pick_bn(rows, cols, num_sms);
+    while (d % bn != 0) bn = bn == 256 ? 192 : 128;
+    return bn;
+  };
+  const int bn_qkv = bn_for(M, 3 * d), bn_cq = bn_for(M, d), bn_ckv = bn_for(B * TL, 2 * d);
 
   for (int l = 0; l < cfg.num_layers; ++l) {
     const BlockWeights& b = wt.blocks[l];
@@ -417,9 +426,15 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
     if (l == tap_block && tap_dst != nullptr)
       B2_CUDA(cudaMemcpyAsync(tap_dst, w.x_res, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, s));
   }
-  // ---- head + unpatchify (+ CFG combine)
-  launch_head(w.x_res, w.e, wt.head_mod, wt.head_wt, wt.head_b, B, F, Hp, Wp, d, cfg.out_dim, eps, in.out,
-              in.cfg_pairs, in.cfg_scale, s);
+  // ---- head (model.py:349-359) + unpatchify (:565-588) + CFG combine (text2video.py:243-244)
+  {
+    const int P = cfg.out_dim * 4;
+    launch_head_table(wt.head_mod, w.e, w.headtab, B, d, s);
+    launch_ln_affine(w.x_res, w.u3, w.headtab, w.headtab + d, 2 * d, M, L, d, eps, s, /*split=*/true);
+    GemmParams p{}; p.M = M; p.N = P; p.K = 3 * d; p.bias = wt.head_b; p.out_f = w.y; p.ld_f = P;
+    gemm_linear(EPI_F32, w.u3, 3 * d, wt.head_w3, 3 * d, p, num_sms, s);
+    launch_unpatchify(w.y, P, B, F, Hp, Wp, cfg.out_dim, in.out, in.cfg_pairs, in.cfg_scale, s);
+  }
   last_flops = flops(B, L);
 }
 

@@ -33,13 +33,15 @@ struct DitWeights {
   float *time0_w, *time0_b, *time2_w, *time2_b, *timep_w, *timep_b;
   float* modulation;                     // [layers, 6, dim]
   std::vector<BlockWeights> blocks;
-  float *head_mod, *head_wt, *head_b;    // head weight stored transposed [dim, P]
+  float *head_mod, *head_w32, *head_b;   // head weight fp32 [P, dim] as loaded
+  __half* head_w3;                       // fp16 [P, 3 dim] = [hi | lo | hi] (built at finalize)
   float *img_ln0_w, *img_ln0_b; __half* img_fc1_w; float* img_fc1_b; __half* img_fc3_w; float* img_fc3_b;
   float *img_ln4_w, *img_ln4_b;
 };
 
 struct DitWorkspace {
   float* x_res; __half *u, *qk, *vt, *att, *hid; float* ssq; __half* patch;
+  __half* u3; float* y; float* headtab;  // head: split activations [M, 3 dim], projection [M, P], modulation table
   __half *ctx16, *ctx_h, *ctx_e, *kc, *vtc; float* ssq_c;
   float *e, *e0, *modtab, *tscratch, *t_items;
   __half* clip16; float* clip_f; __half* clip_g; float* img_f; __half *ctx_img, *ki, *vti; float* ssq_i;

@@ -22,12 +22,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ------------------------------------------------------------------ LayerNorm * a + b -> fp16
 // model.py:91-104 (+ :293,:315 modulation, :313 affine norm3).  One warp per row, row kept in registers.
-template <int NV>
-__global__ void __launch_bounds__(256) ln_affine_kernel(const float* __restrict__ x, __half* __restrict__ out,
+// SPLIT: the fp16 output row is [hi | hi | lo] (3 * DIM wide) with hi = fp16(y), lo = fp16(y - hi); against
+// a weight packed as [w_hi | w_lo | w_hi] one fp16 tensor-core GEMM then reproduces the fp32 product to
+// ~2^-22 (used for the head, which the reference evaluates in fp32: model.py:356-358).
+template <int NV, bool SPLIT>
+__global__ void __launch_bounds__(128) ln_affine_kernel(const float* __restrict__ x, __half* __restrict__ out,
                                                         const float* __restrict__ a, const float* __restrict__ b,
                                                         long long item_stride, int M, int rows_per_item, float eps) {
   constexpr int DIM = NV * 128;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * DIM);
@@ -46,13 +49,20 @@ __global__ void __launch_bounds__(256) ln_affine_kernel(const float* __restrict_
   const long long ioff = (long long)(rows_per_item > 0 ? row / rows_per_item : 0) * item_stride;
   const float4* ar = reinterpret_cast<const float4*>(a + ioff);
   const float4* br = reinterpret_cast<const float4*>(b + ioff);
-  uint2* orow = reinterpret_cast<uint2*>(out + (long long)row * DIM);
+  uint2* orow = reinterpret_cast<uint2*>(out + (long long)row * DIM * (SPLIT ? 3 : 1));
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const float4 aa = __ldg(ar + i * 32 + lane), bb = __ldg(br + i * 32 + lane);
     const float y0 = (v[i].x - mean) * rstd * aa.x + bb.x, y1 = (v[i].y - mean) * rstd * aa.y + bb.y;
     const float y2 = (v[i].z - mean) * rstd * aa.z + bb.z, y3 = (v[i].w - mean) * rstd * aa.w + bb.w;
-    orow[i * 32 + lane] = make_uint2(pack_h2(y0, y1), pack_h2(y2, y3));
+    const uint2 hi = make_uint2(pack_h2(y0, y1), pack_h2(y2, y3));
+    orow[i * 32 + lane] = hi;
+    if (SPLIT) {
+      const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x));
+      const float2 h23 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
+      orow[DIM / 4 + i * 32 + lane] = hi;
+      orow[DIM / 2 + i * 32 + lane] = make_uint2(pack_h2(y0 - h01.x, y1 - h01.y), pack_h2(y2 - h23.x, y3 - h23.y));
+    }
   }
 }
 
@@ -67,15 +77,23 @@ struct RmsRopeParams {
   int M, rows_per_item; float eps;
 };
 
-__global__ void __launch_bounds__(192) rms_rope_kernel(const RmsRopeParams p) {
-  const int row = blockIdx.x, slice = blockIdx.y;
-  float tot = 0.f;
-  for (int i = 0; i < p.ssq_n; ++i) tot += p.ssq[(long long)row * p.ssq_ld + slice * p.ssq_n + i];
+// one warp per (row, slice): 16-byte pieces strided across the lanes, 8 warps per block
+__global__ void __launch_bounds__(256) rms_rope_kernel(const RmsRopeParams p, int nslices) {
+  const int lane = threadIdx.x & 31;
+  const long long unit = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (unit >= (long long)p.M * nslices) return;
+  const int row = (int)(unit / nslices), slice = (int)(unit % nslices);
+  float part = lane < p.ssq_n ? p.ssq[(long long)row * p.ssq_ld + slice * p.ssq_n + lane] : 0.f;
+  float tot = warp_sum(part);                            // fixed shuffle tree: deterministic
+  if (p.ssq_n > 32) {
+    tot = 0.f;
+    for (int i = 0; i < p.ssq_n; ++i) tot += p.ssq[(long long)row * p.ssq_ld + slice * p.ssq_n + i];
+  }
   const float inv = rsqrtf(tot / (float)p.dim + p.eps);
   __half* xr = p.x + (long long)row * p.ld + (long long)slice * p.dim;
   const float* g = p.gamma[slice];
   const int tok = row % p.rows_per_item;
-  for (int ci = threadIdx.x; ci < p.dim / 8; ci += blockDim.x) {
+  for (int ci = lane; ci < p.dim / 8; ci += 32) {
     const int col = ci * 8;
     uint4 raw = *reinterpret_cast<const uint4*>(xr + col);
     const __half2* h = reinterpret_cast<const __half2*>(&raw);
@@ -205,74 +223,51 @@ __global__ void pad_cast_rows_kernel(ItemPtrs src, RowCounts rows_in, int B, int
   }
 }
 
-// ------------------------------------------------------------------ head + unpatchify (+ CFG)
-// model.py:349-359 in fp32: y = Linear(LN(x) * (1 + m1) + m0), (m0, m1) = head.modulation + e;
-// model.py:565-588: out[c, f, 2h+q, 2w+r] = y[token(f,h,w), (2q+r)*out_dim + c].
-// With cfg_pairs > 0 item b (cond) and item b+cfg_pairs (uncond) are combined as
-// uncond + s (cond - uncond)  (text2video.py:243-244) before the store.
-constexpr int HEAD_ROWS = 8;
+// ------------------------------------------------------------------ head: modulation table, unpatchify (+ CFG)
+// model.py:349-359: y = Linear(LN(x) * (1 + m1) + m0), (m0, m1) = head.modulation + e (note: e, not e0).
+// tab[item][0] = 1 + m1, tab[item][1] = m0
+__global__ void head_table_kernel(const float* __restrict__ head_mod, const float* __restrict__ e,
+                                  float* __restrict__ tab, int B, int dim) {
+  const int n = B * dim;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int b = i / dim, c = i % dim;
+    const float ev = e[i];
+    tab[((long long)b * 2) * dim + c] = 1.0f + head_mod[dim + c] + ev;
+    tab[((long long)b * 2 + 1) * dim + c] = head_mod[c] + ev;
+  }
+}
 
-__global__ void __launch_bounds__(256)
-head_kernel(const float* __restrict__ x, const float* __restrict__ e, const float* __restrict__ head_mod,
-            const float* __restrict__ w_t, const float* __restrict__ bias, int L, int Hp, int Wp, int F, int dim,
-            int out_dim, float eps, ItemPtrsMut out, int cfg_pairs, const float* __restrict__ cfg_scale_p) {
-  extern __shared__ float sm[];
-  float* u = sm;                          // [HEAD_ROWS][dim]
-  float* yv = sm + HEAD_ROWS * dim;       // [HEAD_ROWS][64]
+// [w | ...] fp32 [P, d] -> fp16 [P, 3d] = [hi | lo | hi]  (pairs with the [hi | hi | lo] activation rows)
+__global__ void split_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int P, int d) {
+  const long long n = (long long)P * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = i / d, c = i % d;
+    const __half hi = __float2half_rn(w[i]);
+    const __half lo = __float2half_rn(w[i] - __half2float(hi));
+    __half* o = out + (long long)r * 3 * d;
+    o[c] = hi; o[d + c] = lo; o[2 * d + c] = hi;
+  }
+}
+
+// model.py:565-588: out[c, f, 2h+q, 2w+r] = y[token(f,h,w), (2q+r)*out_dim + c].  With cfg_pairs > 0 item b
+// (cond) and item b+cfg_pairs (uncond) are combined as uncond + s (cond - uncond) (text2video.py:243-244).
+__global__ void unpatchify_kernel(const float* __restrict__ y, int ldy, int L, int Hp, int Wp, int F, int out_dim,
+                                  ItemPtrsMut out, int n_out, int cfg_pairs, const float* __restrict__ cfg_scale_p) {
   const int P = out_dim * 4;
-  const int toks_per_block = cfg_pairs > 0 ? HEAD_ROWS / 2 : HEAD_ROWS;
-  const int tok0 = blockIdx.x * toks_per_block;
-  const int oitem = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  {  // LayerNorm + modulation of row `warp`
-    const int tl = cfg_pairs > 0 ? (warp & 3) : warp;
-    const int item = cfg_pairs > 0 ? (warp < 4 ? oitem : oitem + cfg_pairs) : oitem;
-    const int tok = tok0 + tl;
-    float* ur = u + warp * dim;
-    if (tok < L) {
-      const float* xr = x + ((long long)item * L + tok) * dim;
-      float s = 0.f;
-      for (int k = lane; k < dim; k += 32) s += xr[k];
-      const float mean = warp_sum(s) / dim;
-      float q = 0.f;
-      for (int k = lane; k < dim; k += 32) { const float d = xr[k] - mean; q += d * d; }
-      const float rstd = rsqrtf(warp_sum(q) / dim + eps);
-      const float* er = e + (long long)item * dim;
-      for (int k = lane; k < dim; k += 32)
-        ur[k] = (xr[k] - mean) * rstd * (1.0f + head_mod[dim + k] + er[k]) + (head_mod[k] + er[k]);
-    } else {
-      for (int k = lane; k < dim; k += 32) ur[k] = 0.f;
+  const long long n = (long long)n_out * L * P;
+  const float sc = cfg_pairs > 0 ? __ldg(cfg_scale_p) : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int o = i % P;
+    const int tok = (i / P) % L;
+    const int item = i / ((long long)P * L);
+    float v = y[((long long)item * L + tok) * ldy + o];
+    if (cfg_pairs > 0) {
+      const float un = y[((long long)(item + cfg_pairs) * L + tok) * ldy + o];
+      v = un + sc * (v - un);
     }
-  }
-  __syncthreads();
-  {
-    const int o = threadIdx.x & 63, g = threadIdx.x >> 6;      // rows 2g, 2g+1
-    float a0 = 0.f, a1 = 0.f;
-    if (o < P) {
-      const float* u0 = u + (2 * g) * dim;
-      const float* u1 = u0 + dim;
-#pragma unroll 4
-      for (int k = 0; k < dim; ++k) {
-        const float w = __ldg(w_t + (long long)k * P + o);
-        a0 = fmaf(u0[k], w, a0);
-        a1 = fmaf(u1[k], w, a1);
-      }
-      a0 += bias[o]; a1 += bias[o];
-    }
-    yv[(2 * g) * 64 + o] = a0;
-    yv[(2 * g + 1) * 64 + o] = a1;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < toks_per_block * P; i += blockDim.x) {
-    const int tl = i / P, o = i % P;
-    const int tok = tok0 + tl;
-    if (tok >= L) continue;
-    float v = yv[tl * 64 + o];
-    if (cfg_pairs > 0) { const float un = yv[(tl + 4) * 64 + o]; v = un + __ldg(cfg_scale_p) * (v - un); }
     const int w = tok % Wp, h = (tok / Wp) % Hp, f = tok / (Wp * Hp);
     const int c = o % out_dim, qr = o / out_dim, q = qr >> 1, r = qr & 1;
-    out.p[oitem][(((long long)c * F + f) * (2 * Hp) + 2 * h + q) * (2 * Wp) + 2 * w + r] = v;
+    out.p[item][(((long long)c * F + f) * (2 * Hp) + 2 * h + q) * (2 * Wp) + 2 * w + r] = v;
   }
 }
 
@@ -329,12 +324,15 @@ inline int grid_for(long long n, int block = 256) {
 }  // namespace
 
 void launch_ln_affine(const float* x, __half* out, const float* a, const float* b, long long item_stride, int M,
-                      int rows_per_item, int dim, float eps, cudaStream_t s) {
+                      int rows_per_item, int dim, float eps, cudaStream_t s, bool split) {
   B2_CHECK(dim % 128 == 0, "LayerNorm width %d must be a multiple of 128", dim);
-  const int grid = (M + 7) / 8;
-  ProfScope prof(PC_NORM, 0.0, 6.0 * M * dim, s);
-#define B2_LN_CASE(NV) \
-  case NV: ln_affine_kernel<NV><<<grid, 256, 0, s>>>(x, out, a, b, item_stride, M, rows_per_item, eps); break;
+  const int grid = (M + 3) / 4;
+  ProfScope prof(PC_NORM, 0.0, (split ? 10.0 : 6.0) * M * dim, s);
+#define B2_LN_CASE(NV)                                                                                         \
+  case NV:                                                                                                     \
+    if (split) ln_affine_kernel<NV, true><<<grid, 128, 0, s>>>(x, out, a, b, item_stride, M, rows_per_item, eps); \
+    else ln_affine_kernel<NV, false><<<grid, 128, 0, s>>>(x, out, a, b, item_stride, M, rows_per_item, eps);      \
+    break;
   switch (dim / 128) {
     B2_LN_CASE(1) B2_LN_CASE(2) B2_LN_CASE(3) B2_LN_CASE(4) B2_LN_CASE(8) B2_LN_CASE(10) B2_LN_CASE(12)
     B2_LN_CASE(16) B2_LN_CASE(40)
@@ -354,7 +352,7 @@ void launch_rms_rope(__half* x, long long ld, int dim, int nslices, const float*
   p.cs = reinterpret_cast<const float2*>(cs_table);
   p.M = M; p.rows_per_item = rows_per_item; p.eps = eps;
   ProfScope prof(PC_NORM, 0.0, 4.0 * M * dim * nslices, s);
-  rms_rope_kernel<<<dim3(M, nslices), 192, 0, s>>>(p);
+  rms_rope_kernel<<<(unsigned)(((long long)M * nslices + 7) / 8), 256, 0, s>>>(p, nslices);
   B2_CUDA(cudaGetLastError());
   count_launch();
 }
@@ -404,22 +402,24 @@ void launch_pad_cast_rows(ItemPtrs src, int src_dtype, const int* rows_in, int B
   count_launch();
 }
 
-void launch_head(const float* x, const float* e, const float* head_mod, const float* w_t, const float* bias, int B,
-                 int F, int Hp, int Wp, int dim, int out_dim, float eps, ItemPtrsMut out, int cfg_pairs,
-                 const float* cfg_scale, cudaStream_t s) {
-  B2_CHECK(out_dim * 4 <= 64, "head output width %d > 64", out_dim * 4);
+void launch_head_table(const float* head_mod, const float* e, float* tab, int B, int dim, cudaStream_t s) {
+  head_table_kernel<<<grid_for((long long)B * dim), 256, 0, s>>>(head_mod, e, tab, B, dim);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void launch_split_weight(const float* w, __half* out, int P, int d, cudaStream_t s) {
+  split_weight_kernel<<<grid_for((long long)P * d), 256, 0, s>>>(w, out, P, d);
+  B2_CUDA(cudaGetLastError());
+}
+
+void launch_unpatchify(const float* y, int ldy, int B, int F, int Hp, int Wp, int out_dim, ItemPtrsMut out,
+                       int cfg_pairs, const float* cfg_scale, cudaStream_t s) {
   const int L = F * Hp * Wp;
-  const size_t smem = (size_t)(HEAD_ROWS * dim + HEAD_ROWS * 64) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > configured) {
-    B2_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  ProfScope prof(PC_OTHER, 2.0 * B * L * dim * out_dim * 4, 4.0 * B * L * dim, s);
-  const int tpb = cfg_pairs > 0 ? HEAD_ROWS / 2 : HEAD_ROWS;
   const int n_out = cfg_pairs > 0 ? cfg_pairs : B;
-  head_kernel<<<dim3((L + tpb - 1) / tpb, n_out), 256, smem, s>>>(x, e, head_mod, w_t, bias, L, Hp, Wp, F, dim, out_dim,
-                                                                  eps, out, cfg_pairs, cfg_scale);
+  ProfScope prof(PC_OTHER, 0.0, 8.0 * B * L * out_dim * 4, s);
+  unpatchify_kernel<<<grid_for((long long)n_out * L * out_dim * 4), 256, 0, s>>>(y, ldy, L, Hp, Wp, F, out_dim, out,
+                                                                                n_out, cfg_pairs, cfg_scale);
   B2_CUDA(cudaGetLastError());
   count_launch();
 }

@@ -16,7 +16,7 @@ int env_flag(const char* name, int dflt) {
   return v ? std::atoi(v) : dflt;
 }
 const int kUseCluster = env_flag("B200_GEMM_CLUSTER", 0);   // 2-CTA W-tile multicast (measured: no gain at cluster 2)
-const int kUseSplit = env_flag("B200_GEMM_SK", 0);          // K-split of the last partial wave
+const int kUseSplit = env_flag("B200_GEMM_SK", 1);          // K-split of the last partial wave (long K only)
 const int kDbg = env_flag("B200_GEMM_DBG", 0);
 
 // default split-K workspace: one per device, sized for a full grid of 128 x 256 fp32 partials.
@@ -102,9 +102,11 @@ void launch_one(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int 
     G = units;
     S = Gmax / units;
   }
-  if (S > KB / 4) S = KB / 4;
+  // the fix-up (partials through L2 + flag wait) costs about as much as 24 K slices of main loop
+  // (measured: K = 1536 tiles got slower, K = 8960 tiles 20 % faster), so only long-K tiles are split
+  if (S > KB / 16) S = KB / 16;
   if (S > 8) S = 8;
-  if (S < 2 || !kUseSplit) S = 1;
+  if (S < 2 || !kUseSplit || KB < 64) S = 1;
   if (units < Gmax) G = units * S;                    // single partial wave: W = 0, R = units
   p.sk = S;
   p.dbg = kDbg;
@@ -179,7 +181,7 @@ void launch_gemm(int epi, int block_n, int cluster, const CUtensorMap& ta, const
     if (cluster == 2) launch_bn<128, 2>(epi, ta, tb, p, num_sms, stream);
     else launch_bn<128, 1>(epi, ta, tb, p, num_sms, stream);
   } else if (block_n == 192) {
-    launch_narrow<192>(epi, ta, tb, p, num_sms, stream);
+    launch_bn<192, 1>(epi, ta, tb, p, num_sms, stream);
   } else if (block_n == 96) {
     launch_narrow<96>(epi, ta, tb, p, num_sms, stream);
   } else if (block_n == 32) {

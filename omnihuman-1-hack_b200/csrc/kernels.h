@@ -58,10 +58,23 @@ void launch_vae_store_rgb(const float* x, float* out, int T, long long HW, int t
 // conv weight [Cout, Cin, taps] (any float dtype staged as fp32) -> fp16 [Cout, taps, cpad], zero padded
 void launch_repack_conv_weight(const float* src, __half* dst, int Cout, int Cin, int taps, int cpad, cudaStream_t s);
 
+// Tile width: fewest (waves x tile cost); narrower tiles re-read A more often (cost factors measured
+// on M = 6240 sweeps).  N = 1536 at M = 3120 -> 192 (200 tiles, 2 waves of 3/4 size) instead of 256
+// (150 tiles = 2 full-size waves on 148 SMs).
 inline int pick_bn(long long M, long long N, int num_sms) {
-  // stream-K balances any tile count, so take the widest tile the problem supports (fewest A re-reads)
-  (void)num_sms;
-  return (N % 256 == 0 && M > 128) ? 256 : 128;
+  const long long tm = (M + 127) / 128;
+  if (tm <= 1 || N % 128 != 0) return 128;
+  int best = 128;
+  double best_cost = 1e30;
+  const int cand[3] = {256, 192, 128};
+  const double factor[3] = {1.0, 1.12, 1.25};
+  for (int i = 0; i < 3; ++i) {
+    if (N % cand[i] != 0) continue;
+    const long long tiles = tm * (N / cand[i]);
+    const double cost = (double)((tiles + num_sms - 1) / num_sms) * cand[i] * factor[i];
+    if (cost < best_cost) { best_cost = cost; best = cand[i]; }
+  }
+  return best;
 }
 
 // ---- attn_tc.cu : softmax(Q K^T / sqrt(128)) V, head_dim 128, non-causal, keys >= klen masked
@@ -85,7 +98,7 @@ struct ItemPtrsMut { float* p[MAX_ITEMS]; };
 
 // LayerNorm(x) * a + b  ->  fp16.  a/b are [dim] vectors, per item when item_stride != 0.
 void launch_ln_affine(const float* x, __half* out, const float* a, const float* b, long long item_stride, int M,
-                      int rows_per_item, int dim, float eps, cudaStream_t s);
+                      int rows_per_item, int dim, float eps, cudaStream_t s, bool split = false);
 // in-place on fp16 [M, ld]: per slice (q at column 0, k at column dim) x * rsqrt(mean(x^2)+eps) * gamma,
 // then optional 3-D RoPE (cos/sin table [rows_per_item, 64] float2).  ssq holds per-N-tile partial sums.
 void launch_rms_rope(__half* x, long long ld, int dim, int nslices, const float* ssq, int ssq_ld, int ssq_n,
@@ -103,10 +116,13 @@ void launch_patchify(ItemPtrs x, ItemPtrs y, int C, int Cy, int F, int H, int W,
 // fp32/bf16/fp16 rows -> fp16 matrix, zero-padded to rows_out rows per item
 void launch_pad_cast_rows(ItemPtrs src, int src_dtype, const int* rows_in, int B, int rows_out, int cols, __half* out,
                           cudaStream_t s);
-// head: LN + modulation + Linear(dim -> P) in fp32, unpatchify scatter, optional fused CFG combine
-void launch_head(const float* x, const float* e, const float* head_mod, const float* w_t, const float* bias, int B,
-                 int F, int Hp, int Wp, int dim, int out_dim, float eps, ItemPtrsMut out, int cfg_pairs,
-                 const float* cfg_scale, cudaStream_t s);
+// head (model.py:349-359, fp32 in the reference): modulation table [B][2][dim] = (1 + m1 + e, m0 + e); the
+// projection runs on the tensor cores with fp16 hi/lo-split operands (launch_ln_affine split = true
+// against launch_split_weight), then unpatchify (+ fused CFG combine) scatters y [B*L, P] to the latents.
+void launch_head_table(const float* head_mod, const float* e, float* tab, int B, int dim, cudaStream_t s);
+void launch_split_weight(const float* w, __half* out, int P, int d, cudaStream_t s);
+void launch_unpatchify(const float* y, int ldy, int B, int F, int Hp, int Wp, int out_dim, ItemPtrsMut out,
+                       int cfg_pairs, const float* cfg_scale, cudaStream_t s);
 // v [B, Lk, H*128] fp16 -> vt [B*H*128, Lp]
 void launch_transpose_v(const __half* v, __half* vt, int B, int Lk, int H, int Lp, cudaStream_t s);
 void launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t s);
