@@ -34,6 +34,16 @@ SHIFT = 5.0          # text2video.py:115
 NUM_STEPS = 50
 
 
+def workload_config(T, S, layers, world, graphs=True):
+    L = 1560 * T
+    return {"workload": f"Wan2.1-T2V-1.3B ({layers} blocks, dim 1536, ffn 8960, 12 heads) CFG denoise step on "
+                        f"latent [16,{T},60,104] (L={L} tokens), guide {GUIDE}, flow shift {SHIFT}, {S} sample(s) per "
+                        f"GPU, cond+uncond co-batched",
+            "samples_per_gpu": S, "parallelism": f"replicas x{world} (independent samples, one all_gather)",
+            "l2_policy": "weights 2.84 GB per forward exceed the 126 MB L2 (no flush needed)",
+            "cuda_graphs": graphs, "operands": "fp16 x fp16 -> fp32 accumulate (model.py:540)"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -131,36 +141,44 @@ def make_device_weights(cfg, seed, device):
     return sd
 
 
-def cpu_baseline(frames, budget_layers=2):
+def cpu_baseline(frames, target_s=12.0):
     """CPU oracle port (oracle/dit_oracle.py, fp32, all host threads) on a bounded sample of the same
-    workload: `budget_layers` of the 30 blocks for both CFG branches + embeddings + head, scaled to 30."""
+    workload: both CFG branches through embeddings + head + as many of the 30 blocks as fit ~target_s of
+    CPU work (at least 2); the measured per-block cost is scaled to 30 blocks."""
     import torch
     from oracle import dit_oracle as O
     cores = torch.get_num_threads()
-    sd = O.make_synthetic_weights(num_layers=budget_layers, seed=0)
     g = torch.Generator().manual_seed(42)
     x = [torch.randn(16, frames, 60, 104, generator=g)]
     ctx = [torch.randn(512, 4096, generator=g)]
     ctx0 = [torch.randn(512, 4096, generator=g)]
     t = torch.tensor([999.0])
     L = 1560 * frames
+    sd = O.make_synthetic_weights(num_layers=2, seed=0)
 
-    def one(nl):
+    def one(sd_, nl):
         t0 = time.perf_counter()
         with torch.no_grad():
-            c = O.dit_forward(sd, x, t, ctx, L, num_layers=nl)[0]
-            u = O.dit_forward(sd, x, t, ctx0, L, num_layers=nl)[0]
+            c = O.dit_forward(sd_, x, t, ctx, L, num_layers=nl)[0]
+            u = O.dit_forward(sd_, x, t, ctx0, L, num_layers=nl)[0]
             O.cfg_combine(c, u, GUIDE)
         return time.perf_counter() - t0
 
-    one(1)                                               # warm-up (thread pool, allocator)
-    t_full = one(budget_layers)
-    t_one = one(1)
-    per_block = max((t_full - t_one) / max(budget_layers - 1, 1), 1e-9)
+    one(sd, 1)                                           # warm-up (thread pool, allocator)
+    t_one = one(sd, 1)
+    t_two = one(sd, 2)
+    per_block = max(t_two - t_one, 1e-9)
+    n_layers = int(max(2, min(CFG_13B["num_layers"], round((target_s - t_one) / per_block))))
+    spent = t_one + t_two
+    if n_layers > 2:                                     # re-measure on the larger sample
+        sd = O.make_synthetic_weights(num_layers=n_layers, seed=0)
+        t_n = one(sd, n_layers)
+        per_block = max((t_n - t_one) / (n_layers - 1), 1e-9)
+        spent += t_n
     step_s = t_one + per_block * (CFG_13B["num_layers"] - 1)
     return {"value": 1.0 / step_s, "unit": "denoise-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{budget_layers} of 30 blocks x 2 CFG branches + embeddings/head at L={L}, fp32 oracle, "
-                      f"block cost scaled to 30 layers ({t_full + t_one:.1f}s of CPU work)"}, step_s
+            "sample": f"{n_layers} of 30 blocks x 2 CFG branches + embeddings/head at L={L}, fp32 CPU oracle "
+                      f"(oracle/dit_oracle.py), block cost scaled to 30 layers ({spent:.1f}s of CPU work)"}, step_s
 
 
 def run_reference(args):
@@ -171,11 +189,9 @@ def run_reference(args):
         return
     import torch
     vals = []
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_baseline(args.frames, 2)
     info = None
     for _ in range(max(1, min(args.steps, 3))):
-        info, step_s = cpu_baseline(args.frames, 2)
+        info, step_s = cpu_baseline(args.frames)
         vals.append(step_s)
     vals.sort()
     step_s = vals[len(vals) // 2]
@@ -185,7 +201,7 @@ def run_reference(args):
             "unit": "denoise-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"Wan2.1-T2V-1.3B CFG denoise step, latent [16,{args.frames},60,104], 1 sample"},
+            "config": workload_config(args.frames, args.samples_per_gpu, args.layers, args.gpus),
             "cpu_baseline": info,
             "e2e": {"value": v, "unit": "denoise-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "host_threads": torch.get_num_threads()}
@@ -349,12 +365,7 @@ def main():
                 "unit": "denoise-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
                 "data": "synthetic",
-                "config": {"workload": f"Wan2.1-T2V-1.3B ({cfg['num_layers']} blocks, dim 1536, ffn 8960, 12 heads) "
-                                       f"CFG denoise step on latent [16,{T},60,104] (L={L} tokens), guide {GUIDE}, "
-                                       f"flow shift {SHIFT}, {S} sample(s) per GPU, cond+uncond co-batched",
-                           "samples_per_gpu": S, "parallelism": f"replicas x{world} (independent samples, one all_gather)",
-                           "l2_policy": "weights 2.84 GB per forward exceed the 126 MB L2 (no flush needed)",
-                           "cuda_graphs": not args.no_graphs, "operands": "fp16 x fp16 -> fp32 accumulate (model.py:540)"},
+                "config": workload_config(T, S, cfg["num_layers"], world, not args.no_graphs),
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "denoise-steps/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / K},

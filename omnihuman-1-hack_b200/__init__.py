@@ -10,4 +10,5 @@ the `b200dit` alias module at the repository root:
 from ._lib import B200Error, LIB_PATH, MAX_ITEMS  # noqa: F401
 from .engine import (DitEngine, VaeEngine, flash_attention, kernel_launches, linear, profile_collect,  # noqa: F401
                      profile_enable)
+from . import parallel  # noqa: F401
 from .wan_shim import install, install_vae, uninstall  # noqa: F401
