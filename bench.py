@@ -41,7 +41,9 @@ def workload_config(T, S, layers, world, graphs=True):
                         f"GPU, cond+uncond co-batched",
             "samples_per_gpu": S, "parallelism": f"replicas x{world} (independent samples, one all_gather)",
             "l2_policy": "weights 2.84 GB per forward exceed the 126 MB L2 (no flush needed)",
-            "cuda_graphs": graphs, "operands": "fp16 x fp16 -> fp32 accumulate (model.py:540)"}
+            "cuda_graphs": graphs, "operands": "fp16 x fp16 -> fp32 accumulate (model.py:540)",
+            "context": "text embedding + cross-attention K/V computed once per trajectory (step-invariant), "
+                       "not counted in per-step FLOPs"}
 
 
 def peaks():
@@ -301,13 +303,22 @@ def main():
     ms_step = ms / K
     value = world * S / (ms_step / 1e3)
 
-    # ---- e2e: public API, pinned-host inputs in, result out, every step
+    # ---- e2e: public API with HOST buffers.  Every step copies that step's inputs (latent, t) from pinned
+    # host memory and the updated latent back; the prompt contexts are per-TRAJECTORY inputs (the reference
+    # encodes them once before its loop, text2video.py:172-182) and are copied in at the first step of each
+    # trajectory of NUM_STEPS steps, inside the timed region.
+    e2e_state = {"ctx": None, "h2d": 0}
+
     def step_e2e(i, hx):
         k = i % NUM_STEPS
+        if k == 0 or e2e_state["ctx"] is None:
+            e2e_state["ctx"] = ([h.to(dev, non_blocking=True) for h in host_ctx],
+                                [h.to(dev, non_blocking=True) for h in host_ctx0])
+            e2e_state["h2d"] += S * 2 * 512 * 4096 * 2
+        cs, c0 = e2e_state["ctx"]
         xs = [h.to(dev, non_blocking=True) for h in hx]
-        cs = [h.to(dev, non_blocking=True) for h in host_ctx]
-        c0 = [h.to(dev, non_blocking=True) for h in host_ctx0]
         tt = torch.full((S,), sig[k] * 1000.0).pin_memory().to(dev, non_blocking=True)
+        e2e_state["h2d"] += S * (16 * T * 60 * 104 * 4 + 4)
         v = eng.forward_cfg(xs, tt, cs, c0, L, GUIDE)
         out = [(xi + (sig[k + 1] - sig[k]) * vi).to("cpu", non_blocking=False) for xi, vi in zip(xs, v)]
         return out
@@ -316,6 +327,7 @@ def main():
     for i in range(2):
         step_e2e(i, hx)
     barrier()
+    e2e_state["ctx"], e2e_state["h2d"] = None, 0
     t0 = time.perf_counter()
     for i in range(K):
         hx_out = step_e2e(i, hx)
@@ -327,7 +339,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e_val = world * S / (e2e_s / K)
-    h2d = S * (16 * T * 60 * 104 * 4 + 2 * 512 * 4096 * 2 + 4)
+    h2d = e2e_state["h2d"] // K
     d2h = S * 16 * T * 60 * 104 * 4
 
     # ---- roofline of the dominant kernel family (tcgen05 GEMM), CUDA events around every launch of real steps
@@ -359,7 +371,8 @@ def main():
 
     if rank == 0:
         from oracle import dit_oracle as O
-        flops_step = 2 * S * O.dit_flops(L, layers=cfg["num_layers"])
+        # context work (text embedding, cross k/v projections) runs once per trajectory, not per step
+        flops_step = 2 * S * O.dit_flops(L, layers=cfg["num_layers"], context_cached=True)
         burst, sustained, hbm, src = peaks()
         line = {"metric": "DiT denoise-steps/sec (Wan2.1-T2V-1.3B, CFG, 480x832)", "value": value,
                 "unit": "denoise-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,

@@ -97,6 +97,14 @@ B200_API int b200dit_forward_cfg(b200dit_engine* e, int32_t n_samples, const flo
                         int32_t context_dtype, const float* const* clip_fea, int32_t F, int32_t H, int32_t W,
                         int32_t seq_len, float guide_scale, float* const* out, void* stream);
 
+/* Step-invariant context work.  WanModel.forward re-embeds the text context and re-projects the
+ * cross-attention keys / values of every block on every call (model.py:532, 176-180 / 214-222) although the
+ * callers pass the same contexts for all steps of a trajectory (text2video.py:238-241, generate.py:227-228).
+ * A non-zero token promises that the NEXT forward call carries exactly the contexts (pointers' contents, row
+ * counts, clip_fea) of the previous call made under the same token; that call then reuses the text embedding
+ * and the per-block cross K / V it cached.  The hint covers one call; without it everything is recomputed. */
+B200_API int b200dit_context_hint(b200dit_engine* e, uint64_t token);
+
 /* Residual-stream taps (the APT discriminator reads block outputs through forward hooks,
  * seaweed_apt/model.py:150-155): after the next forward, copy the fp32 stream [n_items*L, dim] that
  * left block `block_idx` into dst (device).  block_idx < 0 disables. */
@@ -126,7 +134,8 @@ B200_API int b200_flash_attention(const void* q, const void* k, const void* v, c
                                   int32_t Lq, int32_t Lk, int32_t H, float softmax_scale, void* out, void* stream);
 /* nn.Linear: out[M,N] = epilogue(A[M,K] W[N,K]^T + bias).  A, W fp16 device (row-major, leading
  * dimensions lda / ldw in elements), bias fp32 or NULL.  epilogue 0: fp16 store, 1: GELU(tanh) + fp16
- * store, 4: fp32 store.  block_n 0 = automatic, else 128 or 256. */
+ * store, 4: fp32 store.  block_n 0 = automatic, else 128, 144, 192 or 256 (single-CTA 128 x N tiles) or
+ * 1000 + {128, 192, 224, 256} (CTA-pair 256 x N tiles, tcgen05 cta_group::2). */
 B200_API int b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int32_t M,
                          int32_t N, int32_t K, int32_t epilogue, void* out, int64_t ldo, int32_t block_n,
                          void* stream);

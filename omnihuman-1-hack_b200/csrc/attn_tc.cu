@@ -8,6 +8,8 @@
 //   warps 0..7  softmax: two threads per query row (64 keys each); S -> registers, online softmax with
 //               lazy (thresholded) rescaling of O, P_j written to shared memory as the fp16 A operand
 // TMEM columns: S0 [0,128) S1 [128,256) O [256,384).
+#include <cstdlib>
+
 #include "host_util.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -37,6 +39,17 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// Cross-attention folds the query RMSNorm (model.py:179) into the softmax scale: the producing GEMM leaves
+// q un-normalised plus per-row partial sums of squares, norm_q's weight is folded into the cached keys,
+// and the remaining per-row factor rsqrt(mean(q^2) + eps) multiplies the logits of that row.
+__device__ __forceinline__ float q_row_scale(const AttnParams& p, int item, int q_in_item) {
+  if (p.q_ssq == nullptr || q_in_item >= p.Lq) return 1.0f;
+  const float* s = p.q_ssq + ((long long)item * p.Lq + q_in_item) * p.q_ssq_ld;
+  float tot = 0.f;
+  for (int i = 0; i < p.q_ssq_n; ++i) tot += s[2 * i];
+  return rsqrtf(tot / (float)p.q_dim + p.q_eps);
+}
+
 __global__ void __launch_bounds__(320, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
@@ -58,6 +71,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int qt = blockIdx.x, head = blockIdx.y, item = blockIdx.z;
   const int klen = p.klen[item];
   const int n_kv = (klen + TILE - 1) / TILE;
+  pdl_launch();
 
   if (warp == WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_vt);
@@ -77,6 +91,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 256;
+  pdl_wait();
 
   if (warp == WARP_TMA) {
     if (lane == 0) {
@@ -144,7 +159,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int quad = warp & 3, half = warp >> 2;
     const int r = quad * 32 + lane;                         // query row within the tile
     const uint32_t lane_sel = uint32_t(quad * 32) << 16;
-    const float c = p.scale * 1.4426950408889634f;
+    const float c = p.scale * 1.4426950408889634f * q_row_scale(p, item, qt * TILE + r);
     float m_ref = -INFINITY, l_sum = 0.f;
     uint8_t* p_row = smem + OFF_P + half * SUB_BYTES;       // keys [64 half, 64 half + 64) = one SW128 sub-tile
     float* xch = reinterpret_cast<float*>(smem + OFF_XCH);  // [2 parity][2 half][128 rows]
@@ -273,6 +288,278 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Second-generation kernel (default): 64-key steps, ONE thread per query row (no cross-thread
+// exchange), 112 KB of shared memory and 256 TMEM columns per CTA so that TWO CTAs share an SM -- the
+// softmax of one tile overlaps the MMAs and barrier latencies of the other, and 312 query tiles
+// (L = 1560, 24 item-heads) fit in one co-resident wave of 296 + a short tail instead of three waves.
+// P never touches shared memory: the fp16 probabilities are written back into the TMEM columns their
+// logits came from and feed P.V as a TMEM A operand, which leaves room for a 3-deep K ring (profiling
+// showed the softmax warps waiting on S = Q.K^T because K tiles were requested only one step ahead).
+//   warps 0..3  softmax (TMEM lane quadrant = warp id), warp 4 TMA, warp 5 MMA
+//   TMEM columns: S0 / P0 [0,64) S1 / P1 [64,128) O [128,256)
+namespace v2 {
+constexpr int QT = 128, KT = 64;
+constexpr int KSTAGES = 3, VSTAGES = 2;
+constexpr int Q_BYTES = 2 * 128 * 128;      // two [128 queries x 64 d] SW128 sub-tiles
+constexpr int K_BYTES = 2 * 64 * 128;       // two [64 keys x 64 d] sub-tiles
+constexpr int KSUB = 64 * 128;
+constexpr int V_BYTES = 128 * 128;          // V^T [128 d x 64 keys]
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = OFF_Q + Q_BYTES;
+constexpr int OFF_V = OFF_K + KSTAGES * K_BYTES;
+constexpr int OFF_BAR = OFF_V + VSTAGES * V_BYTES;
+constexpr int SMEM = OFF_BAR + 256;         // 114 944 B: two CTAs per SM
+constexpr int W_TMA = 4, W_MMA = 5;
+
+__global__ void __launch_bounds__(192, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [3]
+  uint64_t* k_empty = bars + 4;   // [3]
+  uint64_t* v_full = bars + 7;    // [2]
+  uint64_t* v_empty = bars + 9;   // [2]
+  uint64_t* s_full = bars + 11;   // [2]
+  uint64_t* s_empty = bars + 13;  // [2]
+  uint64_t* p_full = bars + 15;
+  uint64_t* pv_done = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = warp_id(), lane = lane_id();
+  // query-tile index slowest: the partial last tiles of all (item, head) pairs are scheduled last, so
+  // the CTAs that do not fit the first co-resident wave are the cheap ones
+  const int hi = blockIdx.x % (p.heads * p.items), qt = blockIdx.x / (p.heads * p.items);
+  const int head = hi % p.heads, item = hi / p.heads;
+  const int klen = p.klen[item];
+  const int n_kv = (klen + KT - 1) / KT;
+  pdl_launch();
+
+  if (warp == W_TMA && lane == 0) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_vt);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+    }
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 128;
+  pdl_wait();
+
+  if (warp == W_TMA) {
+    if (lane == 0) {
+      const int q_row0 = item * p.Lq + qt * QT;
+      mbar_expect_tx(q_full, Q_BYTES);
+      tma_load_2d(smem + OFF_Q, &tmap_q, q_full, head * 128, q_row0);
+      tma_load_2d(smem + OFF_Q + Q_BYTES / 2, &tmap_q, q_full, head * 128 + 64, q_row0);
+      // K runs one step ahead of V: K_i is needed by Q.K^T a whole softmax step before V_i is needed by P.V
+      for (int i = 0; i <= n_kv; ++i) {
+        if (i < n_kv) {
+          const int st = i % KSTAGES; const uint32_t ph = (i / KSTAGES) & 1;
+          const int k_row0 = item * p.Lk_rows + i * KT;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_expect_tx(&k_full[st], K_BYTES);
+          tma_load_2d(smem + OFF_K + st * K_BYTES, &tmap_k, &k_full[st], head * 128, k_row0);
+          tma_load_2d(smem + OFF_K + st * K_BYTES + KSUB, &tmap_k, &k_full[st], head * 128 + 64, k_row0);
+        }
+        if (i >= 1) {
+          const int j = i - 1, st = j & 1; const uint32_t ph = (j >> 1) & 1;
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_expect_tx(&v_full[st], V_BYTES);
+          tma_load_2d(smem + OFF_V + st * V_BYTES, &tmap_vt, &v_full[st], item * p.Lk_rows + j * KT, head * 128);
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    constexpr uint32_t idesc_qk = umma_idesc_f16(128, KT);
+    constexpr uint32_t idesc_pv = umma_idesc_f16(128, 128);
+    const uint32_t sq = smem_u32(smem + OFF_Q);
+    auto issue_qk = [&](int i) {
+      const int st = i % KSTAGES; const uint32_t kph = (i / KSTAGES) & 1;
+      const int sb = i & 1; const uint32_t sph = (i >> 1) & 1;
+      mbar_wait(&k_full[st], kph);
+      mbar_wait(&s_empty[sb], sph ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sk = smem_u32(smem + OFF_K + st * K_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_f16(tmem_base + sb * KT, umma_desc_sw128(sq + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32),
+                   umma_desc_sw128(sk + (kk >> 2) * KSUB + (kk & 3) * 32), idesc_qk, kk > 0);
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[sb]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < n_kv; ++j) {
+      // S_{j+1} overwrites the buffer that held S_{j-1} / P_{j-1}: issued after P.V of step j-1 (program
+      // order; the tensor pipe executes in issue order), and only once the softmax has read S_{j-1}
+      if (j + 1 < n_kv) issue_qk(j + 1);
+      const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&v_full[st], ph);
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sv = smem_u32(smem + OFF_V + st * V_BYTES);
+        const uint32_t tp = tmem_base + st * KT;          // P_j: fp16 pairs in the first 32 columns of S_j's buffer
+#pragma unroll
+        for (int kk = 0; kk < KT / 16; ++kk)
+          umma_f16_ts(tmem_o, tp + kk * 8, umma_desc_sw128(sv + kk * 32), idesc_pv, (j > 0 || kk > 0));
+        umma_commit(&v_empty[st]);
+        umma_commit(pv_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- softmax: thread r owns query row r of the tile and all 64 keys of the step
+    const int r = warp * 32 + lane;
+    const uint32_t lane_sel = uint32_t(warp * 32) << 16;
+    const int q_in_item = qt * QT + r;
+    if (qt * QT + warp * 32 >= p.Lq) {
+      // a warp whose 32 rows lie beyond the item's last query only keeps the barrier protocol going
+      // (its P rows stay whatever they were: they only reach O rows that are never stored)
+      for (int j = 0; j < n_kv; ++j) {
+        const int sb = j & 1; const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&s_full[sb], ph);
+        if (lane == 0) mbar_arrive(&s_empty[sb]);
+        // stay within one phase of pv_done (mbarrier waits are parity based) and never arrive into a P
+        // phase that is still open: P.V of step j-1 done implies p_full phase j-1 completed
+        if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
+        mbar_arrive(p_full);
+      }
+      mbar_wait(pv_done, (n_kv - 1) & 1);
+    } else {
+    const float c = p.scale * 1.4426950408889634f * q_row_scale(p, item, q_in_item);
+    float m_ref = -INFINITY, l_sum = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int sb = j & 1; const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&s_full[sb], ph);
+      tc_fence_after();
+      float s[KT];
+      {
+        uint32_t t0[32], t1[32];
+        tmem_ld32(tmem_base + lane_sel + sb * KT, t0);
+        tmem_ld32(tmem_base + lane_sel + sb * KT + 32, t1);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(t0[i]); s[32 + i] = __uint_as_float(t1[i]); }
+      }
+
+      const int valid = klen - j * KT;
+      if (valid < KT) {
+#pragma unroll
+        for (int i = 0; i < KT; ++i) if (i >= valid) s[i] = -INFINITY;
+      }
+      float mx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = fmaxf(s[i], s[i + 8]);
+#pragma unroll
+      for (int i = 16; i < KT; i += 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mx[e] = fmaxf(mx[e], s[i + e]);
+      }
+      const float tmax = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+
+      float alpha = 1.f;
+      bool rescale = false;
+      if (j == 0) {
+        m_ref = tmax;
+      } else if ((tmax - m_ref) * c > RESCALE_THRESHOLD) {
+        alpha = ex2((m_ref - tmax) * c);
+        m_ref = tmax;
+        l_sum *= alpha;
+        rescale = true;
+      }
+      const float mc = m_ref * c;
+      float ps0 = 0.f, ps1 = 0.f;
+      uint32_t pk[KT / 2];
+#pragma unroll
+      for (int i = 0; i < KT; i += 2) {
+        const float p0 = ex2(fmaf(s[i], c, -mc)), p1 = ex2(fmaf(s[i + 1], c, -mc));
+        ps0 += p0; ps1 += p1;
+        pk[i >> 1] = pack_h2(p0, p1);
+      }
+      l_sum += ps0 + ps1;
+
+      // P_j replaces the first half of this thread's own S_j row (nobody else touches that TMEM lane)
+      tmem_st32(tmem_base + lane_sel + sb * KT, pk);
+      if (j > 0) {
+        // every step (not only when rescaling): mbarrier waits are parity based, so a waiter must never be
+        // more than one phase away from pv_done; it also guarantees that p_full phase j-1 has completed
+        mbar_wait(pv_done, (j - 1) & 1);                    // O stable: every earlier P.V has completed
+        if (__any_sync(0xffffffffu, rescale)) {
+          tc_fence_after();
+#pragma unroll
+          for (int cidx = 0; cidx < 4; ++cidx) {
+            uint32_t t[32];
+            tmem_ld32(tmem_o + lane_sel + cidx * 32, t);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            tmem_st32(tmem_o + lane_sel + cidx * 32, t);
+          }
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);             // S_j fully read by this warp
+      mbar_arrive(p_full);
+    }
+
+    mbar_wait(pv_done, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_sum;
+    __half* o = p.out + ((long long)item * p.Lq + q_in_item) * p.ldo + head * 128;
+#pragma unroll
+    for (int cidx = 0; cidx < 4; ++cidx) {
+      uint32_t t[32];
+      tmem_ld32(tmem_o + lane_sel + cidx * 32, t);
+      tmem_wait_ld();
+      if (q_in_item < p.Lq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(t[i + e]) * inv_l;
+          uint4* dst = reinterpret_cast<uint4*>(o + cidx * 32 + i);
+          if (p.accumulate) {
+            const uint4 old = *dst;
+            const __half2* oh = reinterpret_cast<const __half2*>(&old);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(oh[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+          }
+          *dst = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        }
+      }
+    }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+}  // namespace v2
+
 }  // namespace
 
 void launch_attention(const AttnParams& p, cudaStream_t stream) {
@@ -280,21 +567,25 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
   for (int i = 0; i < p.items; ++i)
     B2_CHECK(p.klen[i] >= 1 && p.klen[i] <= p.Lk_rows, "attention: item %d has %d valid keys of %d", i, p.klen[i],
              p.Lk_rows);
+  static const bool use_v1 = std::getenv("B200_ATTN_V1") != nullptr && std::atoi(std::getenv("B200_ATTN_V1")) != 0;
   static bool configured = false;
   if (!configured) {
     B2_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
+    B2_CUDA(cudaFuncSetAttribute(v2::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM));
+    B2_CUDA(cudaFuncSetAttribute(v2::attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured = true;
   }
   const uint64_t dim = (uint64_t)p.heads * 128;
   CUtensorMap tq = make_tmap_2d(p.q, (uint64_t)p.items * p.Lq, dim, p.ldq, 128);
-  CUtensorMap tk = make_tmap_2d(p.k, (uint64_t)p.items * p.Lk_rows, dim, p.ldk, 128);
+  CUtensorMap tk = make_tmap_2d(p.k, (uint64_t)p.items * p.Lk_rows, dim, p.ldk, use_v1 ? 128 : v2::KT);
   CUtensorMap tv = make_tmap_2d(p.vt, (uint64_t)p.heads * 128, (uint64_t)p.items * p.Lk_rows, p.ldvt, 128);
   dim3 grid((p.Lq + TILE - 1) / TILE, p.heads, p.items);
+  dim3 grid2(((p.Lq + TILE - 1) / TILE) * p.heads * p.items);
   double keys = 0;
   for (int i = 0; i < p.items; ++i) keys += p.klen[i];
   ProfScope prof(PC_ATTN, 4.0 * p.Lq * keys * 128.0 * p.heads, 0.0, stream);
-  attn_fwd_kernel<<<grid, 320, ATTN_SMEM, stream>>>(tq, tk, tv, p);
-  B2_CUDA(cudaGetLastError());
+  if (use_v1) launch_pdl(attn_fwd_kernel, grid, dim3(320), ATTN_SMEM, stream, tq, tk, tv, p);
+  else launch_pdl(v2::attn_fwd_kernel, grid2, dim3(192), v2::SMEM, stream, tq, tk, tv, p);
   count_launch();
 }
 

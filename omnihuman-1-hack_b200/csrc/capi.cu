@@ -84,6 +84,9 @@ int b200dit_forward_cfg(b200dit_engine* e, int32_t n_samples, const float* const
   });
 }
 
+int b200dit_context_hint(b200dit_engine* e, uint64_t token) {
+  return guarded([&] { B2_CHECK(e, "null engine"); e->impl.ctx_token = token; });
+}
 int b200dit_set_tap(b200dit_engine* e, int32_t block_idx, float* dst) {
   return guarded([&] {
     B2_CHECK(e, "null engine");

@@ -245,15 +245,16 @@ void DitEngine::ensure_workspace(int B, int L) {
   (void)M; (void)Lp;
   size_t bytes = 0;
   auto add = [&](size_t n, size_t esz) { bytes += padded(n * esz); };
+  const size_t nl = cfg.num_layers;
   add(Mx * d, 4); add(Mx * 3 * d, 2); add(Mx * 64, 4); add(nB * 2 * d, 4); add(Mx * d, 2); add(Mx * 2 * d, 2); add(nB * Hn * 128 * Lpx, 2); add(Mx * d, 2); add(Mx * f, 2);
-  add(Mx * (4 * d / 128), 4); add(Mx * cfg.in_dim * 4, 2);
-  add(nB * TL * cfg.text_dim, 2); add(nB * TL * d, 2); add(nB * TL * d, 2); add(nB * TL * d, 2);
-  add(nB * Hn * 128 * TL, 2); add(nB * TL * (2 * d / 128), 4);
+  add(Mx * (d / 16), 4); add(Mx * cfg.in_dim * 4, 2);
+  add(nB * TL * cfg.text_dim, 2); add(nB * TL * d, 2); add(nB * TL * d, 2); add(nl * nB * TL * d, 2);
+  add(nl * nB * Hn * 128 * TL, 2); add(nB * TL * (d / 32), 4);
   add(nB * d, 4); add(nB * 6 * d, 4); add((size_t)cfg.num_layers * nB * 6 * d, 4); add(nB * (cfg.freq_dim + d), 4);
   add(MAX_ITEMS, 4);
   if (cfg.i2v) {
     add(nB * 257 * 1280, 2); add(nB * 257 * 1280, 4); add(nB * 257 * 1280, 2); add(nB * 257 * d, 4);
-    add(nB * 257 * d, 2); add(nB * 257 * d, 2); add(nB * Hn * 128 * 264, 2); add(nB * 257 * (2 * d / 128), 4);
+    add(nB * 257 * d, 2); add(nl * nB * 257 * d, 2); add(nl * nB * Hn * 128 * 264, 2); add(nB * 257 * (d / 32), 4);
   }
   ws.release();
   ws.ensure(bytes + 4096, /*zero=*/true);       // zero: V^T padding columns must stay finite
@@ -267,14 +268,15 @@ void DitEngine::ensure_workspace(int B, int L) {
   w.vt = carve<__half>(p, Hn * 128 * (((size_t)nB * nL + 7) & ~size_t(7)));
   w.att = carve<__half>(p, Mx * d);
   w.hid = carve<__half>(p, Mx * f);
-  w.ssq = carve<float>(p, Mx * (4 * d / 128));      // 2 partial sums per (row, N tile)
+  w.ssq = carve<float>(p, Mx * (d / 16));           // [row][N tile][column half][slice] partial sums of squares
   w.patch = carve<__half>(p, Mx * cfg.in_dim * 4);
   w.ctx16 = carve<__half>(p, nB * TL * cfg.text_dim);
   w.ctx_h = carve<__half>(p, nB * TL * d);
   w.ctx_e = carve<__half>(p, nB * TL * d);
-  w.kc = carve<__half>(p, nB * TL * d);
-  w.vtc = carve<__half>(p, nB * Hn * 128 * TL);
-  w.ssq_c = carve<float>(p, nB * TL * (2 * d / 128));
+  w.kc = carve<__half>(p, nl * nB * TL * d);        // per layer: reused across steps while the contexts stay
+  w.vtc = carve<__half>(p, nl * nB * Hn * 128 * TL);
+  w.kv_stride = nB * TL * d;
+  w.ssq_c = carve<float>(p, nB * TL * (d / 32));
   w.e = carve<float>(p, nB * d);
   w.e0 = carve<float>(p, nB * 6 * d);
   w.modtab = carve<float>(p, (size_t)cfg.num_layers * nB * 6 * d);
@@ -286,11 +288,13 @@ void DitEngine::ensure_workspace(int B, int L) {
     w.clip_g = carve<__half>(p, nB * 257 * 1280);
     w.img_f = carve<float>(p, nB * 257 * d);
     w.ctx_img = carve<__half>(p, nB * 257 * d);
-    w.ki = carve<__half>(p, nB * 257 * d);
-    w.vti = carve<__half>(p, nB * Hn * 128 * 264);
-    w.ssq_i = carve<float>(p, nB * 257 * (2 * d / 128));
+    w.ki = carve<__half>(p, nl * nB * 257 * d);
+    w.vti = carve<__half>(p, nl * nB * Hn * 128 * 264);
+    w.ki_stride = nB * 257 * d; w.vti_stride = nB * Hn * 128 * 264;
+    w.ssq_i = carve<float>(p, nB * 257 * (d / 32));
   }
   ws_B = nB; ws_L = nL;
+  cached_token = 0;                                   // the cached K/V lived in the old workspace
   // workspaces moved: every captured graph holds stale pointers
   for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   graphs.clear();
@@ -325,15 +329,19 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   launch_time_embed(in.t, B, cfg.freq_dim, d, wt.time0_w, wt.time0_b, wt.time2_w, wt.time2_b, wt.timep_w, wt.timep_b,
                     w.tscratch, w.e, w.e0, s);
   launch_mod_table(wt.modulation, w.e0, w.modtab, cfg.num_layers, B, d, s);
-  launch_pad_cast_rows(in.ctx, in.ctx_dtype, in.ctx_rows, B, TL, cfg.text_dim, w.ctx16, s);
-  {
+  // Context-only work (text embedding, cross-attention K/V of every block, the i2v image stream) is
+  // step-invariant: the reference recomputes it every forward (model.py:532,176-180); with a context
+  // hint from the caller (b200dit_context_hint) it is computed once per prompt set and kept per layer.
+  const bool ctx_hit = in.ctx_hit;
+  if (!ctx_hit) launch_pad_cast_rows(in.ctx, in.ctx_dtype, in.ctx_rows, B, TL, cfg.text_dim, w.ctx16, s);
+  if (!ctx_hit) {
     GemmParams p{}; p.M = B * TL; p.N = d; p.K = cfg.text_dim; p.bias = wt.text0_b; p.out_h = w.ctx_h; p.ld_h = d;
     gemm_linear(EPI_GELU_F16, w.ctx16, cfg.text_dim, wt.text0_w, cfg.text_dim, p, num_sms, s);
     GemmParams q{}; q.M = B * TL; q.N = d; q.K = d; q.bias = wt.text2_b; q.out_h = w.ctx_e; q.ld_h = d;
     gemm_linear(EPI_F16, w.ctx_h, d, wt.text2_w, d, q, num_sms, s);
   }
   const bool img = cfg.i2v && in.has_clip;
-  if (img) {   // MLPProj (model.py:362-374): LN -> Linear -> GELU(erf) -> Linear -> LN, default eps 1e-5
+  if (img && !ctx_hit) {   // MLPProj (model.py:362-374): LN -> Linear -> GELU(erf) -> Linear -> LN, default eps 1e-5
     const int R = B * 257;
     launch_ln_affine(in.clip_packed, w.clip16, wt.img_ln0_w, wt.img_ln0_b, 0, R, 0, 1280, 1e-5f, s);
     GemmParams p{}; p.M = R; p.N = 1280; p.K = 1280; p.bias = wt.img_fc1_b; p.out_f = w.clip_f; p.ld_f = 1280;
@@ -351,6 +359,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   for (int i = 0; i < B; ++i) self.klen[i] = L;
   AttnParams cross = self;
   cross.ldq = d; cross.k = w.kc; cross.ldk = d; cross.vt = w.vtc; cross.ldvt = B * TL; cross.Lk_rows = TL;
+  cross.q_dim = d; cross.q_eps = eps;
   for (int i = 0; i < B; ++i) {
     int kl = in.ctx_rows[i] + (img ? 257 : 0);      // model.py:531,537 (+ App. A.12 clamp)
     cross.klen[i] = kl < TL ? kl : TL;
@@ -359,13 +368,12 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   cimg.k = w.ki; cimg.vt = w.vti; cimg.ldvt = (B * 257 + 7) & ~7; cimg.Lk_rows = 257; cimg.accumulate = 1;
   for (int i = 0; i < B; ++i) cimg.klen[i] = 257;
 
-  // tile widths of the GEMMs whose epilogue slices columns at multiples of d (q | k | v boundaries)
-  auto bn_for = [&](long long rows, long long cols) {
-    int bn = pick_bn(rows, cols, num_sms);
-    while (d % bn != 0) bn = bn == 256 ? 192 : 128;
-    return bn;
-  };
-  const int bn_qkv = bn_for(M, 3 * d), bn_cq = bn_for(M, d), bn_ckv = bn_for(B * TL, 2 * d);
+  // tile widths (the QKV-style epilogues route columns per chunk, so tiles may straddle the q | k | v boundaries)
+  const int bn_qkv = pick_bn(M, 3 * d, num_sms, d), bn_cq = pick_bn(M, d, num_sms, d);
+  const int bn_ckv = pick_bn(B * TL, 2 * d, num_sms, d), bn_img = pick_bn(B * 257, 2 * d, num_sms, d);
+  auto ssq_tiles = [](int cols, int bn) { return (cols + bn - 1) / bn; };
+  cross.q_ssq = w.ssq; cross.q_ssq_ld = 4 * ssq_tiles(d, bn_cq); cross.q_ssq_n = 2 * ssq_tiles(d, bn_cq);
+  cimg.q_ssq = cross.q_ssq; cimg.q_ssq_ld = cross.q_ssq_ld; cimg.q_ssq_n = cross.q_ssq_n; cimg.q_dim = d; cimg.q_eps = eps;
 
   for (int l = 0; l < cfg.num_layers; ++l) {
     const BlockWeights& b = wt.blocks[l];
@@ -374,39 +382,51 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
     launch_ln_affine(w.x_res, w.u, mod + d, mod, 6 * d, M, L, d, eps, s);
     {
       GemmParams p{}; p.M = M; p.N = 3 * d; p.K = d; p.bias = b.qkv_b; p.out_h = w.qk; p.ld_h = 2 * d;
-      p.ssq = w.ssq; p.ssq_cols = 2 * d; p.ssq_ld = 4 * d / bn_qkv; p.vt = w.vt; p.vt_col0 = 2 * d; p.vt_ld = Mp;
-      p.vt_rows = d; p.rows_per_item = L;
+      p.ssq = w.ssq; p.ssq_cols = 2 * d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(2 * d, bn_qkv);
+      p.vt = w.vt; p.vt_col0 = 2 * d; p.vt_ld = Mp; p.vt_rows = d; p.rows_per_item = L;
       gemm_linear(EPI_QKV, w.u, d, b.qkv_w, d, p, num_sms, s, bn_qkv);
     }
-    launch_rms_rope(w.qk, 2 * d, d, 2, w.ssq, 4 * d / bn_qkv, 2 * d / bn_qkv, b.norm_q, b.norm_k, cs, M, L, eps, s);
+    launch_rms_rope(w.qk, 2 * d, d, 2, w.ssq, 4 * ssq_tiles(2 * d, bn_qkv), 2 * ssq_tiles(2 * d, bn_qkv), b.norm_q,
+                    b.norm_k, cs, M, L, eps, s);
     launch_attention(self, s);
     {
       GemmParams p{}; p.M = M; p.N = d; p.K = d; p.bias = b.o_b; p.out_f = w.x_res; p.ld_f = d;
       p.gate = mod + 2 * d; p.gate_stride = 6 * d; p.rows_per_item = L;
       gemm_linear(EPI_RESID_F32, w.att, d, b.o_w, d, p, num_sms, s);
     }
-    // ---- cross-attention (model.py:313, 166-186 / 204-230)
+    // ---- cross-attention (model.py:313, 166-186 / 204-230).  q stays un-normalised: norm_q's weight is
+    // folded into the (cached) keys and the per-row rsqrt(mean(q^2)+eps) into the softmax scale.
     launch_ln_affine(w.x_res, w.u, b.norm3_w, b.norm3_b, 0, M, L, d, eps, s);
     {
       GemmParams p{}; p.M = M; p.N = d; p.K = d; p.bias = b.cq_b; p.out_h = w.qk; p.ld_h = d;
-      p.ssq = w.ssq; p.ssq_cols = d; p.ssq_ld = 2 * d / bn_cq; p.vt_col0 = d; p.rows_per_item = L;
+      p.ssq = w.ssq; p.ssq_cols = d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(d, bn_cq); p.vt_col0 = d;
+      p.rows_per_item = L;
       gemm_linear(EPI_QKV, w.u, d, b.cq_w, d, p, num_sms, s, bn_cq);
     }
-    launch_rms_rope(w.qk, d, d, 1, w.ssq, 2 * d / bn_cq, 2 * d / bn_cq, b.cnorm_q, nullptr, nullptr, M, L, eps, s);
-    {
-      GemmParams p{}; p.M = B * TL; p.N = 2 * d; p.K = d; p.bias = b.ckv_b; p.out_h = w.kc; p.ld_h = d;
-      p.ssq = w.ssq_c; p.ssq_cols = d; p.ssq_ld = 2 * d / bn_ckv; p.vt = w.vtc; p.vt_col0 = d; p.vt_ld = B * TL;
-      p.vt_rows = d; p.rows_per_item = TL;
+    __half* kc_l = w.kc + (size_t)l * w.kv_stride;
+    __half* vtc_l = w.vtc + (size_t)l * ((size_t)Hn * 128 * B * TL);
+    if (!ctx_hit) {
+      GemmParams p{}; p.M = B * TL; p.N = 2 * d; p.K = d; p.bias = b.ckv_b; p.out_h = kc_l; p.ld_h = d;
+      p.ssq = w.ssq_c; p.ssq_cols = d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(d, bn_ckv); p.vt = vtc_l;
+      p.vt_col0 = d; p.vt_ld = B * TL; p.vt_rows = d; p.rows_per_item = TL;
       gemm_linear(EPI_QKV, w.ctx_e, d, b.ckv_w, d, p, num_sms, s, bn_ckv);
+      launch_rms_rope(kc_l, d, d, 1, w.ssq_c, 4 * ssq_tiles(d, bn_ckv), 2 * ssq_tiles(d, bn_ckv), b.cnorm_k, nullptr,
+                      nullptr, B * TL, TL, eps, s, b.cnorm_q);
     }
-    launch_rms_rope(w.kc, d, d, 1, w.ssq_c, 2 * d / bn_ckv, 2 * d / bn_ckv, b.cnorm_k, nullptr, nullptr, B * TL, TL, eps, s);
+    cross.k = kc_l; cross.vt = vtc_l;
     launch_attention(cross, s);
     if (img) {
-      GemmParams p{}; p.M = B * 257; p.N = 2 * d; p.K = d; p.bias = b.ckv_img_b; p.out_h = w.ki; p.ld_h = d;
-      p.ssq = w.ssq_i; p.ssq_cols = d; p.ssq_ld = 2 * d / 128; p.vt = w.vti; p.vt_col0 = d; p.vt_ld = (B * 257 + 7) & ~7;
-      p.vt_rows = d; p.rows_per_item = 257;
-      gemm_linear(EPI_QKV, w.ctx_img, d, b.ckv_img_w, d, p, num_sms, s, 128);
-      launch_rms_rope(w.ki, d, d, 1, w.ssq_i, 2 * d / 128, 2 * d / 128, b.cnorm_k_img, nullptr, nullptr, B * 257, 257, eps, s);
+      __half* ki_l = w.ki + (size_t)l * w.ki_stride;
+      __half* vti_l = w.vti + (size_t)l * w.vti_stride;
+      if (!ctx_hit) {
+        GemmParams p{}; p.M = B * 257; p.N = 2 * d; p.K = d; p.bias = b.ckv_img_b; p.out_h = ki_l; p.ld_h = d;
+        p.ssq = w.ssq_i; p.ssq_cols = d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(d, bn_img); p.vt = vti_l;
+        p.vt_col0 = d; p.vt_ld = (B * 257 + 7) & ~7; p.vt_rows = d; p.rows_per_item = 257;
+        gemm_linear(EPI_QKV, w.ctx_img, d, b.ckv_img_w, d, p, num_sms, s, bn_img);
+        launch_rms_rope(ki_l, d, d, 1, w.ssq_i, 4 * ssq_tiles(d, bn_img), 2 * ssq_tiles(d, bn_img), b.cnorm_k_img,
+                        nullptr, nullptr, B * 257, 257, eps, s, b.cnorm_q);
+      }
+      cimg.k = ki_l; cimg.vt = vti_l;
       launch_attention(cimg, s);
     }
     {
@@ -506,6 +526,13 @@ void DitEngine::forward(int n, const float* const* x, const float* const* y, int
     const bool un = cfgm && i >= n;
     in.ctx_rows[i] = un ? rows_b[i - n] : rows_a[i];
   }
+  // context reuse (b200dit_context_hint): valid only for the same token AND the same call signature
+  std::vector<int> sig = {B, ctx_dtype, in.has_clip ? 1 : 0, in.cfg_pairs};
+  for (int i = 0; i < B; ++i) sig.push_back(in.ctx_rows[i]);
+  const uint64_t token = ctx_token;
+  ctx_token = 0;                                       // a hint covers exactly one forward call
+  in.ctx_hit = token != 0 && token == cached_token && sig == cached_sig;
+  if (!in.ctx_hit) { cached_token = token; cached_sig = sig; }
   const int n_out = n;
 
   if (!use_graphs) {
@@ -536,7 +563,8 @@ void DitEngine::forward(int n, const float* const* x, const float* const* y, int
   }
   for (int i = 0; i < n_out; ++i) in.out.p[i] = s_out + i * sio_item_out;
 
-  std::vector<int> key = {B, F, H, W, y_channels, in.cfg_pairs, in.has_clip ? 1 : 0, ctx_dtype, tap_block};
+  std::vector<int> key = {B, F, H, W, y_channels, in.cfg_pairs, in.has_clip ? 1 : 0, ctx_dtype, tap_block,
+                          in.ctx_hit ? 1 : 0};
   for (int i = 0; i < B; ++i) key.push_back(in.ctx_rows[i]);
   if (graphs.size() > 64 && graphs.find(key) == graphs.end()) {
     for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);

@@ -42,7 +42,8 @@ struct DitWeights {
 struct DitWorkspace {
   float* x_res; __half *u, *qk, *vt, *att, *hid; float* ssq; __half* patch;
   __half* u3; float* y; float* headtab;  // head: split activations [M, 3 dim], projection [M, P], modulation table
-  __half *ctx16, *ctx_h, *ctx_e, *kc, *vtc; float* ssq_c;
+  __half *ctx16, *ctx_h, *ctx_e, *kc, *vtc; float* ssq_c;   // kc / vtc: [layers][...] (kept across steps)
+  size_t kv_stride = 0, ki_stride = 0, vti_stride = 0;
   float *e, *e0, *modtab, *tscratch, *t_items;
   __half* clip16; float* clip_f; __half* clip_g; float* img_f; __half *ctx_img, *ki, *vti; float* ssq_i;
 };
@@ -58,6 +59,7 @@ struct FwdInputs {
   ItemPtrsMut out{};
   int cfg_pairs = 0;                     // > 0: items [0,cfg_pairs) cond, [cfg_pairs, 2 cfg_pairs) uncond
   const float* cfg_scale = nullptr;      // device scalar
+  bool ctx_hit = false;                  // context-only work of this call is already cached (same hint token)
 };
 
 struct GraphEntry {
@@ -86,6 +88,7 @@ class DitEngine {
   int tap_block = -1;
   float* tap_dst = nullptr;
   double last_flops = 0.0;
+  uint64_t ctx_token = 0;                // set by b200dit_context_hint, consumed by the next forward
 
  private:
   void alloc_weights();
@@ -100,6 +103,8 @@ class DitEngine {
   DitWeights wt{};
   DitWorkspace w{};
   int ws_B = 0, ws_L = 0;
+  uint64_t cached_token = 0;             // token under which kc / vtc / ki / vti / ctx_e were last computed
+  std::vector<int> cached_sig;
   std::map<long long, std::unique_ptr<DevBuf>> rope_cache;
   // static I/O staging for graph replay
   size_t sio_item_x = 0, sio_item_ctx = 0, sio_item_out = 0;

@@ -32,7 +32,9 @@ __global__ void __launch_bounds__(128) ln_affine_kernel(const float* __restrict_
   constexpr int DIM = NV * 128;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch();
   if (row >= M) return;
+  pdl_wait();
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * DIM);
   float4 v[NV];
   float s = 0.f;
@@ -71,8 +73,9 @@ __global__ void __launch_bounds__(128) ln_affine_kernel(const float* __restrict_
 // producing GEMM), then model.py:42-69: lanes (2j,2j+1) of each head rotate by the token's angle.
 struct RmsRopeParams {
   __half* x; long long ld; int dim;
-  const float* ssq; int ssq_ld; int ssq_n;            // slice s uses partials [s*ssq_n, (s+1)*ssq_n)
+  const float* ssq; int ssq_ld; int ssq_n;            // slice s sums ssq[row*ssq_ld + i*2 + s], i < ssq_n
   const float* gamma[2];
+  const float* gamma_mul;                              // optional second per-channel factor (slice 0 only)
   const float2* cs;                                    // [rows_per_item, 64] (cos, sin) or nullptr
   int M, rows_per_item; float eps;
 };
@@ -81,24 +84,30 @@ struct RmsRopeParams {
 __global__ void __launch_bounds__(256) rms_rope_kernel(const RmsRopeParams p, int nslices) {
   const int lane = threadIdx.x & 31;
   const long long unit = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  pdl_launch();
   if (unit >= (long long)p.M * nslices) return;
+  pdl_wait();
   const int row = (int)(unit / nslices), slice = (int)(unit % nslices);
-  float part = lane < p.ssq_n ? p.ssq[(long long)row * p.ssq_ld + slice * p.ssq_n + lane] : 0.f;
-  float tot = warp_sum(part);                            // fixed shuffle tree: deterministic
-  if (p.ssq_n > 32) {
-    tot = 0.f;
-    for (int i = 0; i < p.ssq_n; ++i) tot += p.ssq[(long long)row * p.ssq_ld + slice * p.ssq_n + i];
-  }
+  float part = 0.f;
+  for (int i = lane; i < p.ssq_n; i += 32) part += p.ssq[(long long)row * p.ssq_ld + i * 2 + slice];
+  const float tot = warp_sum(part);                      // fixed order: deterministic
   const float inv = rsqrtf(tot / (float)p.dim + p.eps);
   __half* xr = p.x + (long long)row * p.ld + (long long)slice * p.dim;
   const float* g = p.gamma[slice];
+  const float* gm = slice == 0 ? p.gamma_mul : nullptr;
   const int tok = row % p.rows_per_item;
   for (int ci = lane; ci < p.dim / 8; ci += 32) {
     const int col = ci * 8;
     uint4 raw = *reinterpret_cast<const uint4*>(xr + col);
     const __half2* h = reinterpret_cast<const __half2*>(&raw);
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + col));
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + col + 4));
+    float4 g0 = __ldg(reinterpret_cast<const float4*>(g + col));
+    float4 g1 = __ldg(reinterpret_cast<const float4*>(g + col + 4));
+    if (gm != nullptr) {
+      const float4 m0 = __ldg(reinterpret_cast<const float4*>(gm + col));
+      const float4 m1 = __ldg(reinterpret_cast<const float4*>(gm + col + 4));
+      g0.x *= m0.x; g0.y *= m0.y; g0.z *= m0.z; g0.w *= m0.w;
+      g1.x *= m1.x; g1.y *= m1.y; g1.z *= m1.z; g1.w *= m1.w;
+    }
     float v[8];
     float2 f;
     f = __half22float2(h[0]); v[0] = f.x * inv * g0.x; v[1] = f.y * inv * g0.y;
@@ -122,6 +131,8 @@ __global__ void __launch_bounds__(256) rms_rope_kernel(const RmsRopeParams p, in
 
 // ------------------------------------------------------------------ timestep embedding (model.py:17-27,526-528)
 __global__ void sinusoid_kernel(const float* __restrict__ t, int B, int freq_dim, float* __restrict__ out) {
+  pdl_launch();
+  pdl_wait();
   const int half = freq_dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -139,6 +150,8 @@ template <bool SILU_IN, bool SILU_OUT>
 __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
                                                            const float* __restrict__ bias, float* __restrict__ out,
                                                            int B, int K, int N) {
+  pdl_launch();
+  pdl_wait();
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (n >= N) return;
   float acc[MAX_ITEMS];
@@ -171,6 +184,8 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
 // mod[layer][item][6][dim] = modulation[layer][6][dim] + e0[item][6][dim]; rows 1 and 4 (scales) get +1
 __global__ void mod_table_kernel(const float* __restrict__ modulation, const float* __restrict__ e0,
                                  float* __restrict__ out, int layers, int B, int dim) {
+  pdl_launch();
+  pdl_wait();
   const long long n = (long long)layers * B * 6 * dim;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int c = i % dim;
@@ -186,6 +201,8 @@ __global__ void mod_table_kernel(const float* __restrict__ modulation, const flo
 // ------------------------------------------------------------------ patchify (model.py:515-518, patch (1,2,2))
 __global__ void patchify_kernel(ItemPtrs x, ItemPtrs y, int C, int Cy, int F, int H, int W, int B,
                                 __half* __restrict__ out, long long ld) {
+  pdl_launch();
+  pdl_wait();
   const int Hp = H / 2, Wp = W / 2, L = F * Hp * Wp, Ct = C + Cy;
   const long long n = (long long)B * L * Ct * 2;                // one thread per (token, c, q) -> 2 outputs
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -212,6 +229,8 @@ template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v
 template <typename T>
 __global__ void pad_cast_rows_kernel(ItemPtrs src, RowCounts rows_in, int B, int rows_out, int cols,
                                      __half* __restrict__ out) {
+  pdl_launch();
+  pdl_wait();
   const long long n = (long long)B * rows_out * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int c = i % cols;
@@ -228,6 +247,8 @@ __global__ void pad_cast_rows_kernel(ItemPtrs src, RowCounts rows_in, int B, int
 // tab[item][0] = 1 + m1, tab[item][1] = m0
 __global__ void head_table_kernel(const float* __restrict__ head_mod, const float* __restrict__ e,
                                   float* __restrict__ tab, int B, int dim) {
+  pdl_launch();
+  pdl_wait();
   const int n = B * dim;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int b = i / dim, c = i % dim;
@@ -253,6 +274,8 @@ __global__ void split_weight_kernel(const float* __restrict__ w, __half* __restr
 // (cond) and item b+cfg_pairs (uncond) are combined as uncond + s (cond - uncond) (text2video.py:243-244).
 __global__ void unpatchify_kernel(const float* __restrict__ y, int ldy, int L, int Hp, int Wp, int F, int out_dim,
                                   ItemPtrsMut out, int n_out, int cfg_pairs, const float* __restrict__ cfg_scale_p) {
+  pdl_launch();
+  pdl_wait();
   const int P = out_dim * 4;
   const long long n = (long long)n_out * L * P;
   const float sc = cfg_pairs > 0 ? __ldg(cfg_scale_p) : 0.f;
@@ -310,6 +333,8 @@ __global__ void transpose_v_kernel(const __half* __restrict__ v, __half* __restr
 }
 
 __global__ void gelu_erf_cast_kernel(const float* __restrict__ x, __half* __restrict__ out, long long n) {
+  pdl_launch();
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i];
     out[i] = __float2half_rn(0.5f * v * (1.0f + erff(v * 0.7071067811865476f)));
@@ -330,8 +355,8 @@ void launch_ln_affine(const float* x, __half* out, const float* a, const float* 
   ProfScope prof(PC_NORM, 0.0, (split ? 10.0 : 6.0) * M * dim, s);
 #define B2_LN_CASE(NV)                                                                                         \
   case NV:                                                                                                     \
-    if (split) ln_affine_kernel<NV, true><<<grid, 128, 0, s>>>(x, out, a, b, item_stride, M, rows_per_item, eps); \
-    else ln_affine_kernel<NV, false><<<grid, 128, 0, s>>>(x, out, a, b, item_stride, M, rows_per_item, eps);      \
+    if (split) launch_pdl(ln_affine_kernel<NV, true>, dim3(grid), dim3(128), 0, s, x, out, a, b, item_stride, M, rows_per_item, eps); \
+    else launch_pdl(ln_affine_kernel<NV, false>, dim3(grid), dim3(128), 0, s, x, out, a, b, item_stride, M, rows_per_item, eps);      \
     break;
   switch (dim / 128) {
     B2_LN_CASE(1) B2_LN_CASE(2) B2_LN_CASE(3) B2_LN_CASE(4) B2_LN_CASE(8) B2_LN_CASE(10) B2_LN_CASE(12)
@@ -345,14 +370,14 @@ void launch_ln_affine(const float* x, __half* out, const float* a, const float* 
 
 void launch_rms_rope(__half* x, long long ld, int dim, int nslices, const float* ssq, int ssq_ld, int ssq_n,
                      const float* gamma0, const float* gamma1, const float* cs_table, int M, int rows_per_item,
-                     float eps, cudaStream_t s) {
+                     float eps, cudaStream_t s, const float* gamma_mul) {
   RmsRopeParams p;
   p.x = x; p.ld = ld; p.dim = dim; p.ssq = ssq; p.ssq_ld = ssq_ld; p.ssq_n = ssq_n;
-  p.gamma[0] = gamma0; p.gamma[1] = gamma1;
+  p.gamma[0] = gamma0; p.gamma[1] = gamma1; p.gamma_mul = gamma_mul;
   p.cs = reinterpret_cast<const float2*>(cs_table);
   p.M = M; p.rows_per_item = rows_per_item; p.eps = eps;
   ProfScope prof(PC_NORM, 0.0, 4.0 * M * dim * nslices, s);
-  rms_rope_kernel<<<(unsigned)(((long long)M * nslices + 7) / 8), 256, 0, s>>>(p, nslices);
+  launch_pdl(rms_rope_kernel, dim3((unsigned)(((long long)M * nslices + 7) / 8)), dim3(256), 0, s, p, nslices);
   B2_CUDA(cudaGetLastError());
   count_launch();
 }
@@ -365,17 +390,21 @@ void launch_time_embed(const float* t, int B, int freq_dim, int dim, const float
   ProfScope prof(PC_OTHER, 0.0, 4.0 * dim * (freq_dim + 7.0 * dim), s);
   float* sin_buf = scratch;                       // [B, freq_dim]
   float* h1 = scratch + (long long)B * freq_dim;  // [B, dim]
-  sinusoid_kernel<<<(B * freq_dim / 2 + 127) / 128, 128, 0, s>>>(t, B, freq_dim, sin_buf);
-  small_linear_kernel<false, true><<<(dim + 7) / 8, 256, 0, s>>>(sin_buf, w0, b0, h1, B, freq_dim, dim);
-  small_linear_kernel<false, false><<<(dim + 7) / 8, 256, 0, s>>>(h1, w2, b2, e, B, dim, dim);
-  small_linear_kernel<true, false><<<(6 * dim + 7) / 8, 256, 0, s>>>(e, wp, bp, e0, B, dim, 6 * dim);
+  launch_pdl(sinusoid_kernel, dim3((B * freq_dim / 2 + 127) / 128), dim3(128), 0, s, t, B, freq_dim, sin_buf);
+  launch_pdl(small_linear_kernel<false, true>, dim3((dim + 7) / 8), dim3(256), 0, s, (const float*)sin_buf, w0, b0, h1, B,
+             freq_dim, dim);
+  launch_pdl(small_linear_kernel<false, false>, dim3((dim + 7) / 8), dim3(256), 0, s, (const float*)h1, w2, b2, e, B, dim,
+             dim);
+  launch_pdl(small_linear_kernel<true, false>, dim3((6 * dim + 7) / 8), dim3(256), 0, s, (const float*)e, wp, bp, e0, B,
+             dim, 6 * dim);
   B2_CUDA(cudaGetLastError());
   count_launch(4);
 }
 
 void launch_mod_table(const float* modulation, const float* e0, float* out, int layers, int B, int dim,
                       cudaStream_t s) {
-  mod_table_kernel<<<grid_for((long long)layers * B * 6 * dim), 256, 0, s>>>(modulation, e0, out, layers, B, dim);
+  launch_pdl(mod_table_kernel, dim3(grid_for((long long)layers * B * 6 * dim)), dim3(256), 0, s, modulation, e0, out,
+             layers, B, dim);
   B2_CUDA(cudaGetLastError());
   count_launch();
 }
@@ -384,7 +413,7 @@ void launch_patchify(ItemPtrs x, ItemPtrs y, int C, int Cy, int F, int H, int W,
                      cudaStream_t s) {
   B2_CHECK(H % 2 == 0 && W % 2 == 0, "latent H, W must be even for the (1,2,2) patch");
   const long long n = (long long)B * F * (H / 2) * (W / 2) * (C + Cy) * 2;
-  patchify_kernel<<<grid_for(n), 256, 0, s>>>(x, y, C, Cy, F, H, W, B, out, ld);
+  launch_pdl(patchify_kernel, dim3(grid_for(n)), dim3(256), 0, s, x, y, C, Cy, F, H, W, B, out, ld);
   B2_CUDA(cudaGetLastError());
   count_launch();
 }
@@ -394,16 +423,16 @@ void launch_pad_cast_rows(ItemPtrs src, int src_dtype, const int* rows_in, int B
   RowCounts rc;
   for (int i = 0; i < MAX_ITEMS; ++i) rc.n[i] = i < B ? rows_in[i] : 0;
   const int g = grid_for((long long)B * rows_out * cols);
-  if (src_dtype == DT_F32) pad_cast_rows_kernel<float><<<g, 256, 0, s>>>(src, rc, B, rows_out, cols, out);
-  else if (src_dtype == DT_F16) pad_cast_rows_kernel<__half><<<g, 256, 0, s>>>(src, rc, B, rows_out, cols, out);
-  else if (src_dtype == DT_BF16) pad_cast_rows_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(src, rc, B, rows_out, cols, out);
+  if (src_dtype == DT_F32) launch_pdl(pad_cast_rows_kernel<float>, dim3(g), dim3(256), 0, s, src, rc, B, rows_out, cols, out);
+  else if (src_dtype == DT_F16) launch_pdl(pad_cast_rows_kernel<__half>, dim3(g), dim3(256), 0, s, src, rc, B, rows_out, cols, out);
+  else if (src_dtype == DT_BF16) launch_pdl(pad_cast_rows_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, s, src, rc, B, rows_out, cols, out);
   else fail("unsupported context dtype %d", src_dtype);
   B2_CUDA(cudaGetLastError());
   count_launch();
 }
 
 void launch_head_table(const float* head_mod, const float* e, float* tab, int B, int dim, cudaStream_t s) {
-  head_table_kernel<<<grid_for((long long)B * dim), 256, 0, s>>>(head_mod, e, tab, B, dim);
+  launch_pdl(head_table_kernel, dim3(grid_for((long long)B * dim)), dim3(256), 0, s, head_mod, e, tab, B, dim);
   B2_CUDA(cudaGetLastError());
   count_launch();
 }
@@ -418,8 +447,8 @@ void launch_unpatchify(const float* y, int ldy, int B, int F, int Hp, int Wp, in
   const int L = F * Hp * Wp;
   const int n_out = cfg_pairs > 0 ? cfg_pairs : B;
   ProfScope prof(PC_OTHER, 0.0, 8.0 * B * L * out_dim * 4, s);
-  unpatchify_kernel<<<grid_for((long long)n_out * L * out_dim * 4), 256, 0, s>>>(y, ldy, L, Hp, Wp, F, out_dim, out,
-                                                                                n_out, cfg_pairs, cfg_scale);
+  launch_pdl(unpatchify_kernel, dim3(grid_for((long long)n_out * L * out_dim * 4)), dim3(256), 0, s, y, ldy, L, Hp, Wp, F,
+             out_dim, out, n_out, cfg_pairs, cfg_scale);
   B2_CUDA(cudaGetLastError());
   count_launch();
 }
@@ -458,7 +487,7 @@ void launch_transpose_f32(const float* src, float* dst, int rows, int cols, cuda
 }
 
 void launch_gelu_erf_cast(const float* x, __half* out, long long n, cudaStream_t s) {
-  gelu_erf_cast_kernel<<<grid_for(n), 256, 0, s>>>(x, out, n);
+  launch_pdl(gelu_erf_cast_kernel, dim3(grid_for(n)), dim3(256), 0, s, x, out, n);
   B2_CUDA(cudaGetLastError());
   count_launch();
 }

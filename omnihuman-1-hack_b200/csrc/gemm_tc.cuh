@@ -4,8 +4,9 @@
 //
 // One CTA per SM.  Roles (10 warps):
 //   warps 0..7  epilogue: TMEM -> registers -> (bias / GELU / gate) -> swizzled shared-memory staging
-//               -> TMA bulk store (or TMA reduce-add for the fp32 residual update), 32 rows x 32
-//               columns per step.  Every TMEM lane quadrant is served by two warps (w, w+4), each
+//               -> TMA bulk store (or TMA reduce-add for the fp32 residual update), 32 rows x CW
+//               columns per step (CW = 32, or 16 for tile widths that are not multiples of 32: the
+//               width is chosen per problem so that the tile count fills whole waves of 148 CTAs).  Every TMEM lane quadrant is served by two warps (w, w+4), each
 //               taking half of the tile's columns, so two instruction streams per sub-partition hide
 //               each other's latencies.  Stores go through TMA because per-thread row stores
 //               (one 64-byte piece of 32 different rows per instruction) measured 30 % of the kernel.
@@ -16,8 +17,12 @@
 // across the otherwise idle CTAs.  A split tile is finished by the CTA that owns its first K slice:
 // the others dump fp32 partial accumulators to a workspace, raise a flag per epilogue warp, and the
 // finisher adds the partials in CTA order -- deterministic, no atomics on the data.
-// Clusters (CL = 2): the two CTAs of a cluster work on vertically adjacent M tiles of the same N
-// tile; each loads half of the W tile and multicasts it into both CTAs' shared memory.
+// CTA pairs (CL = 2, tcgen05 cta_group::2): the two CTAs of a cluster own vertically adjacent M tiles
+// of the same N tile and hold HALF of the W tile each; the leader CTA issues one M = 256 MMA that reads
+// both CTAs' shared memory and writes both CTAs' TMEM.  A 256 x BLOCK_N pair tile moves 128 + BLOCK_N/2
+// operand rows per CTA instead of 128 + BLOCK_N: with single-CTA 128 x 256 tiles the kernel measured
+// bound by L2 -> shared-memory operand traffic (time x tile intensity constant across tile widths),
+// pairs raise the intensity from 85 to 128 FLOP/B.
 // The A operand is either a plain row-major matrix (2-D TMA) or an NDHWC activation volume read
 // through a 4-D TMA window per filter tap (implicit-GEMM causal convolution, used by the VAE).
 #pragma once
@@ -29,8 +34,10 @@ enum EpiMode : int {
   EPI_F16 = 0,       // out (fp16) = acc + bias
   EPI_GELU_F16 = 1,  // out (fp16) = gelu_tanh(acc + bias)
   EPI_RESID_F32 = 2, // out (fp32) += gate[item, col] * (acc + bias)       (TMA reduce-add, gate optional)
-  EPI_QKV = 3,       // cols < vt_col0 -> out (fp16) (+ per-row sum of squares for cols < ssq_cols);
+  EPI_QKV = 3,       // cols < vt_col0 -> out (fp16) (+ per-row sums of squares: slice 0 = cols < ssq_split,
+                     // slice 1 = cols in [ssq_split, ssq_cols));
                      // cols >= vt_col0 -> transposed V store  vt[head*128 + d][global row]
+                     // (all three boundaries are multiples of the chunk width; tiles may straddle them)
   EPI_F32 = 4,       // out (fp32) = acc + bias
 };
 
@@ -52,24 +59,27 @@ struct GemmParams {
   float* out_f; long long ld_f;
   __half* vt; long long vt_ld; int vt_rows;    // EPI_QKV: V^T [vt_rows = heads*128, vt_ld >= M]
   const float* gate; int gate_stride; int rows_per_item;
-  float* ssq; int ssq_ld; int ssq_cols;
+  float* ssq; int ssq_ld; int ssq_cols; int ssq_split;   // ssq[row*ssq_ld + (n_blk*2 + half)*2 + slice]
   int vt_col0;
   ConvGeom cv;
   int sk;                 // K-split factor S of the last (partial) wave's tiles, <= 1: no split
   float* sk_ws;           // [gridDim.x][BLOCK_N][128] fp32 partial accumulators
   int* sk_flags;          // [gridDim.x][8], zero between launches
-  int dbg;                // diagnosis only (B200_GEMM_DBG): bit 0 = skip the epilogue's global stores
+  int dbg;                // diagnosis only (B200_GEMM_DBG): 1 = skip the epilogue's global stores, 2 = no operand
+                          // loads (MMAs run on whatever is in shared memory), 4 = loads but no MMAs
 };
 
 constexpr int WARP_TMA = 8, WARP_MMA = 9;
 constexpr int EPI_WARPS = 8;
 constexpr int STAGING_BYTES = EPI_WARPS * 4096;          // 32 rows x 128 B per epilogue warp
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CL = 1>
 struct GemmCfg {
   static constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_ROWS = BLOCK_N / CL;               // W-tile rows held by one CTA
+  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
+  static_assert(B_BYTES % 1024 == 0, "operand tiles must keep the 1024-byte swizzle alignment");
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BIAS_BYTES = 2 * 2 * 128 * 4;     // [column half][accumulator parity][<= 128 values]
   static constexpr int TAIL_BYTES = STAGING_BYTES + 256 /*barriers*/ + BIAS_BYTES;
@@ -80,7 +90,25 @@ struct GemmCfg {
                                    : 2 * BLOCK_N <= 256 ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TAIL_BYTES;      // dynamic smem is 1024-aligned
   static constexpr int THREADS = 320;
+  static constexpr int CW = (BLOCK_N % 32 == 0) ? 32 : 16;   // epilogue chunk width (columns)
+  static constexpr int NCH = BLOCK_N / CW;
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "tcgen05 N for M = 128: multiples of 16 up to 256");
 };
+
+// this warp's 32 TMEM lanes x CW consecutive fp32 columns
+template <int CW>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CW]) {
+  if constexpr (CW == 32) tmem_ld32(taddr, r);
+  else tmem_ld16(taddr, r);
+}
+// 16-byte piece k of row r inside a [32 rows x ROW_BYTES] staging box laid out with the TMA swizzle
+// of that row width (128B / 64B / 32B swizzle: piece index ^= address bits [7, 7 + log2(pieces)))
+template <int ROW_BYTES>
+__device__ __forceinline__ uint32_t stage_offset(int r, int k) {
+  if constexpr (ROW_BYTES == 128) return r * 128 + ((k ^ (r & 7)) << 4);
+  else if constexpr (ROW_BYTES == 64) return r * 64 + ((k ^ ((r >> 1) & 3)) << 4);
+  else return r * 32 + ((k ^ ((r >> 2) & 1)) << 4);
+}
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   // 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3)   ==   x * sigmoid(2u) = x / (1 + exp(-2u))
@@ -132,7 +160,8 @@ __global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_vt,
                const GemmParams p) {
-  using C = GemmCfg<BLOCK_N>;
+  using C = GemmCfg<BLOCK_N, CL>;
+  constexpr bool PAIR = CL == 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;                 // [8][4096], 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
@@ -146,6 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = warp_id();
   const int lane = lane_id();
   const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  pdl_launch();
 
   const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles_m = (p.M + C::BLOCK_M - 1) / C::BLOCK_M;
@@ -157,22 +187,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_o);
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS); }
+    // pair mode: full[] / acc_empty[] are used in the leader only (it collects both CTAs' loads and both
+    // CTAs' epilogue arrivals); empty[] / acc_full[] exist in both CTAs and are fed by the leader's commits
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS * CL); }
     fence_barrier_init();
   }
-  if (warp == WARP_MMA) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == WARP_MMA) { if (PAIR) tmem_alloc_pair(tmem_slot, C::TMEM_COLS); else tmem_alloc(tmem_slot, C::TMEM_COLS); }
   tc_fence_before();
   if (CL > 1) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above overlapped the previous kernel's tail (programmatic dependent launch).  The weight
+  // operand does not depend on that kernel, so the producer also requests the W tiles of its first
+  // pipeline stages before waiting; activations (A, bias-free inputs, outputs) are touched only after.
+  if (warp != WARP_TMA) pdl_wait();
 
   if (warp == WARP_TMA) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    int pre = 0;                                           // stages whose W tile was requested early
+    if (lane == 0 && !(p.dbg & 2) && !PAIR && !p.cv.enabled) {
+      TileSched s0(units, num_kb, G, cid, p.sk);
+      int unit, kb0, kb1, n_contrib;
+      if (s0.next(unit, kb0, kb1, n_contrib)) {
+        const int n_blk = unit % tiles_n;
+        for (int kb = kb0; kb < kb1 && pre < C::STAGES; ++kb, ++pre) {
+          mbar_expect_tx(&full[pre], C::STAGE_BYTES);
+          tma_load_2d(smem + pre * C::STAGE_BYTES + C::A_BYTES, &tmap_b, &full[pre], kb * C::BLOCK_K, n_blk * BLOCK_N);
+        }
+      }
+    }
+    pdl_wait();
+    if (lane == 0 && !(p.dbg & 2)) {
       int stage = 0; uint32_t phase = 0;
       TileSched sched(units, num_kb, G, cid, p.sk);
       int unit, kb0, kb1, n_contrib;
+      int issued = 0;                                      // k-slices issued so far by this CTA
       while (sched.next(unit, kb0, kb1, n_contrib)) {
         const int m_blk = (unit / tiles_n) * CL + rank, n_blk = unit % tiles_n;
         int ct = 0, ch0 = 0, cw0 = 0;
@@ -187,7 +237,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          if constexpr (PAIR) {
+            // both CTAs signal the leader's barrier; the leader expects the bytes of both halves
+            const uint32_t bar = map_to_cta(&full[stage], 0);
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmap_a, bar, kb * C::BLOCK_K, m_blk * C::BLOCK_M);
+            tma_load_2d_pair(sb, &tmap_b, bar, kb * C::BLOCK_K, n_blk * BLOCK_N + rank * C::B_ROWS);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          const bool w_done = issued < pre;                // this stage's W tile is already in flight
+          ++issued;
+          if (!w_done) mbar_expect_tx(&full[stage], C::STAGE_BYTES);
           if (p.cv.enabled) {
             const int tap = kb / p.cv.cblocks, cb = kb % p.cv.cblocks;
             const int dw = tap % p.cv.kw, dh = (tap / p.cv.kw) % p.cv.kh, dt = tap / (p.cv.kw * p.cv.kh);
@@ -195,21 +256,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           } else {
             tma_load_2d(sa, &tmap_a, &full[stage], kb * C::BLOCK_K, m_blk * C::BLOCK_M);
           }
-          if (CL == 1) {
-            tma_load_2d(sb, &tmap_b, &full[stage], kb * C::BLOCK_K, n_blk * BLOCK_N);
-          } else {
-            // this CTA fetches rows [rank*BN/CL, (rank+1)*BN/CL) of the W tile for every CTA of the cluster
-            constexpr int ROWS = BLOCK_N / CL;
-            tma_load_2d_mc(sb + rank * ROWS * 128, &tmap_b, &full[stage], kb * C::BLOCK_K,
-                           n_blk * BLOCK_N + rank * ROWS, (uint16_t)((1u << CL) - 1));
-          }
+          if (!w_done) tma_load_2d(sb, &tmap_b, &full[stage], kb * C::BLOCK_K, n_blk * BLOCK_N);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == WARP_MMA) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_f16(C::BLOCK_M, BLOCK_N);
+  } else if (warp == WARP_MMA && (!PAIR || rank == 0)) {
+    // ------------------------------------------------------------------ MMA issuer (pair mode: the leader only)
+    constexpr uint32_t idesc = umma_idesc_f16(C::BLOCK_M * CL, BLOCK_N);
     int stage = 0; uint32_t phase = 0;
     int seg = 0;
     TileSched sched(units, num_kb, G, cid, p.sk);
@@ -222,36 +276,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full[stage], phase);
+        if (!(p.dbg & 2)) mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
 #pragma unroll
           for (int k = 0; k < C::BLOCK_K / C::UMMA_K; ++k) {
-            umma_f16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc,
-                     (kb > kb0 || k > 0) ? 1u : 0u);
+            if (p.dbg & 4) break;
+            if constexpr (PAIR)
+              umma_f16_pair(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc,
+                            (kb > kb0 || k > 0) ? 1u : 0u);
+            else
+              umma_f16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc,
+                       (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          // the smem slot is reusable once these MMAs retire; with clusters the peer writes into it too
-          if (CL == 1) umma_commit(&empty[stage]);
-          else umma_commit_mc(&empty[stage], (uint16_t)((1u << CL) - 1));
-          if (kb == kb1 - 1) umma_commit(&acc_full[acc]);
+          // the smem slot (of both CTAs in pair mode) is reusable once these MMAs retire
+          if constexpr (PAIR) {
+            umma_commit_pair(&empty[stage], 3);
+            if (kb == kb1 - 1) umma_commit_pair(&acc_full[acc], 3);
+          } else {
+            umma_commit(&empty[stage]);
+            if (kb == kb1 - 1) umma_commit(&acc_full[acc]);
+          }
         }
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else {
+  } else if (warp < EPI_WARPS) {
     // ------------------------------------------------------------------ epilogue (warps 0..7)
     const int quad = warp & 3;                           // TMEM lane quadrant this warp may access
-    const int half = warp >> 2;                          // which half of the tile's 32-column chunks
-    constexpr int NCH = BLOCK_N / 32;
+    const int half = warp >> 2;                          // which half of the tile's column chunks
+    constexpr int CW = C::CW, NCH = C::NCH;
     constexpr int C_SPLIT = (NCH + 1) / 2;               // half 0: [0, C_SPLIT), half 1: [C_SPLIT, NCH)
     const int c_begin = half ? C_SPLIT : 0, c_end = half ? NCH : C_SPLIT;
     const int r_in_tile = quad * 32 + lane;
     uint8_t* stg_base = staging + warp * 4096;           // this warp's private staging area
     constexpr bool OUT_F32 = (EPI == EPI_RESID_F32 || EPI == EPI_F32);
-    int n_store = 0;                                     // fp16 boxes are 2 KB: two of them alternate
+    constexpr int ROW_BYTES = CW * (OUT_F32 ? 4 : 2);    // 128 / 64 / 32: staging row = TMA box row
+    constexpr int BOX_BYTES = 32 * ROW_BYTES;
+    constexpr int NBUF = BOX_BYTES >= 4096 ? 1 : 2;      // boxes smaller than the staging area alternate
+    int n_store = 0;
     int seg = 0;
     TileSched sched(units, num_kb, G, cid, p.sk);
     int unit, kb0, kb1, n_contrib;
@@ -269,17 +335,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_fence_after();
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_acc + c * 32, r);
+          uint32_t r[CW];
+          tmem_ld_chunk<CW>(t_acc + c * CW, r);
           tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) ws[(c * 32 + j) * 128 + r_in_tile] = __uint_as_float(r[j]);
+          for (int j = 0; j < CW; ++j) ws[(c * CW + j) * 128 + r_in_tile] = __uint_as_float(r[j]);
         }
         tc_fence_before();
         __threadfence();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&acc_empty[acc]);
+          mbar_arrive(&acc_empty[acc]);                   // (the tail K-split is never combined with pair mode)
           st_release_gpu(p.sk_flags + blockIdx.x * EPI_WARPS + warp, 1);
         }
         continue;
@@ -299,8 +365,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float bv[C_SPLIT];
 #pragma unroll
       for (int ci = 0; ci < C_SPLIT; ++ci) {
-        const int col = n_blk * BLOCK_N + (c_begin + ci) * 32 + lane;
-        bv[ci] = (p.bias != nullptr && c_begin + ci < c_end && col < p.N) ? __ldg(p.bias + col) : 0.f;
+        const int col = n_blk * BLOCK_N + (c_begin + ci) * CW + lane;
+        bv[ci] = (p.bias != nullptr && lane < CW && c_begin + ci < c_end && col < p.N) ? __ldg(p.bias + col) : 0.f;
       }
 
       // output coordinates of this warp's 32 rows
@@ -324,31 +390,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // previous user of this parity's bias slot; the 4 warps of a column half write identical values
       float* bias_w = bias_all + (half * 2 + acc) * 128;
       if (p.bias != nullptr) {
+        if (lane < CW) {
 #pragma unroll
-        for (int ci = 0; ci < C_SPLIT; ++ci) bias_w[ci * 32 + lane] = bv[ci];
+          for (int ci = 0; ci < C_SPLIT; ++ci) bias_w[ci * CW + lane] = bv[ci];
+        }
         __syncwarp();
       }
-      float ssq_acc = 0.f;
+      float ssq_a = 0.f, ssq_b = 0.f;                     // EPI_QKV: sums of squares of slice 0 / slice 1
 #pragma unroll 1
       for (int c = c_begin; c < c_end; ++c) {
-        const int col0 = n_blk * BLOCK_N + c * 32;
+        const int col0 = n_blk * BLOCK_N + c * CW;
         if (col0 >= p.N) break;                           // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(t_acc + c * 32, r);
+        uint32_t r[CW];
+        tmem_ld_chunk<CW>(t_acc + c * CW, r);
         tmem_wait_ld();
-        float v[32];
+        float v[CW];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
 #pragma unroll 1
         for (int q = 0; q < n_contrib; ++q) {             // partials in CTA order: deterministic sum
-          const float* ws = p.sk_ws + (size_t)((cid + 1 + q) * CL + rank) * (BLOCK_N * 128) + (c * 32) * 128 + r_in_tile;
+          const float* ws = p.sk_ws + (size_t)((cid + 1 + q) * CL + rank) * (BLOCK_N * 128) + (c * CW) * 128 + r_in_tile;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldcg(ws + j * 128);
+          for (int j = 0; j < CW; ++j) v[j] += __ldcg(ws + j * 128);
         }
         if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(bias_w + (c - c_begin) * 32);     // broadcast LDS.128
+          const float4* b4 = reinterpret_cast<const float4*>(bias_w + (c - c_begin) * CW);     // broadcast LDS.128
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < CW / 4; ++j) {
             const float4 b = b4[j];
             v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
           }
@@ -356,9 +424,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (p.dbg & 1) continue;
 
         // the bulk store that last used this staging box must have finished reading it
-        uint8_t* stg = stg_base + (OUT_F32 ? 0 : (n_store & 1) * 2048);
+        uint8_t* stg = stg_base + (NBUF == 1 ? 0 : (n_store & 1) * BOX_BYTES);
         ++n_store;
-        if (lane == 0) { if (OUT_F32) tma_store_wait_read0(); else tma_store_wait_read1(); }
+        if (lane == 0) { if (NBUF == 1) tma_store_wait_read0(); else tma_store_wait_read1(); }
         __syncwarp();
 
         bool to_vt = false;
@@ -368,44 +436,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (p.gate != nullptr) {
               const float4* g4 = reinterpret_cast<const float4*>(p.gate + (long long)item * p.gate_stride + col0);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < CW / 4; ++j) {
                 const float4 g = __ldg(g4 + j);
                 v[4 * j] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
               }
             }
           }
-          // 32 rows x 128 B, 128-byte swizzle: 16-byte piece k of row r lives at piece k ^ (r & 7)
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) =
+          for (int k = 0; k < CW / 4; ++k)
+            *reinterpret_cast<float4*>(stg + stage_offset<ROW_BYTES>(lane, k)) =
                 make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
         } else if (!to_vt) {
           if constexpr (EPI == EPI_GELU_F16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+            for (int j = 0; j < CW; ++j) v[j] = gelu_tanh_f(v[j]);
           }
-          uint32_t h[16];
+          uint32_t h[CW / 2];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) h[j] = pack_h2(v[2 * j], v[2 * j + 1]);
+          for (int j = 0; j < CW / 2; ++j) h[j] = pack_h2(v[2 * j], v[2 * j + 1]);
           if constexpr (EPI == EPI_QKV) {
             if (col0 < p.ssq_cols) {                      // sum of squares of exactly what attention will read
+              float sq = 0.f;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
+              for (int j = 0; j < CW / 2; ++j) {
                 const float2 f = __half22float2(*reinterpret_cast<__half2*>(&h[j]));
-                ssq_acc = fmaf(f.x, f.x, fmaf(f.y, f.y, ssq_acc));
+                sq = fmaf(f.x, f.x, fmaf(f.y, f.y, sq));
               }
+              if (col0 < p.ssq_split) ssq_a += sq; else ssq_b += sq;
             }
           }
-          // 32 rows x 64 B, 64-byte swizzle: piece k of row r lives at piece k ^ ((r >> 1) & 3)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            *reinterpret_cast<uint4*>(stg + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
+          for (int k = 0; k < CW / 8; ++k)
+            *reinterpret_cast<uint4*>(stg + stage_offset<ROW_BYTES>(lane, k)) =
                 make_uint4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
         } else {
-          // transposed V: staging holds [32 d][32 rows] fp16 (64 B per d, no swizzle)
+          // transposed V: staging holds [CW d][32 rows] fp16 (64 B per d, no swizzle)
           __half* sv = reinterpret_cast<__half*>(stg);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sv[j * 32 + lane] = __float2half_rn(v[j]);
+          for (int j = 0; j < CW; ++j) sv[j * 32 + lane] = __float2half_rn(v[j]);
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -423,13 +491,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
       if constexpr (EPI == EPI_QKV) {
-        // two partial sums per (row, N tile): one from each of the two warps that share the quadrant
-        if (row_ok && n_blk * BLOCK_N < p.ssq_cols) p.ssq[grow * p.ssq_ld + n_blk * 2 + half] = ssq_acc;
+        // two partial sums per (row, N tile, slice): one from each of the two warps that share the quadrant
+        if (row_ok && n_blk * BLOCK_N < p.ssq_cols)
+          *reinterpret_cast<float2*>(p.ssq + grow * p.ssq_ld + (n_blk * 2 + half) * 2) = make_float2(ssq_a, ssq_b);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&acc_empty[acc]);
+        if (PAIR && rank != 0) mbar_arrive_cluster(map_to_cta(&acc_empty[acc], 0));   // the leader's MMA warp waits
+        else mbar_arrive(&acc_empty[acc]);
         for (int q = 0; q < n_contrib; ++q) p.sk_flags[((cid + 1 + q) * CL + rank) * EPI_WARPS + warp] = 0;   // re-arm
       }
     }
@@ -440,7 +510,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (CL > 1) cluster_sync(); else __syncthreads();
   if (warp == WARP_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 

@@ -8,6 +8,8 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -56,7 +58,7 @@ inline PFN_encodeTiled get_encode_tiled() {
 }
 
 // Tensor map of up to 4 dims (dim 0 innermost / contiguous), zero OOB fill.
-// swizzle_bytes: 0 (none), 64 or 128 -- must match how the kernel lays the box out in shared memory.
+// swizzle_bytes: 0 (none), 32, 64 or 128 -- must match how the kernel lays the box out in shared memory.
 inline CUtensorMap make_tmap(const void* base, bool f32, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                              const uint32_t* box, int swizzle_bytes) {
   CUtensorMap m;
@@ -68,7 +70,8 @@ inline CUtensorMap make_tmap(const void* base, bool f32, int rank, const uint64_
   for (int i = 0; i + 1 < rank; ++i)
     B2_CHECK(gstr[i] % 16 == 0, "TMA stride %d = %llu bytes is not a multiple of 16", i, (unsigned long long)gstr[i]);
   const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = get_encode_tiled()(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
                                   const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -87,6 +90,27 @@ inline CUtensorMap make_tmap_2d(const void* base, uint64_t rows, uint64_t cols, 
   uint64_t str[1] = {ld * 2};
   uint32_t box[2] = {64, box_rows};
   return make_tmap_f16(base, 2, dims, str, box);
+}
+
+// Kernel launch with programmatic dependent launch (see ptx.cuh: pdl_launch / pdl_wait).  Only kernels
+// that execute pdl_wait() before touching activation memory may be launched through this helper.
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("B200_PDL");
+    v = e ? (std::atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  B2_CUDA(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
 }
 
 // Simple owning device buffer.

@@ -31,7 +31,7 @@ struct ProfScope {
 // ---- gemm_tc.cu
 void launch_gemm(int epi, int block_n, int cluster, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                  int num_sms, cudaStream_t stream);
-int gemm_cluster_size(int block_n, long long M, bool conv);
+int gemm_cluster_size(int block_n, long long M, long long N, long long K, int num_sms, bool conv);
 void gemm_linear(int epi, const __half* A, long long lda, const __half* W, long long ldw, GemmParams p, int num_sms,
                  cudaStream_t stream, int force_bn = 0);
 void conv_gemm(int epi, const __half* in, int Tbuf, int H, int W, int Cin, const __half* w, int Cout, int kt, int kh,
@@ -58,21 +58,43 @@ void launch_vae_store_rgb(const float* x, float* out, int T, long long HW, int t
 // conv weight [Cout, Cin, taps] (any float dtype staged as fp32) -> fp16 [Cout, taps, cpad], zero padded
 void launch_repack_conv_weight(const float* src, __half* dst, int Cout, int Cin, int taps, int cpad, cudaStream_t s);
 
-// Tile width: fewest (waves x tile cost); narrower tiles re-read A more often (cost factors measured
-// on M = 6240 sweeps).  N = 1536 at M = 3120 -> 192 (200 tiles, 2 waves of 3/4 size) instead of 256
-// (150 tiles = 2 full-size waves on 148 SMs).
-inline int pick_bn(long long M, long long N, int num_sms) {
+// Tile width: the instantiated width with the fewest (waves x tile cost) on this problem.  Widths need
+// not divide N (TMA clips the last tile).  The main loop is paced by shared-memory bandwidth (TMA fill +
+// operand reads of every MMA: 128 + BN rows per K step), so narrower tiles cost more per column; B200
+// sweeps at M = 1560 / 3120 / 6240 (tools/sweep_r1b.py) showed 144- and 208-wide tiles never winning.
+constexpr int kGemmWidths[3] = {256, 192, 128};
+inline double gemm_width_factor(int bn) { return bn == 256 ? 1.0 : bn == 192 ? 1.07 : 1.25; }
+// K-split factor of the last partial wave (see gemm_tc.cuh TileSched): the fix-up costs about 24 K slices,
+// so only long-K tiles are split.  units = whole tiles, G = resident CTAs.
+inline int gemm_tail_split(long long units, int G, int KB) {
+  int S;
+  if (units >= G) {
+    const int R = (int)(units % G);
+    S = R ? G / R : 1;
+  } else {
+    S = (int)(G / units);
+  }
+  if (S > KB / 16) S = KB / 16;
+  if (S > 8) S = 8;
+  if (S < 2 || KB < 64) S = 1;
+  return S;
+}
+inline int pick_bn(long long M, long long N, int num_sms, long long K = 0) {
   const long long tm = (M + 127) / 128;
-  if (tm <= 1 || N % 128 != 0) return 128;
+  if (N <= 128) return 128;
+  const int KB = (int)((K + 63) / 64);
   int best = 128;
   double best_cost = 1e30;
-  const int cand[3] = {256, 192, 128};
-  const double factor[3] = {1.0, 1.12, 1.25};
   for (int i = 0; i < 3; ++i) {
-    if (N % cand[i] != 0) continue;
-    const long long tiles = tm * (N / cand[i]);
-    const double cost = (double)((tiles + num_sms - 1) / num_sms) * cand[i] * factor[i];
-    if (cost < best_cost) { best_cost = cost; best = cand[i]; }
+    const int bn = kGemmWidths[i];
+    const long long tiles = tm * ((N + bn - 1) / bn);
+    double waves = (double)((tiles + num_sms - 1) / num_sms);
+    if (KB >= 64 && tiles % num_sms != 0) {
+      const int S = gemm_tail_split(tiles, num_sms, KB);
+      if (S > 1) waves = (double)(tiles / num_sms) + 1.0 / S + 24.0 / KB;
+    }
+    const double cost = waves * bn * gemm_width_factor(bn);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
 }
@@ -89,6 +111,9 @@ struct AttnParams {
   int klen[MAX_ITEMS];                 // valid keys per item (<= Lk_rows)
   float scale;                         // 1/sqrt(head_dim)
   int accumulate;                      // 1: out += result (fp16 add; i2v second K/V stream)
+  // optional per-row logit factor rsqrt(mean(q^2) + eps) (query RMSNorm folded into the softmax scale):
+  // row sum of squares = sum over i < q_ssq_n of q_ssq[row*q_ssq_ld + 2i]  (the producing GEMM's partials)
+  const float* q_ssq; int q_ssq_ld; int q_ssq_n; int q_dim; float q_eps;
 };
 void launch_attention(const AttnParams& p, cudaStream_t stream);
 
@@ -100,10 +125,12 @@ struct ItemPtrsMut { float* p[MAX_ITEMS]; };
 void launch_ln_affine(const float* x, __half* out, const float* a, const float* b, long long item_stride, int M,
                       int rows_per_item, int dim, float eps, cudaStream_t s, bool split = false);
 // in-place on fp16 [M, ld]: per slice (q at column 0, k at column dim) x * rsqrt(mean(x^2)+eps) * gamma,
-// then optional 3-D RoPE (cos/sin table [rows_per_item, 64] float2).  ssq holds per-N-tile partial sums.
+// then optional 3-D RoPE (cos/sin table [rows_per_item, 64] float2).  ssq holds the producing GEMM's partial
+// sums: slice s = sum over i < ssq_n of ssq[row*ssq_ld + 2i + s].  gamma_mul: extra per-channel factor on slice 0
+// (cross-attention folds norm_q's weight into the cached keys, see dit_engine.cu).
 void launch_rms_rope(__half* x, long long ld, int dim, int nslices, const float* ssq, int ssq_ld, int ssq_n,
                      const float* gamma0, const float* gamma1, const float* cs_table, int M, int rows_per_item,
-                     float eps, cudaStream_t s);
+                     float eps, cudaStream_t s, const float* gamma_mul = nullptr);
 // sinusoid(t) -> time MLP -> e [B, dim], e0 [B, 6*dim]  (all fp32, model.py:526-528)
 void launch_time_embed(const float* t, int B, int freq_dim, int dim, const float* w0, const float* b0, const float* w2,
                        const float* b2, const float* wp, const float* bp, float* scratch, float* e, float* e0,

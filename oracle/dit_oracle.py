@@ -287,9 +287,17 @@ def make_synthetic_weights(dim=1536, ffn_dim=8960, num_heads=12, num_layers=30, 
     return sd
 
 
-def dit_flops(L, Lc=512, dim=1536, ffn=8960, layers=30, text_dim=4096, patch_k=64, freq_dim=256):
-    """Algorithmic FLOPs of one forward, 2 FLOP/MAC, no padding."""
+def dit_flops(L, Lc=512, dim=1536, ffn=8960, layers=30, text_dim=4096, patch_k=64, freq_dim=256,
+              context_cached=False):
+    """Algorithmic FLOPs of one forward, 2 FLOP/MAC, no padding.
+    context_cached: leave out the step-invariant context work (text embedding, cross-attention k/v
+    projections), which SURVEY 8d counts once per prompt rather than once per step."""
     d = dim
-    per_block = 8 * L * d * d + 4 * L * L * d + 4 * L * d * d + 4 * Lc * d * d + 4 * L * Lc * d + 4 * L * d * ffn
-    other = 2 * L * patch_k * d * 2 + 2 * Lc * text_dim * d + 2 * Lc * d * d + 2 * d * (freq_dim + d + 6 * d)
+    ctx_block = 4 * Lc * d * d
+    ctx_other = 2 * Lc * text_dim * d + 2 * Lc * d * d
+    per_block = 8 * L * d * d + 4 * L * L * d + 4 * L * d * d + ctx_block + 4 * L * Lc * d + 4 * L * d * ffn
+    other = 2 * L * patch_k * d * 2 + ctx_other + 2 * d * (freq_dim + d + 6 * d)
+    if context_cached:
+        per_block -= ctx_block
+        other -= ctx_other
     return layers * per_block + other

@@ -20,6 +20,12 @@ def _mk(shape, seed, scale=1.0):
 @pytest.mark.parametrize("M,N,K,bn", [
     (128, 128, 64, 128), (128, 256, 64, 256), (256, 256, 128, 256), (1560, 1536, 1536, 0), (1560, 4608, 1536, 256),
     (1560, 8960, 1536, 0), (1560, 1536, 8960, 128), (300, 384, 200, 128), (77, 96, 72, 128), (6240, 1536, 1536, 256),
+    # tile widths that are not multiples of 32 (16-column epilogue chunks) / do not divide N
+    (3120, 1536, 1536, 144), (3120, 4608, 1536, 192), (300, 384, 200, 144), (3120, 1536, 8960, 144),
+    (3120, 1536, 8960, 0), (1000, 1000, 328, 192),
+    # CTA-pair kernels (tcgen05 cta_group::2, 256 x BN tiles): width + 1000
+    (3120, 4608, 1536, 1256), (300, 384, 200, 1128), (6240, 1536, 1536, 1256), (1560, 8960, 1536, 1192),
+    (128, 256, 64, 1256), (3120, 1536, 8960, 1192), (2000, 1000, 328, 1224),
 ])
 def test_linear_f32(M, N, K, bn):
     import b200dit
@@ -30,13 +36,14 @@ def test_linear_f32(M, N, K, bn):
     assert rel_l2(out, ref) < 3e-4, (M, N, K)
 
 
-@pytest.mark.parametrize("epi", ["f16", "gelu"])
-def test_linear_f16_epilogues(epi):
+@pytest.mark.parametrize("epi,bn", [("f16", 0), ("gelu", 0), ("f16", 144), ("gelu", 192), ("f16", 192), ("f16", 1128),
+                                    ("gelu", 1224), ("gelu", 1256)])
+def test_linear_f16_epilogues(epi, bn):
     import b200dit
     M, N, K = 777, 640, 512
     a, w = _mk((M, K), 4).cuda(), _mk((N, K), 5, 1 / math.sqrt(K)).cuda()
     bias = torch.randn(N, generator=torch.Generator().manual_seed(6)).cuda()
-    out = b200dit.linear(a, w, bias, epi)
+    out = b200dit.linear(a, w, bias, epi, bn)
     ref = a.float() @ w.float().t() + bias
     if epi == "gelu":
         ref = torch.nn.functional.gelu(ref, approximate="tanh")
