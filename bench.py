@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: DiT denoise-steps/sec, Wan2.1-T2V-1.3B, 480x832 latent [16,1,60,104]
-(BASELINE.json configs[1]): one step = cond forward + uncond forward + CFG combine + solver update
-for one sample; every rank (GPU) denoises its own independent sample(s) (weak scaling), one NCCL
+(BASELINE.json configs[1]): one step = cond forward + uncond forward + CFG combine + UniPC solver step
+(the reference's default sampler, text2video.py:204-252: 50 steps, shift 5.0, guide 5.0) for one sample; every rank (GPU) denoises its own independent sample(s) (weak scaling), one NCCL
 all_gather of the final latents closes the timed region.
 
     python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--samples-per-gpu S] [--frames T]
@@ -37,8 +37,8 @@ NUM_STEPS = 50
 def workload_config(T, S, layers, world, graphs=True):
     L = 1560 * T
     return {"workload": f"Wan2.1-T2V-1.3B ({layers} blocks, dim 1536, ffn 8960, 12 heads) CFG denoise step on "
-                        f"latent [16,{T},60,104] (L={L} tokens), guide {GUIDE}, flow shift {SHIFT}, {S} sample(s) per "
-                        f"GPU, cond+uncond co-batched",
+                        f"latent [16,{T},60,104] (L={L} tokens), guide {GUIDE}, UniPC solver step (shift {SHIFT}, "
+                        f"{NUM_STEPS}-step schedule), {S} sample(s) per GPU, cond+uncond co-batched",
             "samples_per_gpu": S, "parallelism": f"replicas x{world} (independent samples, one all_gather)",
             "l2_policy": "weights 2.84 GB per forward exceed the 126 MB L2 (no flush needed)",
             "cuda_graphs": graphs, "operands": "fp16 x fp16 -> fp32 accumulate (model.py:540)",
@@ -52,15 +52,6 @@ def peaks():
         d = json.load(open(p))
         return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
     return 1590.0, 1400.0, 6650.0, "fallback"
-
-
-def sigmas_flow(n, shift):
-    """Flow-matching sigma schedule (fm_solvers_unipc.py:182-211): shift*s/(1+(shift-1)s) on linspace(1, 1/1000)."""
-    out = []
-    for i in range(n):
-        s = 1.0 + (1.0 / 1000.0 - 1.0) * i / n            # linspace(1, 1/1000, n + 1)[:-1]
-        out.append(shift * s / (1.0 + (shift - 1.0) * s))
-    return out + [0.0]
 
 
 class ClockSampler:
@@ -255,18 +246,32 @@ def main():
     host_x = [torch.randn(16, T, 60, 104, generator=g).pin_memory() for _ in range(S)]
     host_ctx = [torch.randn(512, 4096, generator=g).bfloat16().pin_memory() for _ in range(S)]
     host_ctx0 = [torch.randn(512, 4096, generator=g).bfloat16().pin_memory() for _ in range(S)]
-    sig = sigmas_flow(NUM_STEPS, SHIFT)
     lat = [h.to(dev) for h in host_x]
     ctx = [h.to(dev) for h in host_ctx]
     ctx0 = [h.to(dev) for h in host_ctx0]
-    t_dev = [torch.full((S,), sig[i % NUM_STEPS] * 1000.0, device=dev) for i in range(NUM_STEPS)]
+
+    # the reference's sampler (text2video.py:204-211): FlowUniPC, 50 steps, shift 5.0; one scheduler per sample
+    def new_schedulers():
+        out = []
+        for _ in range(S):
+            sc = b200dit.FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+            sc.set_timesteps(NUM_STEPS, device=dev, shift=SHIFT)
+            out.append(sc)
+        return out
+
+    ts_host = new_schedulers()[0].timesteps.cpu().tolist()          # int64 timesteps, as the reference feeds them
+    t_dev = [torch.full((S,), float(t), device=dev) for t in ts_host]
+    t_pin = [torch.full((S,), float(t)).pin_memory() for t in ts_host]
+    state = {"sched": None}
 
     def step_device(i, x):
-        """one denoise step with everything resident in HBM: fused cond/uncond/CFG forward + Euler flow update"""
+        """one denoise step with everything resident in HBM: fused cond/uncond/CFG forward + UniPC update"""
         k = i % NUM_STEPS
+        if k == 0 or state["sched"] is None:
+            state["sched"] = new_schedulers()                       # a new trajectory starts
         v = eng.forward_cfg(x, t_dev[k], ctx, ctx0, L, GUIDE)
-        dt = sig[k + 1] - sig[k]
-        return [xi + dt * vi for xi, vi in zip(x, v)]
+        return [sc.step(vi.unsqueeze(0), ts_host[k], xi.unsqueeze(0), return_dict=False)[0].squeeze(0)
+                for sc, xi, vi in zip(state["sched"], x, v)]
 
     def barrier():
         if world > 1:
@@ -276,6 +281,7 @@ def main():
     x = lat
     for i in range(W):
         x = step_device(i, x)
+    state["sched"] = None
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -307,7 +313,7 @@ def main():
     # host memory and the updated latent back; the prompt contexts are per-TRAJECTORY inputs (the reference
     # encodes them once before its loop, text2video.py:172-182) and are copied in at the first step of each
     # trajectory of NUM_STEPS steps, inside the timed region.
-    e2e_state = {"ctx": None, "h2d": 0}
+    e2e_state = {"ctx": None, "h2d": 0, "sched": None}
 
     def step_e2e(i, hx):
         k = i % NUM_STEPS
@@ -315,12 +321,14 @@ def main():
             e2e_state["ctx"] = ([h.to(dev, non_blocking=True) for h in host_ctx],
                                 [h.to(dev, non_blocking=True) for h in host_ctx0])
             e2e_state["h2d"] += S * 2 * 512 * 4096 * 2
+            e2e_state["sched"] = new_schedulers()
         cs, c0 = e2e_state["ctx"]
         xs = [h.to(dev, non_blocking=True) for h in hx]
-        tt = torch.full((S,), sig[k] * 1000.0).pin_memory().to(dev, non_blocking=True)
+        tt = t_pin[k].to(dev, non_blocking=True)
         e2e_state["h2d"] += S * (16 * T * 60 * 104 * 4 + 4)
         v = eng.forward_cfg(xs, tt, cs, c0, L, GUIDE)
-        out = [(xi + (sig[k + 1] - sig[k]) * vi).to("cpu", non_blocking=False) for xi, vi in zip(xs, v)]
+        out = [sc.step(vi.unsqueeze(0), ts_host[k], xi.unsqueeze(0), return_dict=False)[0].squeeze(0).to("cpu")
+               for sc, xi, vi in zip(e2e_state["sched"], xs, v)]
         return out
 
     hx = host_x
@@ -348,6 +356,7 @@ def main():
         eng.set_graphs(False)
         b200dit.profile_enable(True)
         xs = lat
+        state["sched"] = None
         for i in range(2):
             xs = step_device(i, xs)
         torch.cuda.synchronize()

@@ -140,6 +140,16 @@ B200_API int b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw,
                          int32_t N, int32_t K, int32_t epilogue, void* out, int64_t ldo, int32_t block_n,
                          void* stream);
 
+/* ---- scheduler step (seaweed_apt/wan/utils/fm_solvers_unipc.py:655-739, fm_solvers.py:706-797) ----
+ * Every tensor update of one FlowUniPC / FlowDPMSolver++ step (x0 conversion :318-320, UniC corrector
+ * :486-626, UniP / DPM++ predictor :350-483 / :415-593) is a linear combination of the model output, the
+ * sample and the solver history with scalar coefficients; the host computes the scalars (fp32, as the
+ * reference does) and this call evaluates   out[j] = sum_i coeff[j*n_in + i] * in[i]   for j < n_out in ONE
+ * pass over numel fp32 elements (device pointers, 16-byte aligned; coeff is a host array; n_in <= 6, n_out <= 3;
+ * an output may alias an input).  The reference issues ~20 elementwise kernels and a device->host sync per step. */
+B200_API int b200_solver_lincomb(int32_t n_in, const float* const* in, int32_t n_out, float* const* out,
+                                 const float* coeff, int64_t numel, void* stream);
+
 /* ---- library-wide ---- */
 B200_API const char* b200_last_error(void);
 /* kernels launched by this library in this process so far */

@@ -172,6 +172,23 @@ int b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const fl
   });
 }
 
+int b200_solver_lincomb(int32_t n_in, const float* const* in, int32_t n_out, float* const* out, const float* coeff,
+                        int64_t numel, void* stream) {
+  return guarded([&] {
+    B2_CHECK(in && out && coeff && numel > 0, "null argument");
+    B2_CHECK(n_in >= 1 && n_in <= b2::LINCOMB_MAX_IN && n_out >= 1 && n_out <= b2::LINCOMB_MAX_OUT,
+             "at most %d inputs and %d outputs", b2::LINCOMB_MAX_IN, b2::LINCOMB_MAX_OUT);
+    b2::LinCombParams p{};
+    p.n_in = n_in; p.n_out = n_out; p.n = numel;
+    for (int k = 0; k < n_in; ++k) p.in[k] = in[k];
+    for (int j = 0; j < n_out; ++j) {
+      p.out[j] = out[j];
+      for (int k = 0; k < n_in; ++k) p.c[j][k] = coeff[j * n_in + k];
+    }
+    b2::launch_lincomb(p, static_cast<cudaStream_t>(stream));
+  });
+}
+
 int b200_profile_enable(int32_t enabled) {
   return guarded([&] { b2::prof_enable(enabled != 0); });
 }

@@ -323,7 +323,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   // ---- embeddings
   launch_patchify(in.x, in.y, cfg.in_dim - in.y_channels, in.y_channels, F, Hl, Wl, B, w.patch, Kp, s);
   {
-    GemmParams p{}; p.M = M; p.N = d; p.K = Kp; p.bias = wt.patch_b; p.out_f = w.x_res; p.ld_f = d;
+    GemmParams p{}; p.w_static = 1; p.M = M; p.N = d; p.K = Kp; p.bias = wt.patch_b; p.out_f = w.x_res; p.ld_f = d;
     gemm_linear(EPI_F32, w.patch, Kp, wt.patch_w, Kp, p, num_sms, s);
   }
   launch_time_embed(in.t, B, cfg.freq_dim, d, wt.time0_w, wt.time0_b, wt.time2_w, wt.time2_b, wt.timep_w, wt.timep_b,
@@ -335,19 +335,19 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   const bool ctx_hit = in.ctx_hit;
   if (!ctx_hit) launch_pad_cast_rows(in.ctx, in.ctx_dtype, in.ctx_rows, B, TL, cfg.text_dim, w.ctx16, s);
   if (!ctx_hit) {
-    GemmParams p{}; p.M = B * TL; p.N = d; p.K = cfg.text_dim; p.bias = wt.text0_b; p.out_h = w.ctx_h; p.ld_h = d;
+    GemmParams p{}; p.w_static = 1; p.M = B * TL; p.N = d; p.K = cfg.text_dim; p.bias = wt.text0_b; p.out_h = w.ctx_h; p.ld_h = d;
     gemm_linear(EPI_GELU_F16, w.ctx16, cfg.text_dim, wt.text0_w, cfg.text_dim, p, num_sms, s);
-    GemmParams q{}; q.M = B * TL; q.N = d; q.K = d; q.bias = wt.text2_b; q.out_h = w.ctx_e; q.ld_h = d;
+    GemmParams q{}; q.w_static = 1; q.M = B * TL; q.N = d; q.K = d; q.bias = wt.text2_b; q.out_h = w.ctx_e; q.ld_h = d;
     gemm_linear(EPI_F16, w.ctx_h, d, wt.text2_w, d, q, num_sms, s);
   }
   const bool img = cfg.i2v && in.has_clip;
   if (img && !ctx_hit) {   // MLPProj (model.py:362-374): LN -> Linear -> GELU(erf) -> Linear -> LN, default eps 1e-5
     const int R = B * 257;
     launch_ln_affine(in.clip_packed, w.clip16, wt.img_ln0_w, wt.img_ln0_b, 0, R, 0, 1280, 1e-5f, s);
-    GemmParams p{}; p.M = R; p.N = 1280; p.K = 1280; p.bias = wt.img_fc1_b; p.out_f = w.clip_f; p.ld_f = 1280;
+    GemmParams p{}; p.w_static = 1; p.M = R; p.N = 1280; p.K = 1280; p.bias = wt.img_fc1_b; p.out_f = w.clip_f; p.ld_f = 1280;
     gemm_linear(EPI_F32, w.clip16, 1280, wt.img_fc1_w, 1280, p, num_sms, s);
     launch_gelu_erf_cast(w.clip_f, w.clip_g, (long long)R * 1280, s);
-    GemmParams q{}; q.M = R; q.N = d; q.K = 1280; q.bias = wt.img_fc3_b; q.out_f = w.img_f; q.ld_f = d;
+    GemmParams q{}; q.w_static = 1; q.M = R; q.N = d; q.K = 1280; q.bias = wt.img_fc3_b; q.out_f = w.img_f; q.ld_f = d;
     gemm_linear(EPI_F32, w.clip_g, 1280, wt.img_fc3_w, 1280, q, num_sms, s);
     launch_ln_affine(w.img_f, w.ctx_img, wt.img_ln4_w, wt.img_ln4_b, 0, R, 0, d, 1e-5f, s);
   }
@@ -381,7 +381,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
     // ---- self-attention (model.py:292-296)
     launch_ln_affine(w.x_res, w.u, mod + d, mod, 6 * d, M, L, d, eps, s);
     {
-      GemmParams p{}; p.M = M; p.N = 3 * d; p.K = d; p.bias = b.qkv_b; p.out_h = w.qk; p.ld_h = 2 * d;
+      GemmParams p{}; p.w_static = 1; p.M = M; p.N = 3 * d; p.K = d; p.bias = b.qkv_b; p.out_h = w.qk; p.ld_h = 2 * d;
       p.ssq = w.ssq; p.ssq_cols = 2 * d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(2 * d, bn_qkv);
       p.vt = w.vt; p.vt_col0 = 2 * d; p.vt_ld = Mp; p.vt_rows = d; p.rows_per_item = L;
       gemm_linear(EPI_QKV, w.u, d, b.qkv_w, d, p, num_sms, s, bn_qkv);
@@ -390,7 +390,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
                     b.norm_k, cs, M, L, eps, s);
     launch_attention(self, s);
     {
-      GemmParams p{}; p.M = M; p.N = d; p.K = d; p.bias = b.o_b; p.out_f = w.x_res; p.ld_f = d;
+      GemmParams p{}; p.w_static = 1; p.M = M; p.N = d; p.K = d; p.bias = b.o_b; p.out_f = w.x_res; p.ld_f = d;
       p.gate = mod + 2 * d; p.gate_stride = 6 * d; p.rows_per_item = L;
       gemm_linear(EPI_RESID_F32, w.att, d, b.o_w, d, p, num_sms, s);
     }
@@ -398,7 +398,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
     // folded into the (cached) keys and the per-row rsqrt(mean(q^2)+eps) into the softmax scale.
     launch_ln_affine(w.x_res, w.u, b.norm3_w, b.norm3_b, 0, M, L, d, eps, s);
     {
-      GemmParams p{}; p.M = M; p.N = d; p.K = d; p.bias = b.cq_b; p.out_h = w.qk; p.ld_h = d;
+      GemmParams p{}; p.w_static = 1; p.M = M; p.N = d; p.K = d; p.bias = b.cq_b; p.out_h = w.qk; p.ld_h = d;
       p.ssq = w.ssq; p.ssq_cols = d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(d, bn_cq); p.vt_col0 = d;
       p.rows_per_item = L;
       gemm_linear(EPI_QKV, w.u, d, b.cq_w, d, p, num_sms, s, bn_cq);
@@ -406,7 +406,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
     __half* kc_l = w.kc + (size_t)l * w.kv_stride;
     __half* vtc_l = w.vtc + (size_t)l * ((size_t)Hn * 128 * B * TL);
     if (!ctx_hit) {
-      GemmParams p{}; p.M = B * TL; p.N = 2 * d; p.K = d; p.bias = b.ckv_b; p.out_h = kc_l; p.ld_h = d;
+      GemmParams p{}; p.w_static = 1; p.M = B * TL; p.N = 2 * d; p.K = d; p.bias = b.ckv_b; p.out_h = kc_l; p.ld_h = d;
       p.ssq = w.ssq_c; p.ssq_cols = d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(d, bn_ckv); p.vt = vtc_l;
       p.vt_col0 = d; p.vt_ld = B * TL; p.vt_rows = d; p.rows_per_item = TL;
       gemm_linear(EPI_QKV, w.ctx_e, d, b.ckv_w, d, p, num_sms, s, bn_ckv);
@@ -419,7 +419,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
       __half* ki_l = w.ki + (size_t)l * w.ki_stride;
       __half* vti_l = w.vti + (size_t)l * w.vti_stride;
       if (!ctx_hit) {
-        GemmParams p{}; p.M = B * 257; p.N = 2 * d; p.K = d; p.bias = b.ckv_img_b; p.out_h = ki_l; p.ld_h = d;
+        GemmParams p{}; p.w_static = 1; p.M = B * 257; p.N = 2 * d; p.K = d; p.bias = b.ckv_img_b; p.out_h = ki_l; p.ld_h = d;
         p.ssq = w.ssq_i; p.ssq_cols = d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(d, bn_img); p.vt = vti_l;
         p.vt_col0 = d; p.vt_ld = (B * 257 + 7) & ~7; p.vt_rows = d; p.rows_per_item = 257;
         gemm_linear(EPI_QKV, w.ctx_img, d, b.ckv_img_w, d, p, num_sms, s, bn_img);
@@ -430,16 +430,16 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
       launch_attention(cimg, s);
     }
     {
-      GemmParams p{}; p.M = M; p.N = d; p.K = d; p.bias = b.co_b; p.out_f = w.x_res; p.ld_f = d;
+      GemmParams p{}; p.w_static = 1; p.M = M; p.N = d; p.K = d; p.bias = b.co_b; p.out_f = w.x_res; p.ld_f = d;
       p.rows_per_item = L;
       gemm_linear(EPI_RESID_F32, w.att, d, b.co_w, d, p, num_sms, s);
     }
     // ---- FFN (model.py:314-328)
     launch_ln_affine(w.x_res, w.u, mod + 4 * d, mod + 3 * d, 6 * d, M, L, d, eps, s);
     {
-      GemmParams p{}; p.M = M; p.N = f; p.K = d; p.bias = b.ffn0_b; p.out_h = w.hid; p.ld_h = f;
+      GemmParams p{}; p.w_static = 1; p.M = M; p.N = f; p.K = d; p.bias = b.ffn0_b; p.out_h = w.hid; p.ld_h = f;
       gemm_linear(EPI_GELU_F16, w.u, d, b.ffn0_w, d, p, num_sms, s);
-      GemmParams q{}; q.M = M; q.N = d; q.K = f; q.bias = b.ffn2_b; q.out_f = w.x_res; q.ld_f = d;
+      GemmParams q{}; q.w_static = 1; q.M = M; q.N = d; q.K = f; q.bias = b.ffn2_b; q.out_f = w.x_res; q.ld_f = d;
       q.gate = mod + 5 * d; q.gate_stride = 6 * d; q.rows_per_item = L;
       gemm_linear(EPI_RESID_F32, w.hid, f, b.ffn2_w, f, q, num_sms, s);
     }
@@ -451,7 +451,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
     const int P = cfg.out_dim * 4;
     launch_head_table(wt.head_mod, w.e, w.headtab, B, d, s);
     launch_ln_affine(w.x_res, w.u3, w.headtab, w.headtab + d, 2 * d, M, L, d, eps, s, /*split=*/true);
-    GemmParams p{}; p.M = M; p.N = P; p.K = 3 * d; p.bias = wt.head_b; p.out_f = w.y; p.ld_f = P;
+    GemmParams p{}; p.w_static = 1; p.M = M; p.N = P; p.K = 3 * d; p.bias = wt.head_b; p.out_f = w.y; p.ld_f = P;
     gemm_linear(EPI_F32, w.u3, 3 * d, wt.head_w3, 3 * d, p, num_sms, s);
     launch_unpatchify(w.y, P, B, F, Hp, Wp, cfg.out_dim, in.out, in.cfg_pairs, in.cfg_scale, s);
   }

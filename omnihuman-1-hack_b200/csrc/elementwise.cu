@@ -341,6 +341,46 @@ __global__ void gelu_erf_cast_kernel(const float* __restrict__ x, __half* __rest
   }
 }
 
+// ------------------------------------------------------------------ solver update (fm_solvers*.py step())
+// out_j = sum_i c[j][i] * in_i : one pass over the latents for the x0 conversion, the UniC corrector and the
+// UniP / DPM++ predictor of one scheduler step (the scalar coefficients are computed on the host).
+__global__ void __launch_bounds__(256) lincomb_kernel(const LinCombParams p) {
+  pdl_launch();
+  pdl_wait();
+  const long long n4 = p.n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc[LINCOMB_MAX_OUT];
+#pragma unroll
+    for (int j = 0; j < LINCOMB_MAX_OUT; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < LINCOMB_MAX_IN; ++k) {
+      if (k < p.n_in) {
+        const float4 v = reinterpret_cast<const float4*>(p.in[k])[i];
+#pragma unroll
+        for (int j = 0; j < LINCOMB_MAX_OUT; ++j) {
+          const float c = p.c[j][k];
+          if (j < p.n_out && c != 0.f) {          // an unused term must not contribute 0 * inf
+            acc[j].x = fmaf(c, v.x, acc[j].x); acc[j].y = fmaf(c, v.y, acc[j].y);
+            acc[j].z = fmaf(c, v.z, acc[j].z); acc[j].w = fmaf(c, v.w, acc[j].w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < LINCOMB_MAX_OUT; ++j)
+      if (j < p.n_out) reinterpret_cast<float4*>(p.out[j])[i] = acc[j];
+  }
+  // tail (n not a multiple of 4)
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    for (int j = 0; j < p.n_out; ++j) {
+      float a = 0.f;
+      for (int k = 0; k < p.n_in; ++k) if (p.c[j][k] != 0.f) a = fmaf(p.c[j][k], p.in[k][i], a);
+      p.out[j][i] = a;
+    }
+  }
+}
+
 inline int grid_for(long long n, int block = 256) {
   long long g = (n + block - 1) / block;
   return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -450,6 +490,17 @@ void launch_unpatchify(const float* y, int ldy, int B, int F, int Hp, int Wp, in
   launch_pdl(unpatchify_kernel, dim3(grid_for((long long)n_out * L * out_dim * 4)), dim3(256), 0, s, y, ldy, L, Hp, Wp, F,
              out_dim, out, n_out, cfg_pairs, cfg_scale);
   B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void launch_lincomb(const LinCombParams& p, cudaStream_t s) {
+  B2_CHECK(p.n_in >= 1 && p.n_in <= LINCOMB_MAX_IN && p.n_out >= 1 && p.n_out <= LINCOMB_MAX_OUT, "lincomb: bad term count");
+  for (int k = 0; k < p.n_in; ++k)
+    B2_CHECK(p.in[k] != nullptr && (reinterpret_cast<uintptr_t>(p.in[k]) & 15) == 0, "lincomb: input %d not 16-byte aligned", k);
+  for (int j = 0; j < p.n_out; ++j)
+    B2_CHECK(p.out[j] != nullptr && (reinterpret_cast<uintptr_t>(p.out[j]) & 15) == 0, "lincomb: output %d not 16-byte aligned", j);
+  ProfScope prof(PC_OTHER, 0.0, 4.0 * p.n * (p.n_in + p.n_out), s);
+  launch_pdl(lincomb_kernel, dim3(grid_for((p.n + 3) / 4)), dim3(256), 0, s, p);
   count_launch();
 }
 

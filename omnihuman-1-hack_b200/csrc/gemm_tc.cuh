@@ -65,6 +65,8 @@ struct GemmParams {
   int sk;                 // K-split factor S of the last (partial) wave's tiles, <= 1: no split
   float* sk_ws;           // [gridDim.x][BLOCK_N][128] fp32 partial accumulators
   int* sk_flags;          // [gridDim.x][8], zero between launches
+  int w_static;           // 1: the W operand is a constant (model weight) that no earlier kernel of the stream writes:
+                          // its first tiles may be requested before the programmatic-dependency wait
   int dbg;                // diagnosis only (B200_GEMM_DBG): 1 = skip the epilogue's global stores, 2 = no operand
                           // loads (MMAs run on whatever is in shared memory), 4 = loads but no MMAs
 };
@@ -206,7 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == WARP_TMA) {
     // ------------------------------------------------------------------ TMA producer
     int pre = 0;                                           // stages whose W tile was requested early
-    if (lane == 0 && !(p.dbg & 2) && !PAIR && !p.cv.enabled) {
+    if (lane == 0 && p.w_static && !(p.dbg & 2) && !PAIR && !p.cv.enabled) {
       TileSched s0(units, num_kb, G, cid, p.sk);
       int unit, kb0, kb1, n_contrib;
       if (s0.next(unit, kb0, kb1, n_contrib)) {

@@ -156,6 +156,17 @@ void launch_transpose_f32(const float* src, float* dst, int rows, int cols, cuda
 void launch_convert(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, cudaStream_t s);
 void launch_gelu_erf_cast(const float* x, __half* out, long long n, cudaStream_t s);
 
+// solver update: out_j = sum_i c[j][i] * in_i over n fp32 elements (outputs may alias inputs elementwise)
+constexpr int LINCOMB_MAX_IN = 6, LINCOMB_MAX_OUT = 3;
+struct LinCombParams {
+  const float* in[LINCOMB_MAX_IN];
+  float* out[LINCOMB_MAX_OUT];
+  float c[LINCOMB_MAX_OUT][LINCOMB_MAX_IN];
+  int n_in, n_out;
+  long long n;
+};
+void launch_lincomb(const LinCombParams& p, cudaStream_t s);
+
 enum DType : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
 
 }  // namespace b2

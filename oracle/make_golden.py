@@ -11,6 +11,9 @@ Fixtures (all small enough to commit; weights stored as fp16 = exactly the value
   dit_block_1p3b.pt outputs only (weights by seed): ONE 1.3B-shaped block + head on [16,1,60,104]
                     (BASELINE.json configs[0]); weights regenerate from make_synthetic_weights(seed)
   vae_tiny.pt       WanVAE_ decoder, dim 8, z [16,3,6,8] -> [3,9,48,64]  (vae.py:544-568)
+  solver_traj.pt    FlowUniPC / FlowDPMSolver++ trajectories (fm_solvers_unipc.py, fm_solvers.py) on a toy
+                    velocity field: per case the timesteps and the latent after every step
+                    (`python oracle/make_golden.py solvers` regenerates only this file)
 """
 import os
 import sys
@@ -36,7 +39,38 @@ def run_ref_dit(M, cfg, sd, x, t, ctx, seq_len, clip=None, y=None):
         return [o.clone() for o in m(x, t, ctx, seq_len=seq_len, clip_fea=clip, y=y)]
 
 
+SOLVER_CASES = [("unipc", 10, 5.0), ("unipc", 50, 5.0), ("unipc", 4, 1.0), ("unipc", 1, 5.0),
+                ("dpm++", 10, 5.0), ("dpm++", 50, 1.0), ("dpm++", 20, 3.0), ("dpm++", 2, 5.0)]
+
+
+def make_solver_golden():
+    """The UNMODIFIED reference schedulers, driven the way text2video.py:204-252 drives them."""
+    from oracle import solver_oracle as SO
+    U, D = ref_loader.load_reference_solvers()
+    x0 = torch.randn(1, 16, 2, 6, 8, generator=torch.Generator().manual_seed(77))
+    cases = []
+    for kind, steps, shift in SOLVER_CASES:
+        if kind == "unipc":
+            s = U.FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+            s.set_timesteps(steps, device="cpu", shift=shift)
+            ts = s.timesteps
+        else:
+            s = D.FlowDPMSolverMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+            ts, _ = D.retrieve_timesteps(s, device="cpu", sigmas=D.get_sampling_sigmas(steps, shift))
+        x, traj = x0.clone(), []
+        for t in ts:
+            x = s.step(SO.toy_velocity(x, t), t, x, return_dict=False)[0]
+            traj.append(x.clone())
+        cases.append(dict(kind=kind, steps=steps, shift=shift, timesteps=ts.clone(), sigmas=s.sigmas.clone(),
+                          traj=torch.stack(traj)))
+        print("solver", kind, steps, shift, float(x.std()))
+    torch.save(dict(x0=x0, cases=cases), os.path.join(OUT, "solver_traj.pt"))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "solvers":
+        return make_solver_golden()
+    make_solver_golden()
     M, V = ref_loader.load_reference_modules()
     os.makedirs(OUT, exist_ok=True)
     g = torch.Generator().manual_seed(1234)

@@ -61,11 +61,35 @@ def _install_stubs():
         mo = types.ModuleType("diffusers.models")
         mu = types.ModuleType("diffusers.models.modeling_utils")
 
-        class ConfigMixin:
-            pass
+        class _Config(dict):
+            __getattr__ = dict.__getitem__
 
-        def register_to_config(f):
-            return f
+        class ConfigMixin:
+            """Minimal stand-in for diffusers' ConfigMixin: `self.config` holds the constructor arguments."""
+
+            def register_to_config(self, **kw):
+                cfg = _Config(getattr(self, "_b200_cfg", {}))
+                cfg.update(kw)
+                object.__setattr__(self, "_b200_cfg", cfg)
+
+            @property
+            def config(self):
+                return self._b200_cfg
+
+        def register_to_config(init):
+            import functools
+            import inspect
+
+            @functools.wraps(init)
+            def inner(self, *args, **kwargs):
+                names = [n for i, n in enumerate(inspect.signature(init).parameters) if i > 0]
+                defaults = {n: p.default for n, p in inspect.signature(init).parameters.items() if n != "self"}
+                vals = dict(defaults)
+                vals.update(dict(zip(names, args)))
+                vals.update(kwargs)
+                self.register_to_config(**vals)
+                init(self, *args, **kwargs)
+            return inner
 
         class ModelMixin(torch.nn.Module):
             pass
@@ -74,8 +98,37 @@ def _install_stubs():
         mu.ModelMixin = ModelMixin
         d.configuration_utils, d.models = cu, mo
         mo.modeling_utils = mu
+        # scheduler-side imports of fm_solvers*.py (:11-16)
+        import enum
+        sch = types.ModuleType("diffusers.schedulers")
+        su = types.ModuleType("diffusers.schedulers.scheduling_utils")
+        ut = types.ModuleType("diffusers.utils")
+        tu = types.ModuleType("diffusers.utils.torch_utils")
+
+        class KarrasDiffusionSchedulers(enum.Enum):
+            DDIMScheduler = 1
+
+        class SchedulerMixin:
+            pass
+
+        class SchedulerOutput:
+            def __init__(self, prev_sample):
+                self.prev_sample = prev_sample
+
+        def randn_tensor(shape, generator=None, device=None, dtype=None, layout=None):
+            return torch.randn(shape, generator=generator, device=device, dtype=dtype)
+
+        su.KarrasDiffusionSchedulers, su.SchedulerMixin, su.SchedulerOutput = KarrasDiffusionSchedulers, SchedulerMixin, SchedulerOutput
+        ut.deprecate = lambda *a, **k: None
+        ut.is_scipy_available = lambda: False
+        tu.randn_tensor = randn_tensor
+        ut.torch_utils = tu
+        sch.scheduling_utils = su
+        d.schedulers, d.utils = sch, ut
         sys.modules.update({"diffusers": d, "diffusers.configuration_utils": cu,
-                            "diffusers.models": mo, "diffusers.models.modeling_utils": mu})
+                            "diffusers.models": mo, "diffusers.models.modeling_utils": mu,
+                            "diffusers.schedulers": sch, "diffusers.schedulers.scheduling_utils": su,
+                            "diffusers.utils": ut, "diffusers.utils.torch_utils": tu})
     if "logger" not in sys.modules:
         lg = types.ModuleType("logger")
         lg.logger = logging.getLogger("ref")
@@ -108,3 +161,23 @@ def load_reference_modules(root=None):
     mods["model"].flash_attention = _masked_attention
     # model.py:503 calls torch.cuda.empty_cache(); harmless without CUDA.
     return mods["model"], mods["vae"]
+
+
+def load_reference_solvers(root=None):
+    """Returns (fm_solvers_unipc module, fm_solvers module) of the reference, executed in place
+    (seaweed_apt/wan/utils/fm_solvers_unipc.py, fm_solvers.py)."""
+    root = root or find_reference()
+    if root is None:
+        raise FileNotFoundError("reference tree not available (container-only tool)")
+    _install_stubs()
+    udir = os.path.join(root, "seaweed_apt/wan/utils")
+    out = []
+    for name in ("fm_solvers_unipc", "fm_solvers"):
+        full = "_refwan_utils_" + name
+        if full not in sys.modules:
+            spec = importlib.util.spec_from_file_location(full, os.path.join(udir, name + ".py"))
+            m = importlib.util.module_from_spec(spec)
+            sys.modules[full] = m
+            spec.loader.exec_module(m)
+        out.append(sys.modules[full])
+    return tuple(out)
