@@ -96,42 +96,10 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def make_device_weights(cfg, seed, device):
-    """Reference init (model.py:590-612; head re-initialised as SURVEY 8c), generated on the GPU in fp16."""
-    import torch
-    g = torch.Generator(device=device).manual_seed(seed)
-    d, f = cfg["dim"], cfg["ffn_dim"]
-
-    def xavier(o, i):
-        a = math.sqrt(6.0 / (i + o))
-        return ((torch.rand(o, i, generator=g, device=device) * 2 - 1) * a).half()
-
-    def normal(*s, std=1.0):
-        return (torch.randn(*s, generator=g, device=device) * std).half()
-
-    sd = {"patch_embedding.weight": xavier(d, cfg["in_dim"] * 4).view(d, cfg["in_dim"], 1, 2, 2),
-          "patch_embedding.bias": normal(d, std=0.02),
-          "text_embedding.0.weight": normal(d, cfg["text_dim"], std=0.02), "text_embedding.0.bias": normal(d, std=0.02),
-          "text_embedding.2.weight": normal(d, d, std=0.02), "text_embedding.2.bias": normal(d, std=0.02),
-          "time_embedding.0.weight": normal(d, cfg["freq_dim"], std=0.02), "time_embedding.0.bias": normal(d, std=0.02),
-          "time_embedding.2.weight": normal(d, d, std=0.02), "time_embedding.2.bias": normal(d, std=0.02),
-          "time_projection.1.weight": xavier(6 * d, d), "time_projection.1.bias": normal(6 * d, std=0.02),
-          "head.modulation": normal(1, 2, d) / math.sqrt(d), "head.head.weight": normal(64, d, std=0.02),
-          "head.head.bias": normal(64, std=0.02)}
-    for i in range(cfg["num_layers"]):
-        p = f"blocks.{i}."
-        sd[p + "modulation"] = normal(1, 6, d) / math.sqrt(d)
-        sd[p + "norm3.weight"] = 1.0 + normal(d, std=0.05)
-        sd[p + "norm3.bias"] = normal(d, std=0.02)
-        for att in ("self_attn", "cross_attn"):
-            for n in "qkvo":
-                sd[p + f"{att}.{n}.weight"] = xavier(d, d)
-                sd[p + f"{att}.{n}.bias"] = normal(d, std=0.02)
-            sd[p + f"{att}.norm_q.weight"] = 1.0 + normal(d, std=0.05)
-            sd[p + f"{att}.norm_k.weight"] = 1.0 + normal(d, std=0.05)
-        sd[p + "ffn.0.weight"] = xavier(f, d); sd[p + "ffn.0.bias"] = normal(f, std=0.02)
-        sd[p + "ffn.2.weight"] = xavier(d, f); sd[p + "ffn.2.bias"] = normal(d, std=0.02)
-    return sd
+def make_device_weights(cfg, seed, device, i2v=False):
+    """Random-init weights of the reference architecture (no checkpoint is reachable offline)."""
+    from b200dit import synthetic
+    return synthetic.dit_weights(cfg, seed, device, i2v=i2v)
 
 
 def cpu_baseline(frames, target_s=12.0):
@@ -379,9 +347,8 @@ def main():
                 if prof["attention"]["ms"] > 0 else None}
 
     if rank == 0:
-        from oracle import dit_oracle as O
         # context work (text embedding, cross k/v projections) runs once per trajectory, not per step
-        flops_step = 2 * S * O.dit_flops(L, layers=cfg["num_layers"], context_cached=True)
+        flops_step = 2 * S * b200dit.flops.dit_forward_flops(L, layers=cfg["num_layers"], context_cached=True)
         burst, sustained, hbm, src = peaks()
         line = {"metric": "DiT denoise-steps/sec (Wan2.1-T2V-1.3B, CFG, 480x832)", "value": value,
                 "unit": "denoise-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,

@@ -373,11 +373,12 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LinCombParams p) {
   // tail (n not a multiple of 4)
   for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < p.n;
        i += (long long)gridDim.x * blockDim.x) {
+    float a[LINCOMB_MAX_OUT];
     for (int j = 0; j < p.n_out; ++j) {
-      float a = 0.f;
-      for (int k = 0; k < p.n_in; ++k) if (p.c[j][k] != 0.f) a = fmaf(p.c[j][k], p.in[k][i], a);
-      p.out[j][i] = a;
+      a[j] = 0.f;
+      for (int k = 0; k < p.n_in; ++k) if (p.c[j][k] != 0.f) a[j] = fmaf(p.c[j][k], p.in[k][i], a[j]);
     }
+    for (int j = 0; j < p.n_out; ++j) p.out[j][i] = a[j];     // all reads before any write: outputs may alias inputs
   }
 }
 

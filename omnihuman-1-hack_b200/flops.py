@@ -1,0 +1,51 @@
+"""Algorithmic FLOP counts of the hot path (2 FLOP per MAC, no padding, no recompute).
+Used by bench.py and the tools to turn measured time into TFLOP/s; tests check them against the oracle's
+independent copies."""
+
+
+def dit_forward_flops(L, Lc=512, dim=1536, ffn=8960, layers=30, text_dim=4096, patch_k=64, freq_dim=256,
+                      context_cached=False, extra_kv_tokens=0):
+    """One WanModel.forward over L tokens (model.py:502-563).  Per block: self q,k,v,o projections 8 L d^2,
+    self attention 4 L^2 d, cross q,o 4 L d^2, cross k,v 4 Lc d^2, cross attention 4 L Lc d, FFN 4 L d f.
+    context_cached leaves out the step-invariant context work (text embedding, cross k/v projections), which
+    is counted once per prompt, not per step.  extra_kv_tokens = 257 adds the i2v second K/V stream."""
+    d = dim
+    ctx_block = 4 * Lc * d * d + 4 * extra_kv_tokens * d * d
+    ctx_other = 2 * Lc * text_dim * d + 2 * Lc * d * d
+    per_block = 8 * L * d * d + 4 * L * L * d + 4 * L * d * d + ctx_block + 4 * L * (Lc + extra_kv_tokens) * d + 4 * L * d * ffn
+    other = 2 * L * patch_k * d * 2 + ctx_other + 2 * d * (freq_dim + d + 6 * d)
+    if context_cached:
+        per_block -= ctx_block
+        other -= ctx_other
+    return layers * per_block + other
+
+
+def vae_decode_flops(T, h=60, w=104, dim=96):
+    """WanVAE decode (vae.py:544-568) as the reference executes it: latent frame 0 alone (its upsample3d stages skip
+    time_conv, vae.py:106-108), then T - 1 frames through the full decoder; conv MACs include causal zero padding."""
+    dims = [dim * u for u in (4, 4, 4, 2, 1)]
+    c0 = dims[0]
+
+    def one_pass(t, first):
+        fl, hh, ww, tt = 0.0, h, w, t
+        fl += 2 * tt * hh * ww * 16 * c0 * 27                                     # conv1
+        fl += 2 * (2 * 2 * tt * hh * ww * c0 * c0 * 27)                           # two middle residual blocks
+        fl += tt * (2 * hh * ww * c0 * 3 * c0 + 2 * hh * ww * c0 * c0 + 4 * (hh * ww) ** 2 * c0)   # middle attention
+        for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+            if i in (1, 2, 3):
+                cin = cin // 2
+            for _ in range(3):
+                fl += 2 * tt * hh * ww * 27 * (cin * cout + cout * cout)
+                if cin != cout:
+                    fl += 2 * tt * hh * ww * cin * cout
+                cin = cout
+            if i != 3:
+                if i < 2 and not first:
+                    fl += 2 * tt * hh * ww * 3 * cout * 2 * cout                  # time_conv
+                    tt *= 2
+                hh, ww = 2 * hh, 2 * ww
+                fl += 2 * tt * hh * ww * 9 * cout * (cout // 2)
+        fl += 2 * tt * hh * ww * 27 * dims[-1] * 3                                # head conv
+        return fl
+
+    return one_pass(1, True) + (one_pass(T - 1, False) if T > 1 else 0.0)

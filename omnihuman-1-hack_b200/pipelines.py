@@ -1,0 +1,93 @@
+"""Caller-side loops of the reference, restated over the B200 engine (SURVEY.md section 8 "next" rows:
+the callers either side of the DiT forward).  Host logic only: every tensor operation is an engine call
+(`DitEngine.forward` / `forward_cfg`, `VaeEngine.decode`) or one fused scheduler launch (solvers.py).
+
+  sample()               WanT2V.generate's denoise loop (seaweed_apt/wan/text2video.py:202-252): cond + uncond
+                         forward, CFG, scheduler.step; with `cfg_anneal=True` the OmniHuman loop's linear CFG
+                         annealing (Omnihuman/omnihuman_wan_t2v.py:395-444: cfg_i = s (1 - i/N) + i/N) and its
+                         DPM++ scheduler (:171-176); `clip_fea` / `y` feed the i2v hooks (model.py:511-512, 534-537)
+                         that stand in for the audio-token and pose-stack streams
+  teacher_student_item() APT stage-1 item (seaweed_apt/generate.py:205-229 + distilled_trainer.py:262-289): teacher
+                         cond + uncond at t = 999, v_teacher = u + 7.5 (c - u), student at t = 1000, MSE
+  generate_video()       sample() + WanVAE.decode (text2video.py:258-259)
+"""
+import torch
+
+from . import parallel
+from .solvers import (FlowDPMSolverMultistepScheduler, FlowUniPCMultistepScheduler, get_sampling_sigmas,
+                      retrieve_timesteps)
+
+
+def make_scheduler(solver, steps, shift, device):
+    """text2video.py:204-221."""
+    if solver == "unipc":
+        sch = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+        sch.set_timesteps(steps, device=device, shift=shift)
+        return sch, sch.timesteps
+    if solver == "dpm++":
+        sch = FlowDPMSolverMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+        ts, _ = retrieve_timesteps(sch, device=device, sigmas=get_sampling_sigmas(steps, shift))
+        return sch, ts
+    raise NotImplementedError("Unsupported solver.")
+
+
+@torch.no_grad()
+def sample(engine, noise, context, context_null, steps=50, shift=5.0, guide_scale=5.0, solver="unipc",
+           seq_len=None, clip_fea=None, y=None, cfg_anneal=False, callback=None):
+    """Denoises `noise` (list of [16,T,h,w] fp32, all the same shape) and returns the list of x0 latents.
+    Every sample carries its own scheduler state; all samples are co-batched in one engine call per step."""
+    xs = [n.to(engine.device, torch.float32) for n in noise]
+    n = len(xs)
+    if seq_len is None:
+        _, T, h, w = xs[0].shape
+        seq_len = T * (h // 2) * (w // 2)                                        # text2video.py:161-164
+    scheds = [make_scheduler(solver, steps, shift, engine.device) for _ in range(n)]
+    ts_host = scheds[0][1].cpu().tolist()                                        # one read per trajectory
+    for i, t in enumerate(ts_host):
+        s = guide_scale * (1.0 - i / len(ts_host)) + 1.0 * (i / len(ts_host)) if cfg_anneal else guide_scale
+        tt = torch.full((n,), float(t), device=engine.device)
+        v = engine.forward_cfg(xs, tt, context, context_null, seq_len, s, clip_fea=clip_fea, y=y)
+        xs = [sch.step(vi.unsqueeze(0), t, xi.unsqueeze(0), return_dict=False)[0].squeeze(0)
+              for (sch, _), xi, vi in zip(scheds, xs, v)]
+        if callback is not None:
+            callback(i, t, xs)
+    return xs
+
+
+@torch.no_grad()
+def teacher_student_item(engine, noise, context, context_null, guide_scale=7.5, t_teacher=999.0, t_student=1000.0,
+                         seq_len=1560, student_engine=None):
+    """One distillation item.  With a single weight replica (teacher == student at step 0,
+    distilled_trainer.py:64) the three forwards run as ONE co-batched call of 3 items."""
+    x = noise.to(engine.device, torch.float32)
+    if student_engine is None or student_engine is engine:
+        t = torch.tensor([t_teacher, t_teacher, t_student], device=engine.device)
+        c, u, s = engine.forward([x, x, x], t, [context, context_null, context], seq_len)
+    else:
+        t = torch.tensor([t_teacher], device=engine.device)
+        v = engine.forward_cfg([x], t, [context], [context_null], seq_len, guide_scale)[0]
+        s = student_engine.forward([x], torch.tensor([t_student], device=engine.device), [context], seq_len)[0]
+        return v, s, torch.mean((s - v) ** 2)
+    v_teacher = u + guide_scale * (c - u)                                        # generate.py:229
+    loss = torch.mean((s - v_teacher) ** 2)                                      # distilled_trainer.py:289
+    return v_teacher, s, loss
+
+
+@torch.no_grad()
+def teacher_student_sweep(engine, noises, contexts, context_null, **kw):
+    """generate.py:209-232 over independent seeds, items sharded i % world == rank, one all_gather of
+    (v_teacher, v_student) and of the losses (default mode)."""
+    idx = parallel.shard_indices(len(noises))
+    vt, vs, ls = [], [], []
+    for i in idx:
+        a, b, l = teacher_student_item(engine, noises[i], contexts[i], context_null, **kw)
+        vt.append(a); vs.append(b); ls.append(l.reshape(1))
+    n = len(noises)
+    return (parallel.gather_items(vt, n), parallel.gather_items(vs, n), parallel.gather_items(ls, n))
+
+
+@torch.no_grad()
+def generate_video(engine, vae, noise, context, context_null, **kw):
+    """Denoise + decode (text2video.py:231-259): returns (latents, list of [3, 1+4(T-1), 8h, 8w] videos)."""
+    x0 = sample(engine, noise, context, context_null, **kw)
+    return x0, vae.decode(x0)

@@ -90,3 +90,15 @@ def test_oracle_vs_live_reference():
     with torch.no_grad():
         pix = vae.decode(z[None], [torch.tensor(VO.VAE_MEAN), 1.0 / torch.tensor(VO.VAE_STD)])[0].clamp(-1, 1)
     assert float((VO.vae_decode(vsd, z) - pix).abs().max()) < 1e-5
+
+
+def test_package_flop_counters_match_oracle():
+    """bench.py / tools use omnihuman-1-hack_b200/flops.py; the oracle keeps independent copies (SURVEY 8d formulas)."""
+    import b200dit
+    from oracle import dit_oracle as O, vae_oracle as VO
+    for L in (1560, 6240, 32760):
+        for cached in (False, True):
+            assert b200dit.flops.dit_forward_flops(L, context_cached=cached) == O.dit_flops(L, context_cached=cached)
+    for T in (1, 2, 21):
+        assert abs(b200dit.flops.vae_decode_flops(T) / VO.vae_decode_flops(T) - 1) < 1e-9
+    assert abs(b200dit.flops.dit_forward_flops(1560) / 4.652e12 - 1) < 1e-3          # SURVEY 8d: 4.652 TFLOP / forward

@@ -7,13 +7,12 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import b200dit
-from oracle import vae_oracle as VO
 
 
 def main():
     Ts = [int(a) for a in sys.argv[1:]] or [1, 5, 21]
     torch.cuda.set_device(0)
-    sd = VO.make_synthetic_vae_weights(dim=96, seed=0)
+    sd = b200dit.synthetic.vae_decoder_weights(dim=96, seed=0)
     eng = b200dit.VaeEngine.from_state_dict(sd)
     for T in Ts:
         z = torch.randn(16, T, 60, 104, generator=torch.Generator().manual_seed(T)).cuda()
@@ -33,7 +32,7 @@ def main():
         torch.cuda.synchronize()
         prof = b200dit.profile_collect()
         b200dit.profile_enable(False)
-        fl = VO.vae_decode_flops(T)
+        fl = b200dit.flops.vae_decode_flops(T)
         frames = 1 + 4 * (T - 1)
         conv = prof["conv"]
         print(json.dumps({"T": T, "frames": frames, "ms": ms, "frames_per_s": frames / (ms / 1e3),

@@ -1,0 +1,103 @@
+"""BASELINE.json configs 3, 4 and 5 at full size on the B200 engine (synthetic weights / inputs of the
+reference's shapes).  One JSON line per config; launch under torchrun for N > 1.
+
+    python tools/run_configs.py 3 [--steps 50]     OmniHuman omni-conditions loop shape on the i2v hooks, T = 21
+    torchrun ... tools/run_configs.py 4            APT stage-1 items sharded over the ranks (2 GPUs in BASELINE)
+    torchrun ... tools/run_configs.py 5            81-frame denoise + WanVAE decode per rank, one gather of latents
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import b200dit  # noqa: E402
+from b200dit import parallel, pipelines as P, synthetic  # noqa: E402
+from bench import CFG_13B, make_device_weights  # noqa: E402
+
+
+def timed(fn):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return out, parallel.max_over_ranks(e0.elapsed_time(e1))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("config", type=int, choices=[3, 4, 5])
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--frames", type=int, default=21)
+    ap.add_argument("--items", type=int, default=16)
+    ap.add_argument("--layers", type=int, default=30)
+    a = ap.parse_args()
+    rank, world = parallel.init()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    g = torch.Generator().manual_seed(1000 + rank)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    cfg = dict(CFG_13B, num_layers=a.layers)
+    T = a.frames
+    L = 1560 * T
+
+    if a.config == 3:
+        cfg3 = dict(cfg, in_dim=32)
+        eng = b200dit.DitEngine(**cfg3, i2v=True, device=dev)
+        eng.load_state_dict(make_device_weights(cfg3, 0, dev, i2v=True))
+        x0, y = rn(16, T, 60, 104).to(dev), rn(16, T, 60, 104).to(dev)
+        ctx, ctx0 = rn(200, 4096).bfloat16().to(dev), rn(120, 4096).bfloat16().to(dev)
+        clip = rn(1, 257, 1280).to(dev)
+        run = lambda n: P.sample(eng, [x0], [ctx], [ctx0], steps=n, shift=1.0, guide_scale=7.5, solver="dpm++",
+                                 cfg_anneal=True, clip_fea=clip, y=[y])
+        run(3)                                                # warm-up: eager + capture + replay
+        out, ms = timed(lambda: run(a.steps))
+        fl = 2 * a.steps * eng.last_flops / 2                 # last_flops counts the co-batched pair
+        line = {"config": 3, "workload": f"i2v-hook DiT (in_dim 32, clip_fea 257 tokens, y stack), latent [16,{T},60,104], "
+                f"{a.steps} DPM++ steps, cfg 7.5 annealed", "n_gpus": world, "ms": ms,
+                "denoise_steps_per_s": a.steps / (ms / 1e3), "tflops": 2 * a.steps * (eng.last_flops / 2) / (ms / 1e3) / 1e12,
+                "finite": bool(torch.isfinite(out[0]).all())}
+    elif a.config == 4:
+        eng = b200dit.DitEngine(**cfg, device=dev)
+        eng.load_state_dict(make_device_weights(cfg, 0, dev))
+        gi = torch.Generator().manual_seed(7)                 # identical items on every rank; each rank runs its share
+        noises = [torch.randn(16, 1, 60, 104, generator=gi).to(dev) for _ in range(a.items)]
+        ctxs = [torch.randn(512, 4096, generator=gi).to(dev) for _ in range(a.items)]
+        ctx0 = torch.randn(512, 4096, generator=gi).to(dev)
+        P.teacher_student_sweep(eng, noises[:2 * world], ctxs[:2 * world], ctx0)     # warm-up
+        (vt, vs, ls), ms = timed(lambda: P.teacher_student_sweep(eng, noises, ctxs, ctx0))
+        line = {"config": 4, "workload": f"{a.items} APT stage-1 items (teacher cond+uncond at t=999, cfg 7.5, student at "
+                f"t=1000, MSE) on [16,1,60,104], 3 forwards co-batched per item, items i % world == rank, one all_gather",
+                "n_gpus": world, "ms": ms, "items_per_s": a.items / (ms / 1e3),
+                "forwards_per_s": 3 * a.items / (ms / 1e3), "mean_loss": float(torch.cat(ls).mean()),
+                "gathered": [len(vt), len(vs)]}
+    else:
+        eng = b200dit.DitEngine(**cfg, device=dev)
+        eng.load_state_dict(make_device_weights(cfg, 0, dev))
+        vae = b200dit.VaeEngine.from_state_dict(synthetic.vae_decoder_weights(dim=96, seed=0), device=dev)
+        x0 = rn(16, T, 60, 104).to(dev)
+        ctx, ctx0 = rn(512, 4096).bfloat16().to(dev), rn(512, 4096).bfloat16().to(dev)
+        P.sample(eng, [x0], [ctx], [ctx0], steps=3)
+        lat, ms_d = timed(lambda: P.sample(eng, [x0], [ctx], [ctx0], steps=a.steps, shift=5.0, guide_scale=5.0))
+        vae.decode([lat[0][:, :2]])
+        vid, ms_v = timed(lambda: vae.decode(lat))
+        allv, ms_g = timed(lambda: parallel.gather_items(lat, world))
+        line = {"config": 5, "workload": f"per rank: {a.steps}-step UniPC CFG denoise of [16,{T},60,104] + WanVAE decode to "
+                f"{list(vid[0].shape)}; one all_gather of the final latents", "n_gpus": world, "denoise_ms": ms_d,
+                "vae_decode_ms": ms_v, "gather_ms": ms_g, "videos_per_s": world / ((ms_d + ms_v + ms_g) / 1e3),
+                "denoise_steps_per_s": world * a.steps / (ms_d / 1e3), "gathered": len(allv),
+                "finite": bool(torch.isfinite(vid[0]).all())}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
