@@ -108,7 +108,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tma_load_2d(smem + OFF_K + st * TILE_BYTES + SUB_BYTES, &tmap_k, &k_full[st], head * 128 + 64, k_row0);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_expect_tx(&v_full[st], TILE_BYTES);
-        const int v_row0 = head * 128, v_col0 = item * p.Lk_rows + j * TILE;   // V^T [heads*128, global key]
+        const int v_row0 = head * 128;                                         // V^T [heads*128, global key]
+        const int v_col0 = item * (p.vt_stride ? p.vt_stride : p.Lk_rows) + j * TILE;
         tma_load_2d(smem + OFF_V + st * TILE_BYTES, &tmap_vt, &v_full[st], v_col0, v_row0);
         tma_load_2d(smem + OFF_V + st * TILE_BYTES + SUB_BYTES, &tmap_vt, &v_full[st], v_col0 + 64, v_row0);
       }
@@ -378,7 +379,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const int j = i - 1, st = j & 1; const uint32_t ph = (j >> 1) & 1;
           mbar_wait(&v_empty[st], ph ^ 1);
           mbar_expect_tx(&v_full[st], V_BYTES);
-          tma_load_2d(smem + OFF_V + st * V_BYTES, &tmap_vt, &v_full[st], item * p.Lk_rows + j * KT, head * 128);
+          tma_load_2d(smem + OFF_V + st * V_BYTES, &tmap_vt, &v_full[st],
+                      item * (p.vt_stride ? p.vt_stride : p.Lk_rows) + j * KT, head * 128);
         }
       }
     }
@@ -564,6 +566,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
 void launch_attention(const AttnParams& p, cudaStream_t stream) {
   B2_CHECK(p.items >= 1 && p.items <= MAX_ITEMS, "attention: %d items (max %d)", p.items, MAX_ITEMS);
+  const int vts = p.vt_stride ? p.vt_stride : p.Lk_rows;
+  B2_CHECK(p.items == 1 || vts % 8 == 0, "attention: V^T item stride %d must be a multiple of 8 (TMA needs 16-byte "
+           "aligned tile origins)", vts);
   for (int i = 0; i < p.items; ++i)
     B2_CHECK(p.klen[i] >= 1 && p.klen[i] <= p.Lk_rows, "attention: item %d has %d valid keys of %d", i, p.klen[i],
              p.Lk_rows);
@@ -578,7 +583,7 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
   const uint64_t dim = (uint64_t)p.heads * 128;
   CUtensorMap tq = make_tmap_2d(p.q, (uint64_t)p.items * p.Lq, dim, p.ldq, 128);
   CUtensorMap tk = make_tmap_2d(p.k, (uint64_t)p.items * p.Lk_rows, dim, p.ldk, use_v1 ? 128 : v2::KT);
-  CUtensorMap tv = make_tmap_2d(p.vt, (uint64_t)p.heads * 128, (uint64_t)p.items * p.Lk_rows, p.ldvt, 128);
+  CUtensorMap tv = make_tmap_2d(p.vt, (uint64_t)p.heads * 128, (uint64_t)p.items * vts, p.ldvt, 128);
   dim3 grid((p.Lq + TILE - 1) / TILE, p.heads, p.items);
   dim3 grid2(((p.Lq + TILE - 1) / TILE) * p.heads * p.items);
   double keys = 0;

@@ -133,18 +133,20 @@ int b200_flash_attention(const void* q, const void* k, const void* v, const int3
     B2_CHECK(q && k && v && out, "null argument");
     B2_CHECK(B >= 1 && B <= b2::MAX_ITEMS && Lq >= 1 && Lk >= 1 && H >= 1, "bad attention shape");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int Lp = (B * Lk + 7) & ~7;                 // V^T [H*128, B*Lk] with the leading dimension padded to 8
+    const int Lkp = (Lk + 7) & ~7;                    // V^T [H*128, B*Lkp]: every item starts at a multiple of 8 columns
+    const int Lp = B * Lkp;
     void* vt = nullptr;
     const size_t bytes = (size_t)H * 128 * Lp * 2;
     B2_CUDA(cudaMallocAsync(&vt, bytes, s));
-    b2::launch_transpose_h(static_cast<const __half*>(v), (long long)H * 128, static_cast<__half*>(vt), Lp, B * Lk,
-                           H * 128, s);
+    for (int b = 0; b < B; ++b)
+      b2::launch_transpose_h(static_cast<const __half*>(v) + (size_t)b * Lk * H * 128, (long long)H * 128,
+                             static_cast<__half*>(vt) + (size_t)b * Lkp, Lp, Lk, H * 128, s, Lkp);
     b2::AttnParams p{};
     p.q = static_cast<const __half*>(q); p.ldq = (long long)H * 128;
     p.k = static_cast<const __half*>(k); p.ldk = (long long)H * 128;
     p.vt = static_cast<const __half*>(vt); p.ldvt = Lp;
     p.out = static_cast<__half*>(out); p.ldo = (long long)H * 128;
-    p.items = B; p.heads = H; p.Lq = Lq; p.Lk_rows = Lk;
+    p.items = B; p.heads = H; p.Lq = Lq; p.Lk_rows = Lk; p.vt_stride = Lkp;
     p.scale = softmax_scale > 0.f ? softmax_scale : 0.08838834764831845f;
     for (int i = 0; i < B; ++i) p.klen[i] = k_lens ? (k_lens[i] < Lk ? k_lens[i] : Lk) : Lk;
     b2::launch_attention(p, s);

@@ -24,6 +24,10 @@
 namespace b2 {
 
 namespace {
+// clip_fea carries 257 image tokens per item (model.py:211-212).  Their K / V rows are kept 264 apart so
+// that every item starts at a 16-byte aligned column of the transposed V (a TMA coordinate constraint);
+// the 7 padding rows hold finite values and are masked by klen = 257.
+constexpr int IMG_TOK = 257, IMG_PAD = 264;
 template <class T>
 T* carve(uint8_t*& p, size_t n) {
   T* r = reinterpret_cast<T*>(p);
@@ -253,8 +257,8 @@ void DitEngine::ensure_workspace(int B, int L) {
   add(nB * d, 4); add(nB * 6 * d, 4); add((size_t)cfg.num_layers * nB * 6 * d, 4); add(nB * (cfg.freq_dim + d), 4);
   add(MAX_ITEMS, 4);
   if (cfg.i2v) {
-    add(nB * 257 * 1280, 2); add(nB * 257 * 1280, 4); add(nB * 257 * 1280, 2); add(nB * 257 * d, 4);
-    add(nB * 257 * d, 2); add(nl * nB * 257 * d, 2); add(nl * nB * Hn * 128 * 264, 2); add(nB * 257 * (d / 32), 4);
+    add(nB * IMG_PAD * 1280, 2); add(nB * IMG_PAD * 1280, 4); add(nB * IMG_PAD * 1280, 2); add(nB * IMG_PAD * d, 4);
+    add(nB * IMG_PAD * d, 2); add(nl * nB * IMG_PAD * d, 2); add(nl * nB * Hn * 128 * IMG_PAD, 2); add(nB * IMG_PAD * (d / 32), 4);
   }
   ws.release();
   ws.ensure(bytes + 4096, /*zero=*/true);       // zero: V^T padding columns must stay finite
@@ -283,15 +287,15 @@ void DitEngine::ensure_workspace(int B, int L) {
   w.tscratch = carve<float>(p, nB * (cfg.freq_dim + d));
   w.t_items = carve<float>(p, MAX_ITEMS);
   if (cfg.i2v) {
-    w.clip16 = carve<__half>(p, nB * 257 * 1280);
-    w.clip_f = carve<float>(p, nB * 257 * 1280);
-    w.clip_g = carve<__half>(p, nB * 257 * 1280);
-    w.img_f = carve<float>(p, nB * 257 * d);
-    w.ctx_img = carve<__half>(p, nB * 257 * d);
-    w.ki = carve<__half>(p, nl * nB * 257 * d);
-    w.vti = carve<__half>(p, nl * nB * Hn * 128 * 264);
-    w.ki_stride = nB * 257 * d; w.vti_stride = nB * Hn * 128 * 264;
-    w.ssq_i = carve<float>(p, nB * 257 * (d / 32));
+    w.clip16 = carve<__half>(p, nB * IMG_PAD * 1280);
+    w.clip_f = carve<float>(p, nB * IMG_PAD * 1280);
+    w.clip_g = carve<__half>(p, nB * IMG_PAD * 1280);
+    w.img_f = carve<float>(p, nB * IMG_PAD * d);
+    w.ctx_img = carve<__half>(p, nB * IMG_PAD * d);
+    w.ki = carve<__half>(p, nl * nB * IMG_PAD * d);
+    w.vti = carve<__half>(p, nl * nB * Hn * 128 * IMG_PAD);
+    w.ki_stride = nB * IMG_PAD * d; w.vti_stride = nB * Hn * 128 * IMG_PAD;
+    w.ssq_i = carve<float>(p, nB * IMG_PAD * (d / 32));
   }
   ws_B = nB; ws_L = nL;
   cached_token = 0;                                   // the cached K/V lived in the old workspace
@@ -304,7 +308,7 @@ double DitEngine::flops(int B, int L) const {
   const double d = cfg.dim, f = cfg.ffn_dim, Lc = cfg.text_len;
   double per_block = 8.0 * L * d * d + 4.0 * L * L * d + 4.0 * L * d * d + 4.0 * Lc * d * d + 4.0 * L * Lc * d +
                      4.0 * L * d * f;
-  if (cfg.i2v) per_block += 4.0 * L * 257 * d + 4.0 * 257 * d * d;
+  if (cfg.i2v) per_block += 4.0 * L * IMG_TOK * d + 4.0 * IMG_TOK * d * d;
   double other = 2.0 * L * (cfg.in_dim * 4.0) * d + 2.0 * L * (cfg.out_dim * 4.0) * d + 2.0 * Lc * cfg.text_dim * d +
                  2.0 * Lc * d * d + 2.0 * d * (cfg.freq_dim + d + 6 * d);
   return B * (cfg.num_layers * per_block + other);
@@ -342,7 +346,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   }
   const bool img = cfg.i2v && in.has_clip;
   if (img && !ctx_hit) {   // MLPProj (model.py:362-374): LN -> Linear -> GELU(erf) -> Linear -> LN, default eps 1e-5
-    const int R = B * 257;
+    const int R = B * IMG_PAD;
     launch_ln_affine(in.clip_packed, w.clip16, wt.img_ln0_w, wt.img_ln0_b, 0, R, 0, 1280, 1e-5f, s);
     GemmParams p{}; p.w_static = 1; p.M = R; p.N = 1280; p.K = 1280; p.bias = wt.img_fc1_b; p.out_f = w.clip_f; p.ld_f = 1280;
     gemm_linear(EPI_F32, w.clip16, 1280, wt.img_fc1_w, 1280, p, num_sms, s);
@@ -361,16 +365,16 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   cross.ldq = d; cross.k = w.kc; cross.ldk = d; cross.vt = w.vtc; cross.ldvt = B * TL; cross.Lk_rows = TL;
   cross.q_dim = d; cross.q_eps = eps;
   for (int i = 0; i < B; ++i) {
-    int kl = in.ctx_rows[i] + (img ? 257 : 0);      // model.py:531,537 (+ App. A.12 clamp)
+    int kl = in.ctx_rows[i] + (img ? IMG_TOK : 0);      // model.py:531,537 (+ App. A.12 clamp)
     cross.klen[i] = kl < TL ? kl : TL;
   }
   AttnParams cimg = cross;
-  cimg.k = w.ki; cimg.vt = w.vti; cimg.ldvt = (B * 257 + 7) & ~7; cimg.Lk_rows = 257; cimg.accumulate = 1;
-  for (int i = 0; i < B; ++i) cimg.klen[i] = 257;
+  cimg.k = w.ki; cimg.vt = w.vti; cimg.ldvt = B * IMG_PAD; cimg.Lk_rows = IMG_PAD; cimg.accumulate = 1;
+  for (int i = 0; i < B; ++i) cimg.klen[i] = IMG_TOK;
 
   // tile widths (the QKV-style epilogues route columns per chunk, so tiles may straddle the q | k | v boundaries)
   const int bn_qkv = pick_bn(M, 3 * d, num_sms, d), bn_cq = pick_bn(M, d, num_sms, d);
-  const int bn_ckv = pick_bn(B * TL, 2 * d, num_sms, d), bn_img = pick_bn(B * 257, 2 * d, num_sms, d);
+  const int bn_ckv = pick_bn(B * TL, 2 * d, num_sms, d), bn_img = pick_bn(B * IMG_PAD, 2 * d, num_sms, d);
   auto ssq_tiles = [](int cols, int bn) { return (cols + bn - 1) / bn; };
   cross.q_ssq = w.ssq; cross.q_ssq_ld = 4 * ssq_tiles(d, bn_cq); cross.q_ssq_n = 2 * ssq_tiles(d, bn_cq);
   cimg.q_ssq = cross.q_ssq; cimg.q_ssq_ld = cross.q_ssq_ld; cimg.q_ssq_n = cross.q_ssq_n; cimg.q_dim = d; cimg.q_eps = eps;
@@ -419,12 +423,12 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
       __half* ki_l = w.ki + (size_t)l * w.ki_stride;
       __half* vti_l = w.vti + (size_t)l * w.vti_stride;
       if (!ctx_hit) {
-        GemmParams p{}; p.w_static = 1; p.M = B * 257; p.N = 2 * d; p.K = d; p.bias = b.ckv_img_b; p.out_h = ki_l; p.ld_h = d;
+        GemmParams p{}; p.w_static = 1; p.M = B * IMG_PAD; p.N = 2 * d; p.K = d; p.bias = b.ckv_img_b; p.out_h = ki_l; p.ld_h = d;
         p.ssq = w.ssq_i; p.ssq_cols = d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(d, bn_img); p.vt = vti_l;
-        p.vt_col0 = d; p.vt_ld = (B * 257 + 7) & ~7; p.vt_rows = d; p.rows_per_item = 257;
+        p.vt_col0 = d; p.vt_ld = B * IMG_PAD; p.vt_rows = d; p.rows_per_item = IMG_PAD;
         gemm_linear(EPI_QKV, w.ctx_img, d, b.ckv_img_w, d, p, num_sms, s, bn_img);
         launch_rms_rope(ki_l, d, d, 1, w.ssq_i, 4 * ssq_tiles(d, bn_img), 2 * ssq_tiles(d, bn_img), b.cnorm_k_img,
-                        nullptr, nullptr, B * 257, 257, eps, s, b.cnorm_q);
+                        nullptr, nullptr, B * IMG_PAD, IMG_PAD, eps, s, b.cnorm_q);
       }
       cimg.k = ki_l; cimg.vt = vti_l;
       launch_attention(cimg, s);
@@ -470,7 +474,7 @@ void DitEngine::ensure_static_io(int B, int F, int H, int W) {
   sio_item_out = need_out > sio_item_out ? need_out : sio_item_out;
   sio_item_ctx = (size_t)cfg.text_len * cfg.text_dim * 4;
   size_t bytes = padded(nB * sio_item_x * 4) * 2 + padded(nB * sio_item_ctx) + padded(nB * sio_item_out * 4) +
-                 padded((size_t)nB * 257 * 1280 * 4) + 4096;
+                 padded((size_t)nB * IMG_PAD * 1280 * 4) + 4096;
   sio.release();
   sio.ensure(bytes, true);
   uint8_t* p = sio.as<uint8_t>();
@@ -478,7 +482,7 @@ void DitEngine::ensure_static_io(int B, int F, int H, int W) {
   s_y = carve<float>(p, nB * sio_item_x);
   s_ctx = carve<uint8_t>(p, nB * sio_item_ctx);
   s_out = carve<float>(p, nB * sio_item_out);
-  s_clip = carve<float>(p, (size_t)nB * 257 * 1280);
+  s_clip = carve<float>(p, (size_t)nB * IMG_PAD * 1280);
   s_scale = carve<float>(p, 64);
   sio_B = nB;
 }
@@ -494,6 +498,8 @@ void DitEngine::forward(int n, const float* const* x, const float* const* y, int
            H, W);
   const int Hp = H / 2, Wp = W / 2, L = F * Hp * Wp;
   B2_CHECK(seq_len <= 0 || L <= seq_len, "Max seq len %d exceeds limit %d", L, seq_len);           // model.py:521
+  B2_CHECK(B == 1 || L % 8 == 0, "co-batching needs a token count that is a multiple of 8 (got %d): every item must "
+           "start at a 16-byte aligned column of the transposed V; call once per item instead", L);
   B2_CHECK(y_channels >= 0 && y_channels < cfg.in_dim && (y_channels == 0 || y != nullptr), "bad y_channels %d",
            y_channels);
   B2_CHECK(clip == nullptr || cfg.i2v, "clip_fea given but the engine was not created with i2v=1");
@@ -515,7 +521,7 @@ void DitEngine::forward(int n, const float* const* x, const float* const* y, int
   B2_CUDA(cudaMemcpyAsync(s_scale, &guide_scale, sizeof(float), cudaMemcpyHostToDevice, stream));
   if (clip != nullptr)
     for (int i = 0; i < B; ++i)
-      B2_CUDA(cudaMemcpyAsync(s_clip + (size_t)i * 257 * 1280, clip[i % n], (size_t)257 * 1280 * 4,
+      B2_CUDA(cudaMemcpyAsync(s_clip + (size_t)i * IMG_PAD * 1280, clip[i % n], (size_t)IMG_TOK * 1280 * 4,
                               cudaMemcpyDeviceToDevice, stream));
 
   FwdInputs in;

@@ -52,7 +52,9 @@ void launch_vae_upsample(const float* x, __half* out, int T, int H, int W, int C
 void launch_vae_softmax(const float* sc, long long ld_in, __half* out, long long ld_out, int R, int n, float scale,
                         cudaStream_t s);
 // fp16 [R, C] (leading dimension ld) -> fp16 [C, ldo] transposed
-void launch_transpose_h(const __half* in, long long ld, __half* out, long long ldo, int R, int C, cudaStream_t s);
+// (columns [R, write_cols) of every output row are zero-filled; write_cols = 0 means ldo)
+void launch_transpose_h(const __half* in, long long ld, __half* out, long long ldo, int R, int C, cudaStream_t s,
+                        int write_cols = 0);
 // fp32 [T, HW, 3] -> clamp(-1,1) -> out[c, t0 + t, hw] of a [3, T_total, HW] tensor    (vae.py:661)
 void launch_vae_store_rgb(const float* x, float* out, int T, long long HW, int t0, int T_total, cudaStream_t s);
 // conv weight [Cout, Cin, taps] (any float dtype staged as fp32) -> fp16 [Cout, taps, cpad], zero padded
@@ -108,6 +110,7 @@ struct AttnParams {
   int items, heads;
   int Lq;                              // query rows per item
   int Lk_rows;                         // key rows per item in the k buffer
+  int vt_stride;                       // columns per item in V^T (0 = Lk_rows); item starts must be multiples of 8
   int klen[MAX_ITEMS];                 // valid keys per item (<= Lk_rows)
   float scale;                         // 1/sqrt(head_dim)
   int accumulate;                      // 1: out += result (fp16 add; i2v second K/V stream)

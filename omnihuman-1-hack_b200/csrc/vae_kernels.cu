@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) vae_softmax_kernel(const float* __restric
 }
 
 __global__ void transpose_h_kernel(const __half* __restrict__ in, long long ld, __half* __restrict__ out, long long ldo,
-                                   int R, int C) {
+                                   int R, int C, int write_cols) {
   __shared__ __half tile[32][33];
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -135,7 +135,7 @@ __global__ void transpose_h_kernel(const __half* __restrict__ in, long long ld, 
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int c = c0 + i, r = r0 + tx;
-    if (c < C && r < ldo) out[(long long)c * ldo + r] = tile[tx][i];
+    if (c < C && r < write_cols) out[(long long)c * ldo + r] = tile[tx][i];
   }
 }
 
@@ -205,8 +205,11 @@ void launch_vae_softmax(const float* sc, long long ld_in, __half* out, long long
   count_launch();
 }
 
-void launch_transpose_h(const __half* in, long long ld, __half* out, long long ldo, int R, int C, cudaStream_t s) {
-  transpose_h_kernel<<<dim3((unsigned)((ldo + 31) / 32), (C + 31) / 32), 256, 0, s>>>(in, ld, out, ldo, R, C);
+void launch_transpose_h(const __half* in, long long ld, __half* out, long long ldo, int R, int C, cudaStream_t s,
+                        int write_cols) {
+  if (write_cols <= 0) write_cols = (int)ldo;
+  transpose_h_kernel<<<dim3((unsigned)((write_cols + 31) / 32), (C + 31) / 32), 256, 0, s>>>(in, ld, out, ldo, R, C,
+                                                                                          write_cols);
   B2_CUDA(cudaGetLastError());
   count_launch();
 }

@@ -141,11 +141,14 @@ class DitEngine:
         groups = {}
         for i, u in enumerate(xs):
             groups.setdefault(tuple(u.shape[1:]), []).append(i)
-        n_calls = sum((len(idx) + _lib.MAX_ITEMS - 1) // _lib.MAX_ITEMS for idx in groups.values())
+        # items are co-batched per latent grid; a token count that is not a multiple of 8 cannot be co-batched
+        # (every item must start at a 16-byte aligned column of the transposed V) and runs one item per call
+        chunk = lambda F, H, W: _lib.MAX_ITEMS if (F * (H // 2) * (W // 2)) % 8 == 0 else 1
+        n_calls = sum((len(idx) + chunk(*g) - 1) // chunk(*g) for g, idx in groups.items())
         with torch.cuda.device(self.device):
             for (F, H, W), idx in groups.items():
-                for s in range(0, len(idx), _lib.MAX_ITEMS):
-                    part = idx[s:s + _lib.MAX_ITEMS]
+                for s in range(0, len(idx), chunk(F, H, W)):
+                    part = idx[s:s + chunk(F, H, W)]
                     self._context_hint(n_calls, context, clip_fea)
                     o = [torch.empty((self.cfg["out_dim"], F, H, W), dtype=torch.float32, device=self.device)
                          for _ in part]
@@ -179,6 +182,13 @@ class DitEngine:
         groups = {}
         for i, u in enumerate(xs):
             groups.setdefault(tuple(u.shape[1:]), []).append(i)
+        if any((F * (H // 2) * (W // 2)) % 8 != 0 for (F, H, W) in groups):
+            # token counts that cannot be co-batched: two plain forwards and the combine as one fused launch
+            from .solvers import _lincomb
+            c = self.forward(xs, tt, ctx, seq_len, clip_fea=clips, y=ys)
+            u = self.forward(xs, tt, ctx_n, seq_len, clip_fea=clips, y=ys)
+            g = float(guide_scale)
+            return [_lincomb([ci, ui], [[g, 1.0 - g]], ci)[0] for ci, ui in zip(c, u)]
         half = _lib.MAX_ITEMS // 2
         n_calls = sum((len(idx) + half - 1) // half for idx in groups.values())
         with torch.cuda.device(self.device):

@@ -1,6 +1,6 @@
 """Algorithmic FLOP counts of the hot path (2 FLOP per MAC, no padding, no recompute).
-Used by bench.py and the tools to turn measured time into TFLOP/s; tests check them against the oracle's
-independent copies."""
+Used by bench.py and the tools to turn measured time into TFLOP/s; the test suite keeps independent copies
+and checks the two against each other."""
 
 
 def dit_forward_flops(L, Lc=512, dim=1536, ffn=8960, layers=30, text_dim=4096, patch_k=64, freq_dim=256,

@@ -137,3 +137,22 @@ def test_context_cache_reuse_and_invalidation():
     out3 = eng.forward(g["x"], g["t"], ctx, g["seq_len"])
     for a, b in zip(out2, out3):
         assert rel_l2(a.cpu(), b.cpu()) < 1e-6
+
+
+def test_token_count_not_multiple_of_8():
+    """L = 15 tokens (grid 1x3x5) cannot be co-batched (TMA tile origins); the host side runs one item per call and
+    the CFG path falls back to two forwards + one fused combine -- results must not change."""
+    import b200dit
+    from oracle import dit_oracle as O
+    g = _load("dit_t2v_tiny.pt")
+    sd = {k: v.float() for k, v in g["sd"].items()}
+    eng = b200dit.DitEngine.from_state_dict(sd, num_heads=g["cfg"]["num_heads"])
+    x1, c1, t1 = g["x"][1], g["context"][1], g["t"][1:]
+    assert x1.shape[1] * (x1.shape[2] // 2) * (x1.shape[3] // 2) == 15
+    out = eng.forward([x1, x1], torch.cat([t1, t1]), [c1, c1], g["seq_len"])
+    for o in out:
+        assert rel_l2(o.cpu(), g["out"][1]) < TOL
+    c0 = g["context"][0]
+    cfg = eng.forward_cfg([x1], t1, [c1], [c0], g["seq_len"], 3.0)[0]
+    ru = O.dit_forward(sd, [x1], t1, [c0], g["seq_len"], num_heads=g["cfg"]["num_heads"])[0]
+    assert rel_l2(cfg.cpu(), O.cfg_combine(g["out"][1], ru, 3.0)) < 3 * TOL

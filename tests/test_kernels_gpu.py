@@ -54,6 +54,7 @@ def test_linear_f16_epilogues(epi, bn):
 @pytest.mark.parametrize("B,Lq,Lk,H,klens", [
     (1, 128, 128, 1, None), (1, 256, 256, 2, None), (1, 1560, 1560, 12, None), (2, 300, 512, 3, [77, 512]),
     (1, 200, 257, 2, None), (2, 1560, 512, 12, [512, 1]), (1, 130, 1000, 1, [999]),
+    (2, 200, 257, 2, [257, 100]), (3, 70, 15, 1, None),      # odd key counts: every item's V^T starts on a multiple of 8
 ])
 def test_flash_attention(B, Lq, Lk, H, klens):
     import b200dit
