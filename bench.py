@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """Headline benchmark: DiT denoise-steps/sec, Wan2.1-T2V-1.3B, 480x832 latent [16,1,60,104]
 (BASELINE.json configs[1]): one step = cond forward + uncond forward + CFG combine + UniPC solver step
-(the reference's default sampler, text2video.py:204-252: 50 steps, shift 5.0, guide 5.0) for one sample; every rank (GPU) denoises its own independent sample(s) (weak scaling), one NCCL
-all_gather of the final latents closes the timed region.
+(the reference's default sampler, text2video.py:204-252: 50 steps, shift 5.0, guide 5.0) per sample; every rank (GPU) denoises its own independent samples (weak scaling; default 2 per GPU, run as
+four co-batched items -- samples never interact, model.py:515-527 -- so every GEMM sees 6240 token rows; the
+single-sample rate is reported beside it as `single_sample`), one NCCL all_gather of the final latents closes
+the timed region.
 
     python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--samples-per-gpu S] [--frames T]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
@@ -175,7 +177,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--samples-per-gpu", type=int, default=1)
+    ap.add_argument("--samples-per-gpu", type=int, default=2,
+                    help="independent samples denoised together on each GPU (default 2: cond+uncond of two samples = "
+                         "four co-batched items, 6240 token rows per GEMM -- the north-star's block shape)")
     ap.add_argument("--frames", type=int, default=1, help="latent frames T (1 = configs[1]; 21 = 81-frame video)")
     ap.add_argument("--layers", type=int, default=CFG_13B["num_layers"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -346,6 +350,33 @@ def main():
                 "attention_tflops": (prof["attention"]["flops"] / (prof["attention"]["ms"] / 1e3) / 1e12)
                 if prof["attention"]["ms"] > 0 else None}
 
+    single = None
+    if rank == 0 and S > 1:
+        # the same step for ONE sample per GPU (latency-oriented use: M = 3120 token rows per GEMM)
+        x1, c1, c01 = lat[:1], ctx[:1], ctx0[:1]
+        t1 = [t[:1].contiguous() for t in t_dev]
+
+        def step_one(i, x, sc):
+            v = eng.forward_cfg(x, t1[i], c1, c01, L, GUIDE)
+            return [sc.step(v[0].unsqueeze(0), ts_host[i], x[0].unsqueeze(0), return_dict=False)[0].squeeze(0)]
+
+        for rep in range(2):
+            sc = new_schedulers()[0]
+            xx = x1
+            n1 = min(K, NUM_STEPS)
+            if rep == 1:
+                torch.cuda.synchronize()
+                e0.record()
+            for i in range(n1 if rep == 1 else W):
+                xx = step_one(i, xx, sc)
+            if rep == 1:
+                e1.record()
+                torch.cuda.synchronize()
+                ms1 = e0.elapsed_time(e1) / n1
+                single = {"value": 1e3 / ms1, "unit": "denoise-steps/s", "ms_per_step": ms1, "samples_per_gpu": 1,
+                          "step_tflops": 2 * b200dit.flops.dit_forward_flops(L, layers=cfg["num_layers"],
+                                                                               context_cached=True) / (ms1 / 1e3) / 1e12}
+
     if rank == 0:
         # context work (text embedding, cross k/v projections) runs once per trajectory, not per step
         flops_step = 2 * S * b200dit.flops.dit_forward_flops(L, layers=cfg["num_layers"], context_cached=True)
@@ -361,7 +392,7 @@ def main():
                 "gpu_launches": int(launches),
                 "step_tflops": flops_step / (ms_step / 1e3) / 1e12,
                 "step_frac_of_peak": flops_step / (ms_step / 1e3) / 1e12 / sustained,
-                "roofline": roof}
+                "roofline": roof, "single_sample": single}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"], _ = cpu_baseline(T)
         elif world > 1:

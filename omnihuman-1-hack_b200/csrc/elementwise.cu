@@ -80,52 +80,66 @@ struct RmsRopeParams {
   int M, rows_per_item; float eps;
 };
 
-// one warp per (row, slice): 16-byte pieces strided across the lanes, 8 warps per block
+// One warp per row, both slices (q and k share the token's rotation).  Lane l owns the 16-byte pieces
+// l, l + 32, ... of each slice: their column modulo 128 is the same, so one (cos, sin) fetch per row serves
+// every piece of every head; all pieces of a row are loaded before the first is stored (PIECES is a
+// compile-time count so the loop unrolls and the loads overlap).
+template <int PIECES>
 __global__ void __launch_bounds__(256) rms_rope_kernel(const RmsRopeParams p, int nslices) {
   const int lane = threadIdx.x & 31;
-  const long long unit = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   pdl_launch();
-  if (unit >= (long long)p.M * nslices) return;
+  if (row >= p.M) return;
   pdl_wait();
-  const int row = (int)(unit / nslices), slice = (int)(unit % nslices);
-  float part = 0.f;
-  for (int i = lane; i < p.ssq_n; i += 32) part += p.ssq[(long long)row * p.ssq_ld + i * 2 + slice];
-  const float tot = warp_sum(part);                      // fixed order: deterministic
-  const float inv = rsqrtf(tot / (float)p.dim + p.eps);
-  __half* xr = p.x + (long long)row * p.ld + (long long)slice * p.dim;
-  const float* g = p.gamma[slice];
-  const float* gm = slice == 0 ? p.gamma_mul : nullptr;
-  const int tok = row % p.rows_per_item;
-  for (int ci = lane; ci < p.dim / 8; ci += 32) {
-    const int col = ci * 8;
-    uint4 raw = *reinterpret_cast<const uint4*>(xr + col);
-    const __half2* h = reinterpret_cast<const __half2*>(&raw);
-    float4 g0 = __ldg(reinterpret_cast<const float4*>(g + col));
-    float4 g1 = __ldg(reinterpret_cast<const float4*>(g + col + 4));
-    if (gm != nullptr) {
-      const float4 m0 = __ldg(reinterpret_cast<const float4*>(gm + col));
-      const float4 m1 = __ldg(reinterpret_cast<const float4*>(gm + col + 4));
-      g0.x *= m0.x; g0.y *= m0.y; g0.z *= m0.z; g0.w *= m0.w;
-      g1.x *= m1.x; g1.y *= m1.y; g1.z *= m1.z; g1.w *= m1.w;
+  const int tok = (int)(row % p.rows_per_item);
+  float4 c01 = make_float4(1.f, 0.f, 1.f, 0.f), c23 = c01;
+  if (p.cs != nullptr) {
+    const int j0 = ((lane * 8) & 127) >> 1;              // first complex pair of this lane's pieces within a head
+    const float4* cs4 = reinterpret_cast<const float4*>(p.cs + (long long)tok * 64 + j0);
+    c01 = __ldg(cs4); c23 = __ldg(cs4 + 1);
+  }
+  for (int slice = 0; slice < nslices; ++slice) {
+    float part = 0.f;
+    for (int i = lane; i < p.ssq_n; i += 32) part += p.ssq[row * p.ssq_ld + i * 2 + slice];
+    const float inv = rsqrtf(warp_sum(part) / (float)p.dim + p.eps);      // fixed order: deterministic
+    __half* xr = p.x + row * p.ld + (long long)slice * p.dim;
+    const float* g = p.gamma[slice];
+    const float* gm = slice == 0 ? p.gamma_mul : nullptr;
+    uint4 raw[PIECES];
+#pragma unroll
+    for (int it = 0; it < PIECES; ++it) {
+      const int col = (lane + 32 * it) * 8;
+      if (col < p.dim) raw[it] = *reinterpret_cast<const uint4*>(xr + col);
     }
-    float v[8];
-    float2 f;
-    f = __half22float2(h[0]); v[0] = f.x * inv * g0.x; v[1] = f.y * inv * g0.y;
-    f = __half22float2(h[1]); v[2] = f.x * inv * g0.z; v[3] = f.y * inv * g0.w;
-    f = __half22float2(h[2]); v[4] = f.x * inv * g1.x; v[5] = f.y * inv * g1.y;
-    f = __half22float2(h[3]); v[6] = f.x * inv * g1.z; v[7] = f.y * inv * g1.w;
-    if (p.cs != nullptr) {
-      const int j0 = (col & 127) >> 1;                 // first complex pair of this chunk within its head
-      const float4* cs4 = reinterpret_cast<const float4*>(p.cs + (long long)tok * 64 + j0);
-      const float4 c01 = __ldg(cs4), c23 = __ldg(cs4 + 1);
-      float a, b;
-      a = v[0]; b = v[1]; v[0] = a * c01.x - b * c01.y; v[1] = a * c01.y + b * c01.x;
-      a = v[2]; b = v[3]; v[2] = a * c01.z - b * c01.w; v[3] = a * c01.w + b * c01.z;
-      a = v[4]; b = v[5]; v[4] = a * c23.x - b * c23.y; v[5] = a * c23.y + b * c23.x;
-      a = v[6]; b = v[7]; v[6] = a * c23.z - b * c23.w; v[7] = a * c23.w + b * c23.z;
+#pragma unroll
+    for (int it = 0; it < PIECES; ++it) {
+      const int col = (lane + 32 * it) * 8;
+      if (col >= p.dim) break;
+      const __half2* h = reinterpret_cast<const __half2*>(&raw[it]);
+      float4 g0 = __ldg(reinterpret_cast<const float4*>(g + col));
+      float4 g1 = __ldg(reinterpret_cast<const float4*>(g + col + 4));
+      if (gm != nullptr) {
+        const float4 m0 = __ldg(reinterpret_cast<const float4*>(gm + col));
+        const float4 m1 = __ldg(reinterpret_cast<const float4*>(gm + col + 4));
+        g0.x *= m0.x; g0.y *= m0.y; g0.z *= m0.z; g0.w *= m0.w;
+        g1.x *= m1.x; g1.y *= m1.y; g1.z *= m1.z; g1.w *= m1.w;
+      }
+      float v[8];
+      float2 f;
+      f = __half22float2(h[0]); v[0] = f.x * inv * g0.x; v[1] = f.y * inv * g0.y;
+      f = __half22float2(h[1]); v[2] = f.x * inv * g0.z; v[3] = f.y * inv * g0.w;
+      f = __half22float2(h[2]); v[4] = f.x * inv * g1.x; v[5] = f.y * inv * g1.y;
+      f = __half22float2(h[3]); v[6] = f.x * inv * g1.z; v[7] = f.y * inv * g1.w;
+      if (p.cs != nullptr) {
+        float a, b;
+        a = v[0]; b = v[1]; v[0] = a * c01.x - b * c01.y; v[1] = a * c01.y + b * c01.x;
+        a = v[2]; b = v[3]; v[2] = a * c01.z - b * c01.w; v[3] = a * c01.w + b * c01.z;
+        a = v[4]; b = v[5]; v[4] = a * c23.x - b * c23.y; v[5] = a * c23.y + b * c23.x;
+        a = v[6]; b = v[7]; v[6] = a * c23.z - b * c23.w; v[7] = a * c23.w + b * c23.z;
+      }
+      *reinterpret_cast<uint4*>(xr + col) =
+          make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
     }
-    *reinterpret_cast<uint4*>(xr + col) =
-        make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
   }
 }
 
@@ -418,7 +432,13 @@ void launch_rms_rope(__half* x, long long ld, int dim, int nslices, const float*
   p.cs = reinterpret_cast<const float2*>(cs_table);
   p.M = M; p.rows_per_item = rows_per_item; p.eps = eps;
   ProfScope prof(PC_NORM, 0.0, 4.0 * M * dim * nslices, s);
-  launch_pdl(rms_rope_kernel, dim3((unsigned)(((long long)M * nslices + 7) / 8)), dim3(256), 0, s, p, nslices);
+  B2_CHECK(dim % 8 == 0 && dim <= 256 * 16, "RMSNorm width %d not supported", dim);
+  const dim3 grid((unsigned)((M + 7) / 8));
+  const int pieces = (dim / 8 + 31) / 32;
+  if (pieces <= 1) launch_pdl(rms_rope_kernel<1>, grid, dim3(256), 0, s, p, nslices);
+  else if (pieces <= 2) launch_pdl(rms_rope_kernel<2>, grid, dim3(256), 0, s, p, nslices);
+  else if (pieces <= 6) launch_pdl(rms_rope_kernel<6>, grid, dim3(256), 0, s, p, nslices);
+  else launch_pdl(rms_rope_kernel<16>, grid, dim3(256), 0, s, p, nslices);
   B2_CUDA(cudaGetLastError());
   count_launch();
 }
