@@ -339,10 +339,20 @@ def main():
         gm = prof["gemm"]
         tot_ms = sum(p["ms"] for p in prof.values())
         ach = gm["flops"] / (gm["ms"] / 1e3) / 1e12 if gm["ms"] > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 128xN tiles, fused epilogues)",
+        # DRAM traffic per launch of the same kernel family from the committed `ncu --set full` capture
+        # (profiles/r1_ncu_traffic.json: one capture per GEMM shape of a block at M = 6240), averaged with the
+        # per-block launch mix qkv x1, o / cross-q / cross-o x3, ffn.0 x1, ffn.2 x1
+        traffic, tsrc = None, None
+        tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+        if os.path.isfile(tp) and S == 2 and T == 1:
+            tj = json.load(open(tp))
+            mb = lambda key: sum(v["dram_read_mb"] + v["dram_write_mb"] for k, v in tj.items() if k.startswith(key))
+            traffic = 1e6 * (mb("qkv") + 3 * mb("o-shaped") + mb("ffn.0") + mb("ffn.2")) / 6.0
+            tsrc = "profiles/r1_ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 128xN / 256xN tiles, fused epilogues)",
                 "achieved": ach, "peak": sustained, "peak_burst": burst, "unit": "TFLOP/s", "frac": ach / sustained,
                 "frac_of_burst": ach / burst, "peak_source": src + " (sustained: kernel timed inside a long step)",
-                "traffic": None, "launches_per_step": gm["launches"] // 2,
+                "traffic": traffic, "traffic_source": tsrc, "launches_per_step": gm["launches"] // 2,
                 "avg_launch_us": 1e3 * gm["ms"] / max(gm["launches"], 1),
                 "flops_per_launch": gm["flops"] / max(gm["launches"], 1),
                 "share_of_step": gm["ms"] / tot_ms if tot_ms else None,

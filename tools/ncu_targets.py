@@ -11,7 +11,7 @@ import torch  # noqa: E402
 import b200dit  # noqa: E402
 
 torch.manual_seed(0)
-M = 3120
+M = int(os.environ.get("TARGET_M", "6240"))           # 6240 = cond + uncond of two [16,1,60,104] samples (bench default)
 which = sys.argv[1:] or ["gemm", "attn"]
 if "gemm" in which:
     for (N, K, epi) in [(8960, 1536, "gelu"), (1536, 8960, "f32"), (1536, 1536, "f32"), (4608, 1536, "f16")]:
@@ -21,8 +21,9 @@ if "gemm" in which:
         for _ in range(2):
             b200dit.linear(a, w, bias, epi)
         torch.cuda.synchronize()
+        print(f"gemm M={M} N={N} K={K} epi={epi}", flush=True)
 if "attn" in which:
-    for (B, Lq, Lk) in [(2, 1560, 1560), (2, 1560, 512)]:
+    for (B, Lq, Lk) in [(M // 1560, 1560, 1560), (M // 1560, 1560, 512)]:
         q = torch.randn(B, Lq, 12, 128, device="cuda").half()
         k = torch.randn(B, Lk, 12, 128, device="cuda").half()
         v = torch.randn(B, Lk, 12, 128, device="cuda").half()
