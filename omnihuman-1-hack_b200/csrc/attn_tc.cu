@@ -314,6 +314,14 @@ constexpr int OFF_BAR = OFF_V + VSTAGES * V_BYTES;
 constexpr int SMEM = OFF_BAR + 256;         // 114 944 B: two CTAs per SM
 constexpr int W_TMA = 4, W_MMA = 5;
 
+// One lane polls, the warp follows: 32 lanes (x 4 warps) spinning on one mbarrier word and 128 separate arrivals
+// per step measurably stretched the softmax <-> MMA hand-offs (the MMA pipeline alone, with idle softmax warps,
+// took 85 % of the kernel time before this change).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
@@ -347,7 +355,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
     }
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 4);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -391,36 +399,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     auto issue_qk = [&](int i) {
       const int st = i % KSTAGES; const uint32_t kph = (i / KSTAGES) & 1;
       const int sb = i & 1; const uint32_t sph = (i >> 1) & 1;
-      mbar_wait(&k_full[st], kph);
-      mbar_wait(&s_empty[sb], sph ^ 1);
-      tc_fence_after();
       if (lane == 0) {
+        mbar_wait(&k_full[st], kph);
+        mbar_wait(&s_empty[sb], sph ^ 1);
+        tc_fence_after();
         const uint32_t sk = smem_u32(smem + OFF_K + st * K_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
+        for (int kk = 0; kk < 8; ++kk) {
+          if (p.dbg & 16) break;                             // diagnosis: no Q.K^T MMAs
           umma_f16(tmem_base + sb * KT, umma_desc_sw128(sq + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32),
                    umma_desc_sw128(sk + (kk >> 2) * KSUB + (kk & 3) * 32), idesc_qk, kk > 0);
+        }
         umma_commit(&k_empty[st]);
         umma_commit(&s_full[sb]);
       }
       __syncwarp();
     };
-    mbar_wait(q_full, 0);
+    mbar_wait_warp(q_full, 0, lane);
     issue_qk(0);
     for (int j = 0; j < n_kv; ++j) {
       // S_{j+1} overwrites the buffer that held S_{j-1} / P_{j-1}: issued after P.V of step j-1 (program
       // order; the tensor pipe executes in issue order), and only once the softmax has read S_{j-1}
       if (j + 1 < n_kv) issue_qk(j + 1);
       const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
-      mbar_wait(&v_full[st], ph);
-      mbar_wait(p_full, j & 1);
-      tc_fence_after();
       if (lane == 0) {
+        mbar_wait(&v_full[st], ph);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
         const uint32_t sv = smem_u32(smem + OFF_V + st * V_BYTES);
         const uint32_t tp = tmem_base + st * KT;          // P_j: fp16 pairs in the first 32 columns of S_j's buffer
 #pragma unroll
-        for (int kk = 0; kk < KT / 16; ++kk)
+        for (int kk = 0; kk < KT / 16; ++kk) {
+          if (p.dbg & 32) break;                             // diagnosis: no P.V MMAs
           umma_f16_ts(tmem_o, tp + kk * 8, umma_desc_sw128(sv + kk * 32), idesc_pv, (j > 0 || kk > 0));
+        }
         umma_commit(&v_empty[st]);
         umma_commit(pv_done);
       }
@@ -431,29 +443,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int r = warp * 32 + lane;
     const uint32_t lane_sel = uint32_t(warp * 32) << 16;
     const int q_in_item = qt * QT + r;
-    if (qt * QT + warp * 32 >= p.Lq) {
+    if (qt * QT + warp * 32 >= p.Lq || (p.dbg & 8)) {       // (diagnosis bit 3: every softmax warp idles)
       // a warp whose 32 rows lie beyond the item's last query only keeps the barrier protocol going
       // (its P rows stay whatever they were: they only reach O rows that are never stored)
       for (int j = 0; j < n_kv; ++j) {
         const int sb = j & 1; const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&s_full[sb], ph);
-        if (lane == 0) mbar_arrive(&s_empty[sb]);
         // stay within one phase of pv_done (mbarrier waits are parity based) and never arrive into a P
         // phase that is still open: P.V of step j-1 done implies p_full phase j-1 completed
-        if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
-        mbar_arrive(p_full);
+        if (lane == 0) {
+          mbar_wait(&s_full[sb], ph);
+          mbar_arrive(&s_empty[sb]);
+          if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
+          mbar_arrive(p_full);
+        }
+        __syncwarp();
       }
-      mbar_wait(pv_done, (n_kv - 1) & 1);
+      mbar_wait_warp(pv_done, (n_kv - 1) & 1, lane);
     } else {
     const float c = p.scale * 1.4426950408889634f * q_row_scale(p, item, q_in_item);
     float m_ref = -INFINITY, l_sum = 0.f;
 
     for (int j = 0; j < n_kv; ++j) {
       const int sb = j & 1; const uint32_t ph = (j >> 1) & 1;
-      mbar_wait(&s_full[sb], ph);
+      mbar_wait_warp(&s_full[sb], ph, lane);
       tc_fence_after();
       float s[KT];
-      {
+      if (p.dbg & 2) {                                      // diagnosis: no TMEM reads of S
+#pragma unroll
+        for (int i = 0; i < KT; ++i) s[i] = 0.01f * (float)(i + j);
+      } else {
         uint32_t t0[32], t1[32];
         tmem_ld32(tmem_base + lane_sel + sb * KT, t0);
         tmem_ld32(tmem_base + lane_sel + sb * KT + 32, t1);
@@ -492,18 +510,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       uint32_t pk[KT / 2];
 #pragma unroll
       for (int i = 0; i < KT; i += 2) {
-        const float p0 = ex2(fmaf(s[i], c, -mc)), p1 = ex2(fmaf(s[i + 1], c, -mc));
+        float p0 = fmaf(s[i], c, -mc), p1 = fmaf(s[i + 1], c, -mc);
+        if (!(p.dbg & 1)) { p0 = ex2(p0); p1 = ex2(p1); }   // diagnosis bit 0: no MUFU
         ps0 += p0; ps1 += p1;
         pk[i >> 1] = pack_h2(p0, p1);
       }
       l_sum += ps0 + ps1;
 
       // P_j replaces the first half of this thread's own S_j row (nobody else touches that TMEM lane)
-      tmem_st32(tmem_base + lane_sel + sb * KT, pk);
+      if (!(p.dbg & 4)) tmem_st32(tmem_base + lane_sel + sb * KT, pk);
       if (j > 0) {
         // every step (not only when rescaling): mbarrier waits are parity based, so a waiter must never be
         // more than one phase away from pv_done; it also guarantees that p_full phase j-1 has completed
-        mbar_wait(pv_done, (j - 1) & 1);                    // O stable: every earlier P.V has completed
+        mbar_wait_warp(pv_done, (j - 1) & 1, lane);         // O stable: every earlier P.V has completed
         if (__any_sync(0xffffffffu, rescale)) {
           tc_fence_after();
 #pragma unroll
@@ -520,11 +539,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[sb]);             // S_j fully read by this warp
-      mbar_arrive(p_full);
+      if (lane == 0) {
+        mbar_arrive(&s_empty[sb]);                          // S_j fully read, P_j fully written by this warp
+        mbar_arrive(p_full);
+      }
     }
 
-    mbar_wait(pv_done, (n_kv - 1) & 1);
+    mbar_wait_warp(pv_done, (n_kv - 1) & 1, lane);
     tc_fence_after();
     const float inv_l = 1.0f / l_sum;
     __half* o = p.out + ((long long)item * p.Lq + q_in_item) * p.ldo + head * 128;
@@ -573,6 +594,7 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
     B2_CHECK(p.klen[i] >= 1 && p.klen[i] <= p.Lk_rows, "attention: item %d has %d valid keys of %d", i, p.klen[i],
              p.Lk_rows);
   static const bool use_v1 = std::getenv("B200_ATTN_V1") != nullptr && std::atoi(std::getenv("B200_ATTN_V1")) != 0;
+  static const int dbg = std::getenv("B200_ATTN_DBG") ? std::atoi(std::getenv("B200_ATTN_DBG")) : 0;
   static bool configured = false;
   if (!configured) {
     B2_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM));
@@ -589,8 +611,10 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
   double keys = 0;
   for (int i = 0; i < p.items; ++i) keys += p.klen[i];
   ProfScope prof(PC_ATTN, 4.0 * p.Lq * keys * 128.0 * p.heads, 0.0, stream);
-  if (use_v1) launch_pdl(attn_fwd_kernel, grid, dim3(320), ATTN_SMEM, stream, tq, tk, tv, p);
-  else launch_pdl(v2::attn_fwd_kernel, grid2, dim3(192), v2::SMEM, stream, tq, tk, tv, p);
+  AttnParams pd = p;
+  pd.dbg = dbg;
+  if (use_v1) launch_pdl(attn_fwd_kernel, grid, dim3(320), ATTN_SMEM, stream, tq, tk, tv, pd);
+  else launch_pdl(v2::attn_fwd_kernel, grid2, dim3(192), v2::SMEM, stream, tq, tk, tv, pd);
   count_launch();
 }
 

@@ -117,6 +117,8 @@ struct AttnParams {
   // optional per-row logit factor rsqrt(mean(q^2) + eps) (query RMSNorm folded into the softmax scale):
   // row sum of squares = sum over i < q_ssq_n of q_ssq[row*q_ssq_ld + 2i]  (the producing GEMM's partials)
   const float* q_ssq; int q_ssq_ld; int q_ssq_n; int q_dim; float q_eps;
+  int dbg;                             // diagnosis only (B200_ATTN_DBG): 1 no exp2, 2 no TMEM reads of S, 4 no P store,
+                                       // 8 softmax warps idle (MMA / TMA pipeline alone); results are wrong
 };
 void launch_attention(const AttnParams& p, cudaStream_t stream);
 
