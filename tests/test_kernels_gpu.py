@@ -55,6 +55,8 @@ def test_linear_f16_epilogues(epi, bn):
     (1, 128, 128, 1, None), (1, 256, 256, 2, None), (1, 1560, 1560, 12, None), (2, 300, 512, 3, [77, 512]),
     (1, 200, 257, 2, None), (2, 1560, 512, 12, [512, 1]), (1, 130, 1000, 1, [999]),
     (2, 200, 257, 2, [257, 100]), (3, 70, 15, 1, None),      # odd key counts: every item's V^T starts on a multiple of 8
+    # >= 1024 keys: the two-tiles-per-CTA kernel (ragged key counts, a lone last tile, partial second tile)
+    (2, 300, 1104, 2, [1104, 1030]), (1, 200, 1560, 1, None), (1, 128, 1152, 1, None), (1, 640, 1280, 3, [1025]),
 ])
 def test_flash_attention(B, Lq, Lk, H, klens):
     import b200dit
