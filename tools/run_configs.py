@@ -85,7 +85,7 @@ def main():
         ctx, ctx0 = rn(512, 4096).bfloat16().to(dev), rn(512, 4096).bfloat16().to(dev)
         P.sample(eng, [x0], [ctx], [ctx0], steps=3)
         lat, ms_d = timed(lambda: P.sample(eng, [x0], [ctx], [ctx0], steps=a.steps, shift=5.0, guide_scale=5.0))
-        vae.decode([lat[0][:, :2]])
+        vae.decode(lat)                                       # warm-up at full size (workspaces grow on first sight)
         vid, ms_v = timed(lambda: vae.decode(lat))
         allv, ms_g = timed(lambda: parallel.gather_items(lat, world))
         line = {"config": 5, "workload": f"per rank: {a.steps}-step UniPC CFG denoise of [16,{T},60,104] + WanVAE decode to "
