@@ -117,13 +117,20 @@ B200_API int b200dit_set_graphs(b200dit_engine* e, int32_t enabled);
 /* WanVAE.__init__ -> _video_vae (vae.py:592-616): decoder of width `dim` (96), z_dim 16. */
 B200_API int b200vae_create(int32_t dim, int32_t z_dim, b200vae_engine** out);
 B200_API void b200vae_destroy(b200vae_engine* e);
-/* state_dict entries `conv2.*` and `decoder.*` (encoder keys are accepted and ignored). */
+/* state_dict entries `conv2.*` and `decoder.*`; `conv1.*` and `encoder.*` enable b200vae_encode. */
 B200_API int b200vae_load_weight(b200vae_engine* e, const char* name, const void* data, int32_t dtype, int32_t ndim,
                         const int64_t* shape);
 B200_API int b200vae_finalize(b200vae_engine* e);
 /* WanVAE.decode for one latent (vae.py:657-663 -> 544-568): z fp32 [z_dim, T, h, w] (device) ->
  * out fp32 [3, 1 + 4 (T-1), 8h, 8w], clamped to [-1, 1]. */
 B200_API int b200vae_decode(b200vae_engine* e, const float* z, int32_t T, int32_t h, int32_t w, float* out, void* stream);
+
+/* WanVAE.encode for one video (vae.py:641-655 -> 516-542, Encoder3d :265-366): video fp32 [3, T, H, W] in [-1, 1]
+ * (device), T = 1 + 4k frames, H and W multiples of 8 -> out fp32 [z_dim, 1 + k, H/8, W/8]: the posterior mean,
+ * normalised with the latent mean / std.  Needs the `encoder.*` and `conv1.*` state_dict entries (decode-only
+ * users may omit them). */
+B200_API int b200vae_encode(b200vae_engine* e, const float* video, int32_t T, int32_t H, int32_t W, float* out,
+                            void* stream);
 
 /* ---- operator seam (attention.py:24-130) and its GEMM sibling, exposed for unit parity tests,
  *      micro-benchmarks and for patching `wan.modules.model.flash_attention` directly ---- */

@@ -127,6 +127,13 @@ int b200vae_decode(b200vae_engine* e, const float* z, int32_t T, int32_t h, int3
   });
 }
 
+int b200vae_encode(b200vae_engine* e, const float* video, int32_t T, int32_t H, int32_t W, float* out, void* stream) {
+  return guarded([&] {
+    B2_CHECK(e && video && out, "null argument");
+    e->impl.encode(video, T, H, W, out, static_cast<cudaStream_t>(stream));
+  });
+}
+
 int b200_flash_attention(const void* q, const void* k, const void* v, const int32_t* k_lens, int32_t B, int32_t Lq,
                          int32_t Lk, int32_t H, float softmax_scale, void* out, void* stream) {
   return guarded([&] {

@@ -80,12 +80,14 @@ void gemm_linear(int epi, const __half* A, long long lda, const __half* W, long 
 //   w    [Cout, taps * cpad] K index = ((dt*kh + dh)*kw + dw) * cpad + c,  cpad = ceil(Cin/64)*64
 //   out  pixel-major [T, H, W, ld] through the epilogue selected by `epi`
 void conv_gemm(int epi, const __half* in, int Tbuf, int H, int W, int Cin, const __half* w, int Cout, int kt, int kh,
-               int kw, int T_out, GemmParams p, int num_sms, cudaStream_t stream) {
+               int kw, int T_out, GemmParams p, int num_sms, cudaStream_t stream, int pad_h, int pad_w) {
   B2_CHECK(Cin % 8 == 0, "conv input channels %d must be a multiple of 8 (TMA stride)", Cin);
   B2_CHECK(Tbuf == T_out + kt - 1, "conv buffer has %d frames, expected %d", Tbuf, T_out + kt - 1);
   ConvGeom& g = p.cv;
   g.enabled = 1; g.T = T_out; g.H = H; g.W = W; g.kt = kt; g.kh = kh; g.kw = kw;
-  g.cblocks = (Cin + 63) / 64; g.pad_h = kh / 2; g.pad_w = kw / 2;
+  g.cblocks = (Cin + 63) / 64;
+  g.pad_h = pad_h >= 0 ? pad_h : kh / 2;               // default: "same" padding; taps past the far edge read TMA zero fill
+  g.pad_w = pad_w >= 0 ? pad_w : kw / 2;
   // pick the 128-pixel tile shape that wastes the fewest pixels
   long long best = -1;
   for (int tw = 128; tw >= 8; tw >>= 1) {

@@ -35,7 +35,7 @@ int gemm_cluster_size(int block_n, long long M, long long N, long long K, int nu
 void gemm_linear(int epi, const __half* A, long long lda, const __half* W, long long ldw, GemmParams p, int num_sms,
                  cudaStream_t stream, int force_bn = 0);
 void conv_gemm(int epi, const __half* in, int Tbuf, int H, int W, int Cin, const __half* w, int Cout, int kt, int kh,
-               int kw, int T_out, GemmParams p, int num_sms, cudaStream_t stream);
+               int kw, int T_out, GemmParams p, int num_sms, cudaStream_t stream, int pad_h = -1, int pad_w = -1);
 
 // ---- vae_kernels.cu : HBM-bound passes of the VAE decode (channels-last volumes [T, H, W, C])
 // z fp32 [C, T, h, w] -> (z * std + mean) -> fp16 [T*h*w, C]               (vae.py:547-551)
@@ -59,6 +59,18 @@ void launch_transpose_h(const __half* in, long long ld, __half* out, long long l
 void launch_vae_store_rgb(const float* x, float* out, int T, long long HW, int t0, int T_total, cudaStream_t s);
 // conv weight [Cout, Cin, taps] (any float dtype staged as fp32) -> fp16 [Cout, taps, cpad], zero padded
 void launch_repack_conv_weight(const float* src, __half* dst, int Cout, int Cin, int taps, int cpad, cudaStream_t s);
+// ---- encoder side (vae.py:265-366, 516-542)
+// video fp32 [3, T_total, H, W] frames [t0, t0 + Tc) -> fp16 [Tc, H, W, 8] (channels 3..7 zero: TMA rows are 16 bytes)
+void launch_vae_prep_video(const float* video, __half* out, int T_total, int t0, int Tc, long long HW, cudaStream_t s);
+// space-to-depth for the stride-2 downsample conv (vae.py:93-99): fp32 [T, H, W, C] -> fp16 [T, H/2, W/2, 4C],
+// channel (ph*2 + pw)*C + c holds pixel (2h + ph, 2w + pw); the 3x3 stride-2 conv with (0,1,0,1) zero padding then
+// is a 2x2 stride-1 conv over this volume (weights repacked by launch_repack_down_weight, the absent taps zero)
+void launch_vae_s2d(const float* x, __half* out, int T, int H, int W, int C, cudaStream_t s);
+// Conv2d weight [Cout, Cin, 3, 3] (fp32 staged) -> fp16 [Cout, 4 taps (oh, ow), cpad >= 4 Cin]
+void launch_repack_down_weight(const float* src, __half* dst, int Cout, int Cin, int cpad, cudaStream_t s);
+// mu = first zdim of the 2*zdim channels: fp32 [T, HW, 2 zdim] -> ((x - mean) / std) -> out[c, t0 + t, hw]  (vae.py:533-539)
+void launch_vae_store_mu(const float* x, const float* mean, const float* stdv, float* out, int zdim, int T, long long HW,
+                         int t0, int T_total, cudaStream_t s);
 
 // Tile width: the instantiated width with the fewest (waves x tile cost) on this problem.  Widths need
 // not divide N (TMA clips the last tile).  The main loop is paced by shared-memory bandwidth (TMA fill +

@@ -1,5 +1,5 @@
-// WanVAE decode (seaweed_apt/wan/modules/vae.py:544-568, Decoder3d :369-472) on the tcgen05
-// implicit-GEMM convolution path.
+// WanVAE decode (seaweed_apt/wan/modules/vae.py:544-568, Decoder3d :369-472) and encode (:516-542,
+// Encoder3d :265-366) on the tcgen05 implicit-GEMM convolution path.
 //
 // Layout: every activation is a channels-last volume [T, H, W, C]; the residual stream is fp32, the
 // operand of each convolution (RMS_norm+SiLU output, or a plain cast) is fp16.  A causal 3x3x3
@@ -18,9 +18,11 @@ namespace {
 struct ConvW {
   std::unique_ptr<DevBuf> w, b;
   int cin = 0, cout = 0, kt = 1, kh = 1, kw = 1, cpad = 0;
+  int cin_act = 0;          // channels of the activation volume the conv reads (>= cin: conv1 of the encoder reads 8)
+  bool s2d = false;         // stride-2 Conv2d run as a 2x2 conv over the space-to-depth volume (4 cin channels)
   bool w_loaded = false, b_loaded = false;
 };
-struct PlanItem { int kind; int cin, cout; };   // kind 0 res, 1 up3d, 2 up2d
+struct PlanItem { int kind; int cin, cout; };   // kind 0 res, 1 up3d / down3d, 2 up2d / down2d
 const float kMean[16] = {-0.7571f, -0.7089f, -0.9113f, 0.1075f, -0.1745f, 0.9653f, -0.1517f, 1.5508f,
                          0.4134f, -0.0715f, 0.5517f, -0.3632f, -0.1922f, -0.9497f, 0.2503f, -0.2921f};   // vae.py:629-632
 const float kStd[16] = {2.8184f, 1.4541f, 2.3275f, 2.6558f, 1.2196f, 1.7708f, 2.6052f, 2.0743f,
@@ -30,7 +32,8 @@ const float kStd[16] = {2.8184f, 1.4541f, 2.3275f, 2.6558f, 1.2196f, 1.7708f, 2.
 struct VaeEngine::Impl {
   int dim, zdim, c0, num_sms = 148;
   int chunk_frames = 4;
-  std::vector<PlanItem> plan;
+  std::vector<PlanItem> plan, eplan;
+  bool has_encoder = false;
   std::unordered_map<std::string, ConvW> convs;
   std::unordered_map<std::string, std::unique_ptr<DevBuf>> gammas;
   std::unordered_map<std::string, bool> gamma_loaded;
@@ -39,11 +42,13 @@ struct VaeEngine::Impl {
   bool finalized = false;
   cudaStream_t s = nullptr;
 
-  void add_conv(const std::string& name, int cin, int cout, int kt, int kh, int kw) {
+  void add_conv(const std::string& name, int cin, int cout, int kt, int kh, int kw, bool s2d = false) {
     ConvW c;
-    c.cin = cin; c.cout = cout; c.kt = kt; c.kh = kh; c.kw = kw;
-    const int taps = kt * kh * kw;
-    c.cpad = taps == 1 ? cin : ((cin + 63) / 64) * 64;
+    c.cin = cin; c.cout = cout; c.kt = kt; c.kh = kh; c.kw = kw; c.s2d = s2d;
+    c.cin_act = s2d ? 4 * cin : ((cin + 7) / 8) * 8;
+    if (s2d) { c.kh = 2; c.kw = 2; }
+    const int taps = c.kt * c.kh * c.kw;
+    c.cpad = taps == 1 ? cin : ((c.cin_act + 63) / 64) * 64;
     c.w = std::make_unique<DevBuf>(); c.b = std::make_unique<DevBuf>();
     c.w->ensure((size_t)cout * taps * c.cpad * 2, true);
     c.b->ensure((size_t)cout * 4, true);
@@ -99,8 +104,41 @@ struct VaeEngine::Impl {
     B2_CUDA(cudaMemcpy(consts.as<float>() + 16, kStd, 16 * 4, cudaMemcpyHostToDevice));
   }
 
+  // Encoder3d plan (vae.py:283-314): dims [d,d,2d,4d,4d], 2 res blocks per stage, down2d, down3d, down3d;
+  // registered on the first encoder weight so that decode-only users need not load the encoder
+  void enable_encoder() {
+    if (has_encoder) return;
+    has_encoder = true;
+    const int dims[5] = {dim, dim, dim * 2, dim * 4, dim * 4};
+    for (int i = 0; i < 4; ++i) {
+      int cin = dims[i];
+      const int cout = dims[i + 1];
+      for (int r = 0; r < 2; ++r) { eplan.push_back({0, cin, cout}); cin = cout; }
+      if (i != 3) eplan.push_back({i == 0 ? 2 : 1, cout, cout});
+    }
+    add_conv("conv1", 2 * zdim, 2 * zdim, 1, 1, 1);
+    add_conv("encoder.conv1", 3, dim, 3, 3, 3);
+    for (size_t i = 0; i < eplan.size(); ++i) {
+      const std::string p = "encoder.downsamples." + std::to_string(i) + ".";
+      if (eplan[i].kind == 0) add_res(p, eplan[i].cin, eplan[i].cout);
+      else {
+        add_conv(p + "resample.1", eplan[i].cin, eplan[i].cout, 1, 3, 3, /*s2d=*/true);
+        if (eplan[i].kind == 1) add_conv(p + "time_conv", eplan[i].cin, eplan[i].cout, 3, 1, 1);
+      }
+    }
+    add_res("encoder.middle.0.", c0, c0);
+    add_gamma("encoder.middle.1.norm.gamma", c0);
+    add_conv("encoder.middle.1.to_qkv", c0, 3 * c0, 1, 1, 1);
+    add_conv("encoder.middle.1.proj", c0, c0, 1, 1, 1);
+    add_res("encoder.middle.2.", c0, c0);
+    add_gamma("encoder.head.0.gamma", c0);
+    add_conv("encoder.head.2", c0, 2 * zdim, 3, 3, 3);
+    finalized = false;
+  }
+
   void load(const char* name, const void* data, int dtype, int ndim, const int64_t* shape) {
     std::string n(name);
+    if (n.compare(0, 8, "encoder.") == 0 || n.compare(0, 6, "conv1.") == 0) enable_encoder();
     long long numel = 1;
     for (int i = 0; i < ndim; ++i) numel *= shape[i];
     const size_t esz = dtype == DT_F32 ? 4 : 2;
@@ -135,11 +173,12 @@ struct VaeEngine::Impl {
       B2_CUDA(cudaMemcpy(cw.b->p, tmp.p, numel * 4, cudaMemcpyDeviceToDevice));
       cw.b_loaded = true;
     } else {
-      const int taps = cw.kt * cw.kh * cw.kw;
+      const int taps = cw.s2d ? 9 : cw.kt * cw.kh * cw.kw;
       B2_CHECK(numel == (long long)cw.cout * cw.cin * taps, "weight %s has %lld elements, expected %lld", name, numel,
                (long long)cw.cout * cw.cin * taps);
       stage_f32(tmp);
-      launch_repack_conv_weight(tmp.as<float>(), cw.w->as<__half>(), cw.cout, cw.cin, taps, cw.cpad, 0);
+      if (cw.s2d) launch_repack_down_weight(tmp.as<float>(), cw.w->as<__half>(), cw.cout, cw.cin, cw.cpad, 0);
+      else launch_repack_conv_weight(tmp.as<float>(), cw.w->as<__half>(), cw.cout, cw.cin, taps, cw.cpad, 0);
       B2_CUDA(cudaDeviceSynchronize());
       cw.w_loaded = true;
     }
@@ -185,8 +224,8 @@ struct VaeEngine::Impl {
     const ConvW& c = convs.at(name);
     GemmParams p{};
     p.bias = c.b->as<float>(); p.out_f = out; p.ld_f = (c.cout + 3) & ~3;      // TMA rows are 16-byte multiples
-    conv_gemm(accumulate ? EPI_RESID_F32 : EPI_F32, in, Tc + c.kt - 1, H, W, c.cin, c.w->as<__half>(), c.cout, c.kt,
-              c.kh, c.kw, Tc, p, num_sms, s);
+    conv_gemm(accumulate ? EPI_RESID_F32 : EPI_F32, in, Tc + c.kt - 1, H, W, c.cin_act, c.w->as<__half>(), c.cout, c.kt,
+              c.kh, c.kw, Tc, p, num_sms, s, c.s2d ? 0 : -1, c.s2d ? 0 : -1);
   }
   void linear_1x1(const std::string& name, const __half* in, long long rows, int epi, void* out, bool accumulate) {
     const ConvW& c = convs.at(name);
@@ -272,6 +311,109 @@ struct VaeEngine::Impl {
     return oi;
   }
 
+
+  // Resample downsample2d / downsample3d (vae.py:93-99,138-160): stride-2 Conv2d with (0,1,0,1) zero padding as a
+  // 2x2 conv over the space-to-depth volume; downsample3d then runs a stride-2 temporal conv over
+  // [last frame of the previous chunk | chunk] (the first chunk is only remembered).
+  int down_block(const std::string& p, int xi, int& Tc, int& H, int& W, int C, bool temporal, bool first) {
+    launch_vae_s2d(F[xi].as<float>(), A1.as<__half>(), Tc, H, W, C, s);
+    H /= 2; W /= 2;
+    const int yi = (xi + 1) % 3;
+    run_conv(p + "resample.1", A1.as<__half>(), Tc, H, W, F[yi].as<float>(), false);
+    if (!temporal) return yi;
+    const std::string name = p + "time_conv";
+    const size_t frame = (size_t)H * W * C;
+    auto& hb = hist[name];
+    if (!hb || hist_frame[name] != frame) {
+      hb = std::make_unique<DevBuf>();
+      hb->ensure(frame * 2, true);
+      hist_frame[name] = frame;
+    }
+    if (first) {
+      launch_vae_cast(F[yi].as<float>(), hb->as<__half>(), (long long)frame, s);     // Tc == 1
+      return yi;
+    }
+    B2_CHECK(Tc % 2 == 0, "temporal downsample needs an even number of frames per chunk (got %d)", Tc);
+    B2_CUDA(cudaMemcpyAsync(A0.p, hb->p, frame * 2, cudaMemcpyDeviceToDevice, s));
+    launch_vae_cast(F[yi].as<float>(), A0.as<__half>() + frame, (long long)Tc * frame, s);
+    B2_CUDA(cudaMemcpyAsync(hb->p, A0.as<__half>() + (size_t)Tc * frame, frame * 2, cudaMemcpyDeviceToDevice, s));
+    const int zi = (yi + 1) % 3;
+    for (int k = 0; k < Tc / 2; ++k)          // output frame k = taps over frames 2k, 2k+1, 2k+2 of [last | chunk]
+      run_conv(name, A0.as<__half>() + (size_t)2 * k * frame, 1, H, W, F[zi].as<float>() + (size_t)k * frame, false);
+    Tc /= 2;
+    return zi;
+  }
+
+  void ensure_buffers_enc(int Tc_max, int H, int W, int T_lat) {
+    size_t f32_max = 0, a0_max = 0, a1_max = 0;
+    int Tc = Tc_max;
+    auto upd = [&](size_t& m, size_t v) { if (v > m) m = v; };
+    upd(a0_max, (size_t)(Tc + 2) * H * W * 8);
+    upd(f32_max, (size_t)Tc * H * W * dim);
+    for (auto& it : eplan) {
+      if (it.kind == 0) {
+        upd(f32_max, (size_t)Tc * H * W * it.cout);
+        upd(a0_max, (size_t)(Tc + 2) * H * W * (it.cin > it.cout ? it.cin : it.cout));
+        upd(a1_max, (size_t)Tc * H * W * it.cin);
+      } else {
+        upd(a1_max, (size_t)Tc * H * W * it.cin);          // space-to-depth volume: same element count
+        H /= 2; W /= 2;
+        upd(f32_max, (size_t)Tc * H * W * it.cout);
+        if (it.kind == 1) { upd(a0_max, (size_t)(Tc + 1) * H * W * it.cin); if (Tc > 1) Tc /= 2; }
+      }
+    }
+    upd(a0_max, (size_t)(Tc + 2) * H * W * c0);
+    upd(a1_max, (size_t)Tc * H * W * c0);
+    upd(f32_max, (size_t)T_lat * H * W * 2 * zdim);
+    for (int i = 0; i < 3; ++i) F[i].ensure(f32_max * 4 + 256);
+    A0.ensure(a0_max * 2 + 256);
+    A1.ensure(a1_max * 2 + 256);
+  }
+
+  // WanVAE_.encode (vae.py:516-542): video fp32 [3, T, H, W] (T = 1 + 4k) -> mu fp32 [zdim, 1 + k, H/8, W/8]
+  void encode(const float* video, int T, int H0, int W0, float* out, cudaStream_t stream) {
+    B2_CHECK(finalized, "b200vae_finalize() has not been called");
+    B2_CHECK(has_encoder, "the encoder weights (encoder.*, conv1.*) were not loaded");
+    B2_CHECK(T >= 1 && (T - 1) % 4 == 0, "encode needs 1 + 4k frames (got %d)", T);
+    B2_CHECK(H0 % 8 == 0 && W0 % 8 == 0 && H0 >= 8 && W0 >= 8, "frame size %d x %d must be a multiple of 8", H0, W0);
+    s = stream;
+    hist_fresh.clear();
+    const int T_lat = 1 + (T - 1) / 4;
+    ensure_buffers_enc(T > 1 ? 4 : 1, H0, W0, T_lat);
+    int t0 = 0, f_out = 0;
+    while (t0 < T) {
+      const bool first = t0 == 0;
+      int Tc = first ? 1 : 4;
+      const int Tin = Tc;
+      int H = H0, W = W0;
+      __half* a = begin_causal("encoder.conv1", Tc, H, W, 8);
+      launch_vae_prep_video(video, a, T, t0, Tc, (long long)H * W, s);
+      end_causal("encoder.conv1", Tc, H, W, 8);
+      run_conv("encoder.conv1", A0.as<__half>(), Tc, H, W, F[0].as<float>(), false);
+      int xi = 0;
+      for (size_t i = 0; i < eplan.size(); ++i) {
+        const std::string p = "encoder.downsamples." + std::to_string(i) + ".";
+        if (eplan[i].kind == 0) xi = res_block(p, xi, Tc, H, W, eplan[i].cin, eplan[i].cout);
+        else xi = down_block(p, xi, Tc, H, W, eplan[i].cin, eplan[i].kind == 1, first);
+      }
+      xi = res_block("encoder.middle.0.", xi, Tc, H, W, c0, c0);
+      attn_block("encoder.middle.1.", xi, Tc, H, W, c0);
+      xi = res_block("encoder.middle.2.", xi, Tc, H, W, c0, c0);
+      a = begin_causal("encoder.head.2", Tc, H, W, c0);
+      launch_vae_norm(F[xi].as<float>(), gammas.at("encoder.head.0.gamma")->as<float>(), a, (long long)Tc * H * W, c0, 1, s);
+      end_causal("encoder.head.2", Tc, H, W, c0);
+      const int oi = (xi + 1) % 3, mi = (xi + 2) % 3;
+      run_conv("encoder.head.2", A0.as<__half>(), Tc, H, W, F[oi].as<float>(), false);        // [Tc, h, w, 2 zdim]
+      const long long P = (long long)Tc * H * W;
+      launch_vae_cast(F[oi].as<float>(), A1.as<__half>(), P * 2 * zdim, s);
+      linear_1x1("conv1", A1.as<__half>(), P, EPI_F32, F[mi].p, false);                        // vae.py:533
+      launch_vae_store_mu(F[mi].as<float>(), consts.as<float>(), consts.as<float>() + 16, out, zdim, Tc, (long long)H * W,
+                          f_out, T_lat, s);
+      f_out += Tc;
+      t0 += Tin;
+    }
+  }
+
   void ensure_buffers(int T, int Tc_max, int h, int w) {
     // worst-case element counts over the decoder for a chunk of Tc_max latent frames
     size_t f32_max = 0, a0_max = 0, a1_max = 0;
@@ -354,6 +496,9 @@ void VaeEngine::load_weight(const char* name, const void* data, int dtype, int n
 void VaeEngine::finalize() { impl->finalize(); }
 void VaeEngine::decode(const float* z, int T, int h, int w, float* out, cudaStream_t stream) {
   impl->decode(z, T, h, w, out, stream);
+}
+void VaeEngine::encode(const float* video, int T, int H, int W, float* out, cudaStream_t stream) {
+  impl->encode(video, T, H, W, out, stream);
 }
 
 }  // namespace b2

@@ -15,6 +15,7 @@ class VaeEngine {
   void load_weight(const char* name, const void* data, int dtype, int ndim, const int64_t* shape);
   void finalize();
   void decode(const float* z, int T, int h, int w, float* out, cudaStream_t stream);
+  void encode(const float* video, int T, int H, int W, float* out, cudaStream_t stream);
 
  private:
   struct Impl;

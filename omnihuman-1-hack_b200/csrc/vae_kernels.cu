@@ -162,7 +162,94 @@ __global__ void repack_conv_weight_kernel(const float* __restrict__ src, __half*
   }
 }
 
+__global__ void prep_video_kernel(const float* __restrict__ video, __half* __restrict__ out, int T_total, int t0, int Tc,
+                                  long long HW) {
+  const long long n = (long long)Tc * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / HW, px = i % HW;
+    __half v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = __float2half_rn(c < 3 ? video[((long long)c * T_total + t0 + t) * HW + px] : 0.f);
+    *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// one thread per (output pixel, 4 channels): reads the 2x2 input pixels' channel quads, writes four 8-byte pieces
+__global__ void vae_s2d_kernel(const float* __restrict__ x, __half* __restrict__ out, int T, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const long long n = (long long)T * Ho * Wo * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cq = i % C4;
+    const long long po = i / C4;
+    const int wo = po % Wo, ho = (po / Wo) % Ho;
+    const long long t = po / ((long long)Wo * Ho);
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw) {
+        const float4 v = *reinterpret_cast<const float4*>(x + ((t * H + 2 * ho + ph) * W + 2 * wo + pw) * C + cq * 4);
+        __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+        uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+        *reinterpret_cast<uint2*>(out + po * 4 * C + (ph * 2 + pw) * C + cq * 4) = pk;
+      }
+  }
+}
+
+__global__ void repack_down_weight_kernel(const float* __restrict__ src, __half* __restrict__ dst, int Cout, int Cin,
+                                          int cpad) {
+  const long long n = (long long)Cout * 4 * cpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cc = i % cpad;
+    const int tap = (i / cpad) % 4, oh = tap >> 1, ow = tap & 1;
+    const int o = i / ((long long)cpad * 4);
+    float v = 0.f;
+    if (cc < 4 * Cin) {
+      const int phase = cc / Cin, c = cc % Cin, ph = phase >> 1, pw = phase & 1;
+      const int dh = 2 * oh + ph, dw = 2 * ow + pw;
+      if (dh < 3 && dw < 3) v = src[(((long long)o * Cin + c) * 3 + dh) * 3 + dw];
+    }
+    dst[i] = __float2half_rn(v);
+  }
+}
+
+__global__ void store_mu_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                float* __restrict__ out, int zdim, int T, long long HW, int t0, int T_total) {
+  const long long n = (long long)T * HW * zdim;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = i % zdim;
+    const long long px = (i / zdim) % HW, t = i / ((long long)zdim * HW);
+    const float v = x[(t * HW + px) * 2 * zdim + c];
+    out[((long long)c * T_total + t0 + t) * HW + px] = (v - mean[c]) * (1.0f / stdv[c]);
+  }
+}
+
 }  // namespace
+
+void launch_vae_prep_video(const float* video, __half* out, int T_total, int t0, int Tc, long long HW, cudaStream_t s) {
+  prep_video_kernel<<<grid_for((long long)Tc * HW), 256, 0, s>>>(video, out, T_total, t0, Tc, HW);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void launch_vae_s2d(const float* x, __half* out, int T, int H, int W, int C, cudaStream_t s) {
+  B2_CHECK(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "stride-2 downsample needs even H, W (got %d x %d) and C %% 4 == 0", H, W);
+  ProfScope prof(PC_NORM, 0.0, 6.0 * T * H * W * C, s);
+  vae_s2d_kernel<<<grid_for((long long)T * (H / 2) * (W / 2) * (C / 4)), 256, 0, s>>>(x, out, T, H, W, C);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void launch_repack_down_weight(const float* src, __half* dst, int Cout, int Cin, int cpad, cudaStream_t s) {
+  repack_down_weight_kernel<<<grid_for((long long)Cout * 4 * cpad), 256, 0, s>>>(src, dst, Cout, Cin, cpad);
+  B2_CUDA(cudaGetLastError());
+}
+
+void launch_vae_store_mu(const float* x, const float* mean, const float* stdv, float* out, int zdim, int T, long long HW,
+                         int t0, int T_total, cudaStream_t s) {
+  store_mu_kernel<<<grid_for((long long)T * HW * zdim), 256, 0, s>>>(x, mean, stdv, out, zdim, T, HW, t0, T_total);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
 
 void launch_vae_prep_latent(const float* z, const float* mean, const float* stdv, __half* out, int C, int T, int hw,
                             cudaStream_t s) {

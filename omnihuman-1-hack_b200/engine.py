@@ -248,11 +248,27 @@ class VaeEngine:
         eng.load_state_dict(sd)
         return eng
 
-    def load_state_dict(self, sd):
+    def load_state_dict(self, sd, encoder=None):
+        """`decoder.*` / `conv2.*` always; `encoder.*` / `conv1.*` too when present (encoder=None) or demanded."""
+        self.has_encoder = any(k.startswith("encoder.") for k in sd) if encoder is None else bool(encoder)
+        prefixes = ("decoder.", "conv2.") + (("encoder.", "conv1.") if self.has_encoder else ())
         with torch.cuda.device(self.device):
-            _load_state(lib().b200vae_load_weight, self._h, sd,
-                        lambda n: n.startswith("decoder.") or n.startswith("conv2."))
+            _load_state(lib().b200vae_load_weight, self._h, sd, lambda n: n.startswith(prefixes))
             check(lib().b200vae_finalize(self._h))
+
+    def encode(self, videos):
+        """WanVAE.encode (vae.py:641-655): list of [3, T, H, W] in [-1, 1] (T = 1 + 4k) -> list of fp32
+        [16, 1 + k, H/8, W/8] posterior means, normalised with the latent mean / std."""
+        outs = []
+        with torch.cuda.device(self.device):
+            for v in videos:
+                v = v.to(self.device, torch.float32, non_blocking=True).contiguous()
+                _, T, H, W = v.shape
+                o = torch.empty((self.z_dim, 1 + (T - 1) // 4, H // 8, W // 8), dtype=torch.float32, device=self.device)
+                check(lib().b200vae_encode(self._h, C.c_void_p(v.data_ptr()), T, H, W, C.c_void_p(o.data_ptr()),
+                                           _stream_ptr()))
+                outs.append(o)
+        return outs
 
     def decode(self, zs):
         """List of [16,T,h,w] latents -> list of fp32 [3, 1+4(T-1), 8h, 8w] in [-1, 1]."""

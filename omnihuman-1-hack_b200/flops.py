@@ -49,3 +49,32 @@ def vae_decode_flops(T, h=60, w=104, dim=96):
         return fl
 
     return one_pass(1, True) + (one_pass(T - 1, False) if T > 1 else 0.0)
+
+
+def vae_encode_flops(T, H=480, W=832, dim=96, z_dim=16):
+    """WanVAE encode (vae.py:516-542, Encoder3d :265-366) as the reference executes it: frame 0 alone (its
+    downsample3d stages skip the temporal conv), then chunks of 4 frames; conv MACs incl. zero padding."""
+    dims = [dim * u for u in (1, 1, 2, 4, 4)]
+
+    def chunk(t, first):
+        fl, hh, ww, tt = 0.0, H, W, t
+        fl += 2 * tt * hh * ww * 3 * dims[0] * 27                                 # conv1
+        for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+            for _ in range(2):
+                fl += 2 * tt * hh * ww * 27 * (cin * cout + cout * cout)
+                if cin != cout:
+                    fl += 2 * tt * hh * ww * cin * cout
+                cin = cout
+            if i != 3:
+                hh, ww = hh // 2, ww // 2
+                fl += 2 * tt * hh * ww * 9 * cout * cout                          # stride-2 Conv2d
+                if i > 0 and not first:
+                    tt //= 2
+                    fl += 2 * tt * hh * ww * 3 * cout * cout                      # stride-2 temporal conv
+        c = dims[-1]
+        fl += 2 * (2 * 2 * tt * hh * ww * c * c * 27)                             # two middle residual blocks
+        fl += tt * (2 * hh * ww * c * 3 * c + 2 * hh * ww * c * c + 4 * (hh * ww) ** 2 * c)   # middle attention
+        fl += 2 * tt * hh * ww * 27 * c * 2 * z_dim + 2 * tt * hh * ww * (2 * z_dim) ** 2      # head conv + conv1 (1x1x1)
+        return fl
+
+    return chunk(1, True) + ((T - 1) // 4) * chunk(4, False)

@@ -54,9 +54,10 @@ def dit_weights(cfg, seed, device, i2v=False):
     return sd
 
 
-def vae_decoder_weights(dim=96, z_dim=16, seed=0, device="cpu"):
+def vae_decoder_weights(dim=96, z_dim=16, seed=0, device="cpu", encoder=False):
     """Decoder + conv2 of WanVAE_ (vae.py:369-421, 505-507) with dim_mult [1,2,4,4], 2 res blocks per stage,
-    temporal upsampling in the first two stages (vae.py:597-605)."""
+    temporal upsampling in the first two stages (vae.py:597-605); encoder=True adds Encoder3d + conv1
+    (vae.py:265-314, 504)."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
 
@@ -98,4 +99,26 @@ def vae_decoder_weights(dim=96, z_dim=16, seed=0, device="cpu"):
             idx += 1
     gamma("decoder.head.0.gamma", dims[-1], 3)
     conv("decoder.head.2", 3, dims[-1], 3, 3, 3)
+    if encoder:
+        edims = [dim * u for u in (1, 1, 2, 4, 4)]
+        conv("conv1", 2 * z_dim, 2 * z_dim, 1, 1, 1)
+        conv("encoder.conv1", edims[0], 3, 3, 3, 3)
+        idx = 0
+        for i, (cin, cout) in enumerate(zip(edims[:-1], edims[1:])):
+            for _ in range(2):
+                res(f"encoder.downsamples.{idx}.", cin, cout)
+                cin = cout
+                idx += 1
+            if i != 3:
+                conv(f"encoder.downsamples.{idx}.resample.1", cout, cout, 3, 3)
+                if i > 0:                                          # downsample3d stages (vae.py:94-99)
+                    conv(f"encoder.downsamples.{idx}.time_conv", cout, cout, 3, 1, 1)
+                idx += 1
+        res("encoder.middle.0.", edims[-1], edims[-1])
+        gamma("encoder.middle.1.norm.gamma", edims[-1], 2)
+        conv("encoder.middle.1.to_qkv", 3 * edims[-1], edims[-1], 1, 1)
+        conv("encoder.middle.1.proj", edims[-1], edims[-1], 1, 1, gain=0.5)
+        res("encoder.middle.2.", edims[-1], edims[-1])
+        gamma("encoder.head.0.gamma", edims[-1], 3)
+        conv("encoder.head.2", 2 * z_dim, edims[-1], 3, 3, 3)
     return {k: v.half().float().to(device) for k, v in sd.items()}

@@ -3,7 +3,7 @@
 The reference's own plug-in convention is instance-level monkey-patching
 (`types.MethodType(usp_dit_forward, self.model)`, seaweed_apt/wan/text2video.py:95-98); `install`
 does the same for `WanModel.forward` (model.py:502) and `install_vae` for `WanVAE.decode`
-(vae.py:657).  Callers -- WanT2V.generate (text2video.py:238-241,259), generate.py:227-228,
+(vae.py:657) and, when the encoder weights are present, `WanVAE.encode` (vae.py:641).  Callers -- WanT2V.generate (text2video.py:238-241,259), generate.py:227-228,
 distilled_trainer.py:273-278, eval_ema.py:124,140 -- keep calling `model(x, t=..., context=...,
 seq_len=...)` / `vae.decode(zs)` unchanged.
 
@@ -54,6 +54,9 @@ def install_vae(vae, device=None, engine=None):
     vae._b200_original_decode = original
     vae._b200_engine = eng
     vae.decode = types.MethodType(decode, vae)
+    if getattr(eng, "has_encoder", False) and hasattr(vae, "encode"):      # WanVAE.encode (vae.py:641-655)
+        vae._b200_original_encode = vae.encode
+        vae.encode = types.MethodType(lambda self, videos: eng.encode(videos), vae)
     return eng
 
 
@@ -61,6 +64,9 @@ def uninstall(obj):
     if hasattr(obj, "_b200_original_forward"):
         obj.forward = obj._b200_original_forward
         del obj._b200_original_forward, obj._b200_engine
+    if hasattr(obj, "_b200_original_encode"):
+        obj.encode = obj._b200_original_encode
+        del obj._b200_original_encode
     if hasattr(obj, "_b200_original_decode"):
         obj.decode = obj._b200_original_decode
         del obj._b200_original_decode, obj._b200_engine

@@ -11,6 +11,8 @@ Fixtures (all small enough to commit; weights stored as fp16 = exactly the value
   dit_block_1p3b.pt outputs only (weights by seed): ONE 1.3B-shaped block + head on [16,1,60,104]
                     (BASELINE.json configs[0]); weights regenerate from make_synthetic_weights(seed)
   vae_tiny.pt       WanVAE_ decoder, dim 8, z [16,3,6,8] -> [3,9,48,64]  (vae.py:544-568)
+  vae_enc_tiny.pt   WanVAE_ encoder, dim 8, video [3,9,32,48] -> mu [16,3,4,6]  (vae.py:516-542)
+                    (`python oracle/make_golden.py encode` regenerates only this file)
   solver_traj.pt    FlowUniPC / FlowDPMSolver++ trajectories (fm_solvers_unipc.py, fm_solvers.py) on a toy
                     velocity field: per case the timesteps and the latent after every step
                     (`python oracle/make_golden.py solvers` regenerates only this file)
@@ -67,9 +69,27 @@ def make_solver_golden():
     torch.save(dict(x0=x0, cases=cases), os.path.join(OUT, "solver_traj.pt"))
 
 
+def make_encode_golden():
+    """The UNMODIFIED reference WanVAE_.encode on seeded synthetic weights (vae.py:516-542)."""
+    _, V = ref_loader.load_reference_modules()
+    vsd = VO.make_synthetic_vae_weights(dim=8, seed=6, encoder=True)
+    vae = V.WanVAE_(dim=8, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2, attn_scales=[],
+                    temperal_downsample=[False, True, True]).eval()
+    vae.load_state_dict(vsd, strict=True)
+    video = (torch.rand(3, 9, 32, 48, generator=torch.Generator().manual_seed(8)) * 2 - 1).half().float()
+    mean, std = torch.tensor(VO.VAE_MEAN), torch.tensor(VO.VAE_STD)
+    with torch.no_grad():
+        mu = vae.encode(video[None], [mean, 1.0 / std]).float()[0]
+    torch.save(dict(dim=8, sd=half(vsd), video=video.half(), out=mu), os.path.join(OUT, "vae_enc_tiny.pt"))
+    print("vae_enc_tiny", tuple(mu.shape), float(mu.std()))
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "solvers":
         return make_solver_golden()
+    if len(sys.argv) > 1 and sys.argv[1] == "encode":
+        return make_encode_golden()
+    make_encode_golden()
     make_solver_golden()
     M, V = ref_loader.load_reference_modules()
     os.makedirs(OUT, exist_ok=True)

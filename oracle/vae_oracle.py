@@ -143,7 +143,73 @@ def vae_decode(sd, z, chunks=None, clamp=True, taps=None):
     return out.clamp_(-1, 1) if clamp else out
 
 
-def make_synthetic_vae_weights(dim=96, z_dim=16, seed=0, round_to=torch.float16):
+# ------------------------------------------------------------------------------------------------
+# Encoder (vae.py:265-366 Encoder3d, :516-542 WanVAE_.encode): frames are fed as chunks [1, 4, 4, ...]
+# with the same per-conv two-frame input history; downsample3d keeps the last frame it saw and, except
+# on the first chunk, runs a stride-2 temporal conv over [last frame | chunk] (vae.py:143-160).
+def encoder_plan(dim=96, dim_mult=(1, 2, 4, 4), num_res_blocks=2, temporal_downsample=(False, True, True)):
+    dims = [dim * u for u in [1] + list(dim_mult)]
+    plan = []
+    for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+        for _ in range(num_res_blocks):
+            plan.append(("res", cin, cout))
+            cin = cout
+        if i != len(dim_mult) - 1:
+            plan.append(("down3d" if temporal_downsample[i] else "down2d", cout, cout))
+    return dims[-1], plan
+
+
+def _downsample(sd, p, st, x, kind):
+    """vae.py:93-99,138-160 (downsample2d / downsample3d)."""
+    b, c, t, h, w = x.shape
+    y = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+    y = F.conv2d(F.pad(y, (0, 1, 0, 1)), sd[p + "resample.1.weight"], sd[p + "resample.1.bias"], stride=2)
+    x = y.reshape(b, t, c, y.shape[2], y.shape[3]).permute(0, 2, 1, 3, 4)
+    if kind == "down3d":
+        last = st.hist.get(p + "time_conv")
+        if last is None:                                   # first chunk: remembered, not convolved (:146-148)
+            st.hist[p + "time_conv"] = x.clone()
+        else:
+            keep = x[:, :, -1:].clone()
+            x = F.conv3d(torch.cat([last[:, :, -1:], x], dim=2), sd[p + "time_conv.weight"],
+                         sd[p + "time_conv.bias"], stride=(2, 1, 1))
+            st.hist[p + "time_conv"] = keep
+    return x
+
+
+def encoder_chunk(sd, st, x, plan=None):
+    """Encoder3d.forward with feat_cache (vae.py:316-366) on one chunk of video frames."""
+    c_last, plan = plan or encoder_plan()
+    x = st.causal_conv("encoder.conv1", x, sd["encoder.conv1.weight"], sd["encoder.conv1.bias"])
+    for i, (kind, cin, cout) in enumerate(plan):
+        p = f"encoder.downsamples.{i}."
+        x = _res_block(sd, p, st, x, cin, cout) if kind == "res" else _downsample(sd, p, st, x, kind)
+    x = _res_block(sd, "encoder.middle.0.", st, x, c_last, c_last)
+    x = _attn_block(sd, "encoder.middle.1.", x)
+    x = _res_block(sd, "encoder.middle.2.", st, x, c_last, c_last)
+    x = F.silu(rms_norm_c(x, sd["encoder.head.0.gamma"]))
+    return st.causal_conv("encoder.head.2", x, sd["encoder.head.2.weight"], sd["encoder.head.2.bias"])
+
+
+def vae_encode(sd, video, dim=96):
+    """WanVAE.encode for one video (vae.py:641-648 -> 516-542). video [3,T,H,W] in [-1,1], T = 1 + 4k
+    -> mu [16, 1 + (T-1)/4, H/8, W/8], normalised with the latent mean / std."""
+    T = video.shape[1]
+    zdim = sd["conv1.weight"].shape[0] // 2
+    plan = encoder_plan(dim)
+    st, outs = _Stream(), []
+    x = video[None].float()
+    for i in range(1 + (T - 1) // 4):
+        chunk = x[:, :, :1] if i == 0 else x[:, :, 1 + 4 * (i - 1):1 + 4 * i]
+        outs.append(encoder_chunk(sd, st, chunk, plan))
+    out = torch.cat(outs, dim=2)
+    mu = F.conv3d(out, sd["conv1.weight"], sd["conv1.bias"])[:, :zdim]                 # :533 (mu, log_var chunk)
+    mean = torch.tensor(VAE_MEAN[:zdim]).view(1, zdim, 1, 1, 1)
+    std = torch.tensor(VAE_STD[:zdim]).view(1, zdim, 1, 1, 1)
+    return ((mu - mean) * (1.0 / std))[0]                                              # :534-539, scale = [mean, 1/std]
+
+
+def make_synthetic_vae_weights(dim=96, z_dim=16, seed=0, round_to=torch.float16, encoder=False):
     """Decoder-only synthetic state dict (kaiming-ish conv init, gamma perturbed away from 1, the
     zero-initialised attention `proj` re-randomised so every path is exercised -- SURVEY 8c)."""
     g = torch.Generator().manual_seed(seed)
@@ -183,6 +249,25 @@ def make_synthetic_vae_weights(dim=96, z_dim=16, seed=0, round_to=torch.float16)
                 conv(p + "time_conv", 2 * cin, cin, 3, 1, 1)
     gamma("decoder.head.0.gamma", plan[-1][2], 3)
     conv("decoder.head.2", 3, plan[-1][2], 3, 3, 3)
+    if encoder:
+        c_last, eplan = encoder_plan(dim)
+        conv("conv1", 2 * z_dim, 2 * z_dim, 1, 1, 1)
+        conv("encoder.conv1", eplan[0][1], 3, 3, 3, 3)
+        for i, (kind, cin, cout) in enumerate(eplan):
+            p = f"encoder.downsamples.{i}."
+            if kind == "res":
+                res(p, cin, cout)
+            else:
+                conv(p + "resample.1", cout, cin, 3, 3)
+                if kind == "down3d":
+                    conv(p + "time_conv", cout, cin, 3, 1, 1)
+        res("encoder.middle.0.", c_last, c_last)
+        gamma("encoder.middle.1.norm.gamma", c_last, 2)
+        conv("encoder.middle.1.to_qkv", 3 * c_last, c_last, 1, 1)
+        conv("encoder.middle.1.proj", c_last, c_last, 1, 1, gain=0.5)
+        res("encoder.middle.2.", c_last, c_last)
+        gamma("encoder.head.0.gamma", c_last, 3)
+        conv("encoder.head.2", 2 * z_dim, c_last, 3, 3, 3)
     if round_to is not None:
         sd = {k: v.to(round_to).float() for k, v in sd.items()}
     return sd

@@ -102,3 +102,16 @@ def test_package_flop_counters_match_oracle():
     for T in (1, 2, 21):
         assert abs(b200dit.flops.vae_decode_flops(T) / VO.vae_decode_flops(T) - 1) < 1e-9
     assert abs(b200dit.flops.dit_forward_flops(1560) / 4.652e12 - 1) < 1e-3          # 4.652 TFLOP / forward
+
+
+def test_vae_encode_oracle_vs_golden():
+    """Encoder restatement (oracle/vae_oracle.py:vae_encode) vs the unmodified reference WanVAE_.encode fixture."""
+    g = _load("vae_enc_tiny.pt")
+    sd = {k: v.float() for k, v in g["sd"].items()}
+    mu = VO.vae_encode(sd, g["video"].float(), dim=g["dim"])
+    assert mu.shape == g["out"].shape
+    assert float((mu - g["out"]).abs().max()) < 1e-5
+    import b200dit
+    syn = b200dit.synthetic.vae_decoder_weights(dim=8, seed=0, encoder=True)
+    ref = VO.make_synthetic_vae_weights(dim=8, seed=0, encoder=True)
+    assert set(syn) == set(ref) and all(syn[k].shape == ref[k].shape for k in syn)

@@ -58,3 +58,33 @@ def test_install_vae_shim():
     b200dit.install_vae(v)
     z = torch.randn(16, 2, 4, 6, generator=torch.Generator().manual_seed(1))
     _check(v.decode([z])[0].cpu(), VO.vae_decode(sd, z))
+
+
+def test_golden_vae_encode_tiny():
+    """b200vae_encode vs the unmodified reference WanVAE_.encode (tests/golden/vae_enc_tiny.pt): first chunk of one
+    frame + two chunks of four (stride-2 spatial convs, stride-2 temporal convs with the one-frame history).
+    Tolerance: fp16 operands / fp32 accumulation through 20+ convs on O(0.4) latents: max-abs <= 1e-2."""
+    import b200dit
+    g = torch.load(os.path.join(GOLDEN, "vae_enc_tiny.pt"), map_location="cpu", weights_only=True)
+    sd = {k: v.float() for k, v in g["sd"].items()}
+    vae = b200dit.VaeEngine.from_state_dict(sd)
+    assert vae.has_encoder
+    mu = vae.encode([g["video"].float()])[0].cpu()
+    assert mu.shape == g["out"].shape
+    assert float((mu - g["out"]).abs().max()) < 1e-2
+    mu1 = vae.encode([g["video"].float()[:, :1]])[0].cpu()             # a single image
+    assert float((mu1 - g["out"][:, :1]).abs().max()) < 1e-2
+
+
+def test_vae_encode_dim96_vs_oracle():
+    """Full-width encoder (dim 96) on a small clip vs the CPU oracle; then decode(encode(x)) runs end to end."""
+    import b200dit
+    from oracle import vae_oracle as VO
+    sd = VO.make_synthetic_vae_weights(dim=96, seed=3, encoder=True)
+    vae = b200dit.VaeEngine.from_state_dict(sd)
+    video = torch.rand(3, 5, 64, 96, generator=torch.Generator().manual_seed(4)) * 2 - 1
+    mu = vae.encode([video])[0]
+    ref = VO.vae_encode(sd, video, dim=96)
+    assert float((mu.cpu() - ref).abs().max()) < 1e-2
+    rec = vae.decode([mu])[0]
+    assert rec.shape == video.shape and bool(torch.isfinite(rec).all())
