@@ -196,8 +196,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (lane == 0) {
           mbar_wait(&s_full[sb], ph);
           mbar_arrive(&s_empty[sb]);
-          if (j > 0) mbar_wait(p_full, (j - 1) & 1);         // never arrive into a P phase that is still open
-          if (j > 0 && j == n_kv - 1) mbar_wait(pv_done, (j - 1) & 1);   // (see the active path)
+          if (j > 0) mbar_wait(pv_done, (j - 1) & 1);        // phase discipline: see the active path
           mbar_arrive(p_full);
         }
         __syncwarp();
@@ -264,14 +263,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // P_j replaces the first half of this thread's own S_j row (nobody else touches that TMEM lane)
       if (!(p.dbg & 4)) tmem_st32(tmem_base + lane_sel + sb * KT, pk);
       if (j > 0) {
-        // mbarrier waits are parity based, so a waiter must know the barrier is within one phase of the one
-        // it asks for.  S_j being full means Q.K^T of step j ran, which was issued after P.V of step j-2:
-        //   * pv_done has completed j-1 or j times   -> asking for step j-1 is unambiguous (rescale path only:
-        //     waiting for P.V every step put two barrier hops + the MMAs on the softmax critical path)
-        //   * p_full has completed j-1 or j times    -> asking for phase j-1 is unambiguous; it must have
-        //     completed before this warp arrives for step j (a fast warp must not arrive twice in one phase)
+        // Phase discipline.  mbarrier waits are parity based: a waiter must be provably within one phase of the
+        // barrier, or "completed twice since" looks like "not yet" and the CTA deadlocks.  Waiting for P.V of
+        // step j-1 on EVERY step (not only when O must be rescaled) gives all three guarantees at once:
+        //   * pv_done has completed j-1 or j times here (S_j full => Q.K^T(j) ran => P.V(j-2) ran; P.V(j) needs
+        //     this warp's arrival below), so asking for step j-1 is unambiguous -- also for the final wait;
+        //   * P.V(j-1) issued means the MMA thread has OBSERVED p_full phase j-1, so it can never fall two
+        //     phases behind the arrivals (an earlier version without this wait hung once in ~10^5 launches);
+        //   * p_full phase j-1 is closed before this warp arrives for phase j.
+        mbar_wait_warp(pv_done, (j - 1) & 1, lane);         // O stable: every earlier P.V has completed
         if (__any_sync(0xffffffffu, rescale)) {
-          mbar_wait_warp(pv_done, (j - 1) & 1, lane);       // O stable: every earlier P.V has completed
           tc_fence_after();
 #pragma unroll
           for (int cidx = 0; cidx < 4; ++cidx) {
@@ -289,10 +290,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&s_empty[sb]);                          // S_j fully read, P_j fully written by this warp
-        if (j > 0) mbar_wait(p_full, (j - 1) & 1);
-        // before the LAST arrival catch up with pv_done: once P.V of the final step may be issued the barrier
-        // could get two phases ahead of this waiter, which a parity wait cannot tell from "not yet"
-        if (j > 0 && j == n_kv - 1) mbar_wait(pv_done, (j - 1) & 1);
         mbar_arrive(p_full);
       }
     }
