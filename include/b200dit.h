@@ -109,6 +109,9 @@ B200_API int b200dit_context_hint(b200dit_engine* e, uint64_t token);
  * seaweed_apt/model.py:150-155): after the next forward, copy the fp32 stream [n_items*L, dim] that
  * left block `block_idx` into dst (device).  block_idx < 0 disables. */
 B200_API int b200dit_set_tap(b200dit_engine* e, int32_t block_idx, float* dst);
+/* Several taps at once (the discriminator hooks three blocks, seaweed_apt/model.py:150-155): n <= 8 pairs of
+ * (block index, device destination [n_items*L, dim] fp32); n = 0 disables. */
+B200_API int b200dit_set_taps(b200dit_engine* e, int32_t n, const int32_t* block_idx, float* const* dst);
 
 /* Capture each distinct (n_items, grid, mode) forward into a CUDA graph and replay it (default on). */
 B200_API int b200dit_set_graphs(b200dit_engine* e, int32_t enabled);

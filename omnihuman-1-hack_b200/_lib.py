@@ -38,6 +38,7 @@ SIGNATURES = {
     "b200dit_forward_cfg": (_I, [_P, _I, _PP, _PP, _I, _P, _PP, _IP, _PP, _IP, _I, _PP, _I, _I, _I, _I, _F, _PP, _P]),
     "b200dit_context_hint": (_I, [_P, C.c_uint64]),
     "b200dit_set_tap": (_I, [_P, _I, _P]),
+    "b200dit_set_taps": (_I, [_P, _I, _IP, _PP]),
     "b200dit_set_graphs": (_I, [_P, _I]),
     "b200dit_last_flops": (C.c_double, [_P]),
     "b200vae_create": (_I, [_I, _I, _PP]),

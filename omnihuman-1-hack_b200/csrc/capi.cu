@@ -87,13 +87,21 @@ int b200dit_forward_cfg(b200dit_engine* e, int32_t n_samples, const float* const
 int b200dit_context_hint(b200dit_engine* e, uint64_t token) {
   return guarded([&] { B2_CHECK(e, "null engine"); e->impl.ctx_token = token; });
 }
-int b200dit_set_tap(b200dit_engine* e, int32_t block_idx, float* dst) {
+int b200dit_set_taps(b200dit_engine* e, int32_t n, const int32_t* block_idx, float* const* dst) {
   return guarded([&] {
     B2_CHECK(e, "null engine");
-    B2_CHECK(block_idx < e->impl.cfg.num_layers, "tap block %d out of range", block_idx);
-    e->impl.tap_block = block_idx < 0 ? -1 : block_idx;
-    e->impl.tap_dst = block_idx < 0 ? nullptr : dst;
+    B2_CHECK(n >= 0 && n <= 8 && (n == 0 || (block_idx && dst)), "at most 8 taps");
+    e->impl.taps.clear();
+    for (int i = 0; i < n; ++i) {
+      B2_CHECK(block_idx[i] >= 0 && block_idx[i] < e->impl.cfg.num_layers && dst[i] != nullptr, "tap %d: block %d out of range",
+               i, block_idx[i]);
+      e->impl.taps.emplace_back(block_idx[i], dst[i]);
+    }
   });
+}
+int b200dit_set_tap(b200dit_engine* e, int32_t block_idx, float* dst) {
+  if (block_idx < 0) return b200dit_set_taps(e, 0, nullptr, nullptr);
+  return b200dit_set_taps(e, 1, &block_idx, &dst);
 }
 int b200dit_set_graphs(b200dit_engine* e, int32_t enabled) {
   return guarded([&] { B2_CHECK(e, "null engine"); e->impl.use_graphs = enabled != 0; });

@@ -447,8 +447,9 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
       q.gate = mod + 5 * d; q.gate_stride = 6 * d; q.rows_per_item = L;
       gemm_linear(EPI_RESID_F32, w.hid, f, b.ffn2_w, f, q, num_sms, s);
     }
-    if (l == tap_block && tap_dst != nullptr)
-      B2_CUDA(cudaMemcpyAsync(tap_dst, w.x_res, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, s));
+    for (const auto& tp : taps)
+      if (tp.first == l && tp.second != nullptr)
+        B2_CUDA(cudaMemcpyAsync(tp.second, w.x_res, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, s));
   }
   // ---- head (model.py:349-359) + unpatchify (:565-588) + CFG combine (text2video.py:243-244)
   {
@@ -569,8 +570,12 @@ void DitEngine::forward(int n, const float* const* x, const float* const* y, int
   }
   for (int i = 0; i < n_out; ++i) in.out.p[i] = s_out + i * sio_item_out;
 
-  std::vector<int> key = {B, F, H, W, y_channels, in.cfg_pairs, in.has_clip ? 1 : 0, ctx_dtype, tap_block,
-                          in.ctx_hit ? 1 : 0};
+  std::vector<int> key = {B, F, H, W, y_channels, in.cfg_pairs, in.has_clip ? 1 : 0, ctx_dtype, in.ctx_hit ? 1 : 0,
+                          (int)taps.size()};
+  for (const auto& tp : taps) {                       // a captured graph holds the tap destinations
+    const uintptr_t a = reinterpret_cast<uintptr_t>(tp.second);
+    key.push_back(tp.first); key.push_back((int)(a & 0x7fffffff)); key.push_back((int)((a >> 31) & 0x7fffffff));
+  }
   for (int i = 0; i < B; ++i) key.push_back(in.ctx_rows[i]);
   if (graphs.size() > 64 && graphs.find(key) == graphs.end()) {
     for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);

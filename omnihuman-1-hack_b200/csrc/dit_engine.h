@@ -85,8 +85,7 @@ class DitEngine {
   int num_sms = 148;
   bool finalized = false;
   bool use_graphs = true;
-  int tap_block = -1;
-  float* tap_dst = nullptr;
+  std::vector<std::pair<int, float*>> taps;   // (block index, destination): residual stream after that block
   double last_flops = 0.0;
   uint64_t ctx_token = 0;                // set by b200dit_context_hint, consumed by the next forward
 

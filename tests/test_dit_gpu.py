@@ -156,3 +156,21 @@ def test_token_count_not_multiple_of_8():
     cfg = eng.forward_cfg([x1], t1, [c1], [c0], g["seq_len"], 3.0)[0]
     ru = O.dit_forward(sd, [x1], t1, [c0], g["seq_len"], num_heads=g["cfg"]["num_heads"])[0]
     assert rel_l2(cfg.cpu(), O.cfg_combine(g["out"][1], ru, 3.0)) < 3 * TOL
+
+
+def test_multiple_taps_match_oracle():
+    """b200dit_set_taps: residual stream after several blocks (APT discriminator hooks, seaweed_apt/model.py:150-155)."""
+    import b200dit
+    from oracle import dit_oracle as O
+    g = _load("dit_t2v_tiny.pt")
+    sd = {k: v.float() for k, v in g["sd"].items()}
+    eng = b200dit.DitEngine.from_state_dict(sd, num_heads=g["cfg"]["num_heads"])
+    x, t, c = g["x"][:1], g["t"][:1], g["context"][:1]
+    L = x[0].shape[1] * (x[0].shape[2] // 2) * (x[0].shape[3] // 2)
+    taps = eng.set_taps([0, 1], L)
+    for rep in range(3):                                   # eager, capture, replay
+        eng.forward(x, t, c, g["seq_len"])
+    ref = {0: None, 1: None}
+    O.dit_forward(sd, x, t, c, g["seq_len"], num_heads=g["cfg"]["num_heads"], taps=ref)
+    for k, tap in zip((0, 1), taps):
+        assert rel_l2(tap.cpu(), ref[k][0][:L]) < TOL
