@@ -174,3 +174,33 @@ def test_multiple_taps_match_oracle():
     O.dit_forward(sd, x, t, c, g["seq_len"], num_heads=g["cfg"]["num_heads"], taps=ref)
     for k, tap in zip((0, 1), taps):
         assert rel_l2(tap.cpu(), ref[k][0][:L]) < TOL
+
+
+def test_full_size_properties_30_layers():
+    """BASELINE configs[1] size (30 blocks, [16,1,60,104], 512-row contexts), where the CPU oracle is too slow to
+    run in a test: size-independent properties instead.  (1) the fused CFG launch equals uncond + s (cond - uncond)
+    of two separate forwards (same kernels, different co-batching: fp32 rounding only); (2) co-batching two samples
+    does not change either result beyond the K-split association (<= 1e-5 rel); (3) replays are bit-identical;
+    (4) the context cache changes nothing."""
+    import b200dit
+    from bench import CFG_13B, make_device_weights
+    dev = torch.device("cuda", 0)
+    eng = b200dit.DitEngine(**CFG_13B, device=dev)
+    eng.load_state_dict(make_device_weights(CFG_13B, 0, dev))
+    g = torch.Generator().manual_seed(11)
+    xa, xb = (torch.randn(16, 1, 60, 104, generator=g).to(dev) for _ in range(2))
+    c, c0 = (torch.randn(512, 4096, generator=g).bfloat16().to(dev) for _ in range(2))
+    t = torch.tensor([640.0], device=dev)
+    cond = eng.forward([xa], t, [c], 1560)[0]
+    unc = eng.forward([xa], t, [c0], 1560)[0]
+    fused = eng.forward_cfg([xa], t, [c], [c0], 1560, 5.0)[0]
+    assert bool(torch.isfinite(fused).all())
+    assert rel_l2(fused.cpu(), (unc + 5.0 * (cond - unc)).cpu()) < 2e-5
+    both = eng.forward_cfg([xa, xb], t.expand(2).contiguous(), [c, c], [c0, c0], 1560, 5.0)
+    assert rel_l2(both[0].cpu(), fused.cpu()) < 1e-5
+    outs = [eng.forward_cfg([xa, xb], t.expand(2).contiguous(), [c, c], [c0, c0], 1560, 5.0) for _ in range(3)]
+    for o in outs:
+        assert torch.equal(o[0], both[0]) and torch.equal(o[1], both[1])
+    eng.cache_context = False
+    again = eng.forward_cfg([xa, xb], t.expand(2).contiguous(), [c, c], [c0, c0], 1560, 5.0)
+    assert torch.equal(again[0], both[0]) and torch.equal(again[1], both[1])
