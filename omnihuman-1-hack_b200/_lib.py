@@ -41,6 +41,7 @@ SIGNATURES = {
     "b200dit_set_taps": (_I, [_P, _I, _IP, _PP]),
     "b200dit_set_graphs": (_I, [_P, _I]),
     "b200dit_last_flops": (C.c_double, [_P]),
+    "b200dit_nonfinite_rows": (_I, [_P, _P, C.POINTER(C.c_uint32)]),
     "b200vae_create": (_I, [_I, _I, _PP]),
     "b200vae_destroy": (None, [_P]),
     "b200vae_load_weight": (_I, [_P, C.c_char_p, _P, _I, _I, C.POINTER(C.c_int64)]),

@@ -107,6 +107,12 @@ int b200dit_set_graphs(b200dit_engine* e, int32_t enabled) {
   return guarded([&] { B2_CHECK(e, "null engine"); e->impl.use_graphs = enabled != 0; });
 }
 double b200dit_last_flops(const b200dit_engine* e) { return e ? e->impl.last_flops : 0.0; }
+int b200dit_nonfinite_rows(b200dit_engine* e, void* stream, uint32_t* count) {
+  return guarded([&] {
+    B2_CHECK(e && count, "null argument");
+    *count = e->impl.nonfinite_rows(reinterpret_cast<cudaStream_t>(stream));
+  });
+}
 
 int b200vae_create(int32_t dim, int32_t z_dim, b200vae_engine** out) {
   return guarded([&] {

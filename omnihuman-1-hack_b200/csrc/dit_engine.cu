@@ -48,7 +48,16 @@ DitEngine::DitEngine(const b200dit_config& c) : cfg(c) {
   int dev = 0;
   B2_CUDA(cudaGetDevice(&dev));
   B2_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  bad.ensure(sizeof(unsigned int), /*zero=*/true);
   alloc_weights();
+}
+
+unsigned int DitEngine::nonfinite_rows(cudaStream_t stream) {
+  unsigned int n = 0;
+  B2_CUDA(cudaMemcpyAsync(&n, bad.p, sizeof(n), cudaMemcpyDeviceToHost, stream));
+  B2_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(n), stream));
+  B2_CUDA(cudaStreamSynchronize(stream));
+  return n;
 }
 
 DitEngine::~DitEngine() {
@@ -383,7 +392,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
     const BlockWeights& b = wt.blocks[l];
     const float* mod = w.modtab + (size_t)l * B * 6 * d;      // [B][6][d]: shift1,1+scale1,gate1,shift2,1+scale2,gate2
     // ---- self-attention (model.py:292-296)
-    launch_ln_affine(w.x_res, w.u, mod + d, mod, 6 * d, M, L, d, eps, s);
+    launch_ln_affine(w.x_res, w.u, mod + d, mod, 6 * d, M, L, d, eps, s, false, bad.as<unsigned int>());
     {
       GemmParams p{}; p.w_static = 1; p.M = M; p.N = 3 * d; p.K = d; p.bias = b.qkv_b; p.out_h = w.qk; p.ld_h = 2 * d;
       p.ssq = w.ssq; p.ssq_cols = 2 * d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(2 * d, bn_qkv);
@@ -400,7 +409,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
     }
     // ---- cross-attention (model.py:313, 166-186 / 204-230).  q stays un-normalised: norm_q's weight is
     // folded into the (cached) keys and the per-row rsqrt(mean(q^2)+eps) into the softmax scale.
-    launch_ln_affine(w.x_res, w.u, b.norm3_w, b.norm3_b, 0, M, L, d, eps, s);
+    launch_ln_affine(w.x_res, w.u, b.norm3_w, b.norm3_b, 0, M, L, d, eps, s, false, bad.as<unsigned int>());
     {
       GemmParams p{}; p.w_static = 1; p.M = M; p.N = d; p.K = d; p.bias = b.cq_b; p.out_h = w.qk; p.ld_h = d;
       p.ssq = w.ssq; p.ssq_cols = d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(d, bn_cq); p.vt_col0 = d;
@@ -439,7 +448,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
       gemm_linear(EPI_RESID_F32, w.att, d, b.co_w, d, p, num_sms, s);
     }
     // ---- FFN (model.py:314-328)
-    launch_ln_affine(w.x_res, w.u, mod + 4 * d, mod + 3 * d, 6 * d, M, L, d, eps, s);
+    launch_ln_affine(w.x_res, w.u, mod + 4 * d, mod + 3 * d, 6 * d, M, L, d, eps, s, false, bad.as<unsigned int>());
     {
       GemmParams p{}; p.w_static = 1; p.M = M; p.N = f; p.K = d; p.bias = b.ffn0_b; p.out_h = w.hid; p.ld_h = f;
       gemm_linear(EPI_GELU_F16, w.u, d, b.ffn0_w, d, p, num_sms, s);
@@ -455,7 +464,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   {
     const int P = cfg.out_dim * 4;
     launch_head_table(wt.head_mod, w.e, w.headtab, B, d, s);
-    launch_ln_affine(w.x_res, w.u3, w.headtab, w.headtab + d, 2 * d, M, L, d, eps, s, /*split=*/true);
+    launch_ln_affine(w.x_res, w.u3, w.headtab, w.headtab + d, 2 * d, M, L, d, eps, s, /*split=*/true, bad.as<unsigned int>());
     GemmParams p{}; p.w_static = 1; p.M = M; p.N = P; p.K = 3 * d; p.bias = wt.head_b; p.out_f = w.y; p.ld_f = P;
     gemm_linear(EPI_F32, w.u3, 3 * d, wt.head_w3, 3 * d, p, num_sms, s);
     launch_unpatchify(w.y, P, B, F, Hp, Wp, cfg.out_dim, in.out, in.cfg_pairs, in.cfg_scale, s);

@@ -80,6 +80,9 @@ class DitEngine {
                const float* const* clip, int F, int H, int W, int seq_len, bool cfg, float guide_scale,
                float* const* out, cudaStream_t stream);
   double flops(int B, int L) const;
+  // rows of the residual stream that reached a LayerNorm as inf / NaN since the last call (an fp16 operand that
+  // overflowed upstream); reads a device counter after synchronising `stream`, then clears it
+  unsigned int nonfinite_rows(cudaStream_t stream);
 
   b200dit_config cfg;
   int num_sms = 148;
@@ -98,7 +101,7 @@ class DitEngine {
   void enqueue(const FwdInputs& in, cudaStream_t s);
 
   std::unordered_map<std::string, Slot> slots;
-  DevBuf w16, w32, ws, sio;
+  DevBuf w16, w32, ws, sio, bad;
   DitWeights wt{};
   DitWorkspace w{};
   int ws_B = 0, ws_L = 0;

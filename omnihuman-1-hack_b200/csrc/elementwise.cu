@@ -28,7 +28,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <int NV, bool SPLIT>
 __global__ void __launch_bounds__(128) ln_affine_kernel(const float* __restrict__ x, __half* __restrict__ out,
                                                         const float* __restrict__ a, const float* __restrict__ b,
-                                                        long long item_stride, int M, int rows_per_item, float eps) {
+                                                        long long item_stride, int M, int rows_per_item, float eps,
+                                                        unsigned int* __restrict__ bad_rows) {
   constexpr int DIM = NV * 128;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -47,7 +48,11 @@ __global__ void __launch_bounds__(128) ln_affine_kernel(const float* __restrict_
     const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
     q += dx * dx + dy * dy + dz * dz + dw * dw;
   }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / DIM) + eps);
+  const float var = warp_sum(q) * (1.0f / DIM);
+  // an fp16 operand that overflowed upstream reaches the residual stream as inf / NaN: count the rows (the
+  // comparison is false for NaN too); the engine reports the total through b200dit_nonfinite_rows
+  if (bad_rows != nullptr && lane == 0 && !(var < __int_as_float(0x7f800000))) atomicAdd(bad_rows, 1u);
+  const float rstd = rsqrtf(var + eps);
   const long long ioff = (long long)(rows_per_item > 0 ? row / rows_per_item : 0) * item_stride;
   const float4* ar = reinterpret_cast<const float4*>(a + ioff);
   const float4* br = reinterpret_cast<const float4*>(b + ioff);
@@ -404,14 +409,14 @@ inline int grid_for(long long n, int block = 256) {
 }  // namespace
 
 void launch_ln_affine(const float* x, __half* out, const float* a, const float* b, long long item_stride, int M,
-                      int rows_per_item, int dim, float eps, cudaStream_t s, bool split) {
+                      int rows_per_item, int dim, float eps, cudaStream_t s, bool split, unsigned int* bad_rows) {
   B2_CHECK(dim % 128 == 0, "LayerNorm width %d must be a multiple of 128", dim);
   const int grid = (M + 3) / 4;
   ProfScope prof(PC_NORM, 0.0, (split ? 10.0 : 6.0) * M * dim, s);
 #define B2_LN_CASE(NV)                                                                                         \
   case NV:                                                                                                     \
-    if (split) launch_pdl(ln_affine_kernel<NV, true>, dim3(grid), dim3(128), 0, s, x, out, a, b, item_stride, M, rows_per_item, eps); \
-    else launch_pdl(ln_affine_kernel<NV, false>, dim3(grid), dim3(128), 0, s, x, out, a, b, item_stride, M, rows_per_item, eps);      \
+    if (split) launch_pdl(ln_affine_kernel<NV, true>, dim3(grid), dim3(128), 0, s, x, out, a, b, item_stride, M, rows_per_item, eps, bad_rows); \
+    else launch_pdl(ln_affine_kernel<NV, false>, dim3(grid), dim3(128), 0, s, x, out, a, b, item_stride, M, rows_per_item, eps, bad_rows); \
     break;
   switch (dim / 128) {
     B2_LN_CASE(1) B2_LN_CASE(2) B2_LN_CASE(3) B2_LN_CASE(4) B2_LN_CASE(8) B2_LN_CASE(10) B2_LN_CASE(12)

@@ -138,9 +138,11 @@ void launch_attention(const AttnParams& p, cudaStream_t stream);
 struct ItemPtrs { const float* p[MAX_ITEMS]; };
 struct ItemPtrsMut { float* p[MAX_ITEMS]; };
 
-// LayerNorm(x) * a + b  ->  fp16.  a/b are [dim] vectors, per item when item_stride != 0.
+// LayerNorm(x) * a + b  ->  fp16.  a/b are [dim] vectors, per item when item_stride != 0.  bad_rows (optional
+// device counter) is incremented once per row whose variance is inf / NaN.
 void launch_ln_affine(const float* x, __half* out, const float* a, const float* b, long long item_stride, int M,
-                      int rows_per_item, int dim, float eps, cudaStream_t s, bool split = false);
+                      int rows_per_item, int dim, float eps, cudaStream_t s, bool split = false,
+                      unsigned int* bad_rows = nullptr);
 // in-place on fp16 [M, ld]: per slice (q at column 0, k at column dim) x * rsqrt(mean(x^2)+eps) * gamma,
 // then optional 3-D RoPE (cos/sin table [rows_per_item, 64] float2).  ssq holds the producing GEMM's partial
 // sums: slice s = sum over i < ssq_n of ssq[row*ssq_ld + 2i + s].  gamma_mul: extra per-channel factor on slice 0

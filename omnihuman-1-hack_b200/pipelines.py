@@ -33,9 +33,11 @@ def make_scheduler(solver, steps, shift, device):
 
 @torch.no_grad()
 def sample(engine, noise, context, context_null, steps=50, shift=5.0, guide_scale=5.0, solver="unipc",
-           seq_len=None, clip_fea=None, y=None, cfg_anneal=False, callback=None):
+           seq_len=None, clip_fea=None, y=None, cfg_anneal=False, callback=None, check_overflow=True):
     """Denoises `noise` (list of [16,T,h,w] fp32, all the same shape) and returns the list of x0 latents.
-    Every sample carries its own scheduler state; all samples are co-batched in one engine call per step."""
+    Every sample carries its own scheduler state; all samples are co-batched in one engine call per step.
+    `check_overflow`: one read of the engine's overflow guard after the last step (the engine computes with fp16
+    operands where the reference autocasts to bf16); raises FloatingPointError instead of returning NaN latents."""
     xs = [n.to(engine.device, torch.float32) for n in noise]
     n = len(xs)
     if seq_len is None:
@@ -51,6 +53,10 @@ def sample(engine, noise, context, context_null, steps=50, shift=5.0, guide_scal
               for (sch, _), xi, vi in zip(scheds, xs, v)]
         if callback is not None:
             callback(i, t, xs)
+    if check_overflow:
+        bad = engine.nonfinite_rows()
+        if bad:
+            raise FloatingPointError(f"{bad} residual-stream rows overflowed the fp16 operand range during sampling")
     return xs
 
 

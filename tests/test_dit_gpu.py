@@ -139,6 +139,27 @@ def test_context_cache_reuse_and_invalidation():
         assert rel_l2(a.cpu(), b.cpu()) < 1e-6
 
 
+def test_overflow_guard_counts_nonfinite_rows():
+    """b200dit_nonfinite_rows: 0 on a healthy forward; an FFN whose hidden activations exceed the fp16 range
+    (65504) poisons the residual stream and every later LayerNorm counts the rows."""
+    import b200dit
+    g = _load("dit_t2v_tiny.pt")
+    sd = {k: v.float() for k, v in g["sd"].items()}
+    heads = g["cfg"]["num_heads"]
+    eng = b200dit.DitEngine.from_state_dict(sd, num_heads=heads)
+    eng.forward(g["x"], g["t"], g["context"], g["seq_len"])
+    assert eng.nonfinite_rows() == 0
+    hot = dict(sd)
+    hot["blocks.0.ffn.0.weight"] = sd["blocks.0.ffn.0.weight"] * 3e6
+    eng2 = b200dit.DitEngine.from_state_dict(hot, num_heads=heads)
+    out = eng2.forward(g["x"], g["t"], g["context"], g["seq_len"])
+    n = eng2.nonfinite_rows()
+    assert n > 0 and not all(torch.isfinite(o).all() for o in out)
+    assert eng2.nonfinite_rows() == 0                                   # reading clears the counter
+    eng.forward(g["x"], g["t"], g["context"], g["seq_len"])
+    assert eng.nonfinite_rows() == 0
+
+
 def test_token_count_not_multiple_of_8():
     """L = 15 tokens (grid 1x3x5) cannot be co-batched (TMA tile origins); the host side runs one item per call and
     the CFG path falls back to two forwards + one fused combine -- results must not change."""
