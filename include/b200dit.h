@@ -142,6 +142,26 @@ B200_API int b200vae_decode(b200vae_engine* e, const float* z, int32_t T, int32_
 B200_API int b200vae_encode(b200vae_engine* e, const float* video, int32_t T, int32_t H, int32_t W, float* out,
                             void* stream);
 
+/* ---- APT discriminator heads (seaweed_apt/model.py:86-186), SURVEY.md 8f row F4 ----
+ * WanAPTDiscriminator.forward = backbone forward at a shifted timestep (b200dit_forward + b200dit_set_taps on
+ * the three hooked blocks, model.py:150-163) followed by the part this handle replaces: three single-query
+ * cross-attention heads (WanCrossAttentionDiscriminatorBlock, model.py:19-83) on the block outputs, concat,
+ * LayerNorm(3 dim), Linear(3 dim, 1) (model.py:117-121, 166-181). */
+typedef struct b200disc_engine b200disc_engine;
+/* dim = num_heads * 128; qk_norm / eps as WanModel's (model.py:97-115 passes the backbone's). */
+B200_API int b200disc_create(int32_t dim, int32_t num_heads, int32_t qk_norm, float eps, b200disc_engine** out);
+B200_API void b200disc_destroy(b200disc_engine* e);
+/* WanAPTDiscriminator state_dict entries outside `backbone.`: `cross_attn_16.*`, `cross_attn_26.*`,
+ * `cross_attn_36.*` (query_token, norm, q/k/v/o_proj, q_norm, k_norm) and `final_proj.{0,1}.*`. */
+B200_API int b200disc_load_weight(b200disc_engine* e, const char* name, const void* data, int32_t dtype, int32_t ndim,
+                                  const int64_t* shape);
+B200_API int b200disc_finalize(b200disc_engine* e);
+/* taps[i]: device fp32 [n_items * rows_per_item, dim], the output of the block feeding head i (the buffers
+ * b200dit_set_taps fills).  logits: device fp32 [n_items].  feats: optional device fp32 [3, n_items, dim], the
+ * three head tokens (return_features=True, model.py:183-184). */
+B200_API int b200disc_forward(b200disc_engine* e, const float* const* taps, int32_t n_items, int32_t rows_per_item,
+                              float* logits, float* feats, void* stream);
+
 /* ---- operator seam (attention.py:24-130) and its GEMM sibling, exposed for unit parity tests,
  *      micro-benchmarks and for patching `wan.modules.model.flash_attention` directly ---- */
 /* flash_attention(q, k, v, k_lens=...) with head_dim 128, non-causal: q [B, Lq, H, 128], k / v

@@ -48,6 +48,11 @@ SIGNATURES = {
     "b200vae_finalize": (_I, [_P]),
     "b200vae_decode": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "b200vae_encode": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "b200disc_create": (_I, [_I, _I, _I, _F, _PP]),
+    "b200disc_destroy": (None, [_P]),
+    "b200disc_load_weight": (_I, [_P, C.c_char_p, _P, _I, _I, C.POINTER(C.c_int64)]),
+    "b200disc_finalize": (_I, [_P]),
+    "b200disc_forward": (_I, [_P, _PP, _I, _I, _P, _P, _P]),
     "b200_flash_attention": (_I, [_P, _P, _P, _IP, _I, _I, _I, _I, _F, _P, _P]),
     "b200_linear": (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _I, _P, _L, _I, _P]),
     "b200_solver_lincomb": (_I, [_I, _PP, _I, _PP, C.POINTER(C.c_float), _L, _P]),

@@ -5,6 +5,7 @@
 
 #include "../../include/b200dit.h"
 #include "dit_engine.h"
+#include "disc_engine.h"
 #include "vae_engine.h"
 
 struct b200dit_engine {
@@ -14,6 +15,10 @@ struct b200dit_engine {
 struct b200vae_engine {
   b2::VaeEngine impl;
   b200vae_engine(int dim, int z) : impl(dim, z) {}
+};
+struct b200disc_engine {
+  b2::DiscEngine impl;
+  b200disc_engine(int dim, int heads, bool qk_norm, float eps) : impl(dim, heads, qk_norm, eps) {}
 };
 
 static thread_local std::string g_err;
@@ -172,6 +177,34 @@ int b200_flash_attention(const void* q, const void* k, const void* v, const int3
     for (int i = 0; i < B; ++i) p.klen[i] = k_lens ? (k_lens[i] < Lk ? k_lens[i] : Lk) : Lk;
     b2::launch_attention(p, s);
     B2_CUDA(cudaFreeAsync(vt, s));
+  });
+}
+
+int b200disc_create(int32_t dim, int32_t num_heads, int32_t qk_norm, float eps, b200disc_engine** out) {
+  return guarded([&] {
+    B2_CHECK(out != nullptr, "null argument");
+    int ndev = 0;
+    cudaError_t er = cudaGetDeviceCount(&ndev);
+    B2_CHECK(er == cudaSuccess && ndev > 0, "no CUDA device available: the B200 engine has no CPU fallback");
+    *out = new b200disc_engine(dim, num_heads, qk_norm != 0, eps);
+  });
+}
+void b200disc_destroy(b200disc_engine* e) { delete e; }
+int b200disc_load_weight(b200disc_engine* e, const char* name, const void* data, int32_t dtype, int32_t ndim,
+                         const int64_t* shape) {
+  return guarded([&] {
+    B2_CHECK(e && name && data && shape, "null argument");
+    e->impl.load_weight(name, data, dtype, ndim, shape);
+  });
+}
+int b200disc_finalize(b200disc_engine* e) {
+  return guarded([&] { B2_CHECK(e, "null engine"); e->impl.finalize(); });
+}
+int b200disc_forward(b200disc_engine* e, const float* const* taps, int32_t n_items, int32_t rows_per_item,
+                     float* logits, float* feats, void* stream) {
+  return guarded([&] {
+    B2_CHECK(e, "null engine");
+    e->impl.forward(taps, n_items, rows_per_item, logits, feats, static_cast<cudaStream_t>(stream));
   });
 }
 

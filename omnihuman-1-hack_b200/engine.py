@@ -224,11 +224,16 @@ class DitEngine:
         check(lib().b200dit_set_tap(self._h, int(block_idx), C.c_void_p(self._tap.data_ptr())))
         return self._tap
 
-    def set_taps(self, block_indices, n_rows):
+    def set_taps(self, block_indices, n_rows, buffers=None):
         """Residual stream after several blocks (the APT discriminator hooks three, seaweed_apt/model.py:150-155);
-        returns one fp32 [n_rows, dim] tensor per block, refreshed by every following forward."""
+        returns one fp32 [n_rows, dim] tensor per block, refreshed by every following forward.  `buffers`
+        re-registers tensors returned by an earlier call instead of allocating new ones."""
         idx = [int(b) for b in block_indices]
-        self._tap = [torch.empty((n_rows, self.cfg["dim"]), dtype=torch.float32, device=self.device) for _ in idx]
+        if buffers is not None:
+            assert len(buffers) == len(idx) and all(b.shape == (n_rows, self.cfg["dim"]) for b in buffers)
+            self._tap = list(buffers)
+        else:
+            self._tap = [torch.empty((n_rows, self.cfg["dim"]), dtype=torch.float32, device=self.device) for _ in idx]
         check(lib().b200dit_set_taps(self._h, len(idx), int_array(idx), ptr_array([t.data_ptr() for t in self._tap])))
         return self._tap
 

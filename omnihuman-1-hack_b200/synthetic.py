@@ -54,6 +54,29 @@ def dit_weights(cfg, seed, device, i2v=False):
     return sd
 
 
+def disc_head_weights(dim, seed, device="cpu", names=(16, 26, 36)):
+    """Random weights with the reference discriminator's key names (seaweed_apt/model.py:97-121 + :19-42):
+    three single-query heads `cross_attn_<n>.*` and `final_proj.{0,1}.*`.  fp32, CPU generator by default so the
+    same seed gives the same values on every machine (the golden fixture stores only the seed)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    rn = lambda *s, std=1.0: torch.randn(*s, generator=g, device=device) * std
+    sd = {}
+    for n in names:
+        p = f"cross_attn_{n}."
+        sd[p + "query_token"] = rn(1, 1, dim) / math.sqrt(dim)
+        for nm in ("norm", "q_norm", "k_norm"):
+            sd[p + nm + ".weight"] = 1.0 + rn(dim, std=0.1)
+            sd[p + nm + ".bias"] = rn(dim, std=0.05)
+        for nm in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            sd[p + nm + ".weight"] = rn(dim, dim) / math.sqrt(dim)
+            sd[p + nm + ".bias"] = rn(dim, std=0.05)
+    sd["final_proj.0.weight"] = 1.0 + rn(3 * dim, std=0.1)
+    sd["final_proj.0.bias"] = rn(3 * dim, std=0.05)
+    sd["final_proj.1.weight"] = rn(1, 3 * dim) / math.sqrt(3 * dim)
+    sd["final_proj.1.bias"] = rn(1, std=0.05)
+    return sd
+
+
 def vae_decoder_weights(dim=96, z_dim=16, seed=0, device="cpu", encoder=False):
     """Decoder + conv2 of WanVAE_ (vae.py:369-421, 505-507) with dim_mult [1,2,4,4], 2 res blocks per stage,
     temporal upsampling in the first two stages (vae.py:597-605); encoder=True adds Encoder3d + conv1

@@ -84,7 +84,52 @@ def make_encode_golden():
     print("vae_enc_tiny", tuple(mu.shape), float(mu.std()))
 
 
+DISC_CFG = dict(dim=128, ffn_dim=128, num_heads=1, num_layers=36, text_dim=32, in_dim=16, i2v=False, freq_dim=256)
+
+
+def make_disc_golden():
+    """The UNMODIFIED WanAPTDiscriminator (seaweed_apt/model.py:86-186) over a 36-block tiny backbone (the
+    reference hooks blocks[15], [25], [35]).  Weights come from b200dit.synthetic with the stored seeds, so the
+    fixture holds only inputs and the reference's outputs.  Two cases: one latent frame (timestep shift s = 1)
+    and three (s = 12)."""
+    import importlib
+    syn = importlib.import_module("omnihuman-1-hack_b200.synthetic")
+    from oracle import disc_oracle as DO
+    M, _ = ref_loader.load_reference_modules()
+    A = ref_loader.load_reference_apt()
+    cfg = DISC_CFG
+    seed_backbone, seed_heads = 4242, 4343
+    sd = {k: v.float() for k, v in syn.dit_weights(cfg, seed_backbone, "cpu").items()}
+    hw = syn.disc_head_weights(cfg["dim"], seed_heads)
+    wan = M.WanModel(model_type="t2v", in_dim=cfg["in_dim"], dim=cfg["dim"], ffn_dim=cfg["ffn_dim"],
+                     num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], text_dim=cfg["text_dim"],
+                     use_checkpoint=False).eval()
+    wan.load_state_dict(sd, strict=True)
+    disc = A.WanAPTDiscriminator(wan).eval()
+    missing, unexpected = disc.load_state_dict(hw, strict=False)
+    assert not unexpected and all(k.startswith("backbone.") for k in missing), (missing, unexpected)
+    g = torch.Generator().manual_seed(99)
+    cases = []
+    for frames, t in ((1, [0.3, 0.9]), (3, [0.25, 0.6])):
+        x = torch.randn(2, 16, frames, 8, 8, generator=g)
+        ctx = [torch.randn(12, cfg["text_dim"], generator=g), torch.randn(7, cfg["text_dim"], generator=g)]
+        tt = torch.tensor(t)
+        seq_len = frames * 16
+        with torch.no_grad():
+            logit, feats = disc(x, tt, ctx, seq_len, return_features=True)
+        o_logit, o_feats = DO.disc_forward(sd, hw, x, tt, ctx, seq_len, cfg["num_heads"])
+        err = max(float((a - b).abs().max()) for a, b in zip([logit] + feats, [o_logit] + o_feats))
+        print(f"disc golden frames={frames}: logit {logit.flatten().tolist()} oracle max abs err {err:.2e}")
+        assert err < 1e-4
+        cases.append(dict(x=x, t=tt, context=ctx, seq_len=seq_len, logit=logit.clone(),
+                          feats=[f.clone() for f in feats]))
+    torch.save(dict(cfg=cfg, seed_backbone=seed_backbone, seed_heads=seed_heads, cases=cases),
+               os.path.join(OUT, "disc_tiny.pt"))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "disc":
+        return make_disc_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "solvers":
         return make_solver_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "encode":

@@ -62,7 +62,11 @@ def _install_stubs():
         mu = types.ModuleType("diffusers.models.modeling_utils")
 
         class _Config(dict):
-            __getattr__ = dict.__getitem__
+            def __getattr__(self, name):
+                try:
+                    return self[name]
+                except KeyError:
+                    raise AttributeError(name) from None
 
         class ConfigMixin:
             """Minimal stand-in for diffusers' ConfigMixin: `self.config` holds the constructor arguments."""
@@ -181,3 +185,37 @@ def load_reference_solvers(root=None):
             spec.loader.exec_module(m)
         out.append(sys.modules[full])
     return tuple(out)
+
+
+def load_reference_apt(root=None):
+    """Returns the reference's seaweed_apt/model.py module (WanCrossAttentionDiscriminatorBlock,
+    WanAPTDiscriminator), executed in place; its `wan.modules.*` imports resolve to the modules loaded by
+    load_reference_modules (T5 is never touched by the discriminator and is stubbed)."""
+    root = root or find_reference()
+    if root is None:
+        raise FileNotFoundError("reference tree not available (container-only tool)")
+    full = "_ref_apt_model"
+    if full in sys.modules:
+        return sys.modules[full]
+    model, vae = load_reference_modules(root)
+    wan = types.ModuleType("wan"); wan.__path__ = []
+    wm = types.ModuleType("wan.modules"); wm.__path__ = []
+    t5 = types.ModuleType("wan.modules.t5"); t5.T5EncoderModel = object
+    added = {"wan": wan, "wan.modules": wm, "wan.modules.model": model, "wan.modules.t5": t5, "wan.modules.vae": vae}
+    saved = {k: sys.modules.get(k) for k in added}
+    sys.modules.update(added)
+    try:
+        spec = importlib.util.spec_from_file_location(full, os.path.join(root, "seaweed_apt/model.py"))
+        m = importlib.util.module_from_spec(spec)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            spec.loader.exec_module(m)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    sys.modules[full] = m
+    return m

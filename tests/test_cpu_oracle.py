@@ -115,3 +115,45 @@ def test_vae_encode_oracle_vs_golden():
     syn = b200dit.synthetic.vae_decoder_weights(dim=8, seed=0, encoder=True)
     ref = VO.make_synthetic_vae_weights(dim=8, seed=0, encoder=True)
     assert set(syn) == set(ref) and all(syn[k].shape == ref[k].shape for k in syn)
+
+
+def _disc_weights(g):
+    import b200dit
+    sd = {k: v.float() for k, v in b200dit.synthetic.dit_weights(g["cfg"], g["seed_backbone"], "cpu").items()}
+    return sd, b200dit.synthetic.disc_head_weights(g["cfg"]["dim"], g["seed_heads"])
+
+
+def test_disc_oracle_vs_golden():
+    """The discriminator restatement (backbone at the shifted timestep, taps 16/26/36, three heads, final_proj)
+    against the UNMODIFIED WanAPTDiscriminator's logits and tokens (oracle/make_golden.py disc)."""
+    from oracle import disc_oracle as DO
+    g = torch.load(os.path.join(GOLDEN, "disc_tiny.pt"))
+    sd, hw = _disc_weights(g)
+    for case in g["cases"]:
+        logit, feats = DO.disc_forward(sd, hw, case["x"], case["t"], case["context"], case["seq_len"],
+                                       g["cfg"]["num_heads"])
+        assert torch.allclose(logit, case["logit"], atol=2e-5)
+        for a, r in zip(feats, case["feats"]):
+            assert rel_l2(a, r) < 1e-5
+    assert float(DO.timestep_shift(torch.tensor(0.5), 1)) == 0.5
+    assert abs(float(DO.timestep_shift(torch.tensor(0.5), 3)) - 6.0 / 6.5) < 1e-7
+
+
+@pytest.mark.skipif(ref_loader.find_reference() is None, reason="reference tree not mounted (container-only check)")
+@pytest.mark.parametrize("qk_norm", [True, False])
+def test_disc_head_oracle_vs_live_reference(qk_norm):
+    """One head at several heads / ragged token counts against the reference class executed in place."""
+    from oracle import disc_oracle as DO
+    A = ref_loader.load_reference_apt()
+    torch.manual_seed(5)
+    blk = A.WanCrossAttentionDiscriminatorBlock(256, 2, qk_norm=qk_norm, eps=1e-6).eval()
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    x = torch.randn(3, 37, 256) * 2.0 + 0.3
+    w = {"h." + k: v for k, v in blk.state_dict().items()}
+    with torch.no_grad():
+        ref = blk(x)
+    out = DO.disc_head(x, w, "h.", 2, qk_norm=qk_norm)
+    assert out.shape == ref.shape == (3, 1, 256)
+    assert rel_l2(out, ref) < 1e-6
