@@ -5,6 +5,7 @@
 // One 128-query tile per CTA, 64-key steps, two CTAs per SM (namespace v2; the first kernel -- 128-key steps,
 // one CTA per SM, P through shared memory -- and a two-tiles-per-CTA variant with shared K / V tiles were
 // measured slower and removed).
+#include <algorithm>
 #include <cstdlib>
 
 #include "host_util.h"
@@ -86,10 +87,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int warp = warp_id(), lane = lane_id();
   // query-tile index slowest: the partial last tiles of all (item, head) pairs are scheduled last, so
   // the CTAs that do not fit the first co-resident wave are the cheap ones
-  const int hi = blockIdx.x % (p.heads * p.items), qt = blockIdx.x / (p.heads * p.items);
+  // the last p.split_tiles tiles of that order are cut into p.split_parts CTAs each along the key axis
+  int tile = blockIdx.x, part = 0, parts = 1;
+  if (p.split_tiles > 0) {
+    const int n_plain = (int)gridDim.x - p.split_tiles * p.split_parts;
+    if (tile >= n_plain) {
+      const int b = tile - n_plain;
+      tile = n_plain + b / p.split_parts; part = b % p.split_parts; parts = p.split_parts;
+    }
+  }
+  const int hi = tile % (p.heads * p.items), qt = tile / (p.heads * p.items);
   const int head = hi % p.heads, item = hi / p.heads;
   const int klen = p.klen[item];
-  const int n_kv = (klen + KT - 1) / KT;
+  const int n_kv_all = (klen + KT - 1) / KT;
+  const int j0 = part * n_kv_all / parts;                   // this CTA's key steps: [j0, j0 + n_kv)
+  const int n_kv = (part + 1) * n_kv_all / parts - j0;      // >= 1: the launcher keeps parts <= n_kv_all
   pdl_launch();
 
   if (warp == W_TMA && lane == 0) {
@@ -122,7 +134,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int i = 0; i <= n_kv; ++i) {
         if (i < n_kv) {
           const int st = i % KSTAGES; const uint32_t ph = (i / KSTAGES) & 1;
-          const int k_row0 = item * p.Lk_rows + i * KT;
+          const int k_row0 = item * p.Lk_rows + (j0 + i) * KT;
           mbar_wait(&k_empty[st], ph ^ 1);
           mbar_expect_tx(&k_full[st], K_BYTES);
           tma_load_2d(smem + OFF_K + st * K_BYTES, &tmap_k, &k_full[st], head * 128, k_row0);
@@ -133,7 +145,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           mbar_wait(&v_empty[st], ph ^ 1);
           mbar_expect_tx(&v_full[st], V_BYTES);
           tma_load_2d(smem + OFF_V + st * V_BYTES, &tmap_vt, &v_full[st],
-                      item * (p.vt_stride ? p.vt_stride : p.Lk_rows) + j * KT, head * 128);
+                      item * (p.vt_stride ? p.vt_stride : p.Lk_rows) + (j0 + j) * KT, head * 128);
         }
       }
     }
@@ -223,7 +235,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(t0[i]); s[32 + i] = __uint_as_float(t1[i]); }
       }
 
-      const int valid = klen - j * KT;
+      const int valid = klen - (j0 + j) * KT;
       if (valid < KT) {
 #pragma unroll
         for (int i = 0; i < KT; ++i) if (i >= valid) s[i] = -INFINITY;
@@ -296,6 +308,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
     mbar_wait_warp(pv_done, (n_kv - 1) & 1, lane);          // pv_done has completed n_kv - 1 or n_kv times here
     tc_fence_after();
+    if (parts > 1) {
+      // partial tile: un-normalised O row (relative to m_ref), its reference in log2 units and its running sum
+      const int slot = (tile - ((int)gridDim.x - p.split_tiles * p.split_parts)) * parts + part;
+      float* wo = p.split_ws + ((long long)slot * QT + r) * 128;
+      float* wml = p.split_ws + (long long)p.split_tiles * parts * QT * 128 + ((long long)slot * QT + r) * 2;
+#pragma unroll
+      for (int cidx = 0; cidx < 4; ++cidx) {
+        uint32_t t[32];
+        tmem_ld32(tmem_o + lane_sel + cidx * 32, t);
+        tmem_wait_ld();
+        if (q_in_item < p.Lq) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<uint4*>(wo + cidx * 32 + i) = make_uint4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+        }
+      }
+      if (q_in_item < p.Lq) *reinterpret_cast<float2*>(wml) = make_float2(m_ref * c, l_sum);
+    } else {
     const float inv_l = 1.0f / l_sum;
     __half* o = p.out + ((long long)item * p.Lq + q_in_item) * p.ldo + head * 128;
 #pragma unroll
@@ -321,6 +351,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
     }
+    }
     tc_fence_before();
   }
 
@@ -328,6 +359,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// Merges the partial rows of the split tiles: O = sum_p 2^(m_p - M) O_p / sum_p 2^(m_p - M) l_p, M = max_p m_p.
+// One warp per query row, lanes across the 128 channels; grid = split tiles.
+__global__ void __launch_bounds__(256) attn_combine_kernel(const AttnParams p, int n_plain) {
+  pdl_launch();
+  pdl_wait();
+  const int tile = n_plain + blockIdx.x, parts = p.split_parts;
+  const int hi = tile % (p.heads * p.items), qt = tile / (p.heads * p.items);
+  const int head = hi % p.heads, item = hi / p.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* ws_o = p.split_ws + (long long)blockIdx.x * parts * QT * 128;
+  const float* ws_ml = p.split_ws + (long long)p.split_tiles * parts * QT * 128 + (long long)blockIdx.x * parts * QT * 2;
+  for (int r = warp; r < QT; r += 8) {
+    const int q_in_item = qt * QT + r;
+    if (q_in_item >= p.Lq) break;
+    float M = -INFINITY;
+    for (int q = 0; q < parts; ++q) M = fmaxf(M, ws_ml[(q * QT + r) * 2]);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float l = 0.f;
+    for (int q = 0; q < parts; ++q) {
+      const float2 ml = *reinterpret_cast<const float2*>(ws_ml + (q * QT + r) * 2);
+      const float w = ex2(ml.x - M);
+      const float4 o = *reinterpret_cast<const float4*>(ws_o + ((long long)q * QT + r) * 128 + lane * 4);
+      acc.x = fmaf(w, o.x, acc.x); acc.y = fmaf(w, o.y, acc.y); acc.z = fmaf(w, o.z, acc.z); acc.w = fmaf(w, o.w, acc.w);
+      l = fmaf(w, ml.y, l);
+    }
+    const float inv = 1.0f / l;
+    float v[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
+    uint2* dst = reinterpret_cast<uint2*>(p.out + ((long long)item * p.Lq + q_in_item) * p.ldo + head * 128 + lane * 4);
+    if (p.accumulate) {
+      const uint2 old = *dst;
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&old.x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&old.y));
+      v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
+    }
+    *dst = make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
   }
 }
 }  // namespace v2
@@ -359,9 +428,37 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
   ProfScope prof(PC_ATTN, 4.0 * p.Lq * keys * 128.0 * p.heads, 0.0, stream);
   AttnParams pd = p;
   pd.dbg = dbg;
-  dim3 grid(((p.Lq + TILE - 1) / TILE) * p.heads * p.items);
+  const int n_tiles = ((p.Lq + TILE - 1) / TILE) * p.heads * p.items;
+  // Tail split: tiles run in co-resident waves of two CTAs per SM.  When the last wave holds only a few tiles, cut
+  // each of them along the key axis so that the wave is as wide as the machine and proportionally shorter.
+  static const int slots = [] {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return 2 * sms;
+  }();
+  const char* split_env = std::getenv("B200_ATTN_SPLIT");               // 0 disables, n > 1 = at most n parts (A/B runs)
+  const int split_mode = split_env ? std::atoi(split_env) : 1;
+  const int max_parts = split_mode > 1 ? split_mode : 4;      // 4 measured best (4 / 8 / 16 within 1 %)
+  const char* steps_env = std::getenv("B200_ATTN_SPLIT_MINSTEPS");
+  const int min_steps = steps_env ? std::max(1, std::atoi(steps_env)) : 2;
+  pd.split_tiles = 0; pd.split_parts = 1;
+  const int rem = n_tiles % slots;
+  if (p.split_ws != nullptr && split_mode && rem > 0) {
+    int min_kv = 1 << 30;
+    for (int i = 0; i < p.items; ++i) min_kv = std::min(min_kv, (p.klen[i] + v2::KT - 1) / v2::KT);
+    const int parts = std::min(std::min(slots / rem, max_parts), min_kv / min_steps);   // at least two key steps per part
+    if (parts >= 2 && (long long)rem * parts * (TILE * 128 + 2 * TILE) * 4 <= ATTN_SPLIT_WS_BYTES) {
+      pd.split_tiles = rem; pd.split_parts = parts;
+    }
+  }
+  dim3 grid(n_tiles - pd.split_tiles + pd.split_tiles * pd.split_parts);
   launch_pdl(v2::attn_fwd_kernel, grid, dim3(192), v2::SMEM, stream, tq, tk, tv, pd);
   count_launch();
+  if (pd.split_tiles > 0) {
+    launch_pdl(v2::attn_combine_kernel, dim3(pd.split_tiles), dim3(256), 0, stream, pd, n_tiles - pd.split_tiles);
+    count_launch();
+  }
 }
 
 }  // namespace b2

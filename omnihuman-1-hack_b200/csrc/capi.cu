@@ -175,7 +175,11 @@ int b200_flash_attention(const void* q, const void* k, const void* v, const int3
     p.items = B; p.heads = H; p.Lq = Lq; p.Lk_rows = Lk; p.vt_stride = Lkp;
     p.scale = softmax_scale > 0.f ? softmax_scale : 0.08838834764831845f;
     for (int i = 0; i < B; ++i) p.klen[i] = k_lens ? (k_lens[i] < Lk ? k_lens[i] : Lk) : Lk;
+    void* split = nullptr;                            // scratch for the tail split (stream-ordered, like vt)
+    B2_CUDA(cudaMallocAsync(&split, b2::ATTN_SPLIT_WS_BYTES, s));
+    p.split_ws = static_cast<float*>(split);
     b2::launch_attention(p, s);
+    B2_CUDA(cudaFreeAsync(split, s));
     B2_CUDA(cudaFreeAsync(vt, s));
   });
 }

@@ -49,6 +49,7 @@ DitEngine::DitEngine(const b200dit_config& c) : cfg(c) {
   B2_CUDA(cudaGetDevice(&dev));
   B2_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   bad.ensure(sizeof(unsigned int), /*zero=*/true);
+  attn_split.ensure(ATTN_SPLIT_WS_BYTES);
   alloc_weights();
 }
 
@@ -369,6 +370,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   self.q = w.qk; self.ldq = 2 * d; self.k = w.qk + d; self.ldk = 2 * d; self.vt = w.vt; self.ldvt = Mp;
   self.out = w.att; self.ldo = d; self.items = B; self.heads = Hn; self.Lq = L; self.Lk_rows = L;
   self.scale = 1.0f / std::sqrt(128.0f);
+  self.split_ws = attn_split.as<float>();
   for (int i = 0; i < B; ++i) self.klen[i] = L;
   AttnParams cross = self;
   cross.ldq = d; cross.k = w.kc; cross.ldk = d; cross.vt = w.vtc; cross.ldvt = B * TL; cross.Lk_rows = TL;

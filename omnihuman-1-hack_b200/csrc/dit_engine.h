@@ -101,7 +101,7 @@ class DitEngine {
   void enqueue(const FwdInputs& in, cudaStream_t s);
 
   std::unordered_map<std::string, Slot> slots;
-  DevBuf w16, w32, ws, sio, bad;
+  DevBuf w16, w32, ws, sio, bad, attn_split;
   DitWeights wt{};
   DitWorkspace w{};
   int ws_B = 0, ws_L = 0;

@@ -131,7 +131,14 @@ struct AttnParams {
   const float* q_ssq; int q_ssq_ld; int q_ssq_n; int q_dim; float q_eps;
   int dbg;                             // diagnosis only (B200_ATTN_DBG): 1 no exp2, 2 no TMEM reads of S, 4 no P store,
                                        // 8 softmax warps idle (MMA / TMA pipeline alone); results are wrong
+  // Tail split (optional; launch_attention decides).  Query tiles are dispatched in whole co-resident waves of
+  // 2 CTAs per SM; when the last wave is mostly empty its tiles are cut along the key axis into `split_parts`
+  // CTAs each, which leave un-normalised partial rows (O, running max, running sum) in `split_ws`, and
+  // attn_combine_kernel merges them.  split_ws: ATTN_SPLIT_WS_BYTES of device scratch, or nullptr (never split).
+  float* split_ws;
+  int split_tiles, split_parts;        // set by launch_attention
 };
+constexpr long long ATTN_SPLIT_WS_BYTES = 512ll * (128 * 128 + 2 * 128) * 4;    // up to 512 partial tiles
 void launch_attention(const AttnParams& p, cudaStream_t stream);
 
 // ---- elementwise.cu

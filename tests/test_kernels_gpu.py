@@ -57,6 +57,9 @@ def test_linear_f16_epilogues(epi, bn):
     (2, 200, 257, 2, [257, 100]), (3, 70, 15, 1, None),      # odd key counts: every item's V^T starts on a multiple of 8
     # >= 1024 keys: the two-tiles-per-CTA kernel (ragged key counts, a lone last tile, partial second tile)
     (2, 300, 1104, 2, [1104, 1030]), (1, 200, 1560, 1, None), (1, 128, 1152, 1, None), (1, 640, 1280, 3, [1025]),
+    # tail split: 312 / 624 tiles on 296 co-resident slots leave 16 / 32 tiles for the last wave, which are cut
+    # into 4 (self-attention, 25 key steps) or 3 (cross-attention, 6+ key steps) parts along the key axis
+    (2, 1560, 1560, 12, None), (4, 1560, 512, 12, [512, 400, 384, 512]),
 ])
 def test_flash_attention(B, Lq, Lk, H, klens):
     import b200dit
@@ -67,6 +70,21 @@ def test_flash_attention(B, Lq, Lk, H, klens):
     for b in range(B):
         ref = O.softmax_attention(q[b].cpu().float(), k[b].cpu().float(), v[b].cpu().float(), klens[b] if klens else None)
         assert rel_l2(out[b].cpu().float(), ref) < 2e-3, (b,)
+
+
+def test_flash_attention_tail_split_matches_unsplit(monkeypatch):
+    """B200_ATTN_SPLIT=0 runs every tile in one CTA; the split path must agree to fp16 rounding of the output."""
+    import b200dit
+    B, L, H = 2, 1560, 12
+    q, k, v = _mk((B, L, H, 128), 13).cuda(), _mk((B, L, H, 128), 14).cuda(), _mk((B, L, H, 128), 15).cuda()
+    a = b200dit.flash_attention(q, k, v)
+    monkeypatch.setenv("B200_ATTN_SPLIT", "0")
+    b = b200dit.flash_attention(q, k, v)
+    monkeypatch.delenv("B200_ATTN_SPLIT")
+    c = b200dit.flash_attention(q, k, v)
+    assert torch.equal(a, c)                                   # deterministic
+    assert rel_l2(a.float(), b.float()) < 3e-4
+    assert (a.float() - b.float()).abs().max() < 4e-3
 
 
 def test_flash_attention_large_logits():
