@@ -363,41 +363,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 // Merges the partial rows of the split tiles: O = sum_p 2^(m_p - M) O_p / sum_p 2^(m_p - M) l_p, M = max_p m_p.
-// One warp per query row, lanes across the 128 channels; grid = split tiles.
+// One warp per query row, lanes across the 128 channels; grid (split tiles, 16 groups of 8 rows).  Lane q holds
+// part q's (m, l), so the per-part weights come from one load + shuffles and the partial rows load back to back.
+constexpr int MAX_PARTS = 16;
 __global__ void __launch_bounds__(256) attn_combine_kernel(const AttnParams p, int n_plain) {
   pdl_launch();
-  pdl_wait();
   const int tile = n_plain + blockIdx.x, parts = p.split_parts;
   const int hi = tile % (p.heads * p.items), qt = tile / (p.heads * p.items);
   const int head = hi % p.heads, item = hi / p.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.y * 8 + warp, q_in_item = qt * QT + r;
+  if (q_in_item >= p.Lq) return;
+  pdl_wait();
   const float* ws_o = p.split_ws + (long long)blockIdx.x * parts * QT * 128;
   const float* ws_ml = p.split_ws + (long long)p.split_tiles * parts * QT * 128 + (long long)blockIdx.x * parts * QT * 2;
-  for (int r = warp; r < QT; r += 8) {
-    const int q_in_item = qt * QT + r;
-    if (q_in_item >= p.Lq) break;
-    float M = -INFINITY;
-    for (int q = 0; q < parts; ++q) M = fmaxf(M, ws_ml[(q * QT + r) * 2]);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float l = 0.f;
-    for (int q = 0; q < parts; ++q) {
-      const float2 ml = *reinterpret_cast<const float2*>(ws_ml + (q * QT + r) * 2);
-      const float w = ex2(ml.x - M);
-      const float4 o = *reinterpret_cast<const float4*>(ws_o + ((long long)q * QT + r) * 128 + lane * 4);
-      acc.x = fmaf(w, o.x, acc.x); acc.y = fmaf(w, o.y, acc.y); acc.z = fmaf(w, o.z, acc.z); acc.w = fmaf(w, o.w, acc.w);
-      l = fmaf(w, ml.y, l);
-    }
-    const float inv = 1.0f / l;
-    float v[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
-    uint2* dst = reinterpret_cast<uint2*>(p.out + ((long long)item * p.Lq + q_in_item) * p.ldo + head * 128 + lane * 4);
-    if (p.accumulate) {
-      const uint2 old = *dst;
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&old.x));
-      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&old.y));
-      v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
-    }
-    *dst = make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
+  float2 ml = make_float2(-INFINITY, 0.f);
+  if (lane < parts) ml = *reinterpret_cast<const float2*>(ws_ml + (lane * QT + r) * 2);
+  float M = ml.x;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+  const float w_mine = lane < parts ? ex2(ml.x - M) : 0.f;
+  float l = w_mine * ml.y;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int q = 0; q < parts; ++q) {
+    const float w = __shfl_sync(0xffffffffu, w_mine, q);
+    const float4 o = *reinterpret_cast<const float4*>(ws_o + ((long long)q * QT + r) * 128 + lane * 4);
+    acc.x = fmaf(w, o.x, acc.x); acc.y = fmaf(w, o.y, acc.y); acc.z = fmaf(w, o.z, acc.z); acc.w = fmaf(w, o.w, acc.w);
   }
+  const float inv = 1.0f / l;
+  float v[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
+  uint2* dst = reinterpret_cast<uint2*>(p.out + ((long long)item * p.Lq + q_in_item) * p.ldo + head * 128 + lane * 4);
+  if (p.accumulate) {
+    const uint2 old = *dst;
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&old.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&old.y));
+    v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y;
+  }
+  *dst = make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
 }
 }  // namespace v2
 
@@ -439,7 +444,7 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
   }();
   const char* split_env = std::getenv("B200_ATTN_SPLIT");               // 0 disables, n > 1 = at most n parts (A/B runs)
   const int split_mode = split_env ? std::atoi(split_env) : 1;
-  const int max_parts = split_mode > 1 ? split_mode : 4;      // 4 measured best (4 / 8 / 16 within 1 %)
+  const int max_parts = split_mode > 1 ? std::min(split_mode, v2::MAX_PARTS) : 4;      // 4 measured best (4 / 8 / 16 within 1 %)
   const char* steps_env = std::getenv("B200_ATTN_SPLIT_MINSTEPS");
   const int min_steps = steps_env ? std::max(1, std::atoi(steps_env)) : 2;
   pd.split_tiles = 0; pd.split_parts = 1;
@@ -456,7 +461,7 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
   launch_pdl(v2::attn_fwd_kernel, grid, dim3(192), v2::SMEM, stream, tq, tk, tv, pd);
   count_launch();
   if (pd.split_tiles > 0) {
-    launch_pdl(v2::attn_combine_kernel, dim3(pd.split_tiles), dim3(256), 0, stream, pd, n_tiles - pd.split_tiles);
+    launch_pdl(v2::attn_combine_kernel, dim3(pd.split_tiles, TILE / 8), dim3(256), 0, stream, pd, n_tiles - pd.split_tiles);
     count_launch();
   }
 }

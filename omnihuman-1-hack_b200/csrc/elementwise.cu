@@ -437,13 +437,14 @@ void launch_rms_rope(__half* x, long long ld, int dim, int nslices, const float*
   p.cs = reinterpret_cast<const float2*>(cs_table);
   p.M = M; p.rows_per_item = rows_per_item; p.eps = eps;
   ProfScope prof(PC_NORM, 0.0, 4.0 * M * dim * nslices, s);
-  B2_CHECK(dim % 8 == 0 && dim <= 256 * 16, "RMSNorm width %d not supported", dim);
+  B2_CHECK(dim % 8 == 0 && dim <= 256 * 20, "RMSNorm width %d not supported", dim);
   const dim3 grid((unsigned)((M + 7) / 8));
   const int pieces = (dim / 8 + 31) / 32;
   if (pieces <= 1) launch_pdl(rms_rope_kernel<1>, grid, dim3(256), 0, s, p, nslices);
   else if (pieces <= 2) launch_pdl(rms_rope_kernel<2>, grid, dim3(256), 0, s, p, nslices);
   else if (pieces <= 6) launch_pdl(rms_rope_kernel<6>, grid, dim3(256), 0, s, p, nslices);
-  else launch_pdl(rms_rope_kernel<16>, grid, dim3(256), 0, s, p, nslices);
+  else if (pieces <= 16) launch_pdl(rms_rope_kernel<16>, grid, dim3(256), 0, s, p, nslices);
+  else launch_pdl(rms_rope_kernel<20>, grid, dim3(256), 0, s, p, nslices);     // dim 5120 (Wan 14B)
   B2_CUDA(cudaGetLastError());
   count_launch();
 }

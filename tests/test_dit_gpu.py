@@ -160,6 +160,25 @@ def test_overflow_guard_counts_nonfinite_rows():
     assert eng.nonfinite_rows() == 0
 
 
+def test_14b_width_block_vs_oracle():
+    """The widths of the reference's 14B configuration (dim 5120, 40 heads; ffn narrowed to keep the CPU oracle and
+    the weight set small): one block + head on a 6 x 10 token grid, two items, against the fp32 oracle."""
+    import b200dit
+    from oracle import dit_oracle as O
+    cfg = dict(dim=5120, ffn_dim=1024, num_heads=40, num_layers=1, text_dim=64, in_dim=16, freq_dim=256)
+    sd = {k: v.float() for k, v in b200dit.synthetic.dit_weights(cfg, 3, "cpu").items()}
+    eng = b200dit.DitEngine.from_state_dict(sd, num_heads=40)
+    gen = torch.Generator().manual_seed(8)
+    x = [torch.randn(16, 1, 12, 20, generator=gen) for _ in range(2)]
+    ctx = [torch.randn(20, 64, generator=gen), torch.randn(9, 64, generator=gen)]
+    t = torch.tensor([900.0, 250.0])
+    out = eng.forward(x, t, ctx, 60)
+    ref = O.dit_forward(sd, x, t, ctx, 60, num_heads=40)
+    for a, r in zip(out, ref):
+        assert rel_l2(a.cpu(), r) < TOL
+    assert eng.nonfinite_rows() == 0
+
+
 def test_token_count_not_multiple_of_8():
     """L = 15 tokens (grid 1x3x5) cannot be co-batched (TMA tile origins); the host side runs one item per call and
     the CFG path falls back to two forwards + one fused combine -- results must not change."""
