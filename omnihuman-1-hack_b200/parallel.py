@@ -79,6 +79,41 @@ def sharded_map(fn, items, group=None):
     return gather_items(local, len(items), group=group)
 
 
+def send_to(t, dst):
+    """Point-to-point half of the pair-split exchange (pipelines.teacher_student_pair_split)."""
+    dist.send(t.contiguous(), dst)
+
+
+def recv_from(like, src):
+    buf = torch.empty_like(like)
+    dist.recv(buf, src)
+    return buf
+
+
+def gather_from_ranks(local, counts, group=None):
+    """all_gather of per-rank stacks whose lengths differ: `local` is this rank's list of same-shape tensors
+    (possibly empty), counts[r] the length of rank r's list.  Returns the per-rank lists on every rank."""
+    w = world_size()
+    if w == 1:
+        return [list(local)]
+    proto_shape, dtype, device = None, None, None
+    if local:
+        proto_shape, dtype, device = tuple(local[0].shape), local[0].dtype, local[0].device
+    meta = [None] * w
+    dist.all_gather_object(meta, (proto_shape, str(dtype) if dtype else None), group=group)
+    shape = next(m[0] for m in meta if m[0] is not None)
+    if dtype is None:
+        dtype = getattr(torch, next(m[1] for m in meta if m[1] is not None).split(".")[-1])
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    n = max(counts)
+    buf = torch.zeros((n,) + shape, dtype=dtype, device=device)
+    for j, t in enumerate(local):
+        buf[j].copy_(t)
+    out = [torch.empty_like(buf) for _ in range(w)]
+    dist.all_gather(out, buf, group=group)
+    return [[out[r][j] for j in range(counts[r])] for r in range(w)]
+
+
 def max_over_ranks(value, device=None):
     """Timing reduction used by bench.py: every multi-GPU number is the max over ranks."""
     if world_size() == 1:

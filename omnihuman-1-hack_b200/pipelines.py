@@ -93,6 +93,46 @@ def teacher_student_sweep(engine, noises, contexts, context_null, **kw):
 
 
 @torch.no_grad()
+def teacher_student_pair_split(engine, noises, contexts, context_null, guide_scale=7.5, t_teacher=999.0,
+                               t_student=1000.0, seq_len=1560):
+    """The other sharding of SURVEY 8d config 4 (the north star's literal reading): the teacher's cond / uncond
+    pair of ONE item is split over a rank pair.  Rank 2k runs teacher-cond and the student co-batched, rank 2k+1
+    teacher-uncond and sends its [16,T,h,w] prediction (0.4 MB at 480p) to rank 2k, which forms
+    v_teacher = u + s (c - u) (generate.py:229) and the MSE (distilled_trainer.py:289).  Pair k owns items
+    i % (world / 2) == k; one all_gather of (v_teacher, v_student, loss) at the end, as in the default mode.
+    Returns the same triple as teacher_student_sweep.  Slower than the default mode (two forwards on one rank
+    against one on the other); kept because it is the sharding the north star names."""
+    r, w = parallel.rank(), parallel.world_size()
+    if w % 2:
+        raise ValueError("pair-split needs an even number of ranks")
+    pairs, k, role = w // 2, r // 2, r % 2
+    n = len(noises)
+    mine = list(range(k, n, pairs))
+    vt, vs, ls = [], [], []
+    for i in mine:
+        x = noises[i].to(engine.device, torch.float32)
+        if role == 0:
+            t = torch.tensor([t_teacher, t_student], device=engine.device)
+            c, s = engine.forward([x, x], t, [contexts[i], contexts[i]], seq_len)
+            u = parallel.recv_from(c, r + 1)
+            v = u + guide_scale * (c - u)
+            vt.append(v); vs.append(s); ls.append(torch.mean((s - v) ** 2).reshape(1))
+        else:
+            u = engine.forward([x], torch.tensor([t_teacher], device=engine.device), [context_null], seq_len)[0]
+            parallel.send_to(u, r - 1)
+    counts = [len(range(q // 2, n, pairs)) if q % 2 == 0 else 0 for q in range(w)]
+    out = []
+    for local in (vt, vs, ls):
+        per_rank = parallel.gather_from_ranks(local, counts)
+        res = [None] * n
+        for q in range(0, w, 2):
+            for j, i in enumerate(range(q // 2, n, pairs)):
+                res[i] = per_rank[q][j]
+        out.append(res)
+    return tuple(out)
+
+
+@torch.no_grad()
 def generate_video(engine, vae, noise, context, context_null, **kw):
     """Denoise + decode (text2video.py:231-259): returns (latents, list of [3, 1+4(T-1), 8h, 8w] videos)."""
     x0 = sample(engine, noise, context, context_null, **kw)

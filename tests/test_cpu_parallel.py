@@ -46,3 +46,58 @@ def test_gloo_world2_shard_and_gather(tmp_path):
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out
         assert f"ok {r}" in out
+
+
+PAIR_WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, os.environ["B200_ROOT"])
+import b200dit
+from b200dit import parallel as par, pipelines as P
+rank, world = par.init("gloo")
+assert world == 2
+
+
+class FakeEngine:
+    """Stand-in with DitEngine.forward's signature: a deterministic per-item function of (x, t, context)."""
+    device = torch.device("cpu")
+
+    def forward(self, xs, t, ctx, seq_len):
+        return [torch.tanh(x * c.mean() + tt / 1000.0) + 0.1 * c.std() for x, tt, c in zip(xs, t, ctx)]
+
+
+g = torch.Generator().manual_seed(3)
+noises = [torch.randn(16, 1, 4, 6, generator=g) for _ in range(5)]
+ctxs = [torch.randn(7, 8, generator=g) for _ in range(5)]
+ctx0 = torch.randn(7, 8, generator=g)
+eng = FakeEngine()
+vt, vs, ls = P.teacher_student_pair_split(eng, noises, ctxs, ctx0, seq_len=6)
+assert len(vt) == len(vs) == len(ls) == 5
+for i in range(5):                                   # every rank holds every item, equal to the unsharded item
+    a, b, l = P.teacher_student_item(eng, noises[i], ctxs[i], ctx0, seq_len=6)
+    assert torch.allclose(vt[i], a, atol=1e-6) and torch.allclose(vs[i], b, atol=1e-6), i
+    assert torch.allclose(ls[i], l.reshape(1), atol=1e-6), i
+# the default mode gives the same triple
+vt2, vs2, ls2 = P.teacher_student_sweep(eng, noises, ctxs, ctx0, seq_len=6)
+for i in range(5):
+    assert torch.allclose(vt2[i], vt[i], atol=1e-6) and torch.allclose(ls2[i], ls[i], atol=1e-6)
+print("ok", rank)
+'''
+
+
+def test_gloo_world2_pair_split_matches_item(tmp_path):
+    """Config 4, pair-split mode: rank 0 = teacher-cond + student, rank 1 = teacher-uncond, one send per item."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "pair_worker.py"
+    script.write_text(PAIR_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), B200_ROOT=ROOT, CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for r, p in enumerate(procs):
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out
+        assert f"ok {r}" in out

@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--frames", type=int, default=21)
     ap.add_argument("--items", type=int, default=16)
     ap.add_argument("--layers", type=int, default=30)
+    ap.add_argument("--pair-split", action="store_true",
+                    help="config 4: teacher cond / uncond of one item on a rank pair (one send per item)")
     a = ap.parse_args()
     rank, world = parallel.init()
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -70,10 +72,13 @@ def main():
         noises = [torch.randn(16, 1, 60, 104, generator=gi).to(dev) for _ in range(a.items)]
         ctxs = [torch.randn(512, 4096, generator=gi).to(dev) for _ in range(a.items)]
         ctx0 = torch.randn(512, 4096, generator=gi).to(dev)
-        P.teacher_student_sweep(eng, noises[:2 * world], ctxs[:2 * world], ctx0)     # warm-up
-        (vt, vs, ls), ms = timed(lambda: P.teacher_student_sweep(eng, noises, ctxs, ctx0))
+        sweep = P.teacher_student_pair_split if a.pair_split else P.teacher_student_sweep
+        sweep(eng, noises[:2 * world], ctxs[:2 * world], ctx0)     # warm-up
+        (vt, vs, ls), ms = timed(lambda: sweep(eng, noises, ctxs, ctx0))
+        mode = ("pair-split: rank 2k teacher-cond + student, rank 2k+1 teacher-uncond, one 0.4 MB send per item"
+                if a.pair_split else "3 forwards co-batched per item, items i % world == rank")
         line = {"config": 4, "workload": f"{a.items} APT stage-1 items (teacher cond+uncond at t=999, cfg 7.5, student at "
-                f"t=1000, MSE) on [16,1,60,104], 3 forwards co-batched per item, items i % world == rank, one all_gather",
+                f"t=1000, MSE) on [16,1,60,104], {mode}, one all_gather",
                 "n_gpus": world, "ms": ms, "items_per_s": a.items / (ms / 1e3),
                 "forwards_per_s": 3 * a.items / (ms / 1e3), "mean_loss": float(torch.cat(ls).mean()),
                 "gathered": [len(vt), len(vs)]}
