@@ -14,4 +14,4 @@ from . import discriminator, flops, parallel, pipelines, solvers, synthetic  # n
 from .discriminator import AptDiscriminator  # noqa: F401
 from .solvers import (FlowDPMSolverMultistepScheduler, FlowUniPCMultistepScheduler, get_sampling_sigmas,  # noqa: F401
                       retrieve_timesteps)
-from .wan_shim import install, install_vae, uninstall  # noqa: F401
+from .wan_shim import install, install_t2v, install_vae, uninstall  # noqa: F401

@@ -11,10 +11,14 @@ The engine is inference-only: when autograd is recording and any input or parame
 gradient, the call falls through to the ORIGINAL reference forward (the unmodified PyTorch path,
 not a CPU fallback) -- SURVEY.md section 8b "Autograd".
 """
+import math
+import random
+import sys
 import types
 
 import torch
 
+from . import pipelines
 from .engine import DitEngine, VaeEngine
 
 
@@ -60,7 +64,51 @@ def install_vae(vae, device=None, engine=None):
     return eng
 
 
+def install_t2v(pipe, device=None, dit_engine=None, vae_engine=None):
+    """Routes `WanT2V.generate` (seaweed_apt/wan/text2video.py:111-269) through the engines, signature unchanged:
+    prompt encoding stays the pipeline's own T5 (out of scope), noise comes from the same seeded
+    device generator (:167-169,186-195), and the loop (:231-252: cond + uncond forward, CFG, scheduler step) and
+    the decode (:258-259) run as `pipelines.sample` + `VaeEngine.decode`.  `offload_model` is accepted and has
+    nothing to do: the engines keep their own device copies of the weights."""
+    eng = dit_engine or DitEngine.from_module(pipe.model, device=device)
+    vae = vae_engine or VaeEngine.from_state_dict(pipe.vae.model.state_dict(), device=device)
+    original = pipe.generate
+
+    def generate(self, input_prompt, size=(720, 512), frame_num=81, shift=5.0, sample_solver="unipc",
+                 sampling_steps=50, guide_scale=5.0, n_prompt="", seed=-1, offload_model=True):
+        if sample_solver not in ("unipc", "dpm++"):
+            raise NotImplementedError("Unsupported solver.")                                   # :221-222
+        st, ps, sp = self.vae_stride, self.patch_size, getattr(self, "sp_size", 1)
+        shape = (self.vae.model.z_dim, (frame_num - 1) // st[0] + 1, size[1] // st[1], size[0] // st[2])
+        seq_len = math.ceil(shape[2] * shape[3] / (ps[1] * ps[2]) * shape[1] / sp) * sp        # :161-164
+        negative = n_prompt if n_prompt != "" else self.sample_neg_prompt
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(seed if seed >= 0 else random.randint(0, sys.maxsize))
+        enc_dev = torch.device("cpu") if self.t5_cpu else self.device                          # :172-183
+        if not self.t5_cpu:
+            self.text_encoder.model.to(self.device)
+        context = [c.to(self.device) for c in self.text_encoder([input_prompt], enc_dev)]
+        context_null = [c.to(self.device) for c in self.text_encoder([negative], enc_dev)]
+        if not self.t5_cpu and offload_model:
+            self.text_encoder.model.cpu()
+        noise = [torch.randn(*shape, dtype=torch.float32, device=self.device, generator=gen)]
+        x0 = pipelines.sample(eng, noise, context, context_null, steps=sampling_steps, shift=shift,
+                              guide_scale=guide_scale, solver=sample_solver, seq_len=seq_len)
+        videos = vae.decode(x0) if self.rank == 0 else None
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.barrier()
+        return videos[0] if self.rank == 0 else None
+
+    pipe._b200_original_generate = original
+    pipe._b200_engines = (eng, vae)
+    pipe.generate = types.MethodType(generate, pipe)
+    return eng, vae
+
+
 def uninstall(obj):
+    if hasattr(obj, "_b200_original_generate"):
+        obj.generate = obj._b200_original_generate
+        del obj._b200_original_generate, obj._b200_engines
     if hasattr(obj, "_b200_original_forward"):
         obj.forward = obj._b200_original_forward
         del obj._b200_original_forward, obj._b200_engine

@@ -81,3 +81,68 @@ def test_teacher_student_item_vs_oracle():
     assert rel_l2(vs.cpu(), s) < 1e-3
     ref_loss = float(torch.mean((s - ref_t) ** 2))
     assert abs(float(loss) - ref_loss) <= 2e-2 * abs(ref_loss) + 1e-6
+
+
+class _StandInT2V:
+    """The attributes `WanT2V.generate` reads from `self` (text2video.py:63-80,101,108), around tiny random-weight
+    modules; the text encoder is a deterministic stub (T5 is outside the path)."""
+
+    class _Mod:
+        def __init__(self, sd, **attrs):
+            self._sd = sd
+            self.__dict__.update(attrs)
+
+        def state_dict(self):
+            return self._sd
+
+    def __init__(self, dit_sd, vae_sd):
+        import types
+        self.device, self.rank, self.t5_cpu, self.sp_size = torch.device("cuda"), 0, True, 1
+        self.vae_stride, self.patch_size, self.sample_neg_prompt = (4, 8, 8), (1, 2, 2), "bad"
+        self.model = self._Mod(dit_sd, dim=CFG["dim"], ffn_dim=CFG["ffn_dim"], num_heads=CFG["num_heads"],
+                               num_layers=CFG["num_layers"], in_dim=16, out_dim=16, text_dim=CFG["text_dim"],
+                               text_len=512, freq_dim=256, model_type="t2v", eps=1e-6)
+        self.vae = types.SimpleNamespace(model=self._Mod(vae_sd, z_dim=16))
+        self.prompts = []
+
+    def text_encoder(self, texts, device):
+        self.prompts.append(texts[0])
+        g = torch.Generator().manual_seed(sum(map(ord, texts[0])))
+        return [torch.randn(5 + len(texts[0]), CFG["text_dim"], generator=g).to(device)]
+
+    def generate(self, *a, **k):
+        raise AssertionError("the reference loop must not run")
+
+
+def test_install_t2v_generate_signature_and_result():
+    """`install_t2v` keeps WanT2V.generate's signature (text2video.py:111-121): same seeded noise, CFG + solver loop,
+    decode on rank 0; result against the oracle loop + the VAE oracle on the same noise."""
+    import b200dit
+    from oracle import vae_oracle as VO
+    sd = O.make_synthetic_weights(**CFG, seed=5)
+    vsd = VO.make_synthetic_vae_weights(dim=8, seed=2)
+    pipe = _StandInT2V(sd, vsd)
+    eng, vae = b200dit.install_t2v(pipe)
+    video = pipe.generate("a cat", size=(64, 48), frame_num=5, shift=3.0, sample_solver="dpm++", sampling_steps=4,
+                          guide_scale=4.0, seed=11)
+    assert video.shape == (3, 5, 48, 64) and pipe.prompts == ["a cat", "bad"]
+    again = pipe.generate("a cat", size=(64, 48), frame_num=5, shift=3.0, sample_solver="dpm++", sampling_steps=4,
+                          guide_scale=4.0, seed=11)
+    assert torch.equal(video, again)
+    other = pipe.generate("a cat", size=(64, 48), frame_num=5, shift=3.0, sample_solver="dpm++", sampling_steps=4,
+                          guide_scale=4.0, seed=12, n_prompt="worse")
+    assert not torch.equal(video, other) and pipe.prompts[-1] == "worse"
+    with pytest.raises(NotImplementedError):
+        pipe.generate("a cat", sample_solver="euler")
+    # oracle: same noise (device generator, text2video.py:167-169,186-195), same loop, fp32 CPU
+    gen = torch.Generator(device="cuda"); gen.manual_seed(11)
+    noise = torch.randn(16, 2, 6, 8, dtype=torch.float32, device="cuda", generator=gen).cpu()
+    ctx, ctx0 = pipe.text_encoder(["a cat"], "cpu")[0], pipe.text_encoder(["bad"], "cpu")[0]
+    x0 = _oracle_sample(sd, noise, ctx, ctx0, 4, 3.0, 4.0, "dpm++", 2 * 3 * 4, CFG["num_heads"])
+    ref = VO.vae_decode(vsd, x0)
+    err, rel = float((video.cpu() - ref).abs().max()), rel_l2(video.cpu(), ref)
+    print(f"install_t2v: video max-abs {err:.3e} rel-L2 {rel:.3e}")
+    assert rel < 1e-2 and err < 3e-2                     # measured 8e-4 / 2.8e-3 on B200
+    b200dit.uninstall(pipe)
+    with pytest.raises(AssertionError):
+        pipe.generate("a cat")
