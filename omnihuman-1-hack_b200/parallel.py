@@ -79,6 +79,32 @@ def sharded_map(fn, items, group=None):
     return gather_items(local, len(items), group=group)
 
 
+_pair_groups = {}
+
+
+def pair_group():
+    """The process group of this rank's pair (2k, 2k+1).  Every rank creates every pair's group (new_group is a
+    collective over the whole world); for world == 2 the pair is the default group."""
+    w, r = world_size(), rank()
+    if w % 2:
+        raise ValueError("rank pairs need an even world size")
+    if w == 2:
+        return None
+    if not _pair_groups:
+        for k in range(w // 2):
+            _pair_groups[k] = dist.new_group(ranks=[2 * k, 2 * k + 1])
+    return _pair_groups[r // 2]
+
+
+def exchange_pair(t):
+    """One all_gather inside the rank pair: returns (tensor of rank 2k, tensor of rank 2k+1) on both ranks.  This is
+    the per-step exchange of CFG-parallel sampling (pipelines.sample_cfg_parallel): 0.4 MB per 480p latent frame."""
+    t = t.contiguous()
+    out = [torch.empty_like(t), torch.empty_like(t)]
+    dist.all_gather(out, t, group=pair_group())
+    return out[0], out[1]
+
+
 def send_to(t, dst):
     """Point-to-point half of the pair-split exchange (pipelines.teacher_student_pair_split)."""
     dist.send(t.contiguous(), dst)

@@ -61,6 +61,43 @@ def sample(engine, noise, context, context_null, steps=50, shift=5.0, guide_scal
 
 
 @torch.no_grad()
+def sample_cfg_parallel(engine, noise, context, context_null, steps=50, shift=5.0, guide_scale=5.0, solver="unipc",
+                        seq_len=None, cfg_anneal=False, check_overflow=True):
+    """sample() with the cond / uncond pair of every step split over a rank pair (2k, 2k+1) -- the north star's
+    "cond/uncond pair as independent batch items across GPUs", for single-video latency: at T = 21 one forward
+    already fills a B200, so co-batching the pair buys nothing and splitting it halves the step time.
+    Rank 2k runs the conditional forward, rank 2k+1 the unconditional one (text2video.py:238-241); ONE all_gather
+    of the predictions inside the pair per step (8.4 MB at T = 21), then both ranks form u + s (c - u) (:243-244)
+    and take the same scheduler step, so the latents stay bit-identical on the two ranks and nothing else is
+    exchanged.  Every rank of a pair passes the same `noise` / contexts; returns x0 on both."""
+    from .solvers import _lincomb
+    role = parallel.rank() % 2
+    xs = [n.to(engine.device, torch.float32) for n in noise]
+    n = len(xs)
+    if seq_len is None:
+        _, T, h, w = xs[0].shape
+        seq_len = T * (h // 2) * (w // 2)
+    ctx = list(context) if role == 0 else list(context_null)
+    if len(ctx) == 1 and n > 1:
+        ctx = ctx * n
+    scheds = [make_scheduler(solver, steps, shift, engine.device) for _ in range(n)]
+    ts_host = scheds[0][1].cpu().tolist()
+    for i, t in enumerate(ts_host):
+        s = guide_scale * (1.0 - i / len(ts_host)) + 1.0 * (i / len(ts_host)) if cfg_anneal else guide_scale
+        tt = torch.full((n,), float(t), device=engine.device)
+        mine = torch.stack(engine.forward(xs, tt, ctx, seq_len))
+        cond, uncond = parallel.exchange_pair(mine)
+        v = _lincomb([cond, uncond], [[float(s), 1.0 - float(s)]], cond)[0]              # u + s (c - u)
+        xs = [sch.step(v[j].unsqueeze(0), t, xs[j].unsqueeze(0), return_dict=False)[0].squeeze(0)
+              for j, (sch, _) in enumerate(scheds)]
+    if check_overflow:
+        bad = engine.nonfinite_rows()
+        if bad:
+            raise FloatingPointError(f"{bad} residual-stream rows overflowed the fp16 operand range during sampling")
+    return xs
+
+
+@torch.no_grad()
 def teacher_student_item(engine, noise, context, context_null, guide_scale=7.5, t_teacher=999.0, t_student=1000.0,
                          seq_len=1560, student_engine=None):
     """One distillation item.  With a single weight replica (teacher == student at step 0,

@@ -101,3 +101,76 @@ def test_gloo_world2_pair_split_matches_item(tmp_path):
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out
         assert f"ok {r}" in out
+
+
+CFGPAR_WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, os.environ["B200_ROOT"])
+import b200dit
+from b200dit import parallel as par, pipelines as P, solvers as PS
+rank, world = par.init("gloo")
+assert world == 2
+
+
+def cpu_lincomb(inputs, coeffs, like):          # host-logic stand-in for the fused CUDA update (tests only)
+    ins = [t if t is not None else like for t in inputs]
+    return [sum(float(c) * t for c, t in zip(row, ins)) for row in coeffs]
+
+
+PS._lincomb = cpu_lincomb
+
+
+class FakeEngine:
+    device = torch.device("cpu")
+    calls = 0
+
+    def forward(self, xs, t, ctx, seq_len):
+        FakeEngine.calls += len(xs)
+        return [torch.tanh(0.3 * x + c.mean() + tt / 1000.0) - 0.2 * x for x, tt, c in zip(xs, t, ctx)]
+
+    def forward_cfg(self, xs, t, ctx, ctx_n, seq_len, s, clip_fea=None, y=None):
+        if len(ctx_n) == 1 and len(xs) > 1:
+            ctx_n = ctx_n * len(xs)
+        c, u = self.forward(xs, t, ctx, seq_len), self.forward(xs, t, ctx_n, seq_len)
+        return [ui + s * (ci - ui) for ci, ui in zip(c, u)]
+
+    def nonfinite_rows(self):
+        return 0
+
+
+g = torch.Generator().manual_seed(5)
+noise = [torch.randn(16, 2, 4, 6, generator=g) for _ in range(2)]
+ctx = [torch.randn(9, 8, generator=g) for _ in range(2)]
+ctx0 = [torch.randn(4, 8, generator=g)]
+eng = FakeEngine()
+for solver, anneal in (("unipc", False), ("dpm++", True)):
+    FakeEngine.calls = 0
+    out = P.sample_cfg_parallel(eng, noise, ctx, ctx0, steps=5, shift=3.0, guide_scale=4.0, solver=solver, cfg_anneal=anneal)
+    assert FakeEngine.calls == 5 * 2, FakeEngine.calls       # one forward per sample per step on this rank (not two)
+    ref = P.sample(eng, noise, ctx, ctx0, steps=5, shift=3.0, guide_scale=4.0, solver=solver, cfg_anneal=anneal)
+    for a, b in zip(out, ref):
+        assert torch.allclose(a, b, atol=1e-5), float((a - b).abs().max())
+    both = par.exchange_pair(torch.stack(out))               # the two ranks hold identical latents
+    assert torch.equal(both[0], both[1])
+print("ok", rank)
+'''
+
+
+def test_gloo_world2_cfg_parallel_matches_sample(tmp_path):
+    """CFG-parallel sampling: rank 0 conditional, rank 1 unconditional, one exchange per step; same trajectory as
+    the single-process loop, identical on both ranks, half the forwards per rank."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "cfgpar_worker.py"
+    script.write_text(CFGPAR_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), B200_ROOT=ROOT, CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for r, p in enumerate(procs):
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out
+        assert f"ok {r}" in out

@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--frames", type=int, default=21)
     ap.add_argument("--items", type=int, default=16)
     ap.add_argument("--layers", type=int, default=30)
+    ap.add_argument("--cfg-parallel", action="store_true",
+                    help="config 5: one video per rank PAIR, cond / uncond forwards on the two ranks, one exchange per step")
     ap.add_argument("--pair-split", action="store_true",
                     help="config 4: teacher cond / uncond of one item on a rank pair (one send per item)")
     a = ap.parse_args()
@@ -86,10 +88,16 @@ def main():
         eng = b200dit.DitEngine(**cfg, device=dev)
         eng.load_state_dict(make_device_weights(cfg, 0, dev))
         vae = b200dit.VaeEngine.from_state_dict(synthetic.vae_decoder_weights(dim=96, seed=0), device=dev)
+        if a.cfg_parallel:                                    # both ranks of a pair work on the same video
+            g = torch.Generator().manual_seed(1000 + rank // 2)
         x0 = rn(16, T, 60, 104).to(dev)
         ctx, ctx0 = rn(512, 4096).bfloat16().to(dev), rn(512, 4096).bfloat16().to(dev)
-        P.sample(eng, [x0], [ctx], [ctx0], steps=3)
-        lat, ms_d = timed(lambda: P.sample(eng, [x0], [ctx], [ctx0], steps=a.steps, shift=5.0, guide_scale=5.0))
+        run = P.sample_cfg_parallel if a.cfg_parallel else P.sample
+        run(eng, [x0], [ctx], [ctx0], steps=3)
+        lat, ms_d = timed(lambda: run(eng, [x0], [ctx], [ctx0], steps=a.steps, shift=5.0, guide_scale=5.0))
+        if a.cfg_parallel:
+            one = P.sample(eng, [x0], [ctx], [ctx0], steps=a.steps, shift=5.0, guide_scale=5.0)
+            cfgpar_rel = float((lat[0] - one[0]).norm() / one[0].norm())
         vae.decode(lat)                                       # warm-up at full size (workspaces grow on first sight)
         vid, ms_v = timed(lambda: vae.decode(lat))
         allv, ms_g = timed(lambda: parallel.gather_items(lat, world))
@@ -98,6 +106,12 @@ def main():
                 "vae_decode_ms": ms_v, "gather_ms": ms_g, "videos_per_s": world / ((ms_d + ms_v + ms_g) / 1e3),
                 "denoise_steps_per_s": world * a.steps / (ms_d / 1e3), "gathered": len(allv),
                 "finite": bool(torch.isfinite(vid[0]).all())}
+        if a.cfg_parallel:
+            vids = world // 2
+            line.update({"mode": "cfg-parallel: one video per rank pair, cond on rank 2k, uncond on rank 2k+1, one all_gather "
+                         "inside the pair per step", "videos_per_s": vids / ((ms_d + ms_v + ms_g) / 1e3),
+                         "denoise_steps_per_s": vids * a.steps / (ms_d / 1e3),
+                         "latency_ms_per_step": ms_d / a.steps, "rel_l2_vs_single_gpu_loop": cfgpar_rel})
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
