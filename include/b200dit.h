@@ -116,8 +116,8 @@ B200_API int b200dit_set_taps(b200dit_engine* e, int32_t n, const int32_t* block
 /* Capture each distinct (n_items, grid, mode) forward into a CUDA graph and replay it (default on). */
 B200_API int b200dit_set_graphs(b200dit_engine* e, int32_t enabled);
 
-/* Overflow guard.  The engine feeds the tensor cores fp16 operands where the reference autocasts to bf16
- * (seaweed_apt/wan/text2video.py:222, SURVEY.md 8 hard part 1); an activation beyond 65504 becomes inf and
+/* Overflow guard.  GEMM and attention operands are fp16, as in the reference's blocks (autocast(float16),
+ * seaweed_apt/wan/modules/model.py:540; SURVEY.md 8 hard part 1); an activation beyond 65504 becomes inf and
  * reaches the fp32 residual stream as inf / NaN.  Every block LayerNorm and the head LayerNorm count such rows
  * (free: one compare on a statistic they compute anyway).  Writes the count since the previous call to *count
  * (0 for a healthy run), clears it; synchronises `stream`. */

@@ -243,7 +243,7 @@ class DitEngine:
 
     def nonfinite_rows(self):
         """Overflow guard: residual-stream rows that reached a LayerNorm as inf / NaN since the previous call
-        (fp16 operands where the reference runs bf16 autocast, text2video.py:222).  0 on a healthy run.  Blocks
+        (GEMM / attention operands are fp16, like the reference's blocks under autocast(float16), model.py:540).  0 on a healthy run.  Blocks
         until the current stream drains."""
         n = C.c_uint32(0)
         check(lib().b200dit_nonfinite_rows(self._h, torch.cuda.current_stream(self.device).cuda_stream, C.byref(n)))

@@ -37,7 +37,7 @@ def sample(engine, noise, context, context_null, steps=50, shift=5.0, guide_scal
     """Denoises `noise` (list of [16,T,h,w] fp32, all the same shape) and returns the list of x0 latents.
     Every sample carries its own scheduler state; all samples are co-batched in one engine call per step.
     `check_overflow`: one read of the engine's overflow guard after the last step (the engine computes with fp16
-    operands where the reference autocasts to bf16); raises FloatingPointError instead of returning NaN latents."""
+    operands, like the reference's blocks, model.py:540); raises FloatingPointError instead of returning NaN latents."""
     xs = [n.to(engine.device, torch.float32) for n in noise]
     n = len(xs)
     if seq_len is None:
