@@ -96,7 +96,7 @@ def test_heads_at_1p3b_width_vs_oracle(qk_norm):
         hw = {k: v for k, v in hw.items() if "q_norm" not in k and "k_norm" not in k}
     disc = b200dit.AptDiscriminator(eng, hw, tap_blocks=(1, 1, 1), qk_norm=qk_norm)
     gen = torch.Generator().manual_seed(21)
-    for B, L in ((2, 1560), (1, 333)):
+    for B, L in ((2, 1560), (1, 333), (1, 7800)):           # 7800 = a 5-latent-frame video: 61 pooling chunks
         taps = []
         for _ in range(3):
             x = torch.randn(B, L, dim, generator=gen) * (0.5 + torch.rand(dim, generator=gen)) + torch.randn(dim, generator=gen)
@@ -109,3 +109,21 @@ def test_heads_at_1p3b_width_vs_oracle(qk_norm):
             assert rel_l2(a.cpu(), r) < TOL_FEAT
         again = disc.heads([u.reshape(B * L, dim).cuda() for u in taps], B, L)
         assert torch.equal(again, logit)                                     # deterministic reduction order
+
+
+def test_heads_at_14b_width_vs_oracle():
+    """dim 5120 / 40 heads (the reference's 14B widths): three groups of <= 16 heads in the pooling kernel."""
+    import b200dit
+    from oracle import disc_oracle as DO
+    dim, heads = 5120, 40
+    eng = b200dit.DitEngine(dim=dim, ffn_dim=256, num_heads=heads, num_layers=1, text_dim=32)   # weights never used
+    hw = b200dit.synthetic.disc_head_weights(dim, 12)
+    disc = b200dit.AptDiscriminator(eng, hw, tap_blocks=(1, 1, 1))
+    gen = torch.Generator().manual_seed(22)
+    B, L = 2, 200
+    taps = [torch.randn(B, L, dim, generator=gen) * 1.5 + 0.2 for _ in range(3)]
+    logit, feats = disc.heads([u.reshape(B * L, dim).cuda() for u in taps], B, L, return_features=True)
+    r_logit, r_feats = DO.disc_heads(taps, hw, heads)
+    assert (logit.cpu() - r_logit).abs().max() < TOL_LOGIT
+    for a, r in zip(feats, r_feats):
+        assert rel_l2(a.cpu(), r) < TOL_FEAT
