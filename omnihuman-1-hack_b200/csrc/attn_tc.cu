@@ -164,6 +164,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           if (p.dbg & 16) break;                             // diagnosis: no Q.K^T MMAs
+          if (p.dbg & 64)                                    // diagnosis: Q as a TMEM operand (reads O's columns:
+            umma_f16_ts(tmem_base + sb * KT, tmem_o + kk * 8,   // wrong values, right traffic -- no Q re-read from smem)
+                        umma_desc_sw128(sk + (kk >> 2) * KSUB + (kk & 3) * 32), idesc_qk, kk > 0);
+          else
           umma_f16(tmem_base + sb * KT, umma_desc_sw128(sq + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32),
                    umma_desc_sw128(sk + (kk >> 2) * KSUB + (kk & 3) * 32), idesc_qk, kk > 0);
         }

@@ -1,5 +1,6 @@
 """Developer diagnosis (gpurun): which part of the attention step paces it?  B200_ATTN_DBG bits:
-1 no exp2, 2 no TMEM reads of S, 4 no P store, 8 softmax warps idle.  One process per setting."""
+1 no exp2, 2 no TMEM reads of S, 4 no P store, 8 softmax warps idle, 16 no Q.K^T, 32 no P.V, 64 Q.K^T with its A
+operand from TMEM (no Q re-read from shared memory).  One process per setting; `attn_diag.py 0 64 72` picks settings."""
 import os
 import subprocess
 import sys
@@ -32,7 +33,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for dbg in ("0", "1", "2", "4", "3", "7", "8"):
+        for dbg in (sys.argv[1:] or ("0", "1", "2", "4", "3", "7", "8")):
             print(f"B200_ATTN_DBG={dbg}", flush=True)
             subprocess.run(["timeout", "120", sys.executable, os.path.abspath(__file__), "child"],
                            env=dict(os.environ, B200_ATTN_DBG=dbg))
