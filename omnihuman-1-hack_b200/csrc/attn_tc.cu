@@ -2,9 +2,10 @@
 // Replaces the reference operator seam flash_attention (seaweed_apt/wan/modules/attention.py:24-130)
 // for both self-attention (Lk = L) and text/extra-stream cross-attention (Lk <= 512).
 //
-// One 128-query tile per CTA, 64-key steps, two CTAs per SM (namespace v2; the first kernel -- 128-key steps,
-// one CTA per SM, P through shared memory -- and a two-tiles-per-CTA variant with shared K / V tiles were
-// measured slower and removed).
+// One 128-query tile per CTA, 64-key steps, two CTAs per SM (namespace v2); for long sequences two tiles per CTA
+// sharing the K / V tiles (namespace v3).  The first kernel -- 128-key steps, one CTA per SM, P through shared
+// memory -- and an earlier two-tile variant with 128-key steps and one S buffer per tile were measured slower and
+// removed, see DESIGN.md.
 #include <algorithm>
 #include <cstdlib>
 
@@ -411,6 +412,258 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const AttnParams p, i
 }  // namespace v2
 
 
+// ---------------------------------------------------------------------------------------------------
+// Long-sequence kernel: TWO 128-query tiles per CTA share every K / V tile.
+// Per 64-key step of one query tile the v2 kernel moves 32 KB of TMA fill + 32 KB of K / V operand reads + 32 KB of
+// Q re-read through the 128 B/clk shared-memory port in 512 tensor-pipe clocks (192 B/clk asked of a 128 B/clk
+// port): the port, not the tensor pipe, paces it.  Here a K / V tile is filled once and read by both query tiles:
+// 80 KB per tile-step (160 B/clk).  Everything else is the v2 protocol, once per tile: the two tiles have their own
+// MMA warp, softmax warps, S / P double buffer and O accumulator, and share only the TMA warp and the K / V rings
+// (whose "empty" barriers take one tensor-pipe commit from each tile).  One CTA per SM, all 512 TMEM columns:
+//   tile t (0 / 1) at column 256 t:  S0 / P0 [0,64)  S1 / P1 [64,128)  O [128,256)
+//   warps 0..3 softmax of tile 0, 4..7 softmax of tile 1 (TMEM lane quadrant = warp % 4), 8 TMA, 9 / 10 MMA of tile 0 / 1
+// (A variant with Q as a TMEM operand and S single-buffered per tile was correct but slower -- 729 against 929
+// TFLOP/s at L = 12 480: with one S buffer the softmax sits on the tile's critical path.)
+namespace v3 {
+constexpr int QT = 128, KT = 64, TILES = 2;
+constexpr int KSTAGES = 3, VSTAGES = 3;
+constexpr int Q_BYTES = 2 * 128 * 128;       // per tile: two [128 queries x 64 d] SW128 sub-tiles
+constexpr int K_BYTES = 2 * 64 * 128, KSUB = 64 * 128, V_BYTES = 128 * 128;
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = OFF_Q + TILES * Q_BYTES;
+constexpr int OFF_V = OFF_K + KSTAGES * K_BYTES;
+constexpr int OFF_BAR = OFF_V + VSTAGES * V_BYTES;
+constexpr int SMEM = OFF_BAR + 512;          // 164 352 B
+constexpr int W_TMA = 8, W_MMA0 = 9;
+constexpr int COL_TILE = 256;
+
+__global__ void __launch_bounds__(352, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;     // [3]
+  uint64_t* k_empty = bars + 4;    // [3]  count 2: one commit per tile
+  uint64_t* v_full = bars + 7;     // [3]
+  uint64_t* v_empty = bars + 10;   // [3]  count 2
+  uint64_t* s_full = bars + 13;    // [tile][2]
+  uint64_t* s_empty = bars + 17;   // [tile][2]
+  uint64_t* p_full = bars + 21;    // [tile]
+  uint64_t* pv_done = bars + 23;   // [tile]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+
+  const int warp = warp_id(), lane = lane_id();
+  const int hi = blockIdx.x % (p.heads * p.items), qt2 = blockIdx.x / (p.heads * p.items);
+  const int head = hi % p.heads, item = hi / p.heads;
+  const int klen = p.klen[item];
+  const int n_kv = (klen + KT - 1) / KT;
+  pdl_launch();
+
+  if (warp == W_TMA && lane == 0) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_vt);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], TILES); }
+    for (int i = 0; i < VSTAGES; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], TILES); }
+    for (int i = 0; i < TILES * 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
+    for (int t = 0; t < TILES; ++t) { mbar_init(&p_full[t], 4); mbar_init(&pv_done[t], 1); }
+    fence_barrier_init();
+  }
+  if (warp == W_MMA0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_all = *tmem_slot;
+  pdl_wait();
+
+  if (warp == W_TMA) {
+    if (lane == 0) {
+      const int q_row0 = item * p.Lq + qt2 * TILES * QT;
+      mbar_expect_tx(q_full, TILES * Q_BYTES);
+      for (int t = 0; t < TILES; ++t) {
+        tma_load_2d(smem + OFF_Q + t * Q_BYTES, &tmap_q, q_full, head * 128, q_row0 + t * QT);
+        tma_load_2d(smem + OFF_Q + t * Q_BYTES + Q_BYTES / 2, &tmap_q, q_full, head * 128 + 64, q_row0 + t * QT);
+      }
+      for (int i = 0; i <= n_kv; ++i) {                     // K runs one step ahead of V
+        if (i < n_kv) {
+          const int st = i % KSTAGES; const uint32_t ph = (i / KSTAGES) & 1;
+          const int k_row0 = item * p.Lk_rows + i * KT;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_expect_tx(&k_full[st], K_BYTES);
+          tma_load_2d(smem + OFF_K + st * K_BYTES, &tmap_k, &k_full[st], head * 128, k_row0);
+          tma_load_2d(smem + OFF_K + st * K_BYTES + KSUB, &tmap_k, &k_full[st], head * 128 + 64, k_row0);
+        }
+        if (i >= 1) {
+          const int j = i - 1, st = j % VSTAGES; const uint32_t ph = (j / VSTAGES) & 1;
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_expect_tx(&v_full[st], V_BYTES);
+          tma_load_2d(smem + OFF_V + st * V_BYTES, &tmap_vt, &v_full[st],
+                      item * (p.vt_stride ? p.vt_stride : p.Lk_rows) + j * KT, head * 128);
+        }
+      }
+    }
+  } else if (warp >= W_MMA0) {
+    const int t = warp - W_MMA0;
+    const uint32_t tmem_base = tmem_all + t * COL_TILE, tmem_o = tmem_base + 128;
+    constexpr uint32_t idesc_qk = umma_idesc_f16(128, KT);
+    constexpr uint32_t idesc_pv = umma_idesc_f16(128, 128);
+    const uint32_t sq = smem_u32(smem + OFF_Q + t * Q_BYTES);
+    auto issue_qk = [&](int i) {
+      const int st = i % KSTAGES; const uint32_t kph = (i / KSTAGES) & 1;
+      const int sb = i & 1; const uint32_t sph = (i >> 1) & 1;
+      if (lane == 0) {
+        mbar_wait(&k_full[st], kph);
+        mbar_wait(&s_empty[t * 2 + sb], sph ^ 1);
+        tc_fence_after();
+        const uint32_t sk = smem_u32(smem + OFF_K + st * K_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_f16(tmem_base + sb * KT, umma_desc_sw128(sq + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32),
+                   umma_desc_sw128(sk + (kk >> 2) * KSUB + (kk & 3) * 32), idesc_qk, kk > 0);
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[t * 2 + sb]);
+      }
+      __syncwarp();
+    };
+    mbar_wait_warp(q_full, 0, lane);
+    issue_qk(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) issue_qk(j + 1);
+      const int st = j % VSTAGES; const uint32_t ph = (j / VSTAGES) & 1;
+      if (lane == 0) {
+        mbar_wait(&v_full[st], ph);
+        mbar_wait(&p_full[t], j & 1);
+        tc_fence_after();
+        const uint32_t sv = smem_u32(smem + OFF_V + st * V_BYTES);
+        const uint32_t tp = tmem_base + (j & 1) * KT;
+#pragma unroll
+        for (int kk = 0; kk < KT / 16; ++kk)
+          umma_f16_ts(tmem_o, tp + kk * 8, umma_desc_sw128(sv + kk * 32), idesc_pv, (j > 0 || kk > 0));
+        umma_commit(&v_empty[st]);
+        umma_commit(&pv_done[t]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- softmax of tile t: thread = one query row, all 64 keys of the step (the v2 loop)
+    const int t = warp >> 2, quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_sel = uint32_t(quad * 32) << 16;
+    const uint32_t tmem_base = tmem_all + t * COL_TILE, tmem_o = tmem_base + 128;
+    const int q_in_item = (qt2 * TILES + t) * QT + r;
+    const float c = p.scale * 1.4426950408889634f * q_row_scale(p, item, q_in_item);
+    float m_ref = -INFINITY, l_sum = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int sb = j & 1; const uint32_t ph = (j >> 1) & 1;
+      mbar_wait_warp(&s_full[t * 2 + sb], ph, lane);
+      tc_fence_after();
+      float s[KT];
+      {
+        uint32_t t0[32], t1[32];
+        tmem_ld32(tmem_base + lane_sel + sb * KT, t0);
+        tmem_ld32(tmem_base + lane_sel + sb * KT + 32, t1);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(t0[i]); s[32 + i] = __uint_as_float(t1[i]); }
+      }
+      const int valid = klen - j * KT;
+      if (valid < KT) {
+#pragma unroll
+        for (int i = 0; i < KT; ++i) if (i >= valid) s[i] = -INFINITY;
+      }
+      float mx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = fmaxf(s[i], s[i + 8]);
+#pragma unroll
+      for (int i = 16; i < KT; i += 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mx[e] = fmaxf(mx[e], s[i + e]);
+      }
+      const float tmax = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+      float alpha = 1.f;
+      bool rescale = false;
+      if (j == 0) {
+        m_ref = tmax;
+      } else if ((tmax - m_ref) * c > RESCALE_THRESHOLD) {
+        alpha = ex2((m_ref - tmax) * c);
+        m_ref = tmax;
+        l_sum *= alpha;
+        rescale = true;
+      }
+      const float mc = m_ref * c;
+      float ps0 = 0.f, ps1 = 0.f;
+      uint32_t pk[KT / 2];
+#pragma unroll
+      for (int i = 0; i < KT; i += 2) {
+        const float p0 = ex2(fmaf(s[i], c, -mc)), p1 = ex2(fmaf(s[i + 1], c, -mc));
+        ps0 += p0; ps1 += p1;
+        pk[i >> 1] = pack_h2(p0, p1);
+      }
+      l_sum += ps0 + ps1;
+      tmem_st32(tmem_base + lane_sel + sb * KT, pk);
+      if (j > 0) {
+        mbar_wait_warp(&pv_done[t], (j - 1) & 1, lane);      // phase discipline: see v2
+        if (__any_sync(0xffffffffu, rescale)) {
+          tc_fence_after();
+#pragma unroll
+          for (int cidx = 0; cidx < 4; ++cidx) {
+            uint32_t u[32];
+            tmem_ld32(tmem_o + lane_sel + cidx * 32, u);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(__uint_as_float(u[i]) * alpha);
+            tmem_st32(tmem_o + lane_sel + cidx * 32, u);
+          }
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_empty[t * 2 + sb]);
+        mbar_arrive(&p_full[t]);
+      }
+    }
+
+    mbar_wait_warp(&pv_done[t], (n_kv - 1) & 1, lane);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_sum;
+    __half* o = p.out + ((long long)item * p.Lq + q_in_item) * p.ldo + head * 128;
+#pragma unroll
+    for (int cidx = 0; cidx < 4; ++cidx) {
+      uint32_t u[32];
+      tmem_ld32(tmem_o + lane_sel + cidx * 32, u);
+      tmem_wait_ld();
+      if (q_in_item < p.Lq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(u[i + e]) * inv_l;
+          uint4* dst = reinterpret_cast<uint4*>(o + cidx * 32 + i);
+          if (p.accumulate) {
+            const uint4 old = *dst;
+            const __half2* oh = reinterpret_cast<const __half2*>(&old);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(oh[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+          }
+          *dst = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == W_MMA0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_all, 512);
+  }
+}
+}  // namespace v3
+
+
 }  // namespace
 
 void launch_attention(const AttnParams& p, cudaStream_t stream) {
@@ -437,6 +690,36 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
   ProfScope prof(PC_ATTN, 4.0 * p.Lq * keys * 128.0 * p.heads, 0.0, stream);
   AttnParams pd = p;
   pd.dbg = dbg;
+  // long sequences: two query tiles per CTA sharing the K / V tiles (namespace v3, ~10 % faster per tile-step but
+  // coarser work units).  B200_ATTN_PAIR: 0 never, 1 always; unset = when queries and keys are long and the
+  // wave count does not get worse.
+  const char* pair_env = std::getenv("B200_ATTN_PAIR");
+  int min_keys = 1 << 30;
+  for (int i = 0; i < p.items; ++i) min_keys = std::min(min_keys, p.klen[i]);
+  bool use_pair;
+  if (pair_env) {
+    use_pair = std::atoi(pair_env) != 0;
+  } else {
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const long long n1 = (long long)((p.Lq + TILE - 1) / TILE) * p.heads * p.items;
+    const long long n2 = (long long)((p.Lq + 2 * TILE - 1) / (2 * TILE)) * p.heads * p.items;
+    const double waves1 = (double)(n1 / (2 * sms)) + (n1 % (2 * sms) ? (n1 % (2 * sms) <= sms ? 0.4 : 1.0) : 0.0);
+    const double waves2 = (double)((n2 + sms - 1) / sms);
+    use_pair = p.Lq >= 2048 && min_keys >= 2048 && waves2 / 1.1 < waves1;
+  }
+  if (use_pair) {
+    static bool configured3 = false;
+    if (!configured3) {
+      B2_CUDA(cudaFuncSetAttribute(v3::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM));
+      configured3 = true;
+    }
+    pd.split_tiles = 0; pd.split_parts = 1;
+    dim3 grid3(((p.Lq + 2 * TILE - 1) / (2 * TILE)) * p.heads * p.items);
+    launch_pdl(v3::attn_fwd_kernel, grid3, dim3(352), v3::SMEM, stream, tq, tk, tv, pd);
+    count_launch();
+    return;
+  }
   const int n_tiles = ((p.Lq + TILE - 1) / TILE) * p.heads * p.items;
   // Tail split: tiles run in co-resident waves of two CTAs per SM.  When the last wave holds only a few tiles, cut
   // each of them along the key axis so that the wave is as wide as the machine and proportionally shorter.

@@ -87,6 +87,25 @@ def test_flash_attention_tail_split_matches_unsplit(monkeypatch):
     assert (a.float() - b.float()).abs().max() < 4e-3
 
 
+@pytest.mark.parametrize("B,Lq,Lk,H,klens", [
+    (1, 2304, 2304, 2, None),                 # long enough for the two-tiles-per-CTA kernel by default
+    (2, 2100, 2500, 1, [2500, 2049]),         # ragged keys, partial second tile
+])
+def test_flash_attention_long_sequences(B, Lq, Lk, H, klens):
+    test_flash_attention(B, Lq, Lk, H, klens)
+
+
+@pytest.mark.parametrize("B,Lq,Lk,H,klens", [
+    (1, 128, 128, 1, None), (2, 300, 512, 3, [77, 512]), (1, 1560, 1560, 12, None), (3, 70, 15, 1, None),
+    (2, 200, 257, 2, [257, 100]), (1, 640, 1280, 3, [1025]),
+])
+def test_flash_attention_two_tile_kernel_forced(monkeypatch, B, Lq, Lk, H, klens):
+    """B200_ATTN_PAIR=1 sends every shape through the long-sequence kernel (lone / partial second tiles, short and
+    ragged key counts)."""
+    monkeypatch.setenv("B200_ATTN_PAIR", "1")
+    test_flash_attention(B, Lq, Lk, H, klens)
+
+
 def test_flash_attention_large_logits():
     """rows whose running max keeps growing exercise the thresholded O rescale path"""
     import b200dit
