@@ -675,6 +675,12 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
     B2_CHECK(p.klen[i] >= 1 && p.klen[i] <= p.Lk_rows, "attention: item %d has %d valid keys of %d", i, p.klen[i],
              p.Lk_rows);
   static const int dbg = std::getenv("B200_ATTN_DBG") ? std::atoi(std::getenv("B200_ATTN_DBG")) : 0;
+  static const int num_sms = [] {                        // one process drives one GPU (parallel.py)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+  }();
   static bool configured = false;
   if (!configured) {
     B2_CUDA(cudaFuncSetAttribute(v2::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM));
@@ -700,8 +706,7 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
   if (pair_env) {
     use_pair = std::atoi(pair_env) != 0;
   } else {
-    int sms = 148;
-    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int sms = num_sms;
     const long long n1 = (long long)((p.Lq + TILE - 1) / TILE) * p.heads * p.items;
     const long long n2 = (long long)((p.Lq + 2 * TILE - 1) / (2 * TILE)) * p.heads * p.items;
     const double waves1 = (double)(n1 / (2 * sms)) + (n1 % (2 * sms) ? (n1 % (2 * sms) <= sms ? 0.4 : 1.0) : 0.0);
@@ -723,12 +728,7 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
   const int n_tiles = ((p.Lq + TILE - 1) / TILE) * p.heads * p.items;
   // Tail split: tiles run in co-resident waves of two CTAs per SM.  When the last wave holds only a few tiles, cut
   // each of them along the key axis so that the wave is as wide as the machine and proportionally shorter.
-  static const int slots = [] {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return 2 * sms;
-  }();
+  const int slots = 2 * num_sms;
   const char* split_env = std::getenv("B200_ATTN_SPLIT");               // 0 disables, n > 1 = at most n parts (A/B runs)
   const int split_mode = split_env ? std::atoi(split_env) : 1;
   const int max_parts = split_mode > 1 ? std::min(split_mode, v2::MAX_PARTS) : 4;      // 4 measured best (4 / 8 / 16 within 1 %)
