@@ -72,37 +72,39 @@ def install_t2v(pipe, device=None, dit_engine=None, vae_engine=None):
     nothing to do: the engines keep their own device copies of the weights."""
     eng = dit_engine or DitEngine.from_module(pipe.model, device=device)
     vae = vae_engine or VaeEngine.from_state_dict(pipe.vae.model.state_dict(), device=device)
-    original = pipe.generate
-
-    def generate(self, input_prompt, size=(720, 512), frame_num=81, shift=5.0, sample_solver="unipc",
-                 sampling_steps=50, guide_scale=5.0, n_prompt="", seed=-1, offload_model=True):
-        if sample_solver not in ("unipc", "dpm++"):
-            raise NotImplementedError("Unsupported solver.")                                   # :221-222
-        st, ps, sp = self.vae_stride, self.patch_size, getattr(self, "sp_size", 1)
-        shape = (self.vae.model.z_dim, (frame_num - 1) // st[0] + 1, size[1] // st[1], size[0] // st[2])
-        seq_len = math.ceil(shape[2] * shape[3] / (ps[1] * ps[2]) * shape[1] / sp) * sp        # :161-164
-        negative = n_prompt if n_prompt != "" else self.sample_neg_prompt
-        gen = torch.Generator(device=self.device)
-        gen.manual_seed(seed if seed >= 0 else random.randint(0, sys.maxsize))
-        enc_dev = torch.device("cpu") if self.t5_cpu else self.device                          # :172-183
-        if not self.t5_cpu:
-            self.text_encoder.model.to(self.device)
-        context = [c.to(self.device) for c in self.text_encoder([input_prompt], enc_dev)]
-        context_null = [c.to(self.device) for c in self.text_encoder([negative], enc_dev)]
-        if not self.t5_cpu and offload_model:
-            self.text_encoder.model.cpu()
-        noise = [torch.randn(*shape, dtype=torch.float32, device=self.device, generator=gen)]
-        x0 = pipelines.sample(eng, noise, context, context_null, steps=sampling_steps, shift=shift,
-                              guide_scale=guide_scale, solver=sample_solver, seq_len=seq_len)
-        videos = vae.decode(x0) if self.rank == 0 else None
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.barrier()
-        return videos[0] if self.rank == 0 else None
-
-    pipe._b200_original_generate = original
+    pipe._b200_original_generate = pipe.generate
     pipe._b200_engines = (eng, vae)
-    pipe.generate = types.MethodType(generate, pipe)
+    pipe.generate = types.MethodType(_t2v_generate, pipe)
     return eng, vae
+
+
+def _t2v_generate(self, input_prompt, size=(720, 512), frame_num=81, shift=5.0, sample_solver='unipc',
+                  sampling_steps=50, guide_scale=5.0, n_prompt="", seed=-1, offload_model=True):
+    """Body of the patched `WanT2V.generate`; parameter names and defaults are the reference's (text2video.py:111-121,
+    checked by tests/test_cpu_abi.py)."""
+    eng, vae = self._b200_engines
+    if sample_solver not in ("unipc", "dpm++"):
+        raise NotImplementedError("Unsupported solver.")                                   # :221-222
+    st, ps, sp = self.vae_stride, self.patch_size, getattr(self, "sp_size", 1)
+    shape = (self.vae.model.z_dim, (frame_num - 1) // st[0] + 1, size[1] // st[1], size[0] // st[2])
+    seq_len = math.ceil(shape[2] * shape[3] / (ps[1] * ps[2]) * shape[1] / sp) * sp        # :161-164
+    negative = n_prompt if n_prompt != "" else self.sample_neg_prompt
+    gen = torch.Generator(device=self.device)
+    gen.manual_seed(seed if seed >= 0 else random.randint(0, sys.maxsize))
+    enc_dev = torch.device("cpu") if self.t5_cpu else self.device                          # :172-183
+    if not self.t5_cpu:
+        self.text_encoder.model.to(self.device)
+    context = [c.to(self.device) for c in self.text_encoder([input_prompt], enc_dev)]
+    context_null = [c.to(self.device) for c in self.text_encoder([negative], enc_dev)]
+    if not self.t5_cpu and offload_model:
+        self.text_encoder.model.cpu()
+    noise = [torch.randn(*shape, dtype=torch.float32, device=self.device, generator=gen)]
+    x0 = pipelines.sample(eng, noise, context, context_null, steps=sampling_steps, shift=shift,
+                          guide_scale=guide_scale, solver=sample_solver, seq_len=seq_len)
+    videos = vae.decode(x0) if self.rank == 0 else None
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.barrier()
+    return videos[0] if self.rank == 0 else None
 
 
 def uninstall(obj):
