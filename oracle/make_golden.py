@@ -127,7 +127,52 @@ def make_disc_golden():
                os.path.join(OUT, "disc_tiny.pt"))
 
 
+GRAD_KEYS = ["patch_embedding.weight", "text_embedding.0.weight", "time_projection.1.weight", "blocks.0.modulation",
+             "blocks.0.self_attn.q.weight", "blocks.0.self_attn.norm_k.weight", "blocks.0.cross_attn.k.weight",
+             "blocks.0.norm3.weight", "blocks.1.ffn.0.weight", "blocks.1.ffn.2.bias", "blocks.1.self_attn.o.weight",
+             "head.modulation", "head.head.weight"]
+
+
+def make_grad_golden():
+    """Parity target for the NEXT scope row (backward of the student forward): gradients of the APT
+    stage-1 loss (distilled_trainer.py:262-289: student forward at t = 1000, MSE against v_teacher) through the
+    UNMODIFIED WanModel on the tiny t2v fixture's weights and inputs -- d loss / d x for both items, the gradients
+    of GRAD_KEYS in full, and the gradient norm of every parameter."""
+    g = torch.load(os.path.join(OUT, "dit_t2v_tiny.pt"))
+    M, _ = ref_loader.load_reference_modules()
+    cfg = dict(g["cfg"])
+    sd = {k: v.float() for k, v in g["sd"].items()}
+    m = M.WanModel(model_type="t2v", in_dim=cfg["in_dim"], dim=cfg["dim"], ffn_dim=cfg["ffn_dim"],
+                   num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], text_dim=cfg["text_dim"],
+                   use_checkpoint=False).train()
+    m.load_state_dict(sd, strict=True)
+    gen = torch.Generator().manual_seed(123)
+    x = [u.clone().requires_grad_(True) for u in g["x"]]
+    t = torch.full((len(x),), 1000.0)
+    v_teacher = [torch.randn(u.shape, generator=gen) for u in g["x"]]
+    out = m(x, t, g["context"], seq_len=g["seq_len"])
+    loss = sum(torch.nn.functional.mse_loss(o.float(), v) for o, v in zip(out, v_teacher))
+    loss.backward()
+    params = dict(m.named_parameters())
+    rec = dict(t=t, v_teacher=v_teacher, loss=loss.detach().clone(), dx=[u.grad.clone() for u in x],
+               grads={k: params[k].grad.clone() for k in GRAD_KEYS},
+               grad_norms={k: float(p.grad.norm()) for k, p in params.items() if p.grad is not None})
+    # the oracle's autograd on the same problem
+    sd_o = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "freqs"}
+    x_o = [u.clone().requires_grad_(True) for u in g["x"]]
+    out_o = O.dit_forward(sd_o, x_o, t, g["context"], g["seq_len"], num_heads=cfg["num_heads"])
+    loss_o = sum(torch.nn.functional.mse_loss(o, v) for o, v in zip(out_o, v_teacher))
+    loss_o.backward()
+    worst = max(float((sd_o[k].grad - rec["grads"][k]).norm() / rec["grads"][k].norm()) for k in GRAD_KEYS)
+    worst_x = max(float((a.grad - b).norm() / b.norm()) for a, b in zip(x_o, rec["dx"]))
+    print(f"grad golden: loss {float(loss):.6f} (oracle {float(loss_o):.6f}), worst rel-L2 weights {worst:.2e}, inputs {worst_x:.2e}")
+    assert worst < 1e-4 and worst_x < 1e-4
+    torch.save(rec, os.path.join(OUT, "dit_grad_tiny.pt"))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "grads":
+        return make_grad_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "disc":
         return make_disc_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "solvers":

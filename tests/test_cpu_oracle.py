@@ -157,3 +157,23 @@ def test_disc_head_oracle_vs_live_reference(qk_norm):
     out = DO.disc_head(x, w, "h.", 2, qk_norm=qk_norm)
     assert out.shape == ref.shape == (3, 1, 256)
     assert rel_l2(out, ref) < 1e-6
+
+
+def test_dit_oracle_gradients_vs_golden():
+    """Parity target of the next scope row (backward of the student forward): the oracle's autograd
+    through the APT stage-1 loss (student forward at t = 1000, MSE against v_teacher; distilled_trainer.py:262-289)
+    against the gradients of the UNMODIFIED WanModel (oracle/make_golden.py grads)."""
+    g = torch.load(os.path.join(GOLDEN, "dit_t2v_tiny.pt"))
+    r = torch.load(os.path.join(GOLDEN, "dit_grad_tiny.pt"))
+    sd = {k: v.float().clone().requires_grad_(True) for k, v in g["sd"].items() if k != "freqs"}
+    x = [u.clone().requires_grad_(True) for u in g["x"]]
+    out = O.dit_forward(sd, x, r["t"], g["context"], g["seq_len"], num_heads=g["cfg"]["num_heads"])
+    loss = sum(torch.nn.functional.mse_loss(o, v) for o, v in zip(out, r["v_teacher"]))
+    loss.backward()
+    assert abs(float(loss) - float(r["loss"])) < 1e-5
+    for a, b in zip(x, r["dx"]):
+        assert rel_l2(a.grad, b) < 1e-4
+    for k, ref in r["grads"].items():
+        assert rel_l2(sd[k].grad, ref) < 1e-4, k
+    for k, n in r["grad_norms"].items():
+        assert abs(float(sd[k].grad.norm()) - n) <= 1e-4 * max(n, 1e-6) + 1e-9, k
