@@ -16,6 +16,11 @@ Fixtures (all small enough to commit; weights stored as fp16 = exactly the value
   solver_traj.pt    FlowUniPC / FlowDPMSolver++ trajectories (fm_solvers_unipc.py, fm_solvers.py) on a toy
                     velocity field: per case the timesteps and the latent after every step
                     (`python oracle/make_golden.py solvers` regenerates only this file)
+  disc_tiny.pt      WanAPTDiscriminator.forward (seaweed_apt/model.py:123-186) over a 36-block tiny Wan: inputs,
+                    logits and the three head tokens; weights regenerate from b200dit.synthetic by stored seed
+                    (`python oracle/make_golden.py disc`)
+  dit_grad_tiny.pt  gradients of the APT stage-1 loss through WanModel on dit_t2v_tiny's weights and inputs: the
+                    parity target of the backward row, SURVEY 8f F1 (`python oracle/make_golden.py grads`)
 """
 import os
 import sys
