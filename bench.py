@@ -104,71 +104,153 @@ def make_device_weights(cfg, seed, device, i2v=False):
     return synthetic.dit_weights(cfg, seed, device, i2v=i2v)
 
 
-def cpu_baseline(frames, target_s=12.0):
-    """CPU oracle port (oracle/dit_oracle.py, fp32, all host threads) on a bounded sample of the same
-    workload: both CFG branches through embeddings + head + as many of the 30 blocks as fit ~target_s of
-    CPU work (at least 2); the measured per-block cost is scaled to 30 blocks."""
+def _host_threads():
+    """All host cores, set explicitly: torchrun exports OMP_NUM_THREADS=1, which made round 1's reference arm
+    single-threaded under N > 1."""
     import torch
-    from oracle import dit_oracle as O
-    cores = torch.get_num_threads()
-    g = torch.Generator().manual_seed(42)
-    x = [torch.randn(16, frames, 60, 104, generator=g)]
-    ctx = [torch.randn(512, 4096, generator=g)]
-    ctx0 = [torch.randn(512, 4096, generator=g)]
-    t = torch.tensor([999.0])
-    L = 1560 * frames
-    sd = O.make_synthetic_weights(num_layers=2, seed=0)
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return n
 
-    def one(sd_, nl):
+
+class CpuStep:
+    """One whole CFG denoise step of the workload on the CPU oracle port (oracle/dit_oracle.py, fp32): cond forward
+    + uncond forward through all `layers` blocks + the CFG combine -- the reference's algorithm on the host cores."""
+
+    def __init__(self, frames, layers):
+        import torch
+        from oracle import dit_oracle as O
+        self.O, self.torch = O, torch
+        self.cores = _host_threads()
+        g = torch.Generator().manual_seed(42)
+        self.x = [torch.randn(16, frames, 60, 104, generator=g)]
+        self.ctx = [torch.randn(512, 4096, generator=g)]
+        self.ctx0 = [torch.randn(512, 4096, generator=g)]
+        self.t = torch.tensor([999.0])
+        self.L = 1560 * frames
+        self.layers = layers
+        self.sd = O.make_synthetic_weights(num_layers=layers, seed=0)
+
+    def run(self, layers=None):
+        O, nl = self.O, layers or self.layers
         t0 = time.perf_counter()
-        with torch.no_grad():
-            c = O.dit_forward(sd_, x, t, ctx, L, num_layers=nl)[0]
-            u = O.dit_forward(sd_, x, t, ctx0, L, num_layers=nl)[0]
+        with self.torch.no_grad():
+            c = O.dit_forward(self.sd, self.x, self.t, self.ctx, self.L, num_layers=nl)[0]
+            u = O.dit_forward(self.sd, self.x, self.t, self.ctx0, self.L, num_layers=nl)[0]
             O.cfg_combine(c, u, GUIDE)
         return time.perf_counter() - t0
 
-    one(sd, 1)                                           # warm-up (thread pool, allocator)
-    t_one = one(sd, 1)
-    t_two = one(sd, 2)
-    per_block = max(t_two - t_one, 1e-9)
-    n_layers = int(max(2, min(CFG_13B["num_layers"], round((target_s - t_one) / per_block))))
-    spent = t_one + t_two
-    if n_layers > 2:                                     # re-measure on the larger sample
-        sd = O.make_synthetic_weights(num_layers=n_layers, seed=0)
-        t_n = one(sd, n_layers)
-        per_block = max((t_n - t_one) / (n_layers - 1), 1e-9)
-        spent += t_n
-    step_s = t_one + per_block * (CFG_13B["num_layers"] - 1)
-    return {"value": 1.0 / step_s, "unit": "denoise-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{n_layers} of 30 blocks x 2 CFG branches + embeddings/head at L={L}, fp32 CPU oracle "
-                      f"(oracle/dit_oracle.py), block cost scaled to 30 layers ({spent:.1f}s of CPU work)"}, step_s
+
+def cpu_baseline(frames, layers=None, full_steps=1):
+    """cpu_baseline leg of the GPU arm: the CPU oracle port on all host threads on a BOUNDED sample of the same
+    workload.  T = 1: `full_steps` whole 30-block CFG steps (about 6 s each on 16 cores) after a 2-block warm-up --
+    nothing is extrapolated.  T > 1 (a whole step is minutes of CPU): 2 blocks timed, block cost scaled to 30."""
+    layers = layers or CFG_13B["num_layers"]
+    L = 1560 * frames
+    if frames == 1:
+        st = CpuStep(frames, layers)
+        st.run(2)                                            # warm-up: thread pool, allocator
+        ts = sorted(st.run() for _ in range(full_steps))
+        step_s = ts[len(ts) // 2]
+        sample = (f"{full_steps} whole CFG step(s): 2 forwards x {layers} blocks + embeddings/head + combine at L={L}, "
+                  f"fp32 CPU oracle (oracle/dit_oracle.py), after a 2-block warm-up; no extrapolation")
+    else:
+        st = CpuStep(frames, 2)
+        st.run(1)
+        t1, t2 = st.run(1), st.run(2)
+        step_s = t1 + max(t2 - t1, 1e-9) * (layers - 1)
+        sample = (f"2 of {layers} blocks x 2 CFG branches + embeddings/head at L={L}, fp32 CPU oracle, block cost "
+                  f"scaled to {layers} layers (a whole step at T={frames} is minutes of CPU work)")
+    return {"value": 1.0 / step_s, "unit": "denoise-steps/s", "cores": st.cores, "kind": "port", "sample": sample}, step_s
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm's CPU implementation (oracle port; the Python reference
-    itself cannot travel to the GPU box) with all host threads; each step is a bounded sample."""
+    """--impl reference: the reference algorithm's CPU implementation (oracle port; the Python reference itself
+    cannot travel to the GPU box) on all host threads.  Times WHOLE steps (no block extrapolation) and prints the
+    number of steps and warm-ups it really ran: `--steps K --warmup W` are honoured up to a wall-clock budget of
+    about 150 s (a 30-block CFG step is ~6 s on 16 cores); under torchrun rank 0 alone works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    vals = []
-    info = None
-    for _ in range(max(1, min(args.steps, 3))):
-        info, step_s = cpu_baseline(args.frames)
-        vals.append(step_s)
-    vals.sort()
-    step_s = vals[len(vals) // 2]
+    budget_s = float(os.environ.get("B200_REF_BUDGET_S", "150"))
+    st = CpuStep(args.frames, args.layers)
+    st.run(2)                                                # thread pool / allocator warm-up (2 blocks)
+    t_first = st.run()                                       # warm-up step 1 (whole step)
+    warm = 1
+    while warm < args.warmup and (warm + 2) * t_first < 0.2 * budget_s:
+        st.run()
+        warm += 1
+    k = int(max(1, min(args.steps, (budget_s - warm * t_first) // max(t_first, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        st.run()
+    step_s = (time.perf_counter() - t0) / k
     v = 1.0 / step_s
-    info["value"] = v
+    info = {"value": v, "unit": "denoise-steps/s", "cores": st.cores, "kind": "port",
+            "sample": f"{k} whole CFG steps (2 forwards x {args.layers} blocks + embeddings/head + combine, L={st.L}), "
+                      f"{warm} whole-step warm-up(s); requested --steps {args.steps} --warmup {args.warmup}, bounded "
+                      f"by a {budget_s:.0f} s budget; no extrapolation; the CPU runs one sample at a time (the metric counts "
+                      f"sample-steps, so co-batching does not change its meaning)"}
     line = {"impl": "reference", "metric": "DiT denoise-steps/sec (Wan2.1-T2V-1.3B, CFG, 480x832)", "value": v,
-            "unit": "denoise-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "unit": "denoise-steps/s", "n_gpus": args.gpus, "steps": k, "warmup": warm,
+            "steps_requested": args.steps, "warmup_requested": args.warmup,
             "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.frames, args.samples_per_gpu, args.layers, args.gpus),
             "cpu_baseline": info,
             "e2e": {"value": v, "unit": "denoise-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "host_threads": torch.get_num_threads()}
+            "gpu_launches": 0, "host_threads": st.cores}
     print(json.dumps(line), flush=True)
+
+
+BLOCK_SHAPES = [("1 x L=6240 (one sequence, latent [16,4,60,104])", 1, 4), ("4 x L=1560 (bench step: 2 samples x cond/uncond)", 4, 1),
+                ("1 x L=1560", 1, 1), ("1 x L=32760 (T=21)", 1, 21)]
+
+
+def block_table(dev, burst, sustained, shapes=BLOCK_SHAPES):
+    """SURVEY 8(d) fused-block micro-benchmark: ONE WanAttentionBlock (LayerNorm+modulation -> QKV -> RMSNorm/RoPE ->
+    self-attention -> o -> norm3 -> cross-attention -> FFN, context K/V cached) at the four shapes.  Block time =
+    (forward of a 6-block engine - forward of a 2-block engine) / 4 under CUDA graphs, so embeddings, head and
+    launch overheads cancel; device-resident inputs, CUDA events, 3 warm-ups."""
+    import torch
+    import b200dit
+    engs = {}
+    for n in (2, 6):
+        cfg = dict(CFG_13B, num_layers=n)
+        engs[n] = b200dit.DitEngine(**cfg, device=dev)
+        engs[n].load_state_dict(make_device_weights(cfg, 1, dev))
+    g = torch.Generator().manual_seed(9)
+    rows = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, B, T in shapes:
+        L = 1560 * T
+        x = [torch.randn(16, T, 60, 104, generator=g).to(dev) for _ in range(B)]
+        ctx = [torch.randn(512, 4096, generator=g).bfloat16().to(dev) for _ in range(B)]
+        t = torch.full((B,), 500.0, device=dev)
+        reps = 3 if T > 8 else 12
+        ms = {}
+        for n, eng in engs.items():
+            for _ in range(3):
+                eng.forward(x, t, ctx, L)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                eng.forward(x, t, ctx, L)
+            e1.record()
+            torch.cuda.synchronize()
+            ms[n] = e0.elapsed_time(e1) / reps
+        blk_ms = (ms[6] - ms[2]) / 4.0
+        fl = B * b200dit.flops.dit_block_flops(L)
+        tf = fl / (blk_ms / 1e3) / 1e12
+        rows.append({"shape": name, "items": B, "L": L, "block_ms": blk_ms, "block_gflop": fl / 1e9, "tflops": tf,
+                     "frac_of_burst": tf / burst, "frac_of_sustained": tf / sustained})
+    for eng in engs.values():
+        eng.close()
+    return rows
 
 
 def main():
@@ -184,6 +266,7 @@ def main():
     ap.add_argument("--layers", type=int, default=CFG_13B["num_layers"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--no-block-table", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -356,8 +439,10 @@ def main():
             traffic = 1e6 * (mb("qkv") + 3 * mb("o-shaped") + mb("ffn.0") + mb("ffn.2")) / 6.0
             tsrc = "profiles/r1_ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 128xN / 256xN tiles, fused epilogues)",
-                "achieved": ach, "peak": sustained, "peak_burst": burst, "unit": "TFLOP/s", "frac": ach / sustained,
-                "frac_of_burst": ach / burst, "peak_source": src + " (sustained: kernel timed inside a long step)",
+                "achieved": ach, "peak": burst, "peak_sustained": sustained, "unit": "TFLOP/s", "frac": ach / burst,
+                "frac_of_sustained": ach / sustained,
+                "peak_source": src + " MEASURED_PEAKS.json: `peak` = cuBLAS bf16 burst (BASELINE.md section 2's primary "
+                               "denominator), `peak_sustained` = the seconds-long figure under the power cap",
                 "traffic": traffic, "traffic_source": tsrc, "launches_per_step": gm["launches"] // 2,
                 "avg_launch_us": 1e3 * gm["ms"] / max(gm["launches"], 1),
                 "flops_per_launch": gm["flops"] / max(gm["launches"], 1),
@@ -407,8 +492,11 @@ def main():
                         "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / K},
                 "gpu_launches": int(launches),
                 "step_tflops": flops_step / (ms_step / 1e3) / 1e12,
-                "step_frac_of_peak": flops_step / (ms_step / 1e3) / 1e12 / sustained,
+                "step_frac_of_peak": flops_step / (ms_step / 1e3) / 1e12 / burst,
+                "step_frac_of_sustained": flops_step / (ms_step / 1e3) / 1e12 / sustained,
                 "roofline": roof, "single_sample": single}
+        if world == 1 and not args.no_block_table:
+            line["block_table"] = block_table(dev, burst, sustained)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"], _ = cpu_baseline(T)
         elif world > 1:

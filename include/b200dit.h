@@ -60,6 +60,10 @@ typedef struct b200dit_config {
 /* WanModel.__init__ (model.py:388-498): allocates packed-weight storage for the given architecture. */
 B200_API int b200dit_create(const b200dit_config* cfg, b200dit_engine** out);
 B200_API void b200dit_destroy(b200dit_engine* e);
+/* Host-only (needs no GPU): the WanModel.state_dict() keys (model.py:463-498, minus the non-persistent `freqs`)
+ * that an engine of this architecture expects, as "name numel\n" lines.  Returns the bytes needed including
+ * the terminator (call with buf = NULL to size the buffer), -1 on a bad configuration (b200_last_error). */
+B200_API int64_t b200dit_weight_names(const b200dit_config* cfg, char* buf, int64_t cap);
 
 /* WanModel.load_state_dict: one call per state_dict entry, reference key names (model.py:463-498):
  * patch_embedding.{weight,bias}, text_embedding.{0,2}.*, time_embedding.{0,2}.*, time_projection.1.*,
@@ -107,11 +111,12 @@ B200_API int b200dit_context_hint(b200dit_engine* e, uint64_t token);
 
 /* Residual-stream taps (the APT discriminator reads block outputs through forward hooks,
  * seaweed_apt/model.py:150-155): after the next forward, copy the fp32 stream [n_items*L, dim] that
- * left block `block_idx` into dst (device).  block_idx < 0 disables. */
-B200_API int b200dit_set_tap(b200dit_engine* e, int32_t block_idx, float* dst);
+ * left block `block_idx` into dst (device).  block_idx < 0 disables.  `rows` is the capacity of dst in token
+ * rows: a later forward whose n_items*L (2 n_items*L for forward_cfg) exceeds it fails instead of writing past it. */
+B200_API int b200dit_set_tap(b200dit_engine* e, int32_t block_idx, float* dst, int64_t rows);
 /* Several taps at once (the discriminator hooks three blocks, seaweed_apt/model.py:150-155): n <= 8 pairs of
- * (block index, device destination [n_items*L, dim] fp32); n = 0 disables. */
-B200_API int b200dit_set_taps(b200dit_engine* e, int32_t n, const int32_t* block_idx, float* const* dst);
+ * (block index, device destination [rows, dim] fp32, rows >= n_items*L of every later forward); n = 0 disables. */
+B200_API int b200dit_set_taps(b200dit_engine* e, int32_t n, const int32_t* block_idx, float* const* dst, int64_t rows);
 
 /* Capture each distinct (n_items, grid, mode) forward into a CUDA graph and replay it (default on). */
 B200_API int b200dit_set_graphs(b200dit_engine* e, int32_t enabled);

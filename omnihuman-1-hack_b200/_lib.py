@@ -37,8 +37,9 @@ SIGNATURES = {
     "b200dit_forward": (_I, [_P, _I, _PP, _PP, _I, _P, _PP, _IP, _I, _PP, _I, _I, _I, _I, _PP, _P]),
     "b200dit_forward_cfg": (_I, [_P, _I, _PP, _PP, _I, _P, _PP, _IP, _PP, _IP, _I, _PP, _I, _I, _I, _I, _F, _PP, _P]),
     "b200dit_context_hint": (_I, [_P, C.c_uint64]),
-    "b200dit_set_tap": (_I, [_P, _I, _P]),
-    "b200dit_set_taps": (_I, [_P, _I, _IP, _PP]),
+    "b200dit_weight_names": (C.c_int64, [C.POINTER(DitConfig), C.c_char_p, C.c_int64]),
+    "b200dit_set_tap": (_I, [_P, _I, _P, C.c_int64]),
+    "b200dit_set_taps": (_I, [_P, _I, _IP, _PP, C.c_int64]),
     "b200dit_set_graphs": (_I, [_P, _I]),
     "b200dit_last_flops": (C.c_double, [_P]),
     "b200dit_nonfinite_rows": (_I, [_P, _P, C.POINTER(C.c_uint32)]),

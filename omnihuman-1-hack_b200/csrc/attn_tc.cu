@@ -675,13 +675,14 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
     B2_CHECK(p.klen[i] >= 1 && p.klen[i] <= p.Lk_rows, "attention: item %d has %d valid keys of %d", i, p.klen[i],
              p.Lk_rows);
   static const int dbg = std::getenv("B200_ATTN_DBG") ? std::atoi(std::getenv("B200_ATTN_DBG")) : 0;
-  static const int num_sms = [] {                        // one process drives one GPU (parallel.py)
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms;
-  }();
-  static bool configured = false;
+  // function attributes and the SM count are per device (engines accept any device ordinal)
+  static bool configured_dev[64] = {false}, configured3_dev[64] = {false};
+  static int sms_dev[64] = {0};
+  int dev = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  if (sms_dev[dev & 63] == 0) B2_CUDA(cudaDeviceGetAttribute(&sms_dev[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+  const int num_sms = sms_dev[dev & 63];
+  bool& configured = configured_dev[dev & 63];
   if (!configured) {
     B2_CUDA(cudaFuncSetAttribute(v2::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM));
     B2_CUDA(cudaFuncSetAttribute(v2::attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -714,7 +715,7 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
     use_pair = p.Lq >= 2048 && min_keys >= 2048 && waves2 / 1.1 < waves1;
   }
   if (use_pair) {
-    static bool configured3 = false;
+    bool& configured3 = configured3_dev[dev & 63];
     if (!configured3) {
       B2_CUDA(cudaFuncSetAttribute(v3::attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM));
       configured3 = true;

@@ -55,6 +55,18 @@ int b200dit_create(const b200dit_config* cfg, b200dit_engine** out) {
 }
 void b200dit_destroy(b200dit_engine* e) { delete e; }
 
+int64_t b200dit_weight_names(const b200dit_config* cfg, char* buf, int64_t cap) {
+  int64_t need = -1;
+  guarded([&] {
+    B2_CHECK(cfg != nullptr, "null argument");
+    std::string s;
+    for (const auto& kv : b2::DitEngine::weight_names(*cfg)) s += kv.first + " " + std::to_string(kv.second) + "\n";
+    need = (int64_t)s.size() + 1;
+    if (buf != nullptr && cap >= need) memcpy(buf, s.c_str(), (size_t)need);
+  });
+  return need;
+}
+
 int b200dit_load_weight(b200dit_engine* e, const char* name, const void* data, int32_t dtype, int32_t ndim,
                         const int64_t* shape) {
   return guarded([&] {
@@ -92,11 +104,13 @@ int b200dit_forward_cfg(b200dit_engine* e, int32_t n_samples, const float* const
 int b200dit_context_hint(b200dit_engine* e, uint64_t token) {
   return guarded([&] { B2_CHECK(e, "null engine"); e->impl.ctx_token = token; });
 }
-int b200dit_set_taps(b200dit_engine* e, int32_t n, const int32_t* block_idx, float* const* dst) {
+int b200dit_set_taps(b200dit_engine* e, int32_t n, const int32_t* block_idx, float* const* dst, int64_t rows) {
   return guarded([&] {
     B2_CHECK(e, "null engine");
     B2_CHECK(n >= 0 && n <= 8 && (n == 0 || (block_idx && dst)), "at most 8 taps");
+    B2_CHECK(n == 0 || rows > 0, "taps need a positive row capacity");
     e->impl.taps.clear();
+    e->impl.tap_rows = rows;
     for (int i = 0; i < n; ++i) {
       B2_CHECK(block_idx[i] >= 0 && block_idx[i] < e->impl.cfg.num_layers && dst[i] != nullptr, "tap %d: block %d out of range",
                i, block_idx[i]);
@@ -104,9 +118,9 @@ int b200dit_set_taps(b200dit_engine* e, int32_t n, const int32_t* block_idx, flo
     }
   });
 }
-int b200dit_set_tap(b200dit_engine* e, int32_t block_idx, float* dst) {
-  if (block_idx < 0) return b200dit_set_taps(e, 0, nullptr, nullptr);
-  return b200dit_set_taps(e, 1, &block_idx, &dst);
+int b200dit_set_tap(b200dit_engine* e, int32_t block_idx, float* dst, int64_t rows) {
+  if (block_idx < 0) return b200dit_set_taps(e, 0, nullptr, nullptr, 0);
+  return b200dit_set_taps(e, 1, &block_idx, &dst, rows);
 }
 int b200dit_set_graphs(b200dit_engine* e, int32_t enabled) {
   return guarded([&] { B2_CHECK(e, "null engine"); e->impl.use_graphs = enabled != 0; });

@@ -37,7 +37,8 @@ T* carve(uint8_t*& p, size_t n) {
 size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
 }  // namespace
 
-DitEngine::DitEngine(const b200dit_config& c) : cfg(c) {
+namespace {
+void check_config(const b200dit_config& c) {
   B2_CHECK(c.dim > 0 && c.num_heads > 0 && c.dim % c.num_heads == 0, "dim %d not divisible by num_heads %d", c.dim,
            c.num_heads);
   B2_CHECK(c.dim / c.num_heads == 128, "head_dim must be 128 (got %d)", c.dim / c.num_heads);   // attention.py:54 allows <=256
@@ -45,6 +46,23 @@ DitEngine::DitEngine(const b200dit_config& c) : cfg(c) {
   B2_CHECK(c.text_len % 8 == 0 && c.text_len >= 8, "text_len must be a multiple of 8");
   B2_CHECK(c.out_dim * 4 <= 64 && c.in_dim % 2 == 0, "unsupported in/out channels");
   B2_CHECK(c.freq_dim % 4 == 0, "freq_dim must be a multiple of 4");
+}
+}  // namespace
+
+// Host-only: the reference state_dict keys (model.py:463-498) this architecture expects, with element counts.
+// Touches no device, so the key mapping can be checked against a live WanModel on a machine without a GPU.
+std::vector<std::pair<std::string, long long>> DitEngine::weight_names(const b200dit_config& c) {
+  check_config(c);
+  DitEngine e(c, LayoutOnly{});
+  std::vector<std::pair<std::string, long long>> out;
+  for (const auto& kv : e.slots) out.emplace_back(kv.first, kv.second.numel);
+  return out;
+}
+
+DitEngine::DitEngine(const b200dit_config& c, LayoutOnly) : cfg(c), layout_only(true) { alloc_weights(); }
+
+DitEngine::DitEngine(const b200dit_config& c) : cfg(c) {
+  check_config(c);
   int dev = 0;
   B2_CUDA(cudaGetDevice(&dev));
   B2_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -93,8 +111,10 @@ void DitEngine::alloc_weights() {
   }
   Fp(2 * d); Fp(d * P); Fp(P); H(3 * d * P);
   if (i2v) { Fp(1280); Fp(1280); H(1280 * 1280); Fp(1280); H(d * 1280); Fp(d); Fp(d); Fp(d); }
-  w16.ensure(h16 * 2 + 4096);
-  w32.ensure(f32 * 4 + 4096);
+  if (!layout_only) {                 // layout-only: the carve below yields offsets from a null base
+    w16.ensure(h16 * 2 + 4096);
+    w32.ensure(f32 * 4 + 4096);
+  }
   uint8_t* p16 = w16.as<uint8_t>();
   uint8_t* p32 = w32.as<uint8_t>();
   auto W16 = [&](size_t n) { return carve<__half>(p16, n); };
@@ -208,12 +228,14 @@ void DitEngine::load_weight(const char* name, const void* data, int dtype, int n
   B2_CHECK(it != slots.end(), "unexpected weight name '%s' for this architecture", name);
   load_into_slot(it->second, name, data, dtype, ndim, shape);
   finalized = false;
+  cached_token = 0;                  // the cached cross-attention K / V were projected with the old weights
 }
 
 void DitEngine::finalize() {
   for (auto& kv : slots) B2_CHECK(kv.second.loaded, "weight '%s' was never loaded", kv.first.c_str());
   launch_split_weight(wt.head_w32, wt.head_w3, cfg.out_dim * 4, cfg.dim, 0);
   B2_CUDA(cudaDeviceSynchronize());
+  cached_token = 0;
   finalized = true;
 }
 
@@ -522,6 +544,8 @@ void DitEngine::forward(int n, const float* const* x, const float* const* y, int
              cfg.text_len);
     if (cfgm) B2_CHECK(rows_b[i] >= 0 && rows_b[i] <= cfg.text_len, "uncond context %d has %d rows", i, rows_b[i]);
   }
+  B2_CHECK(taps.empty() || (long long)B * L <= tap_rows, "taps were registered for %lld rows but this call has %lld "
+           "(items x tokens%s)", tap_rows, (long long)B * L, cfgm ? ", cond + uncond" : "");
   ensure_workspace(B, L);
   rope_table(F, Hp, Wp);
   ensure_static_io(B, F, H, W);

@@ -72,6 +72,7 @@ class DitEngine {
  public:
   explicit DitEngine(const b200dit_config& c);
   ~DitEngine();
+  static std::vector<std::pair<std::string, long long>> weight_names(const b200dit_config& c);
   void load_weight(const char* name, const void* data, int dtype, int ndim, const int64_t* shape);
   void finalize();
   // user-facing forward (pointers as in the C ABI); cfg: n samples -> 2n items
@@ -89,10 +90,14 @@ class DitEngine {
   bool finalized = false;
   bool use_graphs = true;
   std::vector<std::pair<int, float*>> taps;   // (block index, destination): residual stream after that block
+  long long tap_rows = 0;                     // row capacity of every tap destination
   double last_flops = 0.0;
   uint64_t ctx_token = 0;                // set by b200dit_context_hint, consumed by the next forward
 
  private:
+  struct LayoutOnly {};
+  DitEngine(const b200dit_config& c, LayoutOnly);
+  bool layout_only = false;
   void alloc_weights();
   void add_slot(const std::string& name, void* dst, int dt, long long numel, int tr_rows = 0, int tr_cols = 0);
   void ensure_workspace(int B, int L);

@@ -64,8 +64,13 @@ CUtensorMap make_out_map(const GemmParams& p, bool f32, uint32_t cw) {
 template <int BN, int EPI, int CL>
 void launch_one(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int num_sms, cudaStream_t stream) {
   using C = GemmCfg<BN, CL>;
-  static bool configured = false;
-  static int max_ctas = 0;
+  // function attributes and occupancy are per device: one flag per device ordinal
+  static bool configured_dev[64] = {false};
+  static int max_ctas_dev[64] = {0};
+  int dev_ord = 0;
+  B2_CUDA(cudaGetDevice(&dev_ord));
+  bool& configured = configured_dev[dev_ord & 63];
+  int& max_ctas = max_ctas_dev[dev_ord & 63];
   auto kern = gemm_tc_kernel<BN, EPI, CL>;
   if (!configured) {
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));

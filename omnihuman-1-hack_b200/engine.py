@@ -63,16 +63,43 @@ class DitEngine:
         eng.load_state_dict(sd)
         return eng
 
+    @staticmethod
+    def config_from_module(model):
+        """Architecture of a reference `WanModel` instance from the attributes its constructor sets
+        (model.py:445-460).  Pure Python: runs without a GPU (tests/test_cpu_boundary.py drives it with the real
+        class)."""
+        return dict(dim=model.dim, ffn_dim=model.ffn_dim, num_heads=model.num_heads, num_layers=model.num_layers,
+                    in_dim=model.in_dim, out_dim=model.out_dim, text_dim=model.text_dim, text_len=model.text_len,
+                    freq_dim=model.freq_dim, i2v=(model.model_type == "i2v"), eps=model.eps)
+
+    @staticmethod
+    def expected_weight_names(**cfg):
+        """{state_dict key: element count} an engine of this architecture loads (b200dit_weight_names; host only)."""
+        full = dict(dim=1536, ffn_dim=8960, num_heads=12, num_layers=30, in_dim=16, out_dim=16, text_dim=4096,
+                    text_len=512, freq_dim=256, i2v=0, eps=1e-6)
+        full.update(cfg)
+        full["i2v"] = int(bool(full["i2v"]))
+        c = DitConfig(**full)
+        need = lib().b200dit_weight_names(C.byref(c), None, 0)
+        if need < 0:
+            raise B200Error(lib().b200_last_error().decode("utf-8", "replace"))
+        buf = C.create_string_buffer(int(need))
+        lib().b200dit_weight_names(C.byref(c), buf, need)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n = line.rsplit(" ", 1)
+            out[name] = int(n)
+        return out
+
     @classmethod
     def from_module(cls, model, device=None):
         """Builds an engine from a reference `WanModel` instance (attributes set at model.py:445-460)."""
-        eng = cls(dim=model.dim, ffn_dim=model.ffn_dim, num_heads=model.num_heads, num_layers=model.num_layers,
-                  in_dim=model.in_dim, out_dim=model.out_dim, text_dim=model.text_dim, text_len=model.text_len,
-                  freq_dim=model.freq_dim, i2v=(model.model_type == "i2v"), eps=model.eps, device=device)
+        eng = cls(**cls.config_from_module(model), device=device)
         eng.load_state_dict(model.state_dict())
         return eng
 
     def load_state_dict(self, sd):
+        self._ctx_key = None              # cached cross-attention K / V belong to the old weights
         with torch.cuda.device(self.device):
             _load_state(lib().b200dit_load_weight, self._h, sd, lambda n: n != "freqs")
             check(lib().b200dit_finalize(self._h))
@@ -217,11 +244,11 @@ class DitEngine:
     def set_tap(self, block_idx, n_rows=None):
         """Residual stream after block `block_idx` (APT discriminator taps, seaweed_apt/model.py:150-155)."""
         if block_idx is None or block_idx < 0:
-            check(lib().b200dit_set_tap(self._h, -1, None))
+            check(lib().b200dit_set_tap(self._h, -1, None, 0))
             self._tap = None
             return None
         self._tap = torch.empty((n_rows, self.cfg["dim"]), dtype=torch.float32, device=self.device)
-        check(lib().b200dit_set_tap(self._h, int(block_idx), C.c_void_p(self._tap.data_ptr())))
+        check(lib().b200dit_set_tap(self._h, int(block_idx), C.c_void_p(self._tap.data_ptr()), int(n_rows)))
         return self._tap
 
     def set_taps(self, block_indices, n_rows, buffers=None):
@@ -234,7 +261,8 @@ class DitEngine:
             self._tap = list(buffers)
         else:
             self._tap = [torch.empty((n_rows, self.cfg["dim"]), dtype=torch.float32, device=self.device) for _ in idx]
-        check(lib().b200dit_set_taps(self._h, len(idx), int_array(idx), ptr_array([t.data_ptr() for t in self._tap])))
+        check(lib().b200dit_set_taps(self._h, len(idx), int_array(idx), ptr_array([t.data_ptr() for t in self._tap]),
+                                    int(n_rows)))
         return self._tap
 
     @property
@@ -262,10 +290,14 @@ class VaeEngine:
         with torch.cuda.device(self.device):
             check(lib().b200vae_create(dim, z_dim, C.byref(self._h)))
 
+    @staticmethod
+    def config_from_state_dict(sd):
+        """(dim, z_dim) of a `WanVAE_` from its state_dict shapes (vae.py:388-421,454-472); no GPU needed."""
+        return dict(dim=sd["decoder.head.2.weight"].shape[1], z_dim=sd["conv2.weight"].shape[0])
+
     @classmethod
     def from_state_dict(cls, sd, device=None):
-        dim = sd["decoder.head.2.weight"].shape[1]
-        eng = cls(dim=dim, z_dim=sd["conv2.weight"].shape[0], device=device)
+        eng = cls(**cls.config_from_state_dict(sd), device=device)
         eng.load_state_dict(sd)
         return eng
 

@@ -20,6 +20,14 @@ def dit_forward_flops(L, Lc=512, dim=1536, ffn=8960, layers=30, text_dim=4096, p
     return layers * per_block + other
 
 
+def dit_block_flops(L, Lc=512, dim=1536, ffn=8960):
+    """One WanAttentionBlock (model.py:279-330) over one item of L tokens with the step-invariant context work
+    cached: q,k,v,o 8 L d^2 + self attention 4 L^2 d + cross q,o 4 L d^2 + cross attention 4 L Lc d + FFN 4 L d f
+    (SURVEY 8d's fused-block micro-benchmark counts exactly this)."""
+    d = dim
+    return 8 * L * d * d + 4 * L * L * d + 4 * L * d * d + 4 * L * Lc * d + 4 * L * d * ffn
+
+
 def vae_decode_flops(T, h=60, w=104, dim=96):
     """WanVAE decode (vae.py:544-568) as the reference executes it: latent frame 0 alone (its upsample3d stages skip
     time_conv, vae.py:106-108), then T - 1 frames through the full decoder; conv MACs include causal zero padding."""

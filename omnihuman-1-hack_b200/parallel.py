@@ -56,10 +56,18 @@ def gather_items(local, n_items, group=None):
     w = world_size()
     if w == 1:
         return list(local)
+    if n_items < w:
+        # some ranks own nothing: every rank knows that from (n_items, world) alone, so all of them take the
+        # metadata-exchanging path together instead of one rank failing before the collective (deadlock)
+        counts = [len(range(r, n_items, w)) for r in range(w)]
+        lists = gather_from_ranks(local, counts, group=group)
+        res = [None] * n_items
+        for r in range(w):
+            for j, i in enumerate(range(r, n_items, w)):
+                res[i] = lists[r][j]
+        return res
     per_rank = (n_items + w - 1) // w
-    proto = local[0] if local else None
-    if proto is None:
-        raise ValueError("every rank needs at least one item (n_items >= world size)")
+    proto = local[0]
     buf = torch.zeros((per_rank,) + tuple(proto.shape), dtype=proto.dtype, device=proto.device)
     for j, t in enumerate(local):
         buf[j].copy_(t)
@@ -127,6 +135,8 @@ def gather_from_ranks(local, counts, group=None):
         proto_shape, dtype, device = tuple(local[0].shape), local[0].dtype, local[0].device
     meta = [None] * w
     dist.all_gather_object(meta, (proto_shape, str(dtype) if dtype else None), group=group)
+    if all(m[0] is None for m in meta):       # seen identically by every rank after the exchange: a clean failure
+        raise ValueError("gather_from_ranks: no rank holds an item")
     shape = next(m[0] for m in meta if m[0] is not None)
     if dtype is None:
         dtype = getattr(torch, next(m[1] for m in meta if m[1] is not None).split(".")[-1])

@@ -30,15 +30,38 @@ def _needs_grad(model, x):
     return any(p.requires_grad for p in model.parameters())
 
 
+def _weights_signature(model):
+    """Changes whenever a parameter is updated in place (optimizer.step, EMA copy_, load_state_dict) or replaced:
+    the sum of the tensors' version counters plus their storage addresses."""
+    if not hasattr(model, "parameters"):
+        return None
+    ver, ptr = 0, 0
+    for p in model.parameters():
+        ver += p._version
+        ptr ^= p.data_ptr()
+    return ver, ptr
+
+
 def install(model, device=None, engine=None):
-    """Routes `model.forward` through a DitEngine built from the module's own weights."""
+    """Routes `model.forward` through a DitEngine built from the module's own weights.
+
+    The engine holds a SNAPSHOT of the weights (fp16 GEMM operands repacked on the device).  The reference calls
+    the generator under `torch.no_grad()` while it is being trained (seaweed_apt/apt_trainer.py:118-119,254), so
+    every call compares the parameters' version counters with the snapshot's and reloads the engine when an
+    optimizer step / EMA update / load_state_dict has touched them -- never a stale answer."""
     eng = engine or DitEngine.from_module(model, device=device)
     original = model.forward
+    state = {"sig": _weights_signature(model)}
 
     def forward(self, x, t, context, seq_len, clip_fea=None, y=None):
         xs = list(x) if not isinstance(x, (list, tuple)) else x
         if _needs_grad(self, xs):
             return original(x, t, context, seq_len, clip_fea=clip_fea, y=y)
+        sig = _weights_signature(self)
+        if sig != state["sig"]:
+            eng.load_state_dict(self.state_dict())
+            state["sig"] = sig
+            self._b200_reloads = getattr(self, "_b200_reloads", 0) + 1
         return eng.forward(xs, t, context, seq_len, clip_fea=clip_fea, y=y)
 
     model._b200_original_forward = original

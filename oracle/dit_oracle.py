@@ -24,6 +24,26 @@ import torch.nn.functional as F
 
 EPS = 1e-6
 
+# Yardstick mode (SURVEY section 7 hard part 1): what the reference's OWN GPU path rounds.  Its blocks run under
+# autocast(float16) (model.py:540): every nn.Linear takes fp16 operands and returns fp16, WanRMSNorm casts the
+# normalised value back to fp16 before the weight (model.py:85-88), flash_attention runs q/k/v (and FA2's
+# probabilities) in fp16 and returns fp16 (attention.py:60-76,129).  With the flag on, block_forward applies those
+# roundings to the fp32 restatement, so `rel_l2(autocast-emulated, fp32)` is the reference GPU path's own
+# distance from exact arithmetic -- the scale the engine's own deviation is judged against.
+_AUTOCAST = {"on": False}
+
+
+class emulate_autocast:
+    def __enter__(self):
+        self._old, _AUTOCAST["on"] = _AUTOCAST["on"], True
+
+    def __exit__(self, *a):
+        _AUTOCAST["on"] = self._old
+
+
+def _r16(x):
+    return x.half().float() if _AUTOCAST["on"] else x
+
 
 def sinusoid_256(freq_dim, t):
     """model.py:17-27 -- [cos(t*w_i) | sin(t*w_i)], w_i = 10000^(-i/half), float64."""
@@ -79,22 +99,36 @@ def layer_norm(x, weight=None, bias=None):
 def rms_norm(x, gamma):
     """model.py:80-88 -- over the full channel dim (all heads), fp32, eps 1e-6 (model.py:129-130)."""
     xf = x.float()
-    return xf * torch.rsqrt(xf.pow(2).mean(dim=-1, keepdim=True) + EPS) * gamma
+    return _r16(xf * torch.rsqrt(xf.pow(2).mean(dim=-1, keepdim=True) + EPS)) * gamma
 
 
 def linear(sd, key, x):
     return F.linear(x, sd[key + ".weight"], sd.get(key + ".bias"))
 
 
+def block_linear(sd, key, x):
+    """nn.Linear inside the autocast(float16) region (model.py:540): exact here, fp16 in / fp16 out in yardstick mode."""
+    if not _AUTOCAST["on"]:
+        return linear(sd, key, x)
+    b = sd.get(key + ".bias")
+    return _r16(F.linear(_r16(x), _r16(sd[key + ".weight"]), None if b is None else _r16(b)))
+
+
 def softmax_attention(q, k, v, k_len):
     """attention.py:24-130 semantics: non-causal, scale 1/sqrt(d), keys j >= k_len masked.
     q [Lq, n, d], k/v [Lk, n, d] -> [Lq, n, d] fp32."""
     d = q.shape[-1]
-    qh, kh, vh = (t.float().permute(1, 0, 2) for t in (q, k, v))
+    if q.shape[0] * k.shape[0] * q.shape[1] > (1 << 28):       # long sequences (T = 21: L = 32 760): query chunks
+        step = max(1, (1 << 28) // (k.shape[0] * q.shape[1]))
+        return torch.cat([softmax_attention(q[i:i + step], k, v, k_len) for i in range(0, q.shape[0], step)])
+    qh, kh, vh = (_r16(t.float()).permute(1, 0, 2) for t in (q, k, v))
     s = torch.matmul(qh, kh.transpose(1, 2)) / math.sqrt(d)
     lk = k.shape[0]
     if k_len is not None and k_len < lk:
         s[:, :, k_len:] = float("-inf")
+    if _AUTOCAST["on"]:                     # FA2: un-normalised fp16 probabilities feed P.V, fp32 row sums
+        e = torch.exp(s - s.amax(dim=-1, keepdim=True))
+        return _r16(torch.matmul(_r16(e), vh) / e.sum(dim=-1, keepdim=True)).permute(1, 0, 2).contiguous()
     return torch.matmul(torch.softmax(s, dim=-1), vh).permute(1, 0, 2).contiguous()
 
 
@@ -144,29 +178,29 @@ def block_forward(sd, i, x, e0, grid, ctx, ctx_len, num_heads, n_img=0):
     sh1, sc1, g1, sh2, sc2, g2 = m.unbind(0)
 
     u = layer_norm(x) * (1 + sc1) + sh1                      # :292-293
-    q = rms_norm(linear(sd, p + "self_attn.q", u), sd[p + "self_attn.norm_q.weight"]).view(L, num_heads, hd)
-    k = rms_norm(linear(sd, p + "self_attn.k", u), sd[p + "self_attn.norm_k.weight"]).view(L, num_heads, hd)
-    v = linear(sd, p + "self_attn.v", u).view(L, num_heads, hd)
+    q = rms_norm(block_linear(sd, p + "self_attn.q", u), sd[p + "self_attn.norm_q.weight"]).view(L, num_heads, hd)
+    k = rms_norm(block_linear(sd, p + "self_attn.k", u), sd[p + "self_attn.norm_k.weight"]).view(L, num_heads, hd)
+    v = block_linear(sd, p + "self_attn.v", u).view(L, num_heads, hd)
     ntok = grid[0] * grid[1] * grid[2]
     a = softmax_attention(rope_rotate(q, grid), rope_rotate(k, grid), v, ntok)  # :151-156 (k_lens = seq_lens)
-    x = x + linear(sd, p + "self_attn.o", a.reshape(L, dim)) * g1              # :159-160,296
+    x = x + block_linear(sd, p + "self_attn.o", a.reshape(L, dim)) * g1              # :159-160,296
 
     un = layer_norm(x, sd[p + "norm3.weight"], sd[p + "norm3.bias"])           # :313 (affine)
-    qc = rms_norm(linear(sd, p + "cross_attn.q", un), sd[p + "cross_attn.norm_q.weight"]).view(L, num_heads, hd)
+    qc = rms_norm(block_linear(sd, p + "cross_attn.q", un), sd[p + "cross_attn.norm_q.weight"]).view(L, num_heads, hd)
     ctx_txt = ctx[n_img:]
-    kc = rms_norm(linear(sd, p + "cross_attn.k", ctx_txt), sd[p + "cross_attn.norm_k.weight"]).view(-1, num_heads, hd)
-    vc = linear(sd, p + "cross_attn.v", ctx_txt).view(-1, num_heads, hd)
+    kc = rms_norm(block_linear(sd, p + "cross_attn.k", ctx_txt), sd[p + "cross_attn.norm_k.weight"]).view(-1, num_heads, hd)
+    vc = block_linear(sd, p + "cross_attn.v", ctx_txt).view(-1, num_heads, hd)
     ca = softmax_attention(qc, kc, vc, min(ctx_len, ctx_txt.shape[0]))
     if n_img:
         ctx_img = ctx[:n_img]
-        ki = rms_norm(linear(sd, p + "cross_attn.k_img", ctx_img),
+        ki = rms_norm(block_linear(sd, p + "cross_attn.k_img", ctx_img),
                       sd[p + "cross_attn.norm_k_img.weight"]).view(-1, num_heads, hd)
-        vi = linear(sd, p + "cross_attn.v_img", ctx_img).view(-1, num_heads, hd)
+        vi = block_linear(sd, p + "cross_attn.v_img", ctx_img).view(-1, num_heads, hd)
         ca = ca + softmax_attention(qc, ki, vi, None)                            # :221,228
-    x = x + linear(sd, p + "cross_attn.o", ca.reshape(L, dim))                 # no gate
+    x = x + block_linear(sd, p + "cross_attn.o", ca.reshape(L, dim))                 # no gate
 
     u2 = layer_norm(x) * (1 + sc2) + sh2                                         # :314-315
-    y = linear(sd, p + "ffn.2", F.gelu(linear(sd, p + "ffn.0", u2), approximate="tanh"))
+    y = block_linear(sd, p + "ffn.2", _r16(F.gelu(block_linear(sd, p + "ffn.0", u2), approximate="tanh")))
     return x + y * g2                                                            # :328
 
 

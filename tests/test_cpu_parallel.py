@@ -26,6 +26,14 @@ for i, r in enumerate(res):
     assert torch.equal(r, items[i] * 2 + 1), i                        # original order, every rank
 assert par.max_over_ranks(1.0 + rank) == 2.0
 assert par.shard_indices(7, 1, 4) == [1, 5]
+# fewer items than ranks: rank 1 owns nothing and still takes part in the gather (no deadlock, no early raise)
+one = par.sharded_map(fn, items[:1])
+assert len(one) == 1 and torch.equal(one[0], items[0] * 2 + 1)
+try:
+    par.gather_from_ranks([], [0, 0])
+    raise SystemExit("expected ValueError")
+except ValueError:
+    pass
 print("ok", rank)
 '''
 

@@ -106,6 +106,24 @@ def test_flash_attention_two_tile_kernel_forced(monkeypatch, B, Lq, Lk, H, klens
     test_flash_attention(B, Lq, Lk, H, klens)
 
 
+def test_flash_attention_T21_L32760():
+    """The T = 21 sequence length of configs 3 / 5: Lq = Lk = 32 760 (255 full query tiles + a 120-row tail, 511 full
+    key steps + a 56-key tail) on two heads through the long-sequence kernel, every row against the query-chunked
+    CPU oracle (attention.py:24-130 semantics)."""
+    import b200dit
+    from oracle import dit_oracle as O
+    L, H = 32760, 2
+    q, k, v = _mk((1, L, H, 128), 21).cuda(), _mk((1, L, H, 128), 22).cuda(), _mk((1, L, H, 128), 23).cuda()
+    out = b200dit.flash_attention(q, k, v)
+    ref = O.softmax_attention(q[0].cpu().float(), k[0].cpu().float(), v[0].cpu().float(), None)
+    assert rel_l2(out[0].cpu().float(), ref) < 2e-3
+    assert rel_l2(out[0, -120:].cpu().float(), ref[-120:]) < 2e-3          # the partial last tile
+    # ragged: the second item's keys stop inside a tile
+    out2 = b200dit.flash_attention(q[:, :4096], k, v, k_lens=torch.tensor([20001]))
+    ref2 = O.softmax_attention(q[0, :4096].cpu().float(), k[0].cpu().float(), v[0].cpu().float(), 20001)
+    assert rel_l2(out2[0].cpu().float(), ref2) < 2e-3
+
+
 def test_flash_attention_large_logits():
     """rows whose running max keeps growing exercise the thresholded O rescale path"""
     import b200dit

@@ -40,6 +40,22 @@ def test_vae_dim96_vs_oracle(T, h, w):
     _check(pix, ref)
 
 
+def test_vae_decode_full_resolution_60x104():
+    """The real decode size of every config: latent [16,2,60,104] -> [3,5,480,832] (first chunk of one frame +
+    a second chunk through the temporal upsample; 480x832 exercises the implicit-GEMM pixel-tile picker and TMA
+    border clipping at 60/120/240/480 x 104/208/416/832) against the CPU oracle (vae.py:544-568; ~20-40 s of CPU)."""
+    import b200dit
+    from oracle import vae_oracle as VO
+    sd = VO.make_synthetic_vae_weights(dim=96, seed=3)
+    eng = b200dit.VaeEngine.from_state_dict(sd)
+    z = torch.randn(16, 2, 60, 104, generator=torch.Generator().manual_seed(11))
+    pix = eng.decode([z])[0].cpu()
+    with torch.no_grad():
+        ref = VO.vae_decode(sd, z)
+    print(f"\nVAE 60x104: max-abs {float((pix - ref).abs().max()):.3e} rel-L2 {rel_l2(pix, ref):.3e}")
+    _check(pix, ref)
+
+
 def test_install_vae_shim():
     import b200dit
     from oracle import vae_oracle as VO
