@@ -67,6 +67,7 @@ DitEngine::DitEngine(const b200dit_config& c) : cfg(c) {
   B2_CUDA(cudaGetDevice(&dev));
   B2_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   bad.ensure(sizeof(unsigned int), /*zero=*/true);
+  if (const char* e = std::getenv("B200_FUSE_QKNORM")) fuse_qk_norm = std::atoi(e) != 0;
   attn_split.ensure(ATTN_SPLIT_WS_BYTES);
   alloc_weights();
 }
@@ -395,6 +396,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   self.split_ws = attn_split.as<float>();
   for (int i = 0; i < B; ++i) self.klen[i] = L;
   AttnParams cross = self;
+  if (fuse_qk_norm) { self.q_dim = d; self.q_eps = eps; }     // (q_ssq geometry set below, once the tile width is known)
   cross.ldq = d; cross.k = w.kc; cross.ldk = d; cross.vt = w.vtc; cross.ldvt = B * TL; cross.Lk_rows = TL;
   cross.q_dim = d; cross.q_eps = eps;
   for (int i = 0; i < B; ++i) {
@@ -409,6 +411,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   const int bn_qkv = pick_bn(M, 3 * d, num_sms, d), bn_cq = pick_bn(M, d, num_sms, d);
   const int bn_ckv = pick_bn(B * TL, 2 * d, num_sms, d), bn_img = pick_bn(B * IMG_PAD, 2 * d, num_sms, d);
   auto ssq_tiles = [](int cols, int bn) { return (cols + bn - 1) / bn; };
+  if (fuse_qk_norm) { self.q_ssq = w.ssq; self.q_ssq_ld = 4 * ssq_tiles(2 * d, bn_qkv); self.q_ssq_n = 2 * ssq_tiles(2 * d, bn_qkv); }
   cross.q_ssq = w.ssq; cross.q_ssq_ld = 4 * ssq_tiles(d, bn_cq); cross.q_ssq_n = 2 * ssq_tiles(d, bn_cq);
   cimg.q_ssq = cross.q_ssq; cimg.q_ssq_ld = cross.q_ssq_ld; cimg.q_ssq_n = cross.q_ssq_n; cimg.q_dim = d; cimg.q_eps = eps;
 
@@ -421,10 +424,18 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
       GemmParams p{}; p.w_static = 1; p.M = M; p.N = 3 * d; p.K = d; p.bias = b.qkv_b; p.out_h = w.qk; p.ld_h = 2 * d;
       p.ssq = w.ssq; p.ssq_cols = 2 * d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(2 * d, bn_qkv);
       p.vt = w.vt; p.vt_col0 = 2 * d; p.vt_ld = Mp; p.vt_rows = d; p.rows_per_item = L;
+      if (fuse_qk_norm) {             // q / k leave the epilogue weighted and rotated (model.py:144-146,151-152)
+        p.gamma_a = b.norm_q; p.gamma_b = b.norm_k; p.rope_cs = reinterpret_cast<const float2*>(cs);
+      }
       gemm_linear(EPI_QKV, w.u, d, b.qkv_w, d, p, num_sms, s, bn_qkv);
     }
-    launch_rms_rope(w.qk, 2 * d, d, 2, w.ssq, 4 * ssq_tiles(2 * d, bn_qkv), 2 * ssq_tiles(2 * d, bn_qkv), b.norm_q,
-                    b.norm_k, cs, M, L, eps, s);
+    // what is left of the two RMSNorms is one scalar per row: the key's is applied in place here (half the bytes
+    // of the former norm + rotation pass), the query's rides in the softmax scale of its row (self.q_ssq)
+    if (fuse_qk_norm)
+      launch_scale_rows(w.qk + d, 2 * d, d, w.ssq, 4 * ssq_tiles(2 * d, bn_qkv), 2 * ssq_tiles(2 * d, bn_qkv), 1, M, eps, s);
+    else
+      launch_rms_rope(w.qk, 2 * d, d, 2, w.ssq, 4 * ssq_tiles(2 * d, bn_qkv), 2 * ssq_tiles(2 * d, bn_qkv), b.norm_q,
+                      b.norm_k, cs, M, L, eps, s);
     launch_attention(self, s);
     {
       GemmParams p{}; p.w_static = 1; p.M = M; p.N = d; p.K = d; p.bias = b.o_b; p.out_f = w.x_res; p.ld_f = d;

@@ -89,6 +89,7 @@ class DitEngine {
   int num_sms = 148;
   bool finalized = false;
   bool use_graphs = true;
+  bool fuse_qk_norm = true;              // norm weight + RoPE of q / k inside the QKV GEMM epilogue (B200_FUSE_QKNORM=0: separate pass)
   std::vector<std::pair<int, float*>> taps;   // (block index, destination): residual stream after that block
   long long tap_rows = 0;                     // row capacity of every tap destination
   double last_flops = 0.0;

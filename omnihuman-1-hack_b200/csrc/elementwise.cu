@@ -148,6 +148,41 @@ __global__ void __launch_bounds__(256) rms_rope_kernel(const RmsRopeParams p, in
   }
 }
 
+// ------------------------------------------------------------------ per-row scalar of an RMSNorm, in place on fp16
+// One warp per row; the row's pieces are all loaded before the first is stored.
+template <int PIECES>
+__global__ void __launch_bounds__(256) scale_rows_kernel(__half* __restrict__ x, long long ld, int dim,
+                                                         const float* __restrict__ ssq, int ssq_ld, int ssq_n, int slice,
+                                                         int M, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  pdl_launch();
+  if (row >= M) return;
+  pdl_wait();
+  __half* xr = x + row * ld;
+  uint4 raw[PIECES];
+#pragma unroll
+  for (int it = 0; it < PIECES; ++it) {
+    const int col = (lane + 32 * it) * 8;
+    if (col < dim) raw[it] = *reinterpret_cast<const uint4*>(xr + col);
+  }
+  float part = 0.f;
+  for (int i = lane; i < ssq_n; i += 32) part += ssq[row * ssq_ld + i * 2 + slice];
+  const float inv = rsqrtf(warp_sum(part) / (float)dim + eps);            // fixed order: deterministic
+#pragma unroll
+  for (int it = 0; it < PIECES; ++it) {
+    const int col = (lane + 32 * it) * 8;
+    if (col >= dim) break;
+    __half2* h = reinterpret_cast<__half2*>(&raw[it]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h[e]);
+      h[e] = __floats2half2_rn(f.x * inv, f.y * inv);
+    }
+    *reinterpret_cast<uint4*>(xr + col) = raw[it];
+  }
+}
+
 // ------------------------------------------------------------------ timestep embedding (model.py:17-27,526-528)
 __global__ void sinusoid_kernel(const float* __restrict__ t, int B, int freq_dim, float* __restrict__ out) {
   pdl_launch();
@@ -445,6 +480,21 @@ void launch_rms_rope(__half* x, long long ld, int dim, int nslices, const float*
   else if (pieces <= 6) launch_pdl(rms_rope_kernel<6>, grid, dim3(256), 0, s, p, nslices);
   else if (pieces <= 16) launch_pdl(rms_rope_kernel<16>, grid, dim3(256), 0, s, p, nslices);
   else launch_pdl(rms_rope_kernel<20>, grid, dim3(256), 0, s, p, nslices);     // dim 5120 (Wan 14B)
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void launch_scale_rows(__half* x, long long ld, int dim, const float* ssq, int ssq_ld, int ssq_n, int slice, int M,
+                       float eps, cudaStream_t s) {
+  ProfScope prof(PC_NORM, 0.0, 4.0 * M * dim, s);
+  B2_CHECK(dim % 8 == 0 && dim <= 256 * 20, "row-scale width %d not supported", dim);
+  const dim3 grid((unsigned)((M + 7) / 8));
+  const int pieces = (dim / 8 + 31) / 32;
+  if (pieces <= 1) launch_pdl(scale_rows_kernel<1>, grid, dim3(256), 0, s, x, ld, dim, ssq, ssq_ld, ssq_n, slice, M, eps);
+  else if (pieces <= 2) launch_pdl(scale_rows_kernel<2>, grid, dim3(256), 0, s, x, ld, dim, ssq, ssq_ld, ssq_n, slice, M, eps);
+  else if (pieces <= 6) launch_pdl(scale_rows_kernel<6>, grid, dim3(256), 0, s, x, ld, dim, ssq, ssq_ld, ssq_n, slice, M, eps);
+  else if (pieces <= 16) launch_pdl(scale_rows_kernel<16>, grid, dim3(256), 0, s, x, ld, dim, ssq, ssq_ld, ssq_n, slice, M, eps);
+  else launch_pdl(scale_rows_kernel<20>, grid, dim3(256), 0, s, x, ld, dim, ssq, ssq_ld, ssq_n, slice, M, eps);
   B2_CUDA(cudaGetLastError());
   count_launch();
 }

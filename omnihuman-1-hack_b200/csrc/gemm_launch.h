@@ -113,6 +113,10 @@ void launch_one(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int 
     B2_CHECK(p.ssq_cols % C::CW == 0 && p.ssq_split % C::CW == 0 && p.vt_col0 % C::CW == 0,
              "QKV epilogue: slice boundaries must be multiples of %d columns", C::CW);
     B2_CHECK(p.ssq == nullptr || p.ssq_ld >= 4 * ((p.ssq_cols + BN - 1) / BN), "ssq leading dimension too small");
+    if (p.gamma_a != nullptr) {                        // norm weight (+ RoPE) in the epilogue: see GemmParams
+      B2_CHECK(p.ssq != nullptr && p.rows_per_item > 0, "QKV epilogue with norm weights: ssq / rows_per_item missing");
+      B2_CHECK(p.gamma_b != nullptr || p.ssq_split >= p.ssq_cols, "QKV epilogue: second slice has no norm weight");
+    }
   }
   const CUtensorMap to = make_out_map(p, OUT_F32, C::CW);
   CUtensorMap tv = to;

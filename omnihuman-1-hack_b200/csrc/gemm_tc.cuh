@@ -38,6 +38,7 @@ enum EpiMode : int {
                      // slice 1 = cols in [ssq_split, ssq_cols));
                      // cols >= vt_col0 -> transposed V store  vt[head*128 + d][global row]
                      // (all three boundaries are multiples of the chunk width; tiles may straddle them)
+                     // gamma_a != nullptr: the q | k columns are also multiplied by the norm weight and 3-D-rotated here
   EPI_F32 = 4,       // out (fp32) = acc + bias
 };
 
@@ -65,6 +66,15 @@ struct GemmParams {
   int sk;                 // K-split factor S of the last (partial) wave's tiles, <= 1: no split
   float* sk_ws;           // [gridDim.x][BLOCK_N][128] fp32 partial accumulators
   int* sk_flags;          // [gridDim.x][8], zero between launches
+  // EPI_QKV with gamma_a != nullptr: the q | k columns leave the epilogue multiplied by their RMSNorm weight
+  // (model.py:85-88) and 3-D-rotated (model.py:42-69); `ssq` receives the partial sums of squares of the projection
+  // itself.  What is left of the RMSNorm is ONE scalar per row, rsqrt(mean(x^2) + eps), which commutes with the
+  // weight and the rotation: the query's goes into the softmax scale of its row (attn_tc.cu: q_row_scale), the
+  // key's is applied by scale_rows_kernel.  (A variant that finished the norm inside this epilogue -- the N tiles
+  // of an M block exchanging partial sums through global flags, two passes over the accumulator -- was correct and
+  // SLOWER: it couples the CTAs of the persistent grid wave by wave; see DESIGN.md.)
+  const float* gamma_a; const float* gamma_b;   // norm weights of slice 0 / slice 1, indexed by column within the slice
+  const float2* rope_cs;  // (cos, sin) [rows_per_item][64] for head_dim 128, or nullptr (no rotation)
   int w_static;           // 1: the W operand is a constant (model weight) that no earlier kernel of the stream writes:
                           // its first tiles may be requested before the programmatic-dependency wait
   int dbg;                // diagnosis only (B200_GEMM_DBG): 1 = skip the epilogue's global stores, 2 = no operand
@@ -399,6 +409,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         __syncwarp();
       }
       float ssq_a = 0.f, ssq_b = 0.f;                     // EPI_QKV: sums of squares of slice 0 / slice 1
+      bool fused = false;                                 // EPI_QKV: norm weight + rotation applied here
+      if constexpr (EPI == EPI_QKV) fused = p.gamma_a != nullptr;
 #pragma unroll 1
       for (int c = c_begin; c < c_end; ++c) {
         const int col0 = n_blk * BLOCK_N + c * CW;
@@ -453,11 +465,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < CW; ++j) v[j] = gelu_tanh_f(v[j]);
           }
+          if constexpr (EPI == EPI_QKV) {
+            if (fused && col0 < p.ssq_cols) {
+              // sum of squares of the projection itself, then x * gamma and the rotation of the pairs (2j, 2j+1) of
+              // the 128-wide head; the per-row factor rsqrt(mean(x^2) + eps) commutes with both and is applied later
+              const bool sa = col0 < p.ssq_split;
+              float sq = 0.f;
+#pragma unroll
+              for (int j = 0; j < CW; ++j) sq = fmaf(v[j], v[j], sq);
+              if (sa) ssq_a += sq; else ssq_b += sq;
+              const float4* g4 = reinterpret_cast<const float4*>(sa ? p.gamma_a + col0 : p.gamma_b + (col0 - p.ssq_split));
+#pragma unroll
+              for (int j = 0; j < CW / 4; ++j) {
+                const float4 g = __ldg(g4 + j);
+                v[4 * j] *= g.x; v[4 * j + 1] *= g.y; v[4 * j + 2] *= g.z; v[4 * j + 3] *= g.w;
+              }
+              if (p.rope_cs != nullptr) {
+                const int tok = row_ok ? (int)(grow % p.rows_per_item) : 0;
+                const float4* c4 = reinterpret_cast<const float4*>(p.rope_cs + (long long)tok * 64 + ((col0 & 127) >> 1));
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) {
+                  const float4 cs = __ldg(c4 + j);            // (cos, sin) of two consecutive pairs
+                  const float a0 = v[4 * j], b0 = v[4 * j + 1], a1 = v[4 * j + 2], b1 = v[4 * j + 3];
+                  v[4 * j] = a0 * cs.x - b0 * cs.y; v[4 * j + 1] = a0 * cs.y + b0 * cs.x;
+                  v[4 * j + 2] = a1 * cs.z - b1 * cs.w; v[4 * j + 3] = a1 * cs.w + b1 * cs.z;
+                }
+              }
+            }
+          }
           uint32_t h[CW / 2];
 #pragma unroll
           for (int j = 0; j < CW / 2; ++j) h[j] = pack_h2(v[2 * j], v[2 * j + 1]);
           if constexpr (EPI == EPI_QKV) {
-            if (col0 < p.ssq_cols) {                      // sum of squares of exactly what attention will read
+            if (!fused && col0 < p.ssq_cols) {            // sum of squares of exactly what attention will read
               float sq = 0.f;
 #pragma unroll
               for (int j = 0; j < CW / 2; ++j) {

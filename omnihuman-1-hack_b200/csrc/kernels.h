@@ -157,6 +157,10 @@ void launch_ln_affine(const float* x, __half* out, const float* a, const float* 
 void launch_rms_rope(__half* x, long long ld, int dim, int nslices, const float* ssq, int ssq_ld, int ssq_n,
                      const float* gamma0, const float* gamma1, const float* cs_table, int M, int rows_per_item,
                      float eps, cudaStream_t s, const float* gamma_mul = nullptr);
+// in place on fp16 [M, ld]: x[row, 0:dim] *= rsqrt(sum_i ssq[row*ssq_ld + 2i + slice] / dim + eps), i < ssq_n
+// (the per-row scalar that is left of an RMSNorm whose weight was applied by the producing GEMM's epilogue)
+void launch_scale_rows(__half* x, long long ld, int dim, const float* ssq, int ssq_ld, int ssq_n, int slice, int M,
+                       float eps, cudaStream_t s);
 // sinusoid(t) -> time MLP -> e [B, dim], e0 [B, 6*dim]  (all fp32, model.py:526-528)
 void launch_time_embed(const float* t, int B, int freq_dim, int dim, const float* w0, const float* b0, const float* w2,
                        const float* b2, const float* wp, const float* bp, float* scratch, float* e, float* e0,
