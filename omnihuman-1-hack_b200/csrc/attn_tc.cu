@@ -413,6 +413,339 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const AttnParams p, i
 
 
 // ---------------------------------------------------------------------------------------------------
+// Persistent form of the v2 kernel (default for short and medium sequences): the grid is two CTAs per SM and every
+// CTA walks a list of work units -- whole query tiles first, then the key-axis parts of the left-over tiles -- with
+// its TMEM allocation, barriers and K / V rings kept alive across units.  What this removes (measured on the v2
+// kernel at 4 items x 12 heads, L = 1560: 87 us per launch where 25 steps x 2.1 tiles per slot at the steady-state
+// rate would be 56 us): the per-CTA prologue / epilogue of 624 separately scheduled CTAs, during which the next
+// unit's Q, K and V now stream in and its first Q.K^T runs, and the mostly empty third round of CTAs -- the
+// left-over tiles (tiles mod slots) are cut into as many parts as there are CTAs, so every CTA ends within a few
+// key steps of the others.  Barrier phases run on a step counter that keeps counting across units; per unit there is
+// one extra hand-off, q_empty (last Q.K^T of the unit retired -> the next unit's Q may land).  The O accumulator needs
+// none: a softmax warp arrives on p_full for the first step of the next unit only after it has read its O rows, and
+// the first P.V of that unit waits for p_full.
+namespace v4 {
+using namespace v2;            // tile geometry, shared-memory layout, combine kernel
+
+struct Unit {
+  int item, head, qt, j0, n_kv, klen, parts, slot;
+};
+__device__ __forceinline__ bool decode_unit(const AttnParams& p, int u, Unit& w) {
+  if (u >= p.n_units) return false;
+  const int n_plain = p.n_units - p.split_tiles * p.split_parts;
+  int tile = u, part = 0;
+  w.parts = 1;
+  if (u >= n_plain) {
+    const int b = u - n_plain;
+    tile = n_plain + b / p.split_parts; part = b % p.split_parts; w.parts = p.split_parts;
+  }
+  const int hi = tile % (p.heads * p.items);
+  w.qt = tile / (p.heads * p.items);
+  w.head = hi % p.heads; w.item = hi / p.heads;
+  w.klen = p.klen[w.item];
+  const int n_kv_all = (w.klen + KT - 1) / KT;
+  w.j0 = part * n_kv_all / w.parts;
+  w.n_kv = (part + 1) * n_kv_all / w.parts - w.j0;          // >= 1: the launcher keeps parts <= key steps
+  w.slot = (tile - n_plain) * w.parts + part;
+  return true;
+}
+
+// CTA c owns units c, c + G, c + 2G, ...  The upper half of the grid walks its list rotated by one (last unit -- a
+// short part, when the launch has any -- first): the two CTAs that share an SM then reach their unit boundaries
+// (O read-out, store, pipeline refill) at different times instead of stalling the tensor pipe together.
+struct UnitIter {
+  int c, G, n, i;
+  bool rot;
+  __device__ UnitIter(const AttnParams& p) : c(blockIdx.x), G(gridDim.x), i(0) {
+    n = c < p.n_units ? (p.n_units - 1 - c) / G + 1 : 0;
+    rot = n > 1 && c >= G / 2;
+  }
+  __device__ bool next(const AttnParams& p, Unit& w) {
+    if (i >= n) return false;
+    const int k = rot ? (i == 0 ? n - 1 : i - 1) : i;
+    ++i;
+    return decode_unit(p, c + k * G, w);
+  }
+};
+
+__global__ void __launch_bounds__(192, 2)
+attn_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_vt, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [3]
+  uint64_t* k_empty = bars + 4;   // [3]
+  uint64_t* v_full = bars + 7;    // [2]
+  uint64_t* v_empty = bars + 9;   // [2]
+  uint64_t* s_full = bars + 11;   // [2]
+  uint64_t* s_empty = bars + 13;  // [2]
+  uint64_t* p_full = bars + 15;
+  uint64_t* pv_done = bars + 16;
+  uint64_t* q_empty = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = warp_id(), lane = lane_id();
+  pdl_launch();
+  if (warp == W_TMA && lane == 0) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_vt);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < KSTAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 128;
+  pdl_wait();
+
+  Unit w;
+  if (warp == W_TMA) {
+    if (lane == 0) {
+      uint32_t gk = 0, gv = 0;                               // K / V tiles requested so far (ring position + phase)
+      int ui = 0;
+      for (UnitIter it(p); it.next(p, w); ++ui) {
+        const int q_row0 = w.item * p.Lq + w.qt * QT;
+        if (ui > 0) mbar_wait(q_empty, (ui - 1) & 1);        // every Q.K^T of the previous unit has retired
+        mbar_expect_tx(q_full, Q_BYTES);
+        tma_load_2d(smem + OFF_Q, &tmap_q, q_full, w.head * 128, q_row0);
+        tma_load_2d(smem + OFF_Q + Q_BYTES / 2, &tmap_q, q_full, w.head * 128 + 64, q_row0);
+        const int vcol0 = w.item * (p.vt_stride ? p.vt_stride : p.Lk_rows);
+        for (int i = 0; i <= w.n_kv; ++i) {                  // K runs one step ahead of V
+          if (i < w.n_kv) {
+            const int st = gk % KSTAGES; const uint32_t ph = (gk / KSTAGES) & 1; ++gk;
+            const int k_row0 = w.item * p.Lk_rows + (w.j0 + i) * KT;
+            mbar_wait(&k_empty[st], ph ^ 1);
+            mbar_expect_tx(&k_full[st], K_BYTES);
+            tma_load_2d(smem + OFF_K + st * K_BYTES, &tmap_k, &k_full[st], w.head * 128, k_row0);
+            tma_load_2d(smem + OFF_K + st * K_BYTES + KSUB, &tmap_k, &k_full[st], w.head * 128 + 64, k_row0);
+          }
+          if (i >= 1) {
+            const int st = gv & 1; const uint32_t ph = (gv >> 1) & 1; ++gv;
+            mbar_wait(&v_empty[st], ph ^ 1);
+            mbar_expect_tx(&v_full[st], V_BYTES);
+            tma_load_2d(smem + OFF_V + st * V_BYTES, &tmap_vt, &v_full[st], vcol0 + (w.j0 + i - 1) * KT, w.head * 128);
+          }
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    constexpr uint32_t idesc_qk = umma_idesc_f16(128, KT);
+    constexpr uint32_t idesc_pv = umma_idesc_f16(128, 128);
+    const uint32_t sq = smem_u32(smem + OFF_Q);
+    auto issue_qk = [&](uint32_t g, bool last_of_unit) {
+      const int st = g % KSTAGES; const uint32_t kph = (g / KSTAGES) & 1;
+      const int sb = g & 1; const uint32_t sph = (g >> 1) & 1;
+      if (lane == 0) {
+        mbar_wait(&k_full[st], kph);
+        mbar_wait(&s_empty[sb], sph ^ 1);
+        tc_fence_after();
+        const uint32_t sk = smem_u32(smem + OFF_K + st * K_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_f16(tmem_base + sb * KT, umma_desc_sw128(sq + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32),
+                   umma_desc_sw128(sk + (kk >> 2) * KSUB + (kk & 3) * 32), idesc_qk, kk > 0);
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[sb]);
+        if (last_of_unit) umma_commit(q_empty);
+      }
+      __syncwarp();
+    };
+    uint32_t g = 0;                                          // key steps issued so far, over all units
+    int ui = 0;
+    for (UnitIter it(p); it.next(p, w); ++ui) {
+      mbar_wait_warp(q_full, ui & 1, lane);
+      issue_qk(g, w.n_kv == 1);
+      for (int j = 0; j < w.n_kv; ++j, ++g) {
+        if (j + 1 < w.n_kv) issue_qk(g + 1, j + 2 == w.n_kv);
+        const int st = g & 1; const uint32_t ph = (g >> 1) & 1;
+        if (lane == 0) {
+          mbar_wait(&v_full[st], ph);
+          mbar_wait(p_full, g & 1);
+          tc_fence_after();
+          const uint32_t sv = smem_u32(smem + OFF_V + st * V_BYTES);
+          const uint32_t tp = tmem_base + st * KT;
+#pragma unroll
+          for (int kk = 0; kk < KT / 16; ++kk)
+            umma_f16_ts(tmem_o, tp + kk * 8, umma_desc_sw128(sv + kk * 32), idesc_pv, (j > 0 || kk > 0));
+          umma_commit(&v_empty[st]);
+          umma_commit(pv_done);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- softmax: thread r owns query row r of the tile and all 64 keys of the step
+    const int r = warp * 32 + lane;
+    const uint32_t lane_sel = uint32_t(warp * 32) << 16;
+    uint32_t g = 0;
+    UnitIter it(p);
+    Unit nx;
+    bool more = it.next(p, nx);
+    // the row's logit factor is fetched one unit ahead: its global loads fly under the previous unit's last steps
+    float c_next = more ? p.scale * 1.4426950408889634f * q_row_scale(p, nx.item, nx.qt * QT + r) : 0.f;
+    while (more) {
+      w = nx;
+      const float c = c_next;
+      more = it.next(p, nx);
+      const int q_in_item = w.qt * QT + r;
+      if (w.qt * QT + warp * 32 >= p.Lq) {
+        // a warp whose 32 rows lie beyond the item's last query only keeps the barrier protocol going
+        for (int j = 0; j < w.n_kv; ++j, ++g) {
+          const int sb = g & 1; const uint32_t ph = (g >> 1) & 1;
+          if (lane == 0) {
+            mbar_wait(&s_full[sb], ph);
+            mbar_arrive(&s_empty[sb]);
+            if (j > 0) mbar_wait(pv_done, (g - 1) & 1);
+            mbar_arrive(p_full);
+          }
+          __syncwarp();
+        }
+        if (more) c_next = p.scale * 1.4426950408889634f * q_row_scale(p, nx.item, nx.qt * QT + r);
+        mbar_wait_warp(pv_done, (g - 1) & 1, lane);          // same phase discipline as the active path
+        continue;
+      }
+      float m_ref = -INFINITY, l_sum = 0.f;
+      for (int j = 0; j < w.n_kv; ++j, ++g) {
+        const int sb = g & 1; const uint32_t ph = (g >> 1) & 1;
+        mbar_wait_warp(&s_full[sb], ph, lane);
+        tc_fence_after();
+        float s[KT];
+        {
+          uint32_t t0[32], t1[32];
+          tmem_ld32(tmem_base + lane_sel + sb * KT, t0);
+          tmem_ld32(tmem_base + lane_sel + sb * KT + 32, t1);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(t0[i]); s[32 + i] = __uint_as_float(t1[i]); }
+        }
+        const int valid = w.klen - (w.j0 + j) * KT;
+        if (valid < KT) {
+#pragma unroll
+          for (int i = 0; i < KT; ++i) if (i >= valid) s[i] = -INFINITY;
+        }
+        float mx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx[i] = fmaxf(s[i], s[i + 8]);
+#pragma unroll
+        for (int i = 16; i < KT; i += 8) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) mx[e] = fmaxf(mx[e], s[i + e]);
+        }
+        const float tmax = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+        float alpha = 1.f;
+        bool rescale = false;
+        if (j == 0) {
+          m_ref = tmax;
+        } else if ((tmax - m_ref) * c > RESCALE_THRESHOLD) {
+          alpha = ex2((m_ref - tmax) * c);
+          m_ref = tmax;
+          l_sum *= alpha;
+          rescale = true;
+        }
+        const float mc = m_ref * c;
+        float ps0 = 0.f, ps1 = 0.f;
+        uint32_t pk[KT / 2];
+#pragma unroll
+        for (int i = 0; i < KT; i += 2) {
+          const float p0 = ex2(fmaf(s[i], c, -mc)), p1 = ex2(fmaf(s[i + 1], c, -mc));
+          ps0 += p0; ps1 += p1;
+          pk[i >> 1] = pack_h2(p0, p1);
+        }
+        l_sum += ps0 + ps1;
+        tmem_st32(tmem_base + lane_sel + sb * KT, pk);
+        if (j > 0) {
+          // phase discipline (see v2): wait for P.V of the previous step on every step.  At j == 0 the same wait
+          // already happened at the end of the previous unit.
+          mbar_wait_warp(pv_done, (g - 1) & 1, lane);
+          if (__any_sync(0xffffffffu, rescale)) {
+            tc_fence_after();
+#pragma unroll
+            for (int cidx = 0; cidx < 4; ++cidx) {
+              uint32_t t[32];
+              tmem_ld32(tmem_o + lane_sel + cidx * 32, t);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+              tmem_st32(tmem_o + lane_sel + cidx * 32, t);
+            }
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&s_empty[sb]);
+          mbar_arrive(p_full);
+        }
+      }
+
+      if (more) c_next = p.scale * 1.4426950408889634f * q_row_scale(p, nx.item, nx.qt * QT + r);
+      mbar_wait_warp(pv_done, (g - 1) & 1, lane);            // the unit's last P.V: O is final
+      tc_fence_after();
+      if (w.parts > 1) {
+        float* wo = p.split_ws + ((long long)w.slot * QT + r) * 128;
+        float* wml = p.split_ws + (long long)p.split_tiles * w.parts * QT * 128 + ((long long)w.slot * QT + r) * 2;
+#pragma unroll
+        for (int cidx = 0; cidx < 4; ++cidx) {
+          uint32_t t[32];
+          tmem_ld32(tmem_o + lane_sel + cidx * 32, t);
+          tmem_wait_ld();
+          if (q_in_item < p.Lq) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<uint4*>(wo + cidx * 32 + i) = make_uint4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+          }
+        }
+        if (q_in_item < p.Lq) *reinterpret_cast<float2*>(wml) = make_float2(m_ref * c, l_sum);
+      } else {
+        const float inv_l = 1.0f / l_sum;
+        __half* o = p.out + ((long long)w.item * p.Lq + q_in_item) * p.ldo + w.head * 128;
+#pragma unroll
+        for (int cidx = 0; cidx < 4; ++cidx) {
+          uint32_t t[32];
+          tmem_ld32(tmem_o + lane_sel + cidx * 32, t);
+          tmem_wait_ld();
+          if (q_in_item < p.Lq) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(t[i + e]) * inv_l;
+              uint4* dst = reinterpret_cast<uint4*>(o + cidx * 32 + i);
+              if (p.accumulate) {
+                const uint4 old = *dst;
+                const __half2* oh = reinterpret_cast<const __half2*>(&old);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(oh[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+              }
+              *dst = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+}  // namespace v4
+
+
+// ---------------------------------------------------------------------------------------------------
 // Long-sequence kernel: TWO 128-query tiles per CTA share every K / V tile.
 // Per 64-key step of one query tile the v2 kernel moves 32 KB of TMA fill + 32 KB of K / V operand reads + 32 KB of
 // Q re-read through the 128 B/clk shared-memory port in 512 tensor-pipe clocks (192 B/clk asked of a 128 B/clk
@@ -676,7 +1009,7 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
              p.Lk_rows);
   static const int dbg = std::getenv("B200_ATTN_DBG") ? std::atoi(std::getenv("B200_ATTN_DBG")) : 0;
   // function attributes and the SM count are per device (engines accept any device ordinal)
-  static bool configured_dev[64] = {false}, configured3_dev[64] = {false};
+  static bool configured_dev[64] = {false}, configured3_dev[64] = {false}, configured4_dev[64] = {false};
   static int sms_dev[64] = {0};
   int dev = 0;
   B2_CUDA(cudaGetDevice(&dev));
@@ -727,26 +1060,38 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
     return;
   }
   const int n_tiles = ((p.Lq + TILE - 1) / TILE) * p.heads * p.items;
-  // Tail split: tiles run in co-resident waves of two CTAs per SM.  When the last wave holds only a few tiles, cut
-  // each of them along the key axis so that the wave is as wide as the machine and proportionally shorter.
+  // Work units.  Tiles run two CTAs per SM; the left-over tiles (tiles mod slots) are cut along the key axis so that
+  // the last round is as wide as the machine and proportionally shorter: their part CTAs leave un-normalised rows
+  // (O, running max, running sum) in split_ws and attn_combine_kernel merges them.  Persistent kernel (default,
+  // B200_ATTN_PERSIST=0 for the one-CTA-per-unit v2 kernel): one part per CTA, parts as short as one key step.
   const int slots = 2 * num_sms;
+  static const int persist = std::getenv("B200_ATTN_PERSIST") ? std::atoi(std::getenv("B200_ATTN_PERSIST")) : 1;
   const char* split_env = std::getenv("B200_ATTN_SPLIT");               // 0 disables, n > 1 = at most n parts (A/B runs)
   const int split_mode = split_env ? std::atoi(split_env) : 1;
-  const int max_parts = split_mode > 1 ? std::min(split_mode, v2::MAX_PARTS) : 4;      // 4 measured best (4 / 8 / 16 within 1 %)
+  const int max_parts = split_mode > 1 ? std::min(split_mode, v2::MAX_PARTS) : (persist ? v2::MAX_PARTS : 4);
   const char* steps_env = std::getenv("B200_ATTN_SPLIT_MINSTEPS");
-  const int min_steps = steps_env ? std::max(1, std::atoi(steps_env)) : 2;
+  const int min_steps = steps_env ? std::max(1, std::atoi(steps_env)) : (persist ? 1 : 2);
   pd.split_tiles = 0; pd.split_parts = 1;
   const int rem = n_tiles % slots;
   if (p.split_ws != nullptr && split_mode && rem > 0) {
     int min_kv = 1 << 30;
     for (int i = 0; i < p.items; ++i) min_kv = std::min(min_kv, (p.klen[i] + v2::KT - 1) / v2::KT);
-    const int parts = std::min(std::min(slots / rem, max_parts), min_kv / min_steps);   // at least two key steps per part
-    if (parts >= 2 && (long long)rem * parts * (TILE * 128 + 2 * TILE) * 4 <= ATTN_SPLIT_WS_BYTES) {
-      pd.split_tiles = rem; pd.split_parts = parts;
-    }
+    int parts = std::min(std::min(slots / rem, max_parts), min_kv / min_steps);
+    while (parts >= 2 && (long long)rem * parts * (TILE * 128 + 2 * TILE) * 4 > ATTN_SPLIT_WS_BYTES) --parts;
+    if (parts >= 2) { pd.split_tiles = rem; pd.split_parts = parts; }
   }
-  dim3 grid(n_tiles - pd.split_tiles + pd.split_tiles * pd.split_parts);
-  launch_pdl(v2::attn_fwd_kernel, grid, dim3(192), v2::SMEM, stream, tq, tk, tv, pd);
+  pd.n_units = n_tiles - pd.split_tiles + pd.split_tiles * pd.split_parts;
+  if (persist) {
+    bool& configured4 = configured4_dev[dev & 63];
+    if (!configured4) {
+      B2_CUDA(cudaFuncSetAttribute(v4::attn_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM));
+      B2_CUDA(cudaFuncSetAttribute(v4::attn_persist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      configured4 = true;
+    }
+    launch_pdl(v4::attn_persist_kernel, dim3(std::min(pd.n_units, slots)), dim3(192), v2::SMEM, stream, tq, tk, tv, pd);
+  } else {
+    launch_pdl(v2::attn_fwd_kernel, dim3(pd.n_units), dim3(192), v2::SMEM, stream, tq, tk, tv, pd);
+  }
   count_launch();
   if (pd.split_tiles > 0) {
     launch_pdl(v2::attn_combine_kernel, dim3(pd.split_tiles, TILE / 8), dim3(256), 0, stream, pd, n_tiles - pd.split_tiles);

@@ -137,6 +137,7 @@ struct AttnParams {
   // attn_combine_kernel merges them.  split_ws: ATTN_SPLIT_WS_BYTES of device scratch, or nullptr (never split).
   float* split_ws;
   int split_tiles, split_parts;        // set by launch_attention
+  int n_units;                         // set by launch_attention: whole tiles + parts (= the v2 grid; the persistent kernel's work list)
 };
 constexpr long long ATTN_SPLIT_WS_BYTES = 512ll * (128 * 128 + 2 * 128) * 4;    // up to 512 partial tiles
 void launch_attention(const AttnParams& p, cudaStream_t stream);

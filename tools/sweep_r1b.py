@@ -76,7 +76,7 @@ def sweep_attn():
     from oracle import dit_oracle as O
     torch.manual_seed(1)
     print("attention kernel:", "v1" if os.environ.get("B200_ATTN_V1") else "v2", flush=True)
-    for (B, Lq, Lk, H) in [(2, 1560, 1560, 12), (2, 1560, 512, 12), (4, 1560, 1560, 12), (1, 6240, 6240, 12),
+    for (B, Lq, Lk, H) in [(2, 1560, 1560, 12), (2, 1560, 512, 12), (4, 1560, 1560, 12), (4, 1560, 512, 12), (1, 6240, 6240, 12),
                            (1, 32760, 32760, 12)]:
         q = torch.randn(B, Lq, H, 128, device="cuda").half()
         k = torch.randn(B, Lk, H, 128, device="cuda").half()
