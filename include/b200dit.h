@@ -118,6 +118,13 @@ B200_API int b200dit_set_tap(b200dit_engine* e, int32_t block_idx, float* dst, i
  * (block index, device destination [rows, dim] fp32, rows >= n_items*L of every later forward); n = 0 disables. */
 B200_API int b200dit_set_taps(b200dit_engine* e, int32_t n, const int32_t* block_idx, float* const* dst, int64_t rows);
 
+/* WanModel.forward pads every item's token rows with zeros up to seq_len (model.py:522) and runs the blocks over
+ * all seq_len rows: the padded rows are queries (un-rotated, model.py:66), never keys (model.py:155).  The outputs do
+ * not depend on them, so by default the engine skips them; the block outputs read through the taps do (the APT
+ * discriminator's heads attend over them, seaweed_apt/model.py:162-171).  enabled = 1: forwards whose seq_len exceeds
+ * the token count carry seq_len rows per item, and taps hold [n_items * seq_len, dim]. */
+B200_API int b200dit_set_pad_to_seq_len(b200dit_engine* e, int32_t enabled);
+
 /* Capture each distinct (n_items, grid, mode) forward into a CUDA graph and replay it (default on). */
 B200_API int b200dit_set_graphs(b200dit_engine* e, int32_t enabled);
 
@@ -181,6 +188,17 @@ B200_API int b200_flash_attention(const void* q, const void* k, const void* v, c
 B200_API int b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int32_t M,
                          int32_t N, int32_t K, int32_t epilogue, void* out, int64_t ldo, int32_t block_n,
                          void* stream);
+
+/* OmniHuman audio front-end: OmniConditionsModule.process_audio / OmniHumanWanT2V.process_audio
+ * (Omnihuman/omnihuman_wan_t2v.py:55-60, 180-200; the pre-net is built at :30-34 / :141-145):
+ * tokens = Linear(audio_dim -> D) . SiLU . Linear(D -> D) per frame, then for T > 1 frame t and frame t+1 are
+ * concatenated along the channel axis.  feats: device fp32 [B, T, audio_dim]; w0 fp16 [D, audio_dim], w2 fp16
+ * [D, D] (nn.Linear layout), b0 / b2 fp32 [D] or NULL; out: device fp32 [B, T-1, 2D] (T > 1) or [B, 1, D].
+ * scratch: device memory, 256-byte aligned, >= B*T*(2 audio_dim + 10 D) + 1024 bytes.  Both Linears run on the
+ * tcgen05 GEMM (fp16 operands, fp32 accumulate). */
+B200_API int b200omni_audio_tokens(const float* feats, int32_t B, int32_t T, int32_t audio_dim, int32_t model_dim,
+                                   const void* w0, const float* b0, const void* w2, const float* b2, float* out,
+                                   void* scratch, int64_t scratch_bytes, void* stream);
 
 /* ---- scheduler step (seaweed_apt/wan/utils/fm_solvers_unipc.py:655-739, fm_solvers.py:706-797) ----
  * Every tensor update of one FlowUniPC / FlowDPMSolver++ step (x0 conversion :318-320, UniC corrector

@@ -10,7 +10,8 @@ the `b200dit` alias module at the repository root:
 from ._lib import B200Error, LIB_PATH, MAX_ITEMS  # noqa: F401
 from .engine import (DitEngine, VaeEngine, flash_attention, kernel_launches, linear, profile_collect,  # noqa: F401
                      profile_enable)
-from . import discriminator, flops, parallel, pipelines, solvers, synthetic  # noqa: F401
+from . import discriminator, flops, omni, parallel, pipelines, solvers, synthetic  # noqa: F401
+from .omni import AudioProcessor  # noqa: F401
 from .discriminator import AptDiscriminator  # noqa: F401
 from .solvers import (FlowDPMSolverMultistepScheduler, FlowUniPCMultistepScheduler, get_sampling_sigmas,  # noqa: F401
                       retrieve_timesteps)

@@ -41,6 +41,7 @@ SIGNATURES = {
     "b200dit_set_tap": (_I, [_P, _I, _P, C.c_int64]),
     "b200dit_set_taps": (_I, [_P, _I, _IP, _PP, C.c_int64]),
     "b200dit_set_graphs": (_I, [_P, _I]),
+    "b200dit_set_pad_to_seq_len": (_I, [_P, _I]),
     "b200dit_last_flops": (C.c_double, [_P]),
     "b200dit_nonfinite_rows": (_I, [_P, _P, C.POINTER(C.c_uint32)]),
     "b200vae_create": (_I, [_I, _I, _PP]),
@@ -54,6 +55,7 @@ SIGNATURES = {
     "b200disc_load_weight": (_I, [_P, C.c_char_p, _P, _I, _I, C.POINTER(C.c_int64)]),
     "b200disc_finalize": (_I, [_P]),
     "b200disc_forward": (_I, [_P, _PP, _I, _I, _P, _P, _P]),
+    "b200omni_audio_tokens": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _L, _P]),
     "b200_flash_attention": (_I, [_P, _P, _P, _IP, _I, _I, _I, _I, _F, _P, _P]),
     "b200_linear": (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _I, _P, _L, _I, _P]),
     "b200_solver_lincomb": (_I, [_I, _PP, _I, _PP, C.POINTER(C.c_float), _L, _P]),

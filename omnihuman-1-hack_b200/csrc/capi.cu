@@ -122,6 +122,9 @@ int b200dit_set_tap(b200dit_engine* e, int32_t block_idx, float* dst, int64_t ro
   if (block_idx < 0) return b200dit_set_taps(e, 0, nullptr, nullptr, 0);
   return b200dit_set_taps(e, 1, &block_idx, &dst, rows);
 }
+int b200dit_set_pad_to_seq_len(b200dit_engine* e, int32_t enabled) {
+  return guarded([&] { B2_CHECK(e, "null engine"); e->impl.pad_to_seq_len = enabled != 0; });
+}
 int b200dit_set_graphs(b200dit_engine* e, int32_t enabled) {
   return guarded([&] { B2_CHECK(e, "null engine"); e->impl.use_graphs = enabled != 0; });
 }
@@ -243,6 +246,39 @@ int b200_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const fl
     else { p.out_h = static_cast<__half*>(out); p.ld_h = ldo; }
     b2::gemm_linear(epilogue, static_cast<const __half*>(A), lda, static_cast<const __half*>(W), ldw, p, sms,
                     static_cast<cudaStream_t>(stream), block_n);
+  });
+}
+
+int b200omni_audio_tokens(const float* feats, int32_t B, int32_t T, int32_t audio_dim, int32_t model_dim,
+                          const void* w0, const float* b0, const void* w2, const float* b2, float* out, void* scratch,
+                          int64_t scratch_bytes, void* stream) {
+  return guarded([&] {
+    B2_CHECK(feats && w0 && w2 && out && scratch, "null argument");
+    B2_CHECK(B >= 1 && T >= 1 && audio_dim % 8 == 0 && model_dim % 8 == 0, "audio front-end: widths must be multiples of 8");
+    const long long R = (long long)B * T;
+    auto pad = [](long long b) { return (b + 255) & ~255ll; };
+    const long long need = pad(R * audio_dim * 2) + pad(R * model_dim * 4) + pad(R * model_dim * 2) + pad(R * model_dim * 4);
+    B2_CHECK(scratch_bytes >= need, "audio front-end: scratch has %lld bytes, needs %lld", (long long)scratch_bytes, need);
+    B2_CHECK((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "audio front-end: scratch must be 256-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint8_t* p = static_cast<uint8_t*>(scratch);
+    __half* x16 = reinterpret_cast<__half*>(p); p += pad(R * audio_dim * 2);
+    float* h32 = reinterpret_cast<float*>(p); p += pad(R * model_dim * 4);
+    __half* h16 = reinterpret_cast<__half*>(p); p += pad(R * model_dim * 2);
+    float* tok = reinterpret_cast<float*>(p);
+    int dev = 0, sms = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    b2::launch_convert(feats, b2::DT_F32, x16, b2::DT_F16, R * audio_dim, s);
+    b2::GemmParams g0{};
+    g0.M = (int)R; g0.N = model_dim; g0.K = audio_dim; g0.bias = b0; g0.out_f = h32; g0.ld_f = model_dim; g0.w_static = 1;
+    b2::gemm_linear(b2::EPI_F32, x16, audio_dim, static_cast<const __half*>(w0), audio_dim, g0, sms, s);
+    b2::launch_silu_cast(h32, h16, R * model_dim, s);
+    b2::GemmParams g2{};
+    float* dst = T > 1 ? tok : out;
+    g2.M = (int)R; g2.N = model_dim; g2.K = model_dim; g2.bias = b2; g2.out_f = dst; g2.ld_f = model_dim; g2.w_static = 1;
+    b2::gemm_linear(b2::EPI_F32, h16, model_dim, static_cast<const __half*>(w2), model_dim, g2, sms, s);
+    if (T > 1) b2::launch_concat_adjacent(tok, out, B, T, model_dim, s);
   });
 }
 

@@ -241,14 +241,19 @@ void DitEngine::finalize() {
 }
 
 // float64 RoPE angle table for one grid (model.py:31-38,46-61,487-492), uploaded once per grid.
-const float* DitEngine::rope_table(int F, int Hp, int Wp) {
-  const long long key = ((long long)F << 40) | ((long long)Hp << 20) | Wp;
+// rows > F*Hp*Wp appends identity rows: the reference leaves the padded rows of a sequence un-rotated (model.py:66).
+const float* DitEngine::rope_table(int F, int Hp, int Wp, int rows) {
+  const long long Lg = (long long)F * Hp * Wp;
+  if (rows < Lg) rows = (int)Lg;
+  const long long key = (((long long)F << 40) | ((long long)Hp << 20) | Wp) ^ ((long long)(rows - Lg) << 50);
   auto it = rope_cache.find(key);
   if (it != rope_cache.end()) return it->second->as<float>();
   B2_CHECK(F <= 1024 && Hp <= 1024 && Wp <= 1024, "grid (%d,%d,%d) exceeds the 1024-position RoPE table", F, Hp, Wp);
   const int c = 64, nh = c / 3, nw = c / 3, nf = c - 2 * (c / 3);
   const long long L = (long long)F * Hp * Wp;
-  std::vector<float> tab((size_t)L * c * 2);
+  std::vector<float> tab((size_t)rows * c * 2);
+  for (long long tok = L; tok < rows; ++tok)
+    for (int j = 0; j < c; ++j) { tab[(tok * c + j) * 2] = 1.0f; tab[(tok * c + j) * 2 + 1] = 0.0f; }
   auto freq = [](int j, int npair) { return 1.0 / std::pow(10000.0, (2.0 * j) / (2.0 * npair)); };
   for (int f = 0; f < F; ++f)
     for (int h = 0; h < Hp; ++h)
@@ -350,18 +355,24 @@ double DitEngine::flops(int B, int L) const {
 // The launch sequence.  `in` holds device pointers valid for the duration of the enqueued work.
 void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   const int B = in.B, F = in.F, Hl = in.H, Wl = in.W;
-  const int Hp = Hl / 2, Wp = Wl / 2, L = F * Hp * Wp, M = B * L;
+  const int Hp = Hl / 2, Wp = Wl / 2;
+  const int Ltok = F * Hp * Wp;                                  // tokens of the latent grid
+  const int L = in.pad_rows > Ltok ? in.pad_rows : Ltok;         // rows per item (model.py:522 pads every item to seq_len)
+  const int M = B * L;
   const int d = cfg.dim, f = cfg.ffn_dim, TL = cfg.text_len, Hn = cfg.num_heads;
   const int Mp = (M + 7) & ~7;                 // leading dimension of the transposed V
   const int Kp = cfg.in_dim * 4;
   const float eps = cfg.eps;
-  const float* cs = rope_table(F, Hp, Wp);
+  const float* cs = rope_table(F, Hp, Wp, L);
 
   // ---- embeddings
-  launch_patchify(in.x, in.y, cfg.in_dim - in.y_channels, in.y_channels, F, Hl, Wl, B, w.patch, Kp, s);
+  launch_patchify(in.x, in.y, cfg.in_dim - in.y_channels, in.y_channels, F, Hl, Wl, B, w.patch, Kp, s, L);
   {
     GemmParams p{}; p.w_static = 1; p.M = M; p.N = d; p.K = Kp; p.bias = wt.patch_b; p.out_f = w.x_res; p.ld_f = d;
     gemm_linear(EPI_F32, w.patch, Kp, wt.patch_w, Kp, p, num_sms, s);
+    if (L > Ltok)                                                // the padded rows enter the blocks as exact zeros (model.py:522)
+      for (int i = 0; i < B; ++i)
+        B2_CUDA(cudaMemsetAsync(w.x_res + ((size_t)i * L + Ltok) * d, 0, (size_t)(L - Ltok) * d * sizeof(float), s));
   }
   launch_time_embed(in.t, B, cfg.freq_dim, d, wt.time0_w, wt.time0_b, wt.time2_w, wt.time2_b, wt.timep_w, wt.timep_b,
                     w.tscratch, w.e, w.e0, s);
@@ -394,7 +405,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   self.out = w.att; self.ldo = d; self.items = B; self.heads = Hn; self.Lq = L; self.Lk_rows = L;
   self.scale = 1.0f / std::sqrt(128.0f);
   self.split_ws = attn_split.as<float>();
-  for (int i = 0; i < B; ++i) self.klen[i] = L;
+  for (int i = 0; i < B; ++i) self.klen[i] = Ltok;               // padded rows are queries, never keys (model.py:155)
   AttnParams cross = self;
   if (fuse_qk_norm) { self.q_dim = d; self.q_eps = eps; }     // (q_ssq geometry set below, once the tile width is known)
   cross.ldq = d; cross.k = w.kc; cross.ldk = d; cross.vt = w.vtc; cross.ldvt = B * TL; cross.Lk_rows = TL;
@@ -502,9 +513,9 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
     launch_ln_affine(w.x_res, w.u3, w.headtab, w.headtab + d, 2 * d, M, L, d, eps, s, /*split=*/true, bad.as<unsigned int>());
     GemmParams p{}; p.w_static = 1; p.M = M; p.N = P; p.K = 3 * d; p.bias = wt.head_b; p.out_f = w.y; p.ld_f = P;
     gemm_linear(EPI_F32, w.u3, 3 * d, wt.head_w3, 3 * d, p, num_sms, s);
-    launch_unpatchify(w.y, P, B, F, Hp, Wp, cfg.out_dim, in.out, in.cfg_pairs, in.cfg_scale, s);
+    launch_unpatchify(w.y, P, B, F, Hp, Wp, cfg.out_dim, in.out, in.cfg_pairs, in.cfg_scale, s, L);
   }
-  last_flops = flops(B, L);
+  last_flops = flops(B, Ltok);
 }
 
 void DitEngine::ensure_static_io(int B, int F, int H, int W) {
@@ -543,8 +554,9 @@ void DitEngine::forward(int n, const float* const* x, const float* const* y, int
            H, W);
   const int Hp = H / 2, Wp = W / 2, L = F * Hp * Wp;
   B2_CHECK(seq_len <= 0 || L <= seq_len, "Max seq len %d exceeds limit %d", L, seq_len);           // model.py:521
-  B2_CHECK(B == 1 || L % 8 == 0, "co-batching needs a token count that is a multiple of 8 (got %d): every item must "
-           "start at a 16-byte aligned column of the transposed V; call once per item instead", L);
+  const int Lr = (pad_to_seq_len && seq_len > L) ? seq_len : L;           // rows per item
+  B2_CHECK(B == 1 || Lr % 8 == 0, "co-batching needs a per-item row count that is a multiple of 8 (got %d): every item "
+           "must start at a 16-byte aligned column of the transposed V; call once per item instead", Lr);
   B2_CHECK(y_channels >= 0 && y_channels < cfg.in_dim && (y_channels == 0 || y != nullptr), "bad y_channels %d",
            y_channels);
   B2_CHECK(clip == nullptr || cfg.i2v, "clip_fea given but the engine was not created with i2v=1");
@@ -555,10 +567,10 @@ void DitEngine::forward(int n, const float* const* x, const float* const* y, int
              cfg.text_len);
     if (cfgm) B2_CHECK(rows_b[i] >= 0 && rows_b[i] <= cfg.text_len, "uncond context %d has %d rows", i, rows_b[i]);
   }
-  B2_CHECK(taps.empty() || (long long)B * L <= tap_rows, "taps were registered for %lld rows but this call has %lld "
-           "(items x tokens%s)", tap_rows, (long long)B * L, cfgm ? ", cond + uncond" : "");
-  ensure_workspace(B, L);
-  rope_table(F, Hp, Wp);
+  B2_CHECK(taps.empty() || (long long)B * Lr <= tap_rows, "taps were registered for %lld rows but this call has %lld "
+           "(items x rows%s)", tap_rows, (long long)B * Lr, cfgm ? ", cond + uncond" : "");
+  ensure_workspace(B, Lr);
+  rope_table(F, Hp, Wp, Lr);
   ensure_static_io(B, F, H, W);
 
   const size_t vox = (size_t)F * H * W;
@@ -575,6 +587,7 @@ void DitEngine::forward(int n, const float* const* x, const float* const* y, int
   in.B = B; in.F = F; in.H = H; in.W = W; in.y_channels = y_channels; in.ctx_dtype = ctx_dtype;
   in.t = w.t_items; in.has_clip = clip != nullptr; in.clip_packed = s_clip;
   in.cfg_pairs = cfgm ? n : 0; in.cfg_scale = s_scale;
+  in.pad_rows = Lr > L ? Lr : 0;
   for (int i = 0; i < B; ++i) {
     const bool un = cfgm && i >= n;
     in.ctx_rows[i] = un ? rows_b[i - n] : rows_a[i];
@@ -617,7 +630,7 @@ void DitEngine::forward(int n, const float* const* x, const float* const* y, int
   for (int i = 0; i < n_out; ++i) in.out.p[i] = s_out + i * sio_item_out;
 
   std::vector<int> key = {B, F, H, W, y_channels, in.cfg_pairs, in.has_clip ? 1 : 0, ctx_dtype, in.ctx_hit ? 1 : 0,
-                          (int)taps.size()};
+                          (int)taps.size(), in.pad_rows};
   for (const auto& tp : taps) {                       // a captured graph holds the tap destinations
     const uintptr_t a = reinterpret_cast<uintptr_t>(tp.second);
     key.push_back(tp.first); key.push_back((int)(a & 0x7fffffff)); key.push_back((int)((a >> 31) & 0x7fffffff));

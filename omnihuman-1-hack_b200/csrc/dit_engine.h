@@ -59,6 +59,7 @@ struct FwdInputs {
   ItemPtrsMut out{};
   int cfg_pairs = 0;                     // > 0: items [0,cfg_pairs) cond, [cfg_pairs, 2 cfg_pairs) uncond
   const float* cfg_scale = nullptr;      // device scalar
+  int pad_rows = 0;                      // > tokens: rows per item, the reference's zero-padded seq_len rows carried along
   bool ctx_hit = false;                  // context-only work of this call is already cached (same hint token)
 };
 
@@ -89,6 +90,7 @@ class DitEngine {
   int num_sms = 148;
   bool finalized = false;
   bool use_graphs = true;
+  bool pad_to_seq_len = false;           // carry the seq_len - L padded rows of every item through the blocks (taps see them)
   bool fuse_qk_norm = true;              // norm weight + RoPE of q / k inside the QKV GEMM epilogue (B200_FUSE_QKNORM=0: separate pass)
   std::vector<std::pair<int, float*>> taps;   // (block index, destination): residual stream after that block
   long long tap_rows = 0;                     // row capacity of every tap destination
@@ -103,7 +105,7 @@ class DitEngine {
   void add_slot(const std::string& name, void* dst, int dt, long long numel, int tr_rows = 0, int tr_cols = 0);
   void ensure_workspace(int B, int L);
   void ensure_static_io(int B, int F, int H, int W);
-  const float* rope_table(int F, int Hp, int Wp);
+  const float* rope_table(int F, int Hp, int Wp, int rows = 0);
   void enqueue(const FwdInputs& in, cudaStream_t s);
 
   std::unordered_map<std::string, Slot> slots;

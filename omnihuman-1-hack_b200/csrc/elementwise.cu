@@ -254,7 +254,7 @@ __global__ void mod_table_kernel(const float* __restrict__ modulation, const flo
 
 // ------------------------------------------------------------------ patchify (model.py:515-518, patch (1,2,2))
 __global__ void patchify_kernel(ItemPtrs x, ItemPtrs y, int C, int Cy, int F, int H, int W, int B,
-                                __half* __restrict__ out, long long ld) {
+                                __half* __restrict__ out, long long ld, int rows_per_item) {
   pdl_launch();
   pdl_wait();
   const int Hp = H / 2, Wp = W / 2, L = F * Hp * Wp, Ct = C + Cy;
@@ -267,7 +267,7 @@ __global__ void patchify_kernel(ItemPtrs x, ItemPtrs y, int C, int Cy, int F, in
     const int w = tok % Wp, h = (tok / Wp) % Hp, f = tok / (Wp * Hp);
     const float* src = (c < C) ? x.p[b] + (long long)c * F * H * W : y.p[b] + (long long)(c - C) * F * H * W;
     const float2 v = *reinterpret_cast<const float2*>(src + ((long long)f * H + 2 * h + q) * W + 2 * w);
-    *reinterpret_cast<__half2*>(out + tokg * ld + c * 4 + q * 2) = __floats2half2_rn(v.x, v.y);
+    *reinterpret_cast<__half2*>(out + ((long long)b * rows_per_item + tok) * ld + c * 4 + q * 2) = __floats2half2_rn(v.x, v.y);
   }
 }
 
@@ -327,7 +327,8 @@ __global__ void split_weight_kernel(const float* __restrict__ w, __half* __restr
 // model.py:565-588: out[c, f, 2h+q, 2w+r] = y[token(f,h,w), (2q+r)*out_dim + c].  With cfg_pairs > 0 item b
 // (cond) and item b+cfg_pairs (uncond) are combined as uncond + s (cond - uncond) (text2video.py:243-244).
 __global__ void unpatchify_kernel(const float* __restrict__ y, int ldy, int L, int Hp, int Wp, int F, int out_dim,
-                                  ItemPtrsMut out, int n_out, int cfg_pairs, const float* __restrict__ cfg_scale_p) {
+                                  ItemPtrsMut out, int n_out, int cfg_pairs, const float* __restrict__ cfg_scale_p,
+                                  int rows_per_item) {
   pdl_launch();
   pdl_wait();
   const int P = out_dim * 4;
@@ -337,9 +338,9 @@ __global__ void unpatchify_kernel(const float* __restrict__ y, int ldy, int L, i
     const int o = i % P;
     const int tok = (i / P) % L;
     const int item = i / ((long long)P * L);
-    float v = y[((long long)item * L + tok) * ldy + o];
+    float v = y[((long long)item * rows_per_item + tok) * ldy + o];
     if (cfg_pairs > 0) {
-      const float un = y[((long long)(item + cfg_pairs) * L + tok) * ldy + o];
+      const float un = y[((long long)(item + cfg_pairs) * rows_per_item + tok) * ldy + o];
       v = un + sc * (v - un);
     }
     const int w = tok % Wp, h = (tok / Wp) % Hp, f = tok / (Wp * Hp);
@@ -392,6 +393,28 @@ __global__ void gelu_erf_cast_kernel(const float* __restrict__ x, __half* __rest
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i];
     out[i] = __float2half_rn(0.5f * v * (1.0f + erff(v * 0.7071067811865476f)));
+  }
+}
+
+// ------------------------------------------------------------------ OmniHuman audio front-end (omnihuman_wan_t2v.py:55-60)
+__global__ void silu_cast_kernel(const float* __restrict__ x, __half* __restrict__ out, long long n) {
+  pdl_launch();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    out[i] = __float2half_rn(v / (1.0f + __expf(-v)));
+  }
+}
+// tok [B, T, D] -> out [B, T-1, 2D]: out[b, t] = tok[b, t] | tok[b, t+1]   (torch.cat([a[:, :-1], a[:, 1:]], -1))
+__global__ void concat_adjacent_kernel(const float* __restrict__ tok, float* __restrict__ out, int B, int T, int D) {
+  pdl_launch();
+  pdl_wait();
+  const long long n = (long long)B * (T - 1) * 2 * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (2 * D));
+    const long long bt = i / (2 * D);
+    const int t = (int)(bt % (T - 1)), b = (int)(bt / (T - 1));
+    out[i] = tok[((long long)b * T + t + (c >= D ? 1 : 0)) * D + (c >= D ? c - D : c)];
   }
 }
 
@@ -527,10 +550,11 @@ void launch_mod_table(const float* modulation, const float* e0, float* out, int 
 }
 
 void launch_patchify(ItemPtrs x, ItemPtrs y, int C, int Cy, int F, int H, int W, int B, __half* out, long long ld,
-                     cudaStream_t s) {
+                     cudaStream_t s, int rows_per_item) {
   B2_CHECK(H % 2 == 0 && W % 2 == 0, "latent H, W must be even for the (1,2,2) patch");
   const long long n = (long long)B * F * (H / 2) * (W / 2) * (C + Cy) * 2;
-  launch_pdl(patchify_kernel, dim3(grid_for(n)), dim3(256), 0, s, x, y, C, Cy, F, H, W, B, out, ld);
+  launch_pdl(patchify_kernel, dim3(grid_for(n)), dim3(256), 0, s, x, y, C, Cy, F, H, W, B, out, ld,
+             rows_per_item > 0 ? rows_per_item : F * (H / 2) * (W / 2));
   B2_CUDA(cudaGetLastError());
   count_launch();
 }
@@ -560,12 +584,12 @@ void launch_split_weight(const float* w, __half* out, int P, int d, cudaStream_t
 }
 
 void launch_unpatchify(const float* y, int ldy, int B, int F, int Hp, int Wp, int out_dim, ItemPtrsMut out,
-                       int cfg_pairs, const float* cfg_scale, cudaStream_t s) {
+                       int cfg_pairs, const float* cfg_scale, cudaStream_t s, int rows_per_item) {
   const int L = F * Hp * Wp;
   const int n_out = cfg_pairs > 0 ? cfg_pairs : B;
   ProfScope prof(PC_OTHER, 0.0, 8.0 * B * L * out_dim * 4, s);
   launch_pdl(unpatchify_kernel, dim3(grid_for((long long)n_out * L * out_dim * 4)), dim3(256), 0, s, y, ldy, L, Hp, Wp, F,
-             out_dim, out, n_out, cfg_pairs, cfg_scale);
+             out_dim, out, n_out, cfg_pairs, cfg_scale, rows_per_item > 0 ? rows_per_item : L);
   B2_CUDA(cudaGetLastError());
   count_launch();
 }
@@ -612,6 +636,18 @@ void launch_transpose_v(const __half* v, __half* vt, int B, int Lk, int H, int L
 void launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t s) {
   transpose_f32_kernel<<<grid_for((long long)rows * cols), 256, 0, s>>>(src, dst, rows, cols);
   B2_CUDA(cudaGetLastError());
+}
+
+void launch_silu_cast(const float* x, __half* out, long long n, cudaStream_t s) {
+  launch_pdl(silu_cast_kernel, dim3(grid_for(n)), dim3(256), 0, s, x, out, n);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+void launch_concat_adjacent(const float* tok, float* out, int B, int T, int D, cudaStream_t s) {
+  launch_pdl(concat_adjacent_kernel, dim3(grid_for((long long)B * (T - 1) * 2 * D)), dim3(256), 0, s, tok, out, B, T, D);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
 }
 
 void launch_gelu_erf_cast(const float* x, __half* out, long long n, cudaStream_t s) {

@@ -169,8 +169,9 @@ void launch_time_embed(const float* t, int B, int freq_dim, int dim, const float
 // per-layer AdaLN table: mod[layer][item][6][dim] = modulation[layer] + e0[item], with +1 folded into the scales
 void launch_mod_table(const float* modulation, const float* e0, float* out, int layers, int B, int dim, cudaStream_t s);
 // latent [C,F,H,W] fp32 (+ optional y channel stack) -> fp16 patch rows [B*L, K = (C+Cy)*4], K index c*4+q*2+r
+// (rows_per_item > tokens: every item's rows start rows_per_item apart, the rows in between are left alone)
 void launch_patchify(ItemPtrs x, ItemPtrs y, int C, int Cy, int F, int H, int W, int B, __half* out, long long ld,
-                     cudaStream_t s);
+                     cudaStream_t s, int rows_per_item = 0);
 // fp32/bf16/fp16 rows -> fp16 matrix, zero-padded to rows_out rows per item
 void launch_pad_cast_rows(ItemPtrs src, int src_dtype, const int* rows_in, int B, int rows_out, int cols, __half* out,
                           cudaStream_t s);
@@ -180,12 +181,14 @@ void launch_pad_cast_rows(ItemPtrs src, int src_dtype, const int* rows_in, int B
 void launch_head_table(const float* head_mod, const float* e, float* tab, int B, int dim, cudaStream_t s);
 void launch_split_weight(const float* w, __half* out, int P, int d, cudaStream_t s);
 void launch_unpatchify(const float* y, int ldy, int B, int F, int Hp, int Wp, int out_dim, ItemPtrsMut out,
-                       int cfg_pairs, const float* cfg_scale, cudaStream_t s);
+                       int cfg_pairs, const float* cfg_scale, cudaStream_t s, int rows_per_item = 0);
 // v [B, Lk, H*128] fp16 -> vt [B*H*128, Lp]
 void launch_transpose_v(const __half* v, __half* vt, int B, int Lk, int H, int Lp, cudaStream_t s);
 void launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t s);
 void launch_convert(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, cudaStream_t s);
 void launch_gelu_erf_cast(const float* x, __half* out, long long n, cudaStream_t s);
+void launch_silu_cast(const float* x, __half* out, long long n, cudaStream_t s);
+void launch_concat_adjacent(const float* tok, float* out, int B, int T, int D, cudaStream_t s);
 
 // solver update: out_j = sum_i c[j][i] * in_i over n fp32 elements (outputs may alias inputs elementwise)
 constexpr int LINCOMB_MAX_IN = 6, LINCOMB_MAX_OUT = 3;

@@ -83,26 +83,29 @@ class AptDiscriminator:
         if any(u.shape != xs[0].shape for u in xs):
             raise B200Error("all items of a discriminator batch must share one latent shape")
         L = T * (H // 2) * (W // 2)
-        if seq_len != L:
-            # the reference's heads also attend over the seq_len - L zero-padded rows of the block outputs
-            # (model.py:524-528); that degenerate case is not restated
-            raise NotImplementedError(f"seq_len ({seq_len}) must equal the token count ({L})")
+        if seq_len < L:
+            raise AssertionError(f"Max seq len {L} exceeds limit {seq_len}")                 # wan model.py:521
+        # seq_len > L: the reference's block outputs are [B, seq_len, dim] and its heads attend over the padded rows
+        # too (seaweed_apt/model.py:162-171; wan model.py:522): the backbone carries them for this call
+        R = int(seq_len)
         ts = timestep_shift(torch.as_tensor(t, dtype=torch.float32).reshape(-1), T)
         # one backbone call fills the taps of the items it co-batches (engine.py: at most MAX_ITEMS, one item
-        # when the token count is not a multiple of 8): run the heads once per such call
-        step = MAX_ITEMS if L % 8 == 0 else 1
+        # when the per-item row count is not a multiple of 8): run the heads once per such call
+        step = MAX_ITEMS if (L % 8 == 0 and R % 8 == 0) else 1
         logits, feats = [], []
         for s0 in range(0, n, step):
             part = range(s0, min(n, s0 + step))
             m = len(part)
-            reuse = self._taps if self._rows == m * L else None
-            self._taps = self.backbone.set_taps([b - 1 for b in self.tap_blocks], m * L, buffers=reuse)
-            self._rows = m * L
+            reuse = self._taps if self._rows == m * R else None
+            self._taps = self.backbone.set_taps([b - 1 for b in self.tap_blocks], m * R, buffers=reuse)
+            self._rows = m * R
+            self.backbone.set_pad_to_seq_len(R > L)
             try:
                 self.backbone.forward([xs[i] for i in part], ts[s0:s0 + m], [context[i] for i in part], seq_len)
             finally:
                 self.backbone.set_tap(None)
-            r = self.heads(self._taps, m, L, return_features)
+                self.backbone.set_pad_to_seq_len(False)
+            r = self.heads(self._taps, m, R, return_features)
             logits.append(r[0] if return_features else r)
             if return_features:
                 feats.append(r[1])

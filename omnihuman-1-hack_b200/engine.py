@@ -104,6 +104,11 @@ class DitEngine:
             _load_state(lib().b200dit_load_weight, self._h, sd, lambda n: n != "freqs")
             check(lib().b200dit_finalize(self._h))
 
+    def set_pad_to_seq_len(self, enabled):
+        """Carry the reference's seq_len - L zero-padded rows of every item through the blocks (model.py:522), so that
+        taps hold the [n_items * seq_len, dim] block outputs the APT discriminator reads (b200dit_set_pad_to_seq_len)."""
+        check(lib().b200dit_set_pad_to_seq_len(self._h, int(bool(enabled))))
+
     def set_graphs(self, enabled):
         check(lib().b200dit_set_graphs(self._h, int(bool(enabled))))
 

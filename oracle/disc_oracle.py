@@ -76,9 +76,10 @@ def disc_forward(backbone_sd, w, x, t, context, seq_len, num_heads, tap_blocks=R
     tap_blocks are 1-based block numbers whose outputs feed cross_attn_16 / _26 / _36 in that order."""
     ts = timestep_shift(t, x.shape[2])
     taps = {b - 1: None for b in tap_blocks}
-    dit_oracle.dit_forward(backbone_sd, [u for u in x], ts, context, seq_len, num_heads=num_heads, taps=taps)
-    # the reference's block outputs are [B, seq_len, dim]; with seq_len == L (no padding rows, the only case
-    # restated here) they are exactly the per-item residual streams
+    dit_oracle.dit_forward(backbone_sd, [u for u in x], ts, context, seq_len, num_heads=num_heads, taps=taps,
+                           pad_rows=True)
+    # the reference's block outputs are [B, seq_len, dim]: when seq_len exceeds the token count the heads also
+    # attend over the padded rows (model.py:162-171), which the blocks have turned into non-zero rows
     stacked = [torch.stack(taps[b - 1]) for b in tap_blocks]
-    assert all(s.shape[1] == seq_len for s in stacked), "restated for seq_len == token count only"
+    assert all(s.shape[1] == seq_len for s in stacked)
     return disc_heads(stacked, w, num_heads, qk_norm, eps)

@@ -216,11 +216,14 @@ def head_unpatchify(sd, x, e, grid, out_dim=16, patch=(1, 2, 2)):
 
 
 def dit_forward(sd, x, t, context, seq_len=None, clip_fea=None, y=None, num_heads=12,
-                num_layers=None, text_len=512, freq_dim=256, out_dim=16, taps=None):
+                num_layers=None, text_len=512, freq_dim=256, out_dim=16, taps=None, pad_rows=False):
     """WanModel.forward (model.py:502-563): x list of [C,F,H,W]; t [B]; context list of [Lc,text_dim].
 
     Returns list of fp32 [out_dim, F, H, W]. `taps` (optional dict) receives the fp32 residual
     stream after selected blocks: taps = {k: None} -> filled with a list over items.
+    pad_rows: carry the reference's seq_len - L zero rows per item through the blocks (model.py:522: the padded rows
+    are queries like any other -- un-rotated, model.py:66 -- but never keys, model.py:155); the outputs do not
+    depend on them, the taps (block outputs [seq_len, dim], read by the APT discriminator) do.
     """
     if num_layers is None:
         num_layers = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("blocks."))
@@ -235,6 +238,8 @@ def dit_forward(sd, x, t, context, seq_len=None, clip_fea=None, y=None, num_head
         L = xb.shape[0]
         if seq_len is not None:
             assert L <= seq_len, f"Max seq len {L} exceeds limit {seq_len}"   # :521
+            if pad_rows and seq_len > L:
+                xb = torch.cat([xb, xb.new_zeros(seq_len - L, xb.shape[1])])        # :522
         ctx = text_embed(sd, context[b], text_len)
         ctx_len = context[b].shape[0]
         n_img = 0

@@ -19,6 +19,8 @@ Fixtures (all small enough to commit; weights stored as fp16 = exactly the value
   disc_tiny.pt      WanAPTDiscriminator.forward (seaweed_apt/model.py:123-186) over a 36-block tiny Wan: inputs,
                     logits and the three head tokens; weights regenerate from b200dit.synthetic by stored seed
                     (`python oracle/make_golden.py disc`)
+  omni_audio_tiny.pt  OmniConditionsModule.process_audio (Omnihuman/omnihuman_wan_t2v.py:13-60): audio pre-net weights,
+                    wav2vec-shaped features for T = 5 and T = 1, the reference's tokens (`python oracle/make_golden.py omni`)
   dit_grad_tiny.pt  gradients of the APT stage-1 loss through WanModel on dit_t2v_tiny's weights and inputs: the
                     parity target of the backward row, SURVEY 8f F1 (`python oracle/make_golden.py grads`)
 """
@@ -115,11 +117,12 @@ def make_disc_golden():
     assert not unexpected and all(k.startswith("backbone.") for k in missing), (missing, unexpected)
     g = torch.Generator().manual_seed(99)
     cases = []
-    for frames, t in ((1, [0.3, 0.9]), (3, [0.25, 0.6])):
+    for frames, t, pad in ((1, [0.3, 0.9], 0), (3, [0.25, 0.6], 0), (1, [0.7, 0.45], 8)):
+        # third case: seq_len = tokens + 8 -- the block outputs carry 8 padded rows per item, which the heads see
         x = torch.randn(2, 16, frames, 8, 8, generator=g)
         ctx = [torch.randn(12, cfg["text_dim"], generator=g), torch.randn(7, cfg["text_dim"], generator=g)]
         tt = torch.tensor(t)
-        seq_len = frames * 16
+        seq_len = frames * 16 + pad
         with torch.no_grad():
             logit, feats = disc(x, tt, ctx, seq_len, return_features=True)
         o_logit, o_feats = DO.disc_forward(sd, hw, x, tt, ctx, seq_len, cfg["num_heads"])
@@ -130,6 +133,32 @@ def make_disc_golden():
                           feats=[f.clone() for f in feats]))
     torch.save(dict(cfg=cfg, seed_backbone=seed_backbone, seed_heads=seed_heads, cases=cases),
                os.path.join(OUT, "disc_tiny.pt"))
+
+
+def make_omni_golden():
+    """The UNMODIFIED OmniConditionsModule (Omnihuman/omnihuman_wan_t2v.py:13-94): its own constructor builds the
+    audio pre-net, `process_audio` produces the tokens.  Weights rounded to fp16-representable
+    values (the engine packs GEMM weights as fp16).  Cases: T = 5 frames (adjacent-frame concat) and T = 1."""
+    from oracle import omni_oracle as OO
+    R = ref_loader.load_reference_omni()
+    torch.manual_seed(1234)
+    m = R.OmniConditionsModule(model_dim=128, num_frames=5, audio_dim=32, pose_keypoints=4).eval()
+    with torch.no_grad():
+        for p in m.audio_processor.parameters():
+            p.copy_(p.half().float())
+    sd = {k: v.clone() for k, v in m.audio_processor.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    cases = []
+    for B, T in ((2, 5), (3, 1)):
+        feats = torch.randn(B, T, 32, generator=g)
+        with torch.no_grad():
+            out = m.process_audio(feats)          # (the module's forward() itself raises as shipped: `locals()` at :81
+                                                  # includes `self`; process_audio is the part that executes)
+        err = float((OO.process_audio(sd, feats) - out).abs().max())
+        print(f"omni golden B={B} T={T}: out {tuple(out.shape)} oracle max abs err {err:.2e}")
+        assert err < 1e-5
+        cases.append(dict(feats=feats, out=out.clone()))
+    torch.save(dict(sd=half(sd), model_dim=128, audio_dim=32, cases=cases), os.path.join(OUT, "omni_audio_tiny.pt"))
 
 
 GRAD_KEYS = ["patch_embedding.weight", "text_embedding.0.weight", "time_projection.1.weight", "blocks.0.modulation",
@@ -178,6 +207,8 @@ def make_grad_golden():
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "grads":
         return make_grad_golden()
+    if len(sys.argv) > 1 and sys.argv[1] == "omni":
+        return make_omni_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "disc":
         return make_disc_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "solvers":

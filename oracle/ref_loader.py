@@ -219,3 +219,43 @@ def load_reference_apt(root=None):
                 sys.modules[k] = v
     sys.modules[full] = m
     return m
+
+
+def load_reference_omni(root=None):
+    """Returns the reference's Omnihuman/omnihuman_wan_t2v.py module (OmniConditionsModule, OmniHumanWanT2V),
+    executed in place.  Its heavyweight imports (the `wan` package, omegaconf) are only needed by
+    OmniHumanWanT2V.__init__ (checkpoints, T5) and are stubbed; OmniConditionsModule -- the pre-nets -- is plain
+    torch.nn and runs as shipped."""
+    root = root or find_reference()
+    if root is None:
+        raise FileNotFoundError("reference tree not available (container-only tool)")
+    full = "_ref_omnihuman_wan_t2v"
+    if full in sys.modules:
+        return sys.modules[full]
+    _install_stubs()
+    names = ["wan", "wan.modules", "wan.modules.t5", "wan.modules.vae", "wan.configs", "wan.utils", "wan.utils.fm_solvers",
+             "omegaconf"]
+    stubs = {n: types.ModuleType(n) for n in names}
+    for n in ("wan", "wan.modules", "wan.utils"):
+        stubs[n].__path__ = []
+    stubs["wan"].WanT2V = object
+    stubs["wan.modules.t5"].T5EncoderModel = object
+    stubs["wan.modules.vae"].WanVAE = object
+    stubs["wan.configs"].t2v_14B = {}
+    stubs["wan.utils.fm_solvers"].FlowDPMSolverMultistepScheduler = object
+    stubs["omegaconf"].DictConfig = dict
+    stubs["omegaconf"].OmegaConf = object
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location(full, os.path.join(root, "Omnihuman/omnihuman_wan_t2v.py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    sys.modules[full] = m
+    return m

@@ -177,3 +177,23 @@ def test_dit_oracle_gradients_vs_golden():
         assert rel_l2(sd[k].grad, ref) < 1e-4, k
     for k, n in r["grad_norms"].items():
         assert abs(float(sd[k].grad.norm()) - n) <= 1e-4 * max(n, 1e-6) + 1e-9, k
+
+
+def test_omni_audio_oracle_vs_golden_and_live_reference():
+    """oracle/omni_oracle.process_audio vs the fixture made by the unmodified OmniConditionsModule
+    (Omnihuman/omnihuman_wan_t2v.py:13-60) and, where the tree is mounted, vs the live class."""
+    from oracle import omni_oracle as OO, ref_loader
+    g = torch.load(os.path.join(GOLDEN, "omni_audio_tiny.pt"), map_location="cpu", weights_only=True)
+    sd = {k: v.float() for k, v in g["sd"].items()}
+    for c in g["cases"]:
+        out = OO.process_audio(sd, c["feats"])
+        assert out.shape == c["out"].shape
+        assert float((out - c["out"]).abs().max()) < 1e-5
+    if ref_loader.find_reference() is None:
+        return
+    R = ref_loader.load_reference_omni()
+    m = R.OmniConditionsModule(model_dim=64, num_frames=3, audio_dim=16, pose_keypoints=2).eval()
+    feats = torch.randn(2, 3, 16, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        ref = m.process_audio(feats)
+    assert float((OO.process_audio(m.audio_processor.state_dict(), feats) - ref).abs().max()) < 1e-5

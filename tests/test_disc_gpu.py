@@ -23,7 +23,8 @@ def _golden():
 
 def test_golden_discriminator_forward():
     """WanAPTDiscriminator.forward end to end: backbone at the shifted timestep with the reference's taps
-    (blocks 16 / 26 / 36 of a 36-block tiny Wan), heads, final_proj; one- and three-frame latents."""
+    (blocks 16 / 26 / 36 of a 36-block tiny Wan), heads, final_proj; one- and three-frame latents, and a case whose
+    seq_len exceeds the token count (the heads attend over the padded rows of the block outputs too)."""
     import b200dit
     g, sd, hw = _golden()
     eng = b200dit.DitEngine.from_state_dict(sd, num_heads=g["cfg"]["num_heads"])
@@ -41,7 +42,7 @@ def test_golden_discriminator_forward():
 
 def test_reference_error_behaviour():
     """Default taps on a backbone with fewer than 36 blocks: the reference's hook registration raises IndexError
-    (seaweed_apt/model.py:154); padded sequences are refused."""
+    (seaweed_apt/model.py:154); a seq_len below the token count trips the backbone's assert (wan model.py:521)."""
     import b200dit
     g = torch.load(os.path.join(GOLDEN, "dit_t2v_tiny.pt"))
     eng = b200dit.DitEngine.from_state_dict({k: v.float() for k, v in g["sd"].items()}, num_heads=g["cfg"]["num_heads"])
@@ -51,8 +52,8 @@ def test_reference_error_behaviour():
     disc = b200dit.AptDiscriminator(eng, hw, tap_blocks=(1, 2, 2))
     x = torch.randn(2, 16, 1, 8, 8)
     ctx = [torch.randn(5, g["cfg"]["text_dim"]) for _ in range(2)]
-    with pytest.raises(NotImplementedError):
-        disc(x, torch.tensor([0.5, 0.5]), ctx, 32)
+    with pytest.raises(AssertionError):
+        disc(x, torch.tensor([0.5, 0.5]), ctx, 8)
     bad = dict(hw); del bad["final_proj.1.bias"]
     with pytest.raises(RuntimeError):
         b200dit.AptDiscriminator(eng, bad, tap_blocks=(1, 2, 2))
