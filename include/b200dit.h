@@ -147,6 +147,25 @@ B200_API int b200vae_finalize(b200vae_engine* e);
  * out fp32 [3, 1 + 4 (T-1), 8h, 8w], clamped to [-1, 1]. */
 B200_API int b200vae_decode(b200vae_engine* e, const float* z, int32_t T, int32_t h, int32_t w, float* out, void* stream);
 
+/* Multi-GPU time-chunked decode of ONE latent (reference/seaweed.txt:1039 "time-chunk the VAE").
+ * The reference decodes frame by frame and carries a two-frame cache per causal conv between the iterations
+ * (vae.py:14, 207-217, 554-566).  Here the ranks of one node form a ring: rank r decodes chunks r, r + world, ...
+ * (chunk 0 = latent frame 0, then chunks of `chunk_frames` <= 4 frames) and every causal conv writes its two cache
+ * frames straight into the arena of the rank that decodes the next chunk -- peer stores over NVLink through a CUDA
+ * IPC mapping, followed by a system-scope flag -- so chunk c + 1 runs one conv behind chunk c.
+ *   b200vae_pipe_prepare   sizes / allocates this rank's arena for latents of size (h, w); returns its 64-byte
+ *                          CUDA IPC handle, which the host side hands to the PREVIOUS rank of the ring
+ *   b200vae_pipe_connect   maps the NEXT rank's arena (its handle)
+ *   b200vae_decode_pipelined   all ranks call it with the same z / T / chunk_frames / epoch (epoch: 1, 2, ... one per
+ *                          decode, identical on all ranks -- flags are compared against it, so they are never reset);
+ *                          out = full fp32 [3, 1 + 4 (T - 1), 8h, 8w], of which only this rank's frames are written
+ *   b200vae_pipe_chunks    host-only: number of chunks of that schedule */
+B200_API int b200vae_pipe_prepare(b200vae_engine* e, int32_t h, int32_t w, uint8_t* handle64);
+B200_API int b200vae_pipe_connect(b200vae_engine* e, const uint8_t* next_handle64);
+B200_API int b200vae_decode_pipelined(b200vae_engine* e, const float* z, int32_t T, int32_t h, int32_t w, float* out,
+                                      int32_t rank, int32_t world, int32_t chunk_frames, int32_t epoch, void* stream);
+B200_API int32_t b200vae_pipe_chunks(int32_t T, int32_t chunk_frames);
+
 /* WanVAE.encode for one video (vae.py:641-655 -> 516-542, Encoder3d :265-366): video fp32 [3, T, H, W] in [-1, 1]
  * (device), T = 1 + 4k frames, H and W multiples of 8 -> out fp32 [z_dim, 1 + k, H/8, W/8]: the posterior mean,
  * normalised with the latent mean / std.  Needs the `encoder.*` and `conv1.*` state_dict entries (decode-only

@@ -50,6 +50,10 @@ SIGNATURES = {
     "b200vae_finalize": (_I, [_P]),
     "b200vae_decode": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "b200vae_encode": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "b200vae_pipe_prepare": (_I, [_P, _I, _I, _P]),
+    "b200vae_pipe_connect": (_I, [_P, _P]),
+    "b200vae_decode_pipelined": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P]),
+    "b200vae_pipe_chunks": (_I, [_I, _I]),
     "b200disc_create": (_I, [_I, _I, _I, _F, _PP]),
     "b200disc_destroy": (None, [_P]),
     "b200disc_load_weight": (_I, [_P, C.c_char_p, _P, _I, _I, C.POINTER(C.c_int64)]),

@@ -163,6 +163,28 @@ int b200vae_decode(b200vae_engine* e, const float* z, int32_t T, int32_t h, int3
   });
 }
 
+int b200vae_pipe_prepare(b200vae_engine* e, int32_t h, int32_t w, uint8_t* handle64) {
+  return guarded([&] {
+    B2_CHECK(e && handle64 && h >= 1 && w >= 1, "bad argument");
+    e->impl.pipe_prepare(h, w, handle64);
+  });
+}
+int b200vae_pipe_connect(b200vae_engine* e, const uint8_t* next_handle64) {
+  return guarded([&] {
+    B2_CHECK(e && next_handle64, "null argument");
+    e->impl.pipe_connect(next_handle64);
+  });
+}
+int b200vae_decode_pipelined(b200vae_engine* e, const float* z, int32_t T, int32_t h, int32_t w, float* out, int32_t rank,
+                             int32_t world, int32_t chunk_frames, int32_t epoch, void* stream) {
+  return guarded([&] {
+    B2_CHECK(e && z && out, "null argument");
+    e->impl.decode_pipelined(z, T, h, w, out, rank, world, chunk_frames, epoch, static_cast<cudaStream_t>(stream));
+  });
+}
+int32_t b200vae_pipe_chunks(int32_t T, int32_t chunk_frames) {
+  return (T >= 1 && chunk_frames >= 1) ? b2::VaeEngine::pipe_chunks(T, chunk_frames) : -1;
+}
 int b200vae_encode(b200vae_engine* e, const float* video, int32_t T, int32_t H, int32_t W, float* out, void* stream) {
   return guarded([&] {
     B2_CHECK(e && video && out, "null argument");

@@ -10,6 +10,7 @@
 #include "vae_engine.h"
 
 #include <cmath>
+#include <cstring>
 #include <memory>
 
 namespace b2 {
@@ -27,9 +28,44 @@ const float kMean[16] = {-0.7571f, -0.7089f, -0.9113f, 0.1075f, -0.1745f, 0.9653
                          0.4134f, -0.0715f, 0.5517f, -0.3632f, -0.1922f, -0.9497f, 0.2503f, -0.2921f};   // vae.py:629-632
 const float kStd[16] = {2.8184f, 1.4541f, 2.3275f, 2.6558f, 1.2196f, 1.7708f, 2.6052f, 2.0743f,
                         3.2687f, 2.1526f, 2.8652f, 1.5579f, 1.6382f, 1.1253f, 2.8251f, 1.9160f};       // vae.py:633-636
+// ---- multi-GPU time-chunked decode: hand-off of the per-conv two-frame caches between ranks ----------------
+// Peer flag protocol (system scope): the producer copies two frames into the consumer's arena (peer DMA over
+// NVLink), then a one-thread kernel publishes `value` in the consumer's flag word; the consumer's one-thread kernel
+// spins on its own (local) flag word before the copy-in of that history.  Bounded: traps after ~20 s.
+__global__ void pipe_signal_kernel(int* flag, int value) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+__global__ void pipe_wait_kernel(const int* flag, int value) {
+  const long long t0 = clock64();
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= value) return;
+    if (clock64() - t0 > 40000000000LL) {
+      printf("b200vae: pipeline hand-off timeout (flag %d, waiting for %d)\n", v, value);
+      __trap();
+    }
+    __nanosleep(200);
+  }
+}
 }  // namespace
 
 struct VaeEngine::Impl {
+  // Pipelined decode state.  The arena holds, for every causal conv of the decoder in execution order, the two
+  // history frames its NEXT chunk starts from, followed by one flag word per conv; the previous rank of the ring
+  // writes into it.  `next_arena` is the next rank's arena mapped through CUDA IPC.
+  struct Pipe {
+    bool active = false;
+    int rank = 0, world = 1, chunk = 0, n_chunks = 0, epoch = 0;
+    DevBuf arena;
+    size_t flags_off = 0;
+    int h = 0, w = 0;
+    uint8_t* next_arena = nullptr;
+    std::unordered_map<std::string, std::pair<int, size_t>> slot;    // conv name -> (flag index, byte offset of its frames)
+    std::unordered_map<std::string, size_t> bytes;
+  } pipe;
+
   int dim, zdim, c0, num_sms = 148;
   int chunk_frames = 4;
   std::vector<PlanItem> plan, eplan;
@@ -197,6 +233,23 @@ struct VaeEngine::Impl {
   // Returns where the producer must write the chunk's Tc frames; history (2 frames) is placed in front.
   __half* begin_causal(const std::string& name, int Tc, int H, int W, int C) {
     const size_t frame = (size_t)H * W * C;
+    if (pipe.active) {
+      // chunk c continues from the history that chunk c - 1 -- on the previous rank -- left in this rank's arena.
+      // Chunk 0 starts from the causal zero padding, and so do the time_convs of chunk 1 (chunk 0 skips them,
+      // vae.py:106-108).
+      const auto& sl = pipe.slot.at(name);
+      B2_CHECK(pipe.bytes.at(name) == 2 * frame * 2, "pipelined decode: history of %s changed size", name.c_str());
+      const bool is_time = name.size() > 9 && name.compare(name.size() - 9, 9, "time_conv") == 0;
+      if (pipe.chunk == 0 || (pipe.chunk == 1 && is_time)) {
+        B2_CUDA(cudaMemsetAsync(A0.p, 0, 2 * frame * 2, s));
+      } else {
+        const int* flag = reinterpret_cast<const int*>(pipe.arena.as<uint8_t>() + pipe.flags_off) + sl.first;
+        pipe_wait_kernel<<<1, 1, 0, s>>>(flag, pipe.epoch * 4096 + pipe.chunk);
+        count_launch();
+        B2_CUDA(cudaMemcpyAsync(A0.p, pipe.arena.as<uint8_t>() + sl.second, 2 * frame * 2, cudaMemcpyDeviceToDevice, s));
+      }
+      return A0.as<__half>() + 2 * frame;
+    }
     auto& hb = hist[name];
     if (!hb) {
       hb = std::make_unique<DevBuf>();
@@ -216,6 +269,16 @@ struct VaeEngine::Impl {
   }
   void end_causal(const std::string& name, int Tc, int H, int W, int C) {
     const size_t frame = (size_t)H * W * C;
+    if (pipe.active) {
+      if (pipe.chunk + 1 >= pipe.n_chunks) return;             // nobody continues from the last chunk
+      const auto& sl = pipe.slot.at(name);
+      B2_CUDA(cudaMemcpyAsync(pipe.next_arena + sl.second, A0.as<__half>() + (size_t)Tc * frame, 2 * frame * 2,
+                              cudaMemcpyDeviceToDevice, s));
+      int* flag = reinterpret_cast<int*>(pipe.next_arena + pipe.flags_off) + sl.first;
+      pipe_signal_kernel<<<1, 1, 0, s>>>(flag, pipe.epoch * 4096 + pipe.chunk + 1);
+      count_launch();
+      return;
+    }
     B2_CUDA(cudaMemcpyAsync(hist[name]->p, A0.as<__half>() + (size_t)Tc * frame, 2 * frame * 2,
                             cudaMemcpyDeviceToDevice, s));
   }
@@ -442,7 +505,75 @@ struct VaeEngine::Impl {
     X0.ensure((size_t)T * h * w * zdim * 4 + 256);
   }
 
-  void decode(const float* z, int T, int h, int w, float* out, cudaStream_t stream) {
+  // The causal convs of the decoder in execution order with the size of their two-frame history at latent size
+  // (h, w): the layout of the pipelined decode's arena, identical on every rank.
+  void plan_pipe(int h, int w) {
+    pipe.slot.clear(); pipe.bytes.clear();
+    size_t off = 0;
+    int idx = 0;
+    auto add = [&](const std::string& name, int H, int W, int C) {
+      const size_t b = 2 * (size_t)H * W * C * 2;
+      pipe.slot[name] = {idx++, off};
+      pipe.bytes[name] = b;
+      off += (b + 255) & ~size_t(255);
+    };
+    int H = h, W = w;
+    add("decoder.conv1", H, W, zdim);
+    for (const char* m : {"decoder.middle.0.", "decoder.middle.2."}) {
+      add(std::string(m) + "residual.2", H, W, c0);
+      add(std::string(m) + "residual.6", H, W, c0);
+    }
+    for (size_t i = 0; i < plan.size(); ++i) {
+      const std::string p = "decoder.upsamples." + std::to_string(i) + ".";
+      if (plan[i].kind == 0) {
+        add(p + "residual.2", H, W, plan[i].cin);
+        add(p + "residual.6", H, W, plan[i].cout);
+      } else {
+        if (plan[i].kind == 1) add(p + "time_conv", H, W, plan[i].cin);
+        H *= 2; W *= 2;
+      }
+    }
+    add("decoder.head.2", H, W, dim);
+    pipe.flags_off = off;
+    const size_t total = off + (size_t)idx * sizeof(int) + 256;
+    if (total > pipe.arena.bytes || pipe.h != h || pipe.w != w) {
+      B2_CUDA(cudaDeviceSynchronize());
+      pipe.arena.release();
+      pipe.arena.ensure(total, /*zero=*/true);
+      pipe.next_arena = nullptr;                                // peers must re-open the new allocation
+    }
+    pipe.h = h; pipe.w = w;
+  }
+
+  // Chunk schedule of the pipelined decode: chunk 0 is latent frame 0, chunk k >= 1 holds up to cf frames.
+  static int pipe_chunks(int T, int cf) { return T <= 1 ? 1 : 1 + (T - 1 + cf - 1) / cf; }
+
+  void decode(const float* z, int T, int h, int w, float* out, cudaStream_t stream) { decode_impl(z, T, h, w, out, stream, false); }
+
+  // Ranks of a ring decode ONE latent together: rank r runs chunks r, r + world, ...; every causal conv hands its
+  // two-frame cache (vae.py:207-217) to the rank that runs the next chunk through that rank's arena.  Chunk c + 1
+  // can start a conv as soon as chunk c has produced that conv's input, so the ranks work one layer apart.
+  // `out` is the full [3, 1 + 4 (T - 1), 8h, 8w] video; only this rank's frames are written.
+  void decode_pipelined(const float* z, int T, int h, int w, float* out, int rank, int world, int cf, int epoch,
+                        cudaStream_t stream) {
+    B2_CHECK(world >= 2 && rank >= 0 && rank < world, "pipelined decode needs >= 2 ranks (rank %d of %d)", rank, world);
+    B2_CHECK(cf >= 1 && cf <= chunk_frames, "chunk_frames must be in [1, %d]", chunk_frames);
+    B2_CHECK(pipe.next_arena != nullptr && pipe.h == h && pipe.w == w,
+             "pipelined decode: b200vae_pipe_prepare / b200vae_pipe_connect have not been called for this latent size");
+    B2_CHECK(epoch >= 1 && epoch < (1 << 19), "pipelined decode: epoch out of range");
+    pipe.active = true; pipe.rank = rank; pipe.world = world; pipe.epoch = epoch; pipe.n_chunks = pipe_chunks(T, cf);
+    const int saved = chunk_frames;
+    chunk_frames = cf;
+    try {
+      decode_impl(z, T, h, w, out, stream, true);
+    } catch (...) {
+      pipe.active = false; chunk_frames = saved;
+      throw;
+    }
+    pipe.active = false; chunk_frames = saved;
+  }
+
+  void decode_impl(const float* z, int T, int h, int w, float* out, cudaStream_t stream, bool piped) {
     B2_CHECK(finalized, "b200vae_finalize() has not been called");
     B2_CHECK(T >= 1 && h >= 1 && w >= 1, "bad latent shape");
     s = stream;
@@ -453,11 +584,18 @@ struct VaeEngine::Impl {
     // de-normalise + conv2 over the whole sequence (vae.py:547-553)
     launch_vae_prep_latent(z, consts.as<float>(), consts.as<float>() + 16, Z16.as<__half>(), zdim, T, hw, s);
     linear_1x1("conv2", Z16.as<__half>(), (long long)T * hw, EPI_F32, X0.p, false);
-    int t0 = 0, f_out = 0;
+    int t0 = 0, f_out = 0, chunk_idx = -1;
     while (t0 < T) {
       const bool first = t0 == 0;
       int Tc = first ? 1 : (T - t0 < chunk_frames ? T - t0 : chunk_frames);
       const int Tl = Tc;
+      ++chunk_idx;
+      if (piped && chunk_idx % pipe.world != pipe.rank) {      // another rank's chunk: only advance the frame counters
+        f_out += first ? 1 : 4 * Tc;
+        t0 += Tl;
+        continue;
+      }
+      pipe.chunk = chunk_idx;
       int H = h, W = w;
       // conv1 (vae.py:424-439)
       __half* a = begin_causal("decoder.conv1", Tc, H, W, zdim);
@@ -489,7 +627,10 @@ struct VaeEngine::Impl {
 };
 
 VaeEngine::VaeEngine(int dim, int z_dim) : impl(new Impl(dim, z_dim)) {}
-VaeEngine::~VaeEngine() { delete impl; }
+VaeEngine::~VaeEngine() {
+  if (impl && impl->pipe.next_arena) cudaIpcCloseMemHandle(impl->pipe.next_arena);
+  delete impl;
+}
 void VaeEngine::load_weight(const char* name, const void* data, int dtype, int ndim, const int64_t* shape) {
   impl->load(name, data, dtype, ndim, shape);
 }
@@ -500,5 +641,28 @@ void VaeEngine::decode(const float* z, int T, int h, int w, float* out, cudaStre
 void VaeEngine::encode(const float* video, int T, int H, int W, float* out, cudaStream_t stream) {
   impl->encode(video, T, H, W, out, stream);
 }
+void VaeEngine::pipe_prepare(int h, int w, unsigned char handle[64]) {
+  impl->plan_pipe(h, w);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  cudaIpcMemHandle_t hd;
+  B2_CUDA(cudaIpcGetMemHandle(&hd, impl->pipe.arena.p));
+  memcpy(handle, &hd, 64);
+}
+void VaeEngine::pipe_connect(const unsigned char next_handle[64]) {
+  if (impl->pipe.next_arena != nullptr) {
+    cudaIpcCloseMemHandle(impl->pipe.next_arena);
+    impl->pipe.next_arena = nullptr;
+  }
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, next_handle, 64);
+  void* p = nullptr;
+  B2_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+  impl->pipe.next_arena = static_cast<uint8_t*>(p);
+}
+void VaeEngine::decode_pipelined(const float* z, int T, int h, int w, float* out, int rank, int world, int chunk_frames,
+                                 int epoch, cudaStream_t stream) {
+  impl->decode_pipelined(z, T, h, w, out, rank, world, chunk_frames, epoch, stream);
+}
+int VaeEngine::pipe_chunks(int T, int chunk_frames) { return Impl::pipe_chunks(T, chunk_frames); }
 
 }  // namespace b2

@@ -16,6 +16,12 @@ class VaeEngine {
   void finalize();
   void decode(const float* z, int T, int h, int w, float* out, cudaStream_t stream);
   void encode(const float* video, int T, int H, int W, float* out, cudaStream_t stream);
+  // multi-GPU time-chunked decode (see vae_engine.cu: Pipe)
+  void pipe_prepare(int h, int w, unsigned char handle[64]);
+  void pipe_connect(const unsigned char next_handle[64]);
+  void decode_pipelined(const float* z, int T, int h, int w, float* out, int rank, int world, int chunk_frames, int epoch,
+                        cudaStream_t stream);
+  static int pipe_chunks(int T, int chunk_frames);
 
  private:
   struct Impl;

@@ -150,6 +150,40 @@ def gather_from_ranks(local, counts, group=None):
     return [[out[r][j] for j in range(counts[r])] for r in range(w)]
 
 
+def pipeline_schedule(T, world, chunk_frames):
+    """Chunk schedule of the multi-GPU time-chunked VAE decode (b200vae_decode_pipelined): chunk 0 is latent frame
+    0 alone (one output frame), chunk k >= 1 holds up to `chunk_frames` latent frames (four output frames each);
+    chunk c runs on rank c % world.  Returns [(chunk, rank, first output frame, output frames)]."""
+    out, t0, f0, c = [], 0, 0, 0
+    while t0 < T:
+        tc = 1 if t0 == 0 else min(chunk_frames, T - t0)
+        nf = 1 if t0 == 0 else 4 * tc
+        out.append((c, c % world, f0, nf))
+        t0, f0, c = t0 + tc, f0 + nf, c + 1
+    return out
+
+
+def pipeline_chunk_frames(T, world, max_chunk=4):
+    """Latent frames per chunk for a ring of `world` ranks: the ranks run one conv layer apart, so the decode takes
+    about ceil(chunks / world) rounds of one chunk each.  Larger chunks feed the convolution GEMMs better, so a
+    smaller chunk must win by more than 10 % to be chosen."""
+    best, best_cost = max_chunk, None
+    for cf in range(max_chunk, 0, -1):
+        chunks = len(pipeline_schedule(T, world, cf))
+        cost = ((chunks + world - 1) // world) * min(cf, max(T - 1, 1))
+        if best_cost is None or cost < 0.9 * best_cost:
+            best, best_cost = cf, cost
+    return best
+
+
+def sum_disjoint(t, group=None):
+    """Assembles a tensor of which every rank wrote a disjoint part and left the rest zero: one all_reduce
+    (x + 0 = x exactly).  Used for the frames of the pipelined VAE decode."""
+    if world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
 def max_over_ranks(value, device=None):
     """Timing reduction used by bench.py: every multi-GPU number is the max over ranks."""
     if world_size() == 1:

@@ -26,6 +26,16 @@ for i, r in enumerate(res):
     assert torch.equal(r, items[i] * 2 + 1), i                        # original order, every rank
 assert par.max_over_ranks(1.0 + rank) == 2.0
 assert par.shard_indices(7, 1, 4) == [1, 5]
+# pipelined VAE decode, host side: every rank writes the frames of its chunks, one all_reduce assembles the video
+sched = par.pipeline_schedule(21, 2, 4)
+assert [s[1] for s in sched] == [0, 1, 0, 1, 0, 1] and sched[0][2:] == (0, 1) and sched[1][2:] == (1, 16) and sched[-1][2] + sched[-1][3] == 81
+full = torch.arange(81.0)[None, :, None].expand(3, 81, 4).contiguous()
+mine = torch.zeros_like(full)
+for c, r, f0, nf in sched:
+    if r == rank:
+        mine[:, f0:f0 + nf] = full[:, f0:f0 + nf]
+assert torch.equal(par.sum_disjoint(mine), full)
+assert par.pipeline_chunk_frames(21, 8) == 3 and par.pipeline_chunk_frames(21, 2) == 4 and par.pipeline_chunk_frames(2, 2) == 4
 # fewer items than ranks: rank 1 owns nothing and still takes part in the gather (no deadlock, no early raise)
 one = par.sharded_map(fn, items[:1])
 assert len(one) == 1 and torch.equal(one[0], items[0] * 2 + 1)
