@@ -267,6 +267,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-block-table", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="N > 1: skip the T = 21 and CFG-parallel legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -451,6 +452,61 @@ def main():
                 "attention_tflops": (prof["attention"]["flops"] / (prof["attention"]["ms"] / 1e3) / 1e12)
                 if prof["attention"]["ms"] > 0 else None}
 
+    # ---- multi-GPU legs beyond T = 1 (extra keys): the 81-frame shape of configs 3 / 5 (T = 21, L = 32 760), one
+    # sample per GPU, and -- for an even number of ranks -- CFG-parallel sampling (cond / uncond of ONE video on a
+    # rank pair, one all_gather per step inside the pair): the latency mode of config 5.
+    legs = {}
+    if world > 1 and T == 1 and not args.no_extra_legs:
+        from b200dit import pipelines as P
+        T2, L2 = 21, 1560 * 21
+        g2 = torch.Generator().manual_seed(4242 + rank)
+        x21 = [torch.randn(16, T2, 60, 104, generator=g2).to(dev)]
+        sc21 = b200dit.FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+        sc21.set_timesteps(NUM_STEPS, device=dev, shift=SHIFT)
+
+        def step21(i, x):
+            v = eng.forward_cfg(x, t_dev[i][:1].contiguous(), ctx[:1], ctx0[:1], L2, GUIDE)
+            return [sc21.step(v[0].unsqueeze(0), ts_host[i], x[0].unsqueeze(0), return_dict=False)[0].squeeze(0)]
+
+        xx = x21
+        for i in range(3):                                   # eager, capture, replay
+            xx = step21(i, xx)
+        barrier()
+        e0.record()
+        n21 = 2
+        for i in range(3, 3 + n21):
+            xx = step21(i, xx)
+        e1.record()
+        barrier()
+        ms21 = e0.elapsed_time(e1) / n21
+        tt = torch.tensor([ms21], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms21 = float(tt.item())
+        fl21 = 2 * b200dit.flops.dit_forward_flops(L2, layers=cfg["num_layers"], context_cached=True)
+        legs["t21"] = {"workload": "same CFG denoise step on latent [16,21,60,104] (L=32760), 1 sample per GPU",
+                       "value": world * 1e3 / ms21, "unit": "denoise-steps/s", "ms_per_step": ms21, "steps": n21,
+                       "step_tflops_per_gpu": fl21 / (ms21 / 1e3) / 1e12, "finite": bool(torch.isfinite(xx[0]).all())}
+        if world % 2 == 0:
+            gp = torch.Generator().manual_seed(777 + rank // 2)      # both ranks of a pair hold the same video
+            xp = [torch.randn(16, T2, 60, 104, generator=gp).to(dev)]
+            cp = [torch.randn(512, 4096, generator=gp).bfloat16().to(dev)]
+            c0p = [torch.randn(512, 4096, generator=gp).bfloat16().to(dev)]
+            P.sample_cfg_parallel(eng, xp, cp, c0p, steps=3, shift=SHIFT, guide_scale=GUIDE)
+            barrier()
+            e0.record()
+            nps = 3
+            outp = P.sample_cfg_parallel(eng, xp, cp, c0p, steps=nps, shift=SHIFT, guide_scale=GUIDE)
+            e1.record()
+            barrier()
+            msp = e0.elapsed_time(e1) / nps
+            tt = torch.tensor([msp], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            legs["cfg_parallel_t21"] = {"workload": "one [16,21,60,104] video per rank PAIR: cond forward on rank 2k, uncond on "
+                                        "rank 2k+1, one all_gather (8.4 MB) inside the pair per step, same UniPC step on both",
+                                        "latency_ms_per_step": float(tt.item()), "videos_in_flight": world // 2,
+                                        "value": (world // 2) * 1e3 / float(tt.item()), "unit": "denoise-steps/s",
+                                        "steps": nps, "finite": bool(torch.isfinite(outp[0]).all())}
+
     single = None
     if rank == 0 and S > 1:
         # the same step for ONE sample per GPU (latency-oriented use: M = 3120 token rows per GEMM)
@@ -495,6 +551,7 @@ def main():
                 "step_frac_of_peak": flops_step / (ms_step / 1e3) / 1e12 / burst,
                 "step_frac_of_sustained": flops_step / (ms_step / 1e3) / 1e12 / sustained,
                 "roofline": roof, "single_sample": single}
+        line.update(legs)
         if world == 1 and not args.no_block_table:
             line["block_table"] = block_table(dev, burst, sustained)
         if not args.no_cpu_baseline and world == 1:

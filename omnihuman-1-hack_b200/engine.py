@@ -341,34 +341,38 @@ class VaeEngine:
                 outs.append(o)
         return outs
 
-    def decode_pipelined(self, z, chunk_frames=None):
+    def decode_pipelined(self, z, chunk_frames=None, group=None):
         """Multi-GPU time-chunked decode of ONE latent [16, T, h, w]: every rank of the default
         process group calls this with the same latent and gets the whole fp32 video [3, 1 + 4 (T - 1), 8h, 8w].
         Rank r decodes chunks r, r + world, ... and hands the per-conv two-frame caches (vae.py:207-217) to the
-        next rank through peer memory (b200vae_decode_pipelined); one all_reduce assembles the frames."""
+        next rank through peer memory (b200vae_decode_pipelined); one all_reduce assembles the frames.  `group`: a
+        process group of ranks on one node (default: all ranks), e.g. parallel.pair_group()."""
         import torch.distributed as dist
         from . import parallel
-        world, rank = parallel.world_size(), parallel.rank()
+        if parallel.world_size() == 1:
+            return self.decode([z])[0]
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world == 1:
             return self.decode([z])[0]
         z = z.to(self.device, torch.float32).contiguous()
         _, T, h, w = z.shape
         with torch.cuda.device(self.device):
-            if getattr(self, "_pipe_key", None) != (h, w, world):
+            gkey = id(group) if group is not None else 0
+            if getattr(self, "_pipe_key", None) != (h, w, world, gkey):
                 handle = (C.c_uint8 * 64)()
                 check(lib().b200vae_pipe_prepare(self._h, h, w, handle))
                 handles = [None] * world
-                dist.all_gather_object(handles, bytes(handle))
+                dist.all_gather_object(handles, bytes(handle), group=group)
                 nxt = (C.c_uint8 * 64).from_buffer_copy(handles[(rank + 1) % world])
                 check(lib().b200vae_pipe_connect(self._h, nxt))
-                dist.barrier()                                  # every arena is mapped before anyone writes
-                self._pipe_key, self._pipe_epoch = (h, w, world), 0
+                dist.barrier(group=group)                       # every arena is mapped before anyone writes
+                self._pipe_key, self._pipe_epoch = (h, w, world, gkey), 0
             self._pipe_epoch += 1
             cf = int(chunk_frames or parallel.pipeline_chunk_frames(T, world))
             out = torch.zeros((3, 1 + 4 * (T - 1), 8 * h, 8 * w), dtype=torch.float32, device=self.device)
             check(lib().b200vae_decode_pipelined(self._h, C.c_void_p(z.data_ptr()), T, h, w, C.c_void_p(out.data_ptr()),
                                                  rank, world, cf, self._pipe_epoch, _stream_ptr()))
-            return parallel.sum_disjoint(out)
+            return parallel.sum_disjoint(out, group=group)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

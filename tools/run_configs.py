@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--layers", type=int, default=30)
     ap.add_argument("--cfg-parallel", action="store_true",
                     help="config 5: one video per rank PAIR, cond / uncond forwards on the two ranks, one exchange per step")
+    ap.add_argument("--pipe-decode", action="store_true",
+                    help="config 5 with --cfg-parallel: the rank pair decodes its video together (time-chunked VAE decode)")
     ap.add_argument("--pair-split", action="store_true",
                     help="config 4: teacher cond / uncond of one item on a rank pair (one send per item)")
     a = ap.parse_args()
@@ -98,8 +100,12 @@ def main():
         if a.cfg_parallel:
             one = P.sample(eng, [x0], [ctx], [ctx0], steps=a.steps, shift=5.0, guide_scale=5.0)
             cfgpar_rel = float((lat[0] - one[0]).norm() / one[0].norm())
-        vae.decode(lat)                                       # warm-up at full size (workspaces grow on first sight)
-        vid, ms_v = timed(lambda: vae.decode(lat))
+        if a.cfg_parallel and a.pipe_decode:                  # the pair that denoised the video also decodes it together
+            dec = lambda: [vae.decode_pipelined(lat[0], group=parallel.pair_group())]
+        else:
+            dec = lambda: vae.decode(lat)
+        dec()                                                 # warm-up at full size (workspaces grow on first sight)
+        vid, ms_v = timed(dec)
         allv, ms_g = timed(lambda: parallel.gather_items(lat, world))
         line = {"config": 5, "workload": f"per rank: {a.steps}-step UniPC CFG denoise of [16,{T},60,104] + WanVAE decode to "
                 f"{list(vid[0].shape)}; one all_gather of the final latents", "n_gpus": world, "denoise_ms": ms_d,
@@ -111,7 +117,8 @@ def main():
             line.update({"mode": "cfg-parallel: one video per rank pair, cond on rank 2k, uncond on rank 2k+1, one all_gather "
                          "inside the pair per step", "videos_per_s": vids / ((ms_d + ms_v + ms_g) / 1e3),
                          "denoise_steps_per_s": vids * a.steps / (ms_d / 1e3),
-                         "latency_ms_per_step": ms_d / a.steps, "rel_l2_vs_single_gpu_loop": cfgpar_rel})
+                         "latency_ms_per_step": ms_d / a.steps, "rel_l2_vs_single_gpu_loop": cfgpar_rel,
+                         "vae_decode": "time-chunked across the pair" if a.pipe_decode else "each rank decodes the whole video"})
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
