@@ -135,6 +135,31 @@ B200_API int b200dit_set_graphs(b200dit_engine* e, int32_t enabled);
  * (0 for a healthy run), clears it; synchronises `stream`. */
 B200_API int b200dit_nonfinite_rows(b200dit_engine* e, void* stream, uint32_t* count);
 
+/* ---- Backward of the student forward ----
+ * The APT stage-1 training step (seaweed_apt/distilled_trainer.py:268-301): `v = model(noise, t, context, seq_len)`
+ * under autocast, `loss = mse(v, v_teacher)`, `scaler.scale(loss).backward()`.
+ *
+ * b200dit_train_forward = b200dit_forward for a t2v model (no y / clip_fea), run eagerly, that also keeps the
+ * residual stream at every block boundary -- the reference checkpoints its blocks the same way
+ * (`use_checkpoint`, model.py:544-548).  It must be the engine's latest forward when b200dit_backward runs. */
+B200_API int b200dit_train_forward(b200dit_engine* e, int32_t n_items, const float* const* x, const float* t,
+                                   const void* const* context, const int32_t* context_rows, int32_t context_dtype,
+                                   int32_t F, int32_t H, int32_t W, int32_t seq_len, float* const* out, void* stream);
+/* loss.backward() through WanModel.forward.  dout[i]: device fp32 [out_dim, F, H, W], d loss / d out[i].
+ * loss_scale: the GradScaler factor (distilled_trainer.py:88,301) -- gradients travel multiplied by it through the
+ * fp16 contractions; b200dit_read_grad takes its inverse.  ffn_grad_blocks: the reference runs the FFN of every block
+ * with block_idx > 10 under no_grad (model.py:318-325), i.e. as a constant of the backward: pass 11 to reproduce that,
+ * a negative value to differentiate every FFN.  dx (optional): dx[i] receives d loss / d x[i] (unscaled).
+ * Parameter gradients ACCUMULATE across calls (like `.grad`) until b200dit_zero_grad. */
+B200_API int b200dit_backward(b200dit_engine* e, const float* const* dout, float loss_scale, int32_t ffn_grad_blocks,
+                              float* const* dx, void* stream);
+/* optimizer.zero_grad() (distilled_trainer.py:305). */
+B200_API int b200dit_zero_grad(b200dit_engine* e, void* stream);
+/* `param.grad` of the parameter stored under the reference state_dict key `name`: dst (device fp32, numel elements)
+ * = scale * gradient, or += when accumulate != 0. */
+B200_API int b200dit_read_grad(b200dit_engine* e, const char* name, float* dst, int64_t numel, float scale,
+                               int32_t accumulate, void* stream);
+
 /* ---- WanVAE decode (seaweed_apt/wan/modules/vae.py:619-663) ---- */
 /* WanVAE.__init__ -> _video_vae (vae.py:592-616): decoder of width `dim` (96), z_dim 16. */
 B200_API int b200vae_create(int32_t dim, int32_t z_dim, b200vae_engine** out);

@@ -44,6 +44,10 @@ SIGNATURES = {
     "b200dit_set_pad_to_seq_len": (_I, [_P, _I]),
     "b200dit_last_flops": (C.c_double, [_P]),
     "b200dit_nonfinite_rows": (_I, [_P, _P, C.POINTER(C.c_uint32)]),
+    "b200dit_train_forward": (_I, [_P, _I, _PP, _P, _PP, _IP, _I, _I, _I, _I, _I, _PP, _P]),
+    "b200dit_backward": (_I, [_P, _PP, _F, _I, _PP, _P]),
+    "b200dit_zero_grad": (_I, [_P, _P]),
+    "b200dit_read_grad": (_I, [_P, C.c_char_p, _P, _L, _F, _I, _P]),
     "b200vae_create": (_I, [_I, _I, _PP]),
     "b200vae_destroy": (None, [_P]),
     "b200vae_load_weight": (_I, [_P, C.c_char_p, _P, _I, _I, C.POINTER(C.c_int64)]),

@@ -111,6 +111,9 @@ __global__ void mul_gate_cast_kernel(const float* __restrict__ dx, const float* 
 __global__ void add_f32_kernel(float* __restrict__ a, const float* __restrict__ b, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] += b[i];
 }
+__global__ void fill_f32_kernel(float* __restrict__ p, float v, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
 __global__ void scale_copy_kernel(const float* __restrict__ in, float* __restrict__ out, float s, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = in[i] * s;
 }
@@ -184,11 +187,7 @@ __global__ void __launch_bounds__(256) rms_rope_bwd_kernel(const float* __restri
     s += a * gamma[2 * p] * __half2float(xr[2 * p]) + b * gamma[2 * p + 1] * __half2float(xr[2 * p + 1]);
   }
   s = wsum(s) * r * r * r / dim;
-  __half* o = draw + (long long)row * ldd;
-  for (int c = lane; c < dim; c += 32) {
-    // (this lane wrote exactly the pairs it reads back: columns 2p, 2p+1 with p = lane mod 32 -- re-read through memory)
-  }
-  __syncwarp();
+  __half* o = draw + (long long)row * ldd;       // (every lane re-reads exactly the pairs it wrote above)
   for (int p = lane; p < dim / 2; p += 32) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
@@ -300,7 +299,7 @@ __global__ void small_dx_kernel(const float* __restrict__ dout, const float* __r
 }
 // dW[n, k] += sum_b dout[b, n] act(in[b, k]);  db[n] += sum_b dout[b, n]
 __global__ void small_dw_kernel(const float* __restrict__ dout, const float* __restrict__ in, float* __restrict__ dW,
-                                float* __restrict__ db, int B, int K, int N, int silu_in) {
+                                float* __restrict__ db, int B, int K, int N, int silu_in, float scale) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)N * K) return;
   const int k = i % K, n = i / K;
@@ -310,13 +309,13 @@ __global__ void small_dw_kernel(const float* __restrict__ dout, const float* __r
     acc += dout[(long long)b * N + n] * (silu_in ? silu_f(x) : x);
     accb += dout[(long long)b * N + n];
   }
-  dW[i] += acc;
-  if (k == 0 && db) db[n] += accb;
+  dW[i] += scale * acc;
+  if (k == 0 && db) db[n] += scale * accb;
 }
 // e0 gradient of item b from the per-(layer, item) modulation-table gradients, and the modulation parameter gradients
 // dtab [layers][B][6][dim] -> de0[b][6][dim] = sum_l dtab;  dmod[l][6][dim] += sum_b dtab
 __global__ void modtab_bwd_kernel(const float* __restrict__ dtab, int layers, int B, int dim, float* __restrict__ de0,
-                                  float* __restrict__ dmod) {
+                                  float* __restrict__ dmod, float scale) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long per = 6LL * dim;
   if (i < (long long)B * per) {
@@ -329,13 +328,13 @@ __global__ void modtab_bwd_kernel(const float* __restrict__ dtab, int layers, in
     const int l = i / per; const long long k = i % per;
     float acc = 0.f;
     for (int b = 0; b < B; ++b) acc += dtab[((long long)l * B + b) * per + k];
-    dmod[i] += acc;
+    dmod[i] += scale * acc;
   }
 }
 // head: dtab_h [B][2][dim] (rows: d(1 + m1 + e) i.e. scale row, d(m0 + e) shift row, in the layout of headtab)
 // dhead_mod[2][dim] += sum_b (row1 -> modulation[1], row0 -> modulation[0]);  de[b] += both rows
 __global__ void headtab_bwd_kernel(const float* __restrict__ dscale, const float* __restrict__ dshift, int B, int dim,
-                                   float* __restrict__ dhead_mod, float* __restrict__ de) {
+                                   float* __restrict__ dhead_mod, float* __restrict__ de, float scale) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= dim) return;
   float s0 = 0.f, s1 = 0.f;
@@ -344,8 +343,8 @@ __global__ void headtab_bwd_kernel(const float* __restrict__ dscale, const float
     s0 += a; s1 += c;
     de[(long long)b * dim + i] += a + c;
   }
-  dhead_mod[i] += s0;            // head.modulation[0, 0] is the shift
-  dhead_mod[dim + i] += s1;      // head.modulation[0, 1] is the scale
+  dhead_mod[i] += scale * s0;            // head.modulation[0, 0] is the shift
+  dhead_mod[dim + i] += scale * s1;      // head.modulation[0, 1] is the scale
 }
 
 }  // namespace
@@ -386,6 +385,10 @@ void bw_mul_gate_cast(const float* dx, const float* g, long long g_item_stride, 
 }
 void bw_add(float* a, const float* b, long long n, cudaStream_t s) {
   add_f32_kernel<<<blocks_for(n), 256, 0, s>>>(a, b, n);
+  B2_AFTER();
+}
+void bw_fill(float* p, float v, long long n, cudaStream_t s) {
+  fill_f32_kernel<<<blocks_for(n), 256, 0, s>>>(p, v, n);
   B2_AFTER();
 }
 void bw_scale_copy(const float* in, float* out, float sc, long long n, cudaStream_t s) {
@@ -434,21 +437,22 @@ void bw_small_fwd(const float* in, const float* W, const float* bias, float* out
   B2_AFTER();
 }
 void bw_small_bwd(const float* dout, const float* W, const float* in, float* din, float* dW, float* db, int B, int K, int N,
-                  bool silu_in, bool accumulate_din, cudaStream_t s) {
+                  bool silu_in, bool accumulate_din, float wscale, cudaStream_t s) {
   if (din != nullptr) {
     small_dx_kernel<<<(int)(((long long)B * K + 255) / 256), 256, 0, s>>>(dout, W, in, din, B, K, N, silu_in ? 1 : 0, accumulate_din ? 1 : 0);
     B2_AFTER();
   }
-  small_dw_kernel<<<(int)(((long long)N * K + 255) / 256), 256, 0, s>>>(dout, in, dW, db, B, K, N, silu_in ? 1 : 0);
+  small_dw_kernel<<<(int)(((long long)N * K + 255) / 256), 256, 0, s>>>(dout, in, dW, db, B, K, N, silu_in ? 1 : 0, wscale);
   B2_AFTER();
 }
-void bw_modtab_bwd(const float* dtab, int layers, int B, int dim, float* de0, float* dmod, cudaStream_t s) {
+void bw_modtab_bwd(const float* dtab, int layers, int B, int dim, float* de0, float* dmod, float wscale, cudaStream_t s) {
   const long long n = (long long)(layers > B ? layers : B) * 6 * dim;
-  modtab_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(dtab, layers, B, dim, de0, dmod);
+  modtab_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(dtab, layers, B, dim, de0, dmod, wscale);
   B2_AFTER();
 }
-void bw_headtab_bwd(const float* dscale, const float* dshift, int B, int dim, float* dhead_mod, float* de, cudaStream_t s) {
-  headtab_bwd_kernel<<<(dim + 255) / 256, 256, 0, s>>>(dscale, dshift, B, dim, dhead_mod, de);
+void bw_headtab_bwd(const float* dscale, const float* dshift, int B, int dim, float* dhead_mod, float* de, float wscale,
+                    cudaStream_t s) {
+  headtab_bwd_kernel<<<(dim + 255) / 256, 256, 0, s>>>(dscale, dshift, B, dim, dhead_mod, de, wscale);
   B2_AFTER();
 }
 

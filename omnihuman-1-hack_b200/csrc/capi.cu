@@ -136,6 +136,33 @@ int b200dit_nonfinite_rows(b200dit_engine* e, void* stream, uint32_t* count) {
   });
 }
 
+int b200dit_train_forward(b200dit_engine* e, int32_t n_items, const float* const* x, const float* t,
+                          const void* const* context, const int32_t* context_rows, int32_t context_dtype, int32_t F,
+                          int32_t H, int32_t W, int32_t seq_len, float* const* out, void* stream) {
+  return guarded([&] {
+    B2_CHECK(e && x && t && context && context_rows && out, "null argument");
+    e->impl.train_forward(n_items, x, t, context, context_rows, context_dtype, F, H, W, seq_len, out,
+                          static_cast<cudaStream_t>(stream));
+  });
+}
+int b200dit_backward(b200dit_engine* e, const float* const* dout, float loss_scale, int32_t ffn_grad_blocks,
+                     float* const* dx, void* stream) {
+  return guarded([&] {
+    B2_CHECK(e && dout, "null argument");
+    e->impl.backward(dout, loss_scale, ffn_grad_blocks, dx, static_cast<cudaStream_t>(stream));
+  });
+}
+int b200dit_zero_grad(b200dit_engine* e, void* stream) {
+  return guarded([&] { B2_CHECK(e, "null engine"); e->impl.zero_grad(static_cast<cudaStream_t>(stream)); });
+}
+int b200dit_read_grad(b200dit_engine* e, const char* name, float* dst, int64_t numel, float scale, int32_t accumulate,
+                      void* stream) {
+  return guarded([&] {
+    B2_CHECK(e && name && dst, "null argument");
+    e->impl.read_grad(name, dst, numel, scale, accumulate != 0, static_cast<cudaStream_t>(stream));
+  });
+}
+
 int b200vae_create(int32_t dim, int32_t z_dim, b200vae_engine** out) {
   return guarded([&] {
     B2_CHECK(out != nullptr, "null argument");

@@ -116,6 +116,7 @@ void DitEngine::alloc_weights() {
     w16.ensure(h16 * 2 + 4096);
     w32.ensure(f32 * 4 + 4096);
   }
+  w16_elems = h16 + 2048; w32_elems = f32 + 1024;
   uint8_t* p16 = w16.as<uint8_t>();
   uint8_t* p32 = w32.as<uint8_t>();
   auto W16 = [&](size_t n) { return carve<__half>(p16, n); };
@@ -230,6 +231,7 @@ void DitEngine::load_weight(const char* name, const void* data, int dtype, int n
   load_into_slot(it->second, name, data, dtype, ndim, shape);
   finalized = false;
   cached_token = 0;                  // the cached cross-attention K / V were projected with the old weights
+  w16t_valid = false;                // so were the transposed copies the backward reads
 }
 
 void DitEngine::finalize() {
@@ -428,6 +430,8 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
 
   for (int l = 0; l < cfg.num_layers; ++l) {
     const BlockWeights& b = wt.blocks[l];
+    if (save_x != nullptr)           // train_forward: the block's input, kept for the recompute of the backward
+      B2_CUDA(cudaMemcpyAsync(save_x + (size_t)l * M * d, w.x_res, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, s));
     const float* mod = w.modtab + (size_t)l * B * 6 * d;      // [B][6][d]: shift1,1+scale1,gate1,shift2,1+scale2,gate2
     // ---- self-attention (model.py:292-296)
     launch_ln_affine(w.x_res, w.u, mod + d, mod, 6 * d, M, L, d, eps, s, false, bad.as<unsigned int>());
@@ -507,6 +511,8 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
         B2_CUDA(cudaMemcpyAsync(tp.second, w.x_res, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, s));
   }
   // ---- head (model.py:349-359) + unpatchify (:565-588) + CFG combine (text2video.py:243-244)
+  if (save_x != nullptr)
+    B2_CUDA(cudaMemcpyAsync(save_x + (size_t)cfg.num_layers * M * d, w.x_res, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, s));
   {
     const int P = cfg.out_dim * 4;
     launch_head_table(wt.head_mod, w.e, w.headtab, B, d, s);
@@ -548,6 +554,7 @@ void DitEngine::forward(int n, const float* const* x, const float* const* y, int
                         int ctx_dtype, const float* const* clip, int F, int H, int W, int seq_len, bool cfgm,
                         float guide_scale, float* const* out, cudaStream_t stream) {
   B2_CHECK(finalized, "b200dit_finalize() has not been called (or a weight was reloaded since)");
+  tg.valid = false;                  // the workspaces a pending backward would read are about to be overwritten
   const int B = cfgm ? 2 * n : n;
   B2_CHECK(n >= 1 && B <= MAX_ITEMS, "%d items in one call (max %d)", B, MAX_ITEMS);
   B2_CHECK(F >= 1 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "latent grid (%d,%d,%d) not patchable by (1,2,2)", F,

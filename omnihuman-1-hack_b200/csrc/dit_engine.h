@@ -86,6 +86,21 @@ class DitEngine {
   // overflowed upstream); reads a device counter after synchronising `stream`, then clears it
   unsigned int nonfinite_rows(cudaStream_t stream);
 
+  // ---- F1: gradients of the student forward (dit_backward.cu; seaweed_apt/distilled_trainer.py:268-301).
+  // train_forward = forward() run eagerly with the residual stream kept at every block boundary (the reference
+  // checkpoints per block, model.py:544-548); backward() recomputes one block at a time and accumulates parameter
+  // gradients (multiplied by loss_scale) into an fp32 store that mirrors the packed weights.
+  void train_forward(int n, const float* const* x, const float* t, const void* const* ctx, const int* rows, int ctx_dtype,
+                     int F, int H, int W, int seq_len, float* const* out, cudaStream_t stream);
+  // dout[i]: d loss / d out[i] (fp32 [out_dim, F, H, W]);  dx[i] (optional): receives d loss / d x[i] (unscaled).
+  // ffn_grad_blocks: FFNs of blocks with index >= this value are treated as constants (the reference runs them under
+  // no_grad for block_idx > 10, model.py:318-325); < 0: every FFN takes part.
+  void backward(const float* const* dout, float loss_scale, int ffn_grad_blocks, float* const* dx, cudaStream_t stream);
+  void zero_grad(cudaStream_t stream);
+  // dst (+)= scale * gradient of the parameter stored under the reference key `name` (fp32, numel elements)
+  void read_grad(const char* name, float* dst, long long numel, float scale, bool accumulate, cudaStream_t stream);
+  struct BwdWorkspace;                   // per-block intermediates of the backward (dit_backward.cu)
+
   b200dit_config cfg;
   int num_sms = 148;
   bool finalized = false;
@@ -107,6 +122,22 @@ class DitEngine {
   void ensure_static_io(int B, int F, int H, int W);
   const float* rope_table(int F, int Hp, int Wp, int rows = 0);
   void enqueue(const FwdInputs& in, cudaStream_t s);
+  float* save_x = nullptr;               // set by train_forward: [layers + 1][M, dim] block-boundary residual streams
+
+  // ---- backward state (dit_backward.cu)
+  struct TrainGeom { bool valid = false; int B = 0, F = 0, H = 0, W = 0, L = 0, Ltok = 0; int ctx_rows[MAX_ITEMS] = {0}; };
+  TrainGeom tg;
+  std::unique_ptr<DevBuf> xsave, g16, g32, w16t, bws_buf;
+  bool w16t_valid = false;
+  int bws_B = 0, bws_L = 0;
+  size_t w16_elems = 0, w32_elems = 0;
+  float* grad_of(const void* wptr) const;           // gradient slot mirroring a packed weight pointer
+  const __half* transposed(const __half* w) const;  // W^T in the transposed mirror of the fp16 weights
+  void ensure_grads();
+  void ensure_transposed_weights(cudaStream_t s);
+  void ensure_bwd_workspace(int B, int L);
+  void block_recompute(int l, BwdWorkspace& k, cudaStream_t s);
+  void block_backward(int l, BwdWorkspace& k, bool ffn_grad, cudaStream_t s);
 
   std::unordered_map<std::string, Slot> slots;
   DevBuf w16, w32, ws, sio, bad, attn_split;

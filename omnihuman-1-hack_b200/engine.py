@@ -270,6 +270,64 @@ class DitEngine:
                                     int(n_rows)))
         return self._tap
 
+    # ------------------------------------------------------------------ F1: training step (distilled_trainer.py:268-301)
+    def train_forward(self, x, t, context, seq_len):
+        """`WanModel.forward` for items of ONE latent grid, keeping what `backward` needs (b200dit_train_forward):
+        the residual stream at every block boundary, as the reference's per-block checkpointing does
+        (model.py:544-548).  t2v only (no `y` / `clip_fea`)."""
+        xs, _, ctx, _ = self._prep_items(x, context, None, None)
+        n = len(xs)
+        assert n >= 1 and all(u.shape == xs[0].shape for u in xs), "train_forward takes items of one latent grid"
+        if n > 1 and (xs[0].shape[1] * (xs[0].shape[2] // 2) * (xs[0].shape[3] // 2)) % 8 != 0:
+            raise B200Error("co-batched training items need a token count that is a multiple of 8; call once per item")
+        tt = self._t_tensor(t, n)
+        _, F, H, W = xs[0].shape
+        outs = [torch.empty((self.cfg["out_dim"], F, H, W), dtype=torch.float32, device=self.device) for _ in xs]
+        with torch.cuda.device(self.device):
+            check(lib().b200dit_train_forward(
+                self._h, n, ptr_array([u.data_ptr() for u in xs]), C.c_void_p(tt.data_ptr()),
+                ptr_array([c.data_ptr() for c in ctx]), int_array([c.shape[0] for c in ctx]), _DT[ctx[0].dtype],
+                F, H, W, int(seq_len) if seq_len is not None else 0, ptr_array([o.data_ptr() for o in outs]),
+                _stream_ptr()))
+        self._train_refs = (xs, tt, ctx)                  # inputs stay alive until the backward has run
+        self._train_seq = getattr(self, "_train_seq", 0) + 1
+        return outs
+
+    def backward(self, douts, loss_scale=None, ffn_grad_blocks=11, want_dx=True):
+        """`loss.backward()` through the latest `train_forward` (b200dit_backward).  douts: d loss / d out per item.
+        Parameter gradients accumulate inside the engine (`read_grad`, `zero_grad`); returns d loss / d x per item
+        (or None).  `ffn_grad_blocks=11` reproduces the reference, whose blocks with block_idx > 10 run their FFN
+        under no_grad (model.py:318-325); None differentiates every FFN.  `loss_scale=None` picks a power of two
+        that puts max|dout| near 256 (the contractions carry fp16 operands, like the reference under its
+        GradScaler, distilled_trainer.py:88,301; the stored gradients are unscaled); one device->host read."""
+        ds = [d.to(self.device, torch.float32).contiguous() for d in douts]
+        if loss_scale is None:
+            amax = float(torch.stack([d.abs().max() for d in ds]).max())
+            loss_scale = 1.0 if not (amax > 0.0 and amax < float("inf")) else 2.0 ** int(torch.floor(torch.log2(torch.tensor(256.0 / amax))))
+        dxs = [torch.empty_like(u) for u in self._train_refs[0]] if want_dx else None
+        with torch.cuda.device(self.device):
+            check(lib().b200dit_backward(
+                self._h, ptr_array([d.data_ptr() for d in ds]), float(loss_scale),
+                -1 if ffn_grad_blocks is None else int(ffn_grad_blocks),
+                ptr_array([u.data_ptr() for u in dxs]) if want_dx else None, _stream_ptr()))
+        return dxs
+
+    def zero_grad(self):
+        with torch.cuda.device(self.device):
+            check(lib().b200dit_zero_grad(self._h, _stream_ptr()))
+
+    def read_grad(self, name, shape, out=None, accumulate=False):
+        """Gradient of the parameter stored under the reference key `name` (fp32), b200dit_read_grad."""
+        scale = 1.0
+        if out is None:
+            out = torch.empty(tuple(shape), dtype=torch.float32, device=self.device)
+            accumulate = False
+        assert out.is_contiguous() and out.dtype == torch.float32 and out.device == self.device
+        with torch.cuda.device(self.device):
+            check(lib().b200dit_read_grad(self._h, name.encode(), C.c_void_p(out.data_ptr()), out.numel(), scale,
+                                          int(bool(accumulate)), _stream_ptr()))
+        return out
+
     @property
     def last_flops(self):
         return float(lib().b200dit_last_flops(self._h))

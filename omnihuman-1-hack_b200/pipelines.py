@@ -9,6 +9,8 @@ the callers either side of the DiT forward).  Host logic only: every tensor oper
                          that stand in for the audio-token and pose-stack streams
   teacher_student_item() APT stage-1 item (seaweed_apt/generate.py:205-229 + distilled_trainer.py:262-289): teacher
                          cond + uncond at t = 999, v_teacher = u + 7.5 (c - u), student at t = 1000, MSE
+  student_step()         the APT stage-1 training step (distilled_trainer.py:241-301): student forward at t = 1000,
+                         MSE against the cached v_teacher, backward -- forward AND backward on the engine
   generate_video()       sample() + WanVAE.decode (text2video.py:258-259)
 """
 import torch
@@ -111,9 +113,34 @@ def teacher_student_item(engine, noise, context, context_null, guide_scale=7.5, 
         v = engine.forward_cfg([x], t, [context], [context_null], seq_len, guide_scale)[0]
         s = student_engine.forward([x], torch.tensor([t_student], device=engine.device), [context], seq_len)[0]
         return v, s, torch.mean((s - v) ** 2)
-    v_teacher = u + guide_scale * (c - u)                                        # generate.py:229
-    loss = torch.mean((s - v_teacher) ** 2)                                      # distilled_trainer.py:289
+    from .solvers import _lincomb
+    g = float(guide_scale)                                                       # one fused launch: u + g (c - u) and s - v
+    v_teacher, diff = _lincomb([c, u, s], [[g, 1.0 - g, 0.0], [-g, g - 1.0, 1.0]], c)      # generate.py:229
+    loss = torch.mean(diff * diff)                                               # distilled_trainer.py:289
     return v_teacher, s, loss
+
+
+def student_step(engine, noises, contexts, v_teachers, t_student=1000.0, seq_len=1560, ffn_grad_blocks=11,
+                 grad_accum=1):
+    """`training_step` of distilled_trainer.py:241-301 on the engine: v = student(noise, t = num_train_timesteps,
+    context) (:265-278), loss = mse(v, v_teacher) / gradient_accumulation_steps (:289), loss.backward() (:301).
+    The items (one latent grid) are co-batched; d loss / d v = 2 (v - v_teacher) / numel is one fused launch.
+    Parameter gradients ACCUMULATE in the engine (`engine.read_grad`, `engine.zero_grad`).  Returns the per-item
+    losses (device tensor, un-divided like the `loss_value` the reference logs at :304)."""
+    from .solvers import _lincomb
+    xs = [u.to(engine.device, torch.float32) for u in noises]
+    n = len(xs)
+    t = torch.full((n,), float(t_student), device=engine.device)
+    outs = engine.train_forward(xs, t, contexts, seq_len)
+    numel = outs[0].numel()
+    c = 2.0 / (numel * n * grad_accum)            # F.mse_loss over the [n, 16, T, h, w] batch: mean over all elements
+    douts, losses = [], []
+    for o, v in zip(outs, v_teachers):
+        d = _lincomb([o, v.to(engine.device, torch.float32)], [[c, -c]], o)[0]
+        douts.append(d)
+        losses.append((d * d).sum() * (numel * n * grad_accum / 2.0) ** 2 / numel)
+    engine.backward(douts, ffn_grad_blocks=ffn_grad_blocks, want_dx=False)
+    return torch.stack(losses)
 
 
 @torch.no_grad()

@@ -7,9 +7,11 @@ does the same for `WanModel.forward` (model.py:502) and `install_vae` for `WanVA
 distilled_trainer.py:273-278, eval_ema.py:124,140 -- keep calling `model(x, t=..., context=...,
 seq_len=...)` / `vae.decode(zs)` unchanged.
 
-The engine is inference-only: when autograd is recording and any input or parameter requires a
-gradient, the call falls through to the ORIGINAL reference forward (the unmodified PyTorch path,
-not a CPU fallback) -- SURVEY.md section 8b "Autograd".
+Autograd: when autograd is recording and an input or parameter requires a
+gradient, a t2v call (the student step of seaweed_apt/distilled_trainer.py:268-301) becomes one autograd node per
+latent grid whose backward runs on the engine (`autograd.dit_forward`); calls the engine's backward does not cover
+(`y` / `clip_fea`, contexts that require gradients) fall through to the ORIGINAL reference forward -- the
+unmodified PyTorch path, not a CPU fallback.
 """
 import math
 import random
@@ -18,6 +20,7 @@ import types
 
 import torch
 
+from . import autograd as b200_autograd
 from . import pipelines
 from .engine import DitEngine, VaeEngine
 
@@ -42,8 +45,11 @@ def _weights_signature(model):
     return ver, ptr
 
 
-def install(model, device=None, engine=None):
+def install(model, device=None, engine=None, ffn_grad_blocks=11):
     """Routes `model.forward` through a DitEngine built from the module's own weights.
+
+    Under autograd the backward runs on the engine too; `ffn_grad_blocks=11` reproduces the reference's blocks with
+    block_idx > 10, whose FFN runs under no_grad (model.py:318-325), None differentiates every FFN.
 
     The engine holds a SNAPSHOT of the weights (fp16 GEMM operands repacked on the device).  The reference calls
     the generator under `torch.no_grad()` while it is being trained (seaweed_apt/apt_trainer.py:118-119,254), so
@@ -55,13 +61,18 @@ def install(model, device=None, engine=None):
 
     def forward(self, x, t, context, seq_len, clip_fea=None, y=None):
         xs = list(x) if not isinstance(x, (list, tuple)) else x
-        if _needs_grad(self, xs):
+        grad = _needs_grad(self, xs)
+        if grad and (not b200_autograd.supports(eng, clip_fea, y)
+                     or any(getattr(c, "requires_grad", False) for c in context)):
             return original(x, t, context, seq_len, clip_fea=clip_fea, y=y)
         sig = _weights_signature(self)
         if sig != state["sig"]:
             eng.load_state_dict(self.state_dict())
             state["sig"] = sig
             self._b200_reloads = getattr(self, "_b200_reloads", 0) + 1
+        if grad:
+            return b200_autograd.dit_forward(eng, list(self.named_parameters()), xs, t, context, seq_len,
+                                             ffn_grad_blocks=ffn_grad_blocks)
         return eng.forward(xs, t, context, seq_len, clip_fea=clip_fea, y=y)
 
     model._b200_original_forward = original

@@ -163,13 +163,16 @@ def img_embed(sd, clip_fea):
     return F.layer_norm(x, (x.shape[-1],), sd[p + "4.weight"], sd[p + "4.bias"], 1e-5)
 
 
-def block_forward(sd, i, x, e0, grid, ctx, ctx_len, num_heads, n_img=0):
+def block_forward(sd, i, x, e0, grid, ctx, ctx_len, num_heads, n_img=0, ffn_no_grad=False):
     """model.py:279-330 for one item. x [L, dim] fp32, e0 [6, dim], ctx [n_img + text_len, dim].
 
     n_img > 0 selects the i2v cross-attention (model.py:204-230): the first n_img context rows form
     an un-masked second K/V stream whose attention output is summed before the `o` projection.
     ctx_len is the text key length handed to flash_attention (already incremented by n_img as the
     reference does at model.py:537 -- and clamped by the packed key count).
+    ffn_no_grad: the reference evaluates the FFN of blocks with block_idx > 10 under torch.no_grad()
+    (model.py:318-325; `y + 0 * ffn_input` keeps the graph connected with a zero gradient): same values,
+    the FFN is a constant of the backward (its weights get no gradient, the gate e[5] still does).
     """
     p = f"blocks.{i}."
     L, dim = x.shape
@@ -200,7 +203,13 @@ def block_forward(sd, i, x, e0, grid, ctx, ctx_len, num_heads, n_img=0):
     x = x + block_linear(sd, p + "cross_attn.o", ca.reshape(L, dim))                 # no gate
 
     u2 = layer_norm(x) * (1 + sc2) + sh2                                         # :314-315
-    y = block_linear(sd, p + "ffn.2", _r16(F.gelu(block_linear(sd, p + "ffn.0", u2), approximate="tanh")))
+    ffn = lambda v: block_linear(sd, p + "ffn.2", _r16(F.gelu(block_linear(sd, p + "ffn.0", v), approximate="tanh")))
+    if ffn_no_grad:
+        with torch.no_grad():
+            y = ffn(u2)
+        y = y + 0 * u2                                                           # :325
+    else:
+        y = ffn(u2)
     return x + y * g2                                                            # :328
 
 
@@ -216,7 +225,8 @@ def head_unpatchify(sd, x, e, grid, out_dim=16, patch=(1, 2, 2)):
 
 
 def dit_forward(sd, x, t, context, seq_len=None, clip_fea=None, y=None, num_heads=12,
-                num_layers=None, text_len=512, freq_dim=256, out_dim=16, taps=None, pad_rows=False):
+                num_layers=None, text_len=512, freq_dim=256, out_dim=16, taps=None, pad_rows=False,
+                ffn_no_grad_from=None):
     """WanModel.forward (model.py:502-563): x list of [C,F,H,W]; t [B]; context list of [Lc,text_dim].
 
     Returns list of fp32 [out_dim, F, H, W]. `taps` (optional dict) receives the fp32 residual
@@ -224,6 +234,8 @@ def dit_forward(sd, x, t, context, seq_len=None, clip_fea=None, y=None, num_head
     pad_rows: carry the reference's seq_len - L zero rows per item through the blocks (model.py:522: the padded rows
     are queries like any other -- un-rotated, model.py:66 -- but never keys, model.py:155); the outputs do not
     depend on them, the taps (block outputs [seq_len, dim], read by the APT discriminator) do.
+    ffn_no_grad_from: first block index whose FFN is evaluated under no_grad (the reference: 11, model.py:318;
+    only matters to autograd).
     """
     if num_layers is None:
         num_layers = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("blocks."))
@@ -249,7 +261,8 @@ def dit_forward(sd, x, t, context, seq_len=None, clip_fea=None, y=None, num_head
             n_img = img.shape[0]
             ctx_len = ctx_len + n_img
         for i in range(num_layers):
-            xb = block_forward(sd, i, xb, e0_all[b], grid, ctx, ctx_len, num_heads, n_img)
+            xb = block_forward(sd, i, xb, e0_all[b], grid, ctx, ctx_len, num_heads, n_img,
+                               ffn_no_grad=ffn_no_grad_from is not None and i >= ffn_no_grad_from)
             if taps is not None and i in taps:
                 taps[i] = (taps[i] or []) + [xb.clone()]
         outs.append(head_unpatchify(sd, xb, e_all[b], grid, out_dim))

@@ -44,17 +44,31 @@ def test_real_1p3b_architecture_names():
     assert abs(sum(want.values()) - 1.419e9) < 2e6
 
 
-def test_install_falls_through_under_autograd_on_real_wanmodel():
-    """wan_shim.install's dispatch on the real class without building an engine: under autograd the ORIGINAL forward
-    runs (distilled_trainer.py:268-301 trains through it); the weight signature moves with an in-place update."""
+def test_install_dispatch_under_autograd_on_real_wanmodel():
+    """wan_shim.install's dispatch on the real class without a GPU: under autograd a plain t2v call (the student step,
+    distilled_trainer.py:268-301) goes to the engine's autograd node; what the engine's backward does not cover
+    (contexts that require gradients, `y` / `clip_fea`) falls through to the ORIGINAL forward; the weight signature
+    moves with an in-place update."""
     import b200dit
     from b200dit import wan_shim
     M, _ = ref_loader.load_reference_modules()
     m = M.WanModel(model_type="t2v", use_checkpoint=False, **TINY).train()
 
-    class NoEngine:                                  # no GPU here: the engine path must not be taken
+    class Taken(Exception):
+        pass
+
+    class NoEngine:                                  # no GPU here: records which path the shim takes
+        cfg = dict(i2v=0, out_dim=16)
+        device = torch.device("cpu")
+
         def forward(self, *a, **k):
-            raise AssertionError("engine path taken under autograd")
+            raise AssertionError("inference path taken under autograd")
+
+        def _t_tensor(self, t, n):
+            return torch.as_tensor(t, dtype=torch.float32).reshape(-1)
+
+        def train_forward(self, *a, **k):
+            raise Taken()
 
         def load_state_dict(self, sd):
             self.reloaded = True
@@ -62,8 +76,10 @@ def test_install_falls_through_under_autograd_on_real_wanmodel():
     eng = NoEngine()
     b200dit.install(m, engine=eng)
     x = [torch.randn(16, 1, 4, 4)]
-    out = m(x, t=torch.tensor([500.0]), context=[torch.randn(5, 32)], seq_len=4)
-    assert out[0].shape == (16, 1, 4, 4) and out[0].requires_grad
+    with pytest.raises(Taken):
+        m(x, t=torch.tensor([500.0]), context=[torch.randn(5, 32)], seq_len=4)
+    out = m(x, t=torch.tensor([500.0]), context=[torch.randn(5, 32, requires_grad=True)], seq_len=4)
+    assert out[0].shape == (16, 1, 4, 4) and out[0].requires_grad        # the reference's own graph
     s0 = wan_shim._weights_signature(m)
     with torch.no_grad():
         next(m.parameters()).add_(1.0)

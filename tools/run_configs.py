@@ -40,6 +40,9 @@ def main():
                     help="config 5: one video per rank PAIR, cond / uncond forwards on the two ranks, one exchange per step")
     ap.add_argument("--pipe-decode", action="store_true",
                     help="config 5 with --cfg-parallel: the rank pair decodes its video together (time-chunked VAE decode)")
+    ap.add_argument("--train", action="store_true",
+                    help="config 4: the student training step (forward + backward on the engine, distilled_trainer.py:241-301)")
+    ap.add_argument("--batch", type=int, default=1, help="config 4 --train: items per training step (reference: 1)")
     ap.add_argument("--pair-split", action="store_true",
                     help="config 4: teacher cond / uncond of one item on a rank pair (one send per item)")
     a = ap.parse_args()
@@ -69,6 +72,34 @@ def main():
                 f"{a.steps} DPM++ steps, cfg 7.5 annealed", "n_gpus": world, "ms": ms,
                 "denoise_steps_per_s": a.steps / (ms / 1e3), "tflops": 2 * a.steps * (eng.last_flops / 2) / (ms / 1e3) / 1e12,
                 "finite": bool(torch.isfinite(out[0]).all())}
+    elif a.config == 4 and a.train:
+        # the student's training step: items i % world == rank, forward + backward per step of `batch` items;
+        # gradients accumulate in the engine (DDP's all-reduce of the 5.7 GB fp32 gradient is the trainer's, not timed)
+        eng = b200dit.DitEngine(**cfg, device=dev)
+        eng.load_state_dict(make_device_weights(cfg, 0, dev))
+        gi = torch.Generator().manual_seed(7)
+        noises = [torch.randn(16, 1, 60, 104, generator=gi).to(dev) for _ in range(a.items)]
+        ctxs = [torch.randn(512, 4096, generator=gi).to(dev) for _ in range(a.items)]
+        vts = [torch.randn(16, 1, 60, 104, generator=gi).to(dev) for _ in range(a.items)]
+        mine = list(range(rank, a.items, world))
+
+        def run(idx):
+            ls = []
+            eng.zero_grad()
+            for s0 in range(0, len(idx), a.batch):
+                part = idx[s0:s0 + a.batch]
+                ls.append(P.student_step(eng, [noises[i] for i in part], [ctxs[i] for i in part], [vts[i] for i in part]))
+            return torch.cat(ls)
+        run(mine[:a.batch])                                    # warm-up (workspaces, transposed weights)
+        with torch.no_grad():
+            _, ms_f = timed(lambda: [eng.forward([noises[i]], torch.tensor([1000.0], device=dev), [ctxs[i]], 1560) for i in mine])
+        ls, ms = timed(lambda: run(mine))
+        gn = float(eng.read_grad("blocks.0.self_attn.q.weight", (1536, 1536)).norm())
+        line = {"config": 4, "workload": f"{a.items} APT stage-1 student training steps (forward at t=1000 + MSE + backward, "
+                f"{a.batch} item(s) per step) on [16,1,60,104], FFN of blocks > 10 detached as in model.py:318-325, "
+                "items i % world == rank", "n_gpus": world, "ms": ms, "items_per_s": a.items / (ms / 1e3),
+                "forward_only_ms": ms_f, "fwd_bwd_over_fwd": ms / ms_f, "mean_loss": float(ls.mean()),
+                "grad_norm_blocks0_q": gn, "finite": bool(torch.isfinite(ls).all())}
     elif a.config == 4:
         eng = b200dit.DitEngine(**cfg, device=dev)
         eng.load_state_dict(make_device_weights(cfg, 0, dev))
