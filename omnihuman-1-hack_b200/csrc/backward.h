@@ -24,8 +24,11 @@ void bw_rms_rope_fwd(const __half* raw, long long ld, const float* gamma, const 
                      long long ldo, float* r_out, int M, int dim, float eps, cudaStream_t s);
 void bw_rms_rope_bwd(const float* dout, const __half* raw, long long ld, const float* r, const float* gamma, const float* cs,
                      int rows_per_item, float* dun, __half* draw, long long ldd, int M, int dim, cudaStream_t s);
-void bw_attn_softmax_bwd(const float* S, const float* dP, long long lds, int Lq, int Lk, int klen, float scale, __half* dS,
-                         long long ldk, __half* dST, __half* PT, long long ldq, cudaStream_t s);
+// softmax part of the attention backward for `heads` heads of one item: S, dP fp32 [heads][Lq128][lds] ->
+// dS fp16 [heads][Lq128][ldk], dS^T and P^T fp16 [heads][Lk128][ldq]; stat: [heads * Lq128] float4 scratch
+void bw_attn_softmax_bwd(const float* S, const float* dP, long long lds, int heads, int Lq, int Lq128, int Lk, int Lk128, int klen,
+                         float scale, float* stat, __half* dS, long long ldk, __half* dST, __half* PT, long long ldq,
+                         cudaStream_t s);
 void bw_unpatchify_bwd(ItemPtrs dout, int B, int F, int Hp, int Wp, int out_dim, float scale, __half* dy16, float* dy32,
                        int rows_per_item, cudaStream_t s);
 void bw_patchify_bwd(const float* dpatch, long long ld, int B, int C, int F, int H, int W, float scale, ItemPtrsMut dx,

@@ -19,9 +19,6 @@ inline int blocks_for(long long n, int block = 256) {
   long long b = (n + block - 1) / block;
   return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
 }
-__device__ __forceinline__ float ldv(const void* p, int dt, long long i) {
-  return dt == DT_F32 ? reinterpret_cast<const float*>(p)[i] : __half2float(reinterpret_cast<const __half*>(p)[i]);
-}
 
 // ---------------------------------------------------------------- LayerNorm backward (model.py:91-104)
 // u = xhat * a + b, xhat = (x - mean) rstd.  Given du: dx (+)= rstd (g - mean(g) - xhat mean(g xhat)), g = du * a.
@@ -59,34 +56,61 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x
 
 // ---------------------------------------------------------------- column sums, two stages, fixed order
 // part[(item * chunks + chunk) * dim + c] = sum over the chunk's rows of A[r, c] * B[r, c] * rs[r]
-constexpr int CS_ROWS = 64;
-__global__ void __launch_bounds__(128) colsum_stage1_kernel(const void* __restrict__ A, int a_dt, long long lda,
-                                                            const void* __restrict__ B, int b_dt, long long ldb,
-                                                            const float* __restrict__ rs, int rows_per_item, int dim,
-                                                            float* __restrict__ part, int chunks) {
-  const int c = blockIdx.x * 128 + threadIdx.x;
+// One thread per column PAIR (4- or 8-byte loads), CS_ROWS rows per block, four independent accumulators so the
+// loads of consecutive rows are in flight together.
+constexpr int CS_ROWS = 32;
+template <class TA>
+__device__ __forceinline__ float2 ld2(const TA* p, long long i);
+template <>
+__device__ __forceinline__ float2 ld2<float>(const float* p, long long i) { return *reinterpret_cast<const float2*>(p + i); }
+template <>
+__device__ __forceinline__ float2 ld2<__half>(const __half* p, long long i) {
+  return __half22float2(*reinterpret_cast<const __half2*>(p + i));
+}
+template <class TA, class TB, bool HAS_B>
+__global__ void __launch_bounds__(128) colsum_stage1_kernel(const TA* __restrict__ A, long long lda, const TB* __restrict__ B,
+                                                            long long ldb, const float* __restrict__ rs, int rows_per_item,
+                                                            int dim, float* __restrict__ part, int chunks) {
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
   if (c >= dim) return;
   const int chunk = blockIdx.y, item = blockIdx.z;
   const int r0 = chunk * CS_ROWS, r1 = min(r0 + CS_ROWS, rows_per_item);
-  float acc = 0.f;
+  float2 acc[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  const long long base = (long long)item * rows_per_item;
+#pragma unroll 4
   for (int r = r0; r < r1; ++r) {
-    const long long row = (long long)item * rows_per_item + r;
-    float v = ldv(A, a_dt, row * lda + c);
-    if (B) v *= ldv(B, b_dt, row * ldb + c);
-    if (rs) v *= rs[row];
-    acc += v;
+    const long long row = base + r;
+    float2 v = ld2<TA>(A, row * lda + c);
+    if (HAS_B) { const float2 w = ld2<TB>(B, row * ldb + c); v.x *= w.x; v.y *= w.y; }
+    if (rs) { const float f = rs[row]; v.x *= f; v.y *= f; }
+    acc[(r - r0) & 3].x += v.x; acc[(r - r0) & 3].y += v.y;
   }
-  part[((long long)item * chunks + chunk) * dim + c] = acc;
+  float* o = part + ((long long)item * chunks + chunk) * dim + c;
+  o[0] = (acc[0].x + acc[1].x) + (acc[2].x + acc[3].x);
+  o[1] = (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y);
 }
-__global__ void colsum_stage2_kernel(const float* __restrict__ part, int chunks, int dim, int items, float* __restrict__ out,
-                                     long long out_item_stride, float scale, int accumulate) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= (long long)items * dim) return;
-  const int c = i % dim, item = i / dim;
+// stage 2: block = 32 columns x 8 chunk lanes; lane k adds chunks k, k + 8, ... in order, the 8 partial sums are
+// added in a fixed order too
+__global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* __restrict__ part, int chunks, int dim, int items,
+                                                            float* __restrict__ out, long long out_item_stride, float scale,
+                                                            int accumulate) {
+  __shared__ float sh[8][33];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane, item = blockIdx.y;
   float acc = 0.f;
-  for (int k = 0; k < chunks; ++k) acc += part[((long long)item * chunks + k) * dim + c];
-  float* o = out + (long long)item * out_item_stride + c;
-  *o = accumulate ? *o + scale * acc : scale * acc;
+  if (c < dim) {
+    const float* p = part + (long long)item * chunks * dim + c;
+    for (int k = wy; k < chunks; k += 8) acc += p[(long long)k * dim];
+  }
+  sh[wy][lane] = acc;
+  __syncthreads();
+  if (wy == 0 && c < dim) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][lane];
+    float* o = out + (long long)item * out_item_stride + c;
+    *o = accumulate ? *o + scale * t : scale * t;
+  }
 }
 
 // ---------------------------------------------------------------- gated residual pieces (model.py:296,328)
@@ -197,17 +221,19 @@ __global__ void __launch_bounds__(256) rms_rope_bwd_kernel(const float* __restri
   }
 }
 
-// ---------------------------------------------------------------- attention backward, one (item, head): softmax part
-// S = q k^T (unscaled), dP = dO v^T.  P = softmax(scale S) over keys < klen, D = sum_j P dP,
-// dS = scale P (dP - D).  Writes dS [Lq, ldk], dS^T [Lk, ldq] and P^T [Lk, ldq] as fp16 GEMM operands.
-__global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dP, long long lds,
-                                                               int Lq, int Lk, int klen, float scale, __half* __restrict__ dS,
-                                                               long long ldk, __half* __restrict__ dST, __half* __restrict__ PT,
-                                                               long long ldq) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= Lq) return;
-  const float* sr = S + (long long)row * lds;
-  const float* pr = dP + (long long)row * lds;
+// ---------------------------------------------------------------- attention backward: softmax part, all heads of one item
+// S = q k^T (unscaled) and dP = dO v^T arrive as fp32 [heads][Lq128][lds] from two batched GEMMs.
+// P = softmax(scale S) over keys < klen, D = sum_j P dP, dS = scale P (dP - D).
+// Pass 1 (one warp per row): row maximum, 1 / sum exp and D.
+__global__ void __launch_bounds__(256) attn_rowstat_kernel(const float* __restrict__ S, const float* __restrict__ dP, long long lds,
+                                                           int Lq, int Lq128, int heads, int klen, float scale,
+                                                           float4* __restrict__ stat) {
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (gw >= heads * Lq) return;
+  const int h = gw / Lq, r = gw - h * Lq;
+  const long long row = (long long)h * Lq128 + r;
+  const float* sr = S + row * lds;
+  const float* pr = dP + row * lds;
   float mx = -INFINITY;
   for (int j = lane; j < klen; j += 32) mx = fmaxf(mx, sr[j]);
 #pragma unroll
@@ -218,16 +244,49 @@ __global__ void __launch_bounds__(256) attn_softmax_bwd_kernel(const float* __re
     l += e; dsum += e * pr[j];
   }
   l = wsum(l); dsum = wsum(dsum);
-  const float inv = 1.0f / l, D = dsum * inv;
-  for (int j = lane; j < Lk; j += 32) {
-    float p = 0.f, ds = 0.f;
-    if (j < klen) {
-      p = __expf((sr[j] - mx) * scale) * inv;
-      ds = scale * p * (pr[j] - D);
+  if (lane == 0) stat[row] = make_float4(mx, 1.0f / l, dsum / l, 0.f);
+}
+// Pass 2 (64 x 64 tiles): writes dS [heads][Lq128][ldk] row-major and, through a shared-memory transpose,
+// dS^T and P^T [heads][Lk128][ldq] -- the fp16 operands of dQ = dS K, dK = dS^T Q, dV = P^T dO.
+__global__ void __launch_bounds__(256) attn_ds_tile_kernel(const float* __restrict__ S, const float* __restrict__ dP, long long lds,
+                                                           const float4* __restrict__ stat, int Lq, int Lq128, int Lk, int Lk128,
+                                                           int klen, float scale, __half* __restrict__ dS, long long ldk,
+                                                           __half* __restrict__ dST, __half* __restrict__ PT, long long ldq) {
+  __shared__ __half tds[64][66], tp[64][66];
+  const int h = blockIdx.z, q0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < 64; i += 8) {
+    const int q = q0 + i;
+    float2 pv = make_float2(0.f, 0.f), dv = make_float2(0.f, 0.f);
+    const int j = k0 + 2 * lane;
+    if (q < Lq) {
+      const long long row = (long long)h * Lq128 + q;
+      const float4 st = stat[row];
+      const float* sr = S + row * lds;
+      const float* pr = dP + row * lds;
+      if (j < klen) { pv.x = __expf((sr[j] - st.x) * scale) * st.y; dv.x = scale * pv.x * (pr[j] - st.z); }
+      if (j + 1 < klen) { pv.y = __expf((sr[j + 1] - st.x) * scale) * st.y; dv.y = scale * pv.y * (pr[j + 1] - st.z); }
+      if (j + 1 < Lk) *reinterpret_cast<__half2*>(dS + row * ldk + j) = __floats2half2_rn(dv.x, dv.y);
+      else if (j < Lk) dS[row * ldk + j] = __float2half_rn(dv.x);
     }
-    dS[(long long)row * ldk + j] = __float2half_rn(ds);
-    dST[(long long)j * ldq + row] = __float2half_rn(ds);
-    PT[(long long)j * ldq + row] = __float2half_rn(p);
+    tds[i][2 * lane] = __float2half_rn(dv.x); tds[i][2 * lane + 1] = __float2half_rn(dv.y);
+    tp[i][2 * lane] = __float2half_rn(pv.x); tp[i][2 * lane + 1] = __float2half_rn(pv.y);
+  }
+  __syncthreads();
+  for (int i = warp; i < 64; i += 8) {
+    const int j = k0 + i;
+    if (j >= Lk) continue;
+    const long long row = (long long)h * Lk128 + j;
+    const int q = q0 + 2 * lane;
+    const __half2 a = __halves2half2(tds[2 * lane][i], tds[2 * lane + 1][i]);
+    const __half2 b = __halves2half2(tp[2 * lane][i], tp[2 * lane + 1][i]);
+    if (q + 1 < Lq) {
+      *reinterpret_cast<__half2*>(dST + row * ldq + q) = a;
+      *reinterpret_cast<__half2*>(PT + row * ldq + q) = b;
+    } else if (q < Lq) {
+      dST[row * ldq + q] = __low2half(a);
+      PT[row * ldq + q] = __low2half(b);
+    }
   }
 }
 
@@ -286,16 +345,26 @@ __global__ void __launch_bounds__(256) small_fwd_kernel(const float* __restrict_
   acc = wsum(acc);
   if (lane == 0) out[(long long)b * N + n] = acc + (bias ? bias[n] : 0.f);
 }
-// din[b, k] = act'(in[b, k]) * sum_n dout[b, n] W[n, k]     (thread per (b, k): coalesced over k)
-__global__ void small_dx_kernel(const float* __restrict__ dout, const float* __restrict__ W, const float* __restrict__ in_pre,
-                                float* __restrict__ din, int B, int K, int N, int silu_in, int accumulate) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= (long long)B * K) return;
-  const int k = i % K, b = i / K;
+// din[b, k] = act'(in[b, k]) * sum_n dout[b, n] W[n, k].  Block = 32 columns k x 8 row groups: every warp walks a
+// strided share of the N rows with coalesced 128-byte reads of W, the 8 partial sums meet in shared memory.
+__global__ void __launch_bounds__(256) small_dx_kernel(const float* __restrict__ dout, const float* __restrict__ W, const float* __restrict__ in_pre,
+                                                       float* __restrict__ din, int B, int K, int N, int silu_in, int accumulate) {
+  __shared__ float part[8][33];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane, b = blockIdx.y;
   float acc = 0.f;
-  for (int n = 0; n < N; ++n) acc += dout[(long long)b * N + n] * W[(long long)n * K + k];
-  if (silu_in) acc *= silu_grad_f(in_pre[i]);
-  din[i] = accumulate ? din[i] + acc : acc;
+  if (k < K)
+    for (int n = wy; n < N; n += 8) acc += dout[(long long)b * N + n] * W[(long long)n * K + k];
+  part[wy][lane] = acc;
+  __syncthreads();
+  if (wy == 0 && k < K) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][lane];
+    const long long o = (long long)b * K + k;
+    if (silu_in) t *= silu_grad_f(in_pre[o]);
+    din[o] = accumulate ? din[o] + t : t;
+  }
 }
 // dW[n, k] += sum_b dout[b, n] act(in[b, k]);  db[n] += sum_b dout[b, n]
 __global__ void small_dw_kernel(const float* __restrict__ dout, const float* __restrict__ in, float* __restrict__ dW,
@@ -361,12 +430,24 @@ void bw_ln_bwd(const float* x, const float* du, const float* a, long long a_item
 void bw_colsum(const void* A, int a_dt, long long lda, const void* B, int b_dt, long long ldb, const float* rs, int items,
                int rows_per_item, int dim, float* out, long long out_item_stride, float scale, bool accumulate, float* scratch,
                cudaStream_t s) {
+  B2_CHECK(dim % 2 == 0 && lda % 2 == 0 && (B == nullptr || ldb % 2 == 0), "column sums work on column pairs");
   const int chunks = (rows_per_item + CS_ROWS - 1) / CS_ROWS;
-  colsum_stage1_kernel<<<dim3((dim + 127) / 128, chunks, items), 128, 0, s>>>(A, a_dt, lda, B, b_dt, ldb, rs, rows_per_item, dim,
-                                                                             scratch, chunks);
+  const dim3 grid((dim / 2 + 127) / 128, chunks, items);
+  const float* Af = reinterpret_cast<const float*>(A); const __half* Ah = reinterpret_cast<const __half*>(A);
+  const float* Bf = reinterpret_cast<const float*>(B); const __half* Bh = reinterpret_cast<const __half*>(B);
+  if (B == nullptr) {
+    if (a_dt == DT_F32) colsum_stage1_kernel<float, float, false><<<grid, 128, 0, s>>>(Af, lda, nullptr, 0, rs, rows_per_item, dim, scratch, chunks);
+    else colsum_stage1_kernel<__half, float, false><<<grid, 128, 0, s>>>(Ah, lda, nullptr, 0, rs, rows_per_item, dim, scratch, chunks);
+  } else if (a_dt == DT_F32 && b_dt == DT_F32) {
+    colsum_stage1_kernel<float, float, true><<<grid, 128, 0, s>>>(Af, lda, Bf, ldb, rs, rows_per_item, dim, scratch, chunks);
+  } else if (a_dt == DT_F32 && b_dt == DT_F16) {
+    colsum_stage1_kernel<float, __half, true><<<grid, 128, 0, s>>>(Af, lda, Bh, ldb, rs, rows_per_item, dim, scratch, chunks);
+  } else {
+    fail("bw_colsum: unsupported operand types %d x %d", a_dt, b_dt);
+  }
   B2_AFTER();
-  colsum_stage2_kernel<<<(int)(((long long)items * dim + 255) / 256), 256, 0, s>>>(scratch, chunks, dim, items, out, out_item_stride,
-                                                                                 scale, accumulate ? 1 : 0);
+  colsum_stage2_kernel<<<dim3((dim + 31) / 32, items), 256, 0, s>>>(scratch, chunks, dim, items, out, out_item_stride, scale,
+                                                                    accumulate ? 1 : 0);
   B2_AFTER();
 }
 size_t bw_colsum_scratch_bytes(int items, int rows_per_item, int dim) {
@@ -415,9 +496,14 @@ void bw_rms_rope_bwd(const float* dout, const __half* raw, long long ld, const f
                                                   draw, ldd, M, dim);
   B2_AFTER();
 }
-void bw_attn_softmax_bwd(const float* S, const float* dP, long long lds, int Lq, int Lk, int klen, float scale, __half* dS,
-                         long long ldk, __half* dST, __half* PT, long long ldq, cudaStream_t s) {
-  attn_softmax_bwd_kernel<<<(Lq + 7) / 8, 256, 0, s>>>(S, dP, lds, Lq, Lk, klen, scale, dS, ldk, dST, PT, ldq);
+void bw_attn_softmax_bwd(const float* S, const float* dP, long long lds, int heads, int Lq, int Lq128, int Lk, int Lk128, int klen,
+                         float scale, float* stat, __half* dS, long long ldk, __half* dST, __half* PT, long long ldq,
+                         cudaStream_t s) {
+  B2_CHECK(ldk % 2 == 0 && ldq % 2 == 0 && lds % 2 == 0, "attention backward: odd leading dimension");
+  attn_rowstat_kernel<<<(heads * Lq + 7) / 8, 256, 0, s>>>(S, dP, lds, Lq, Lq128, heads, klen, scale, reinterpret_cast<float4*>(stat));
+  B2_AFTER();
+  attn_ds_tile_kernel<<<dim3((Lk + 63) / 64, (Lq + 63) / 64, heads), 256, 0, s>>>(
+      S, dP, lds, reinterpret_cast<const float4*>(stat), Lq, Lq128, Lk, Lk128, klen, scale, dS, ldk, dST, PT, ldq);
   B2_AFTER();
 }
 void bw_unpatchify_bwd(ItemPtrs dout, int B, int F, int Hp, int Wp, int out_dim, float scale, __half* dy16, float* dy32,
@@ -439,7 +525,7 @@ void bw_small_fwd(const float* in, const float* W, const float* bias, float* out
 void bw_small_bwd(const float* dout, const float* W, const float* in, float* din, float* dW, float* db, int B, int K, int N,
                   bool silu_in, bool accumulate_din, float wscale, cudaStream_t s) {
   if (din != nullptr) {
-    small_dx_kernel<<<(int)(((long long)B * K + 255) / 256), 256, 0, s>>>(dout, W, in, din, B, K, N, silu_in ? 1 : 0, accumulate_din ? 1 : 0);
+    small_dx_kernel<<<dim3((K + 31) / 32, B), 256, 0, s>>>(dout, W, in, din, B, K, N, silu_in ? 1 : 0, accumulate_din ? 1 : 0);
     B2_AFTER();
   }
   small_dw_kernel<<<(int)(((long long)N * K + 255) / 256), 256, 0, s>>>(dout, in, dW, db, B, K, N, silu_in ? 1 : 0, wscale);

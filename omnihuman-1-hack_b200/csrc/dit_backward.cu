@@ -62,8 +62,10 @@ struct DitEngine::BwdWorkspace {
   float *rq, *rk, *rcq, *rck, *y1, *x1, *x2, *y3;
   // adjoint
   float *g, *du, *dq, *dk, *dun, *rstd, *mr, *dctx_e, *dtab, *de0, *de, *dh0, *h0pre, *dsc, *dsh, *colsum_ws, *dy32, *dpatch;
-  __half *dy, *datt, *dqkv, *dkv, *dhid, *dpre, *tA, *tB, *qT, *kT, *dOT, *dS, *dST, *PT, *cpre;
-  float *S, *dP;
+  __half *dy, *datt, *dqkv, *dkv, *dhid, *dpre, *tA, *tB, *qT, *kT, *dOT, *cpre;
+  float *S;                   // scratch of the attention adjoint: S | dP | dS | dS^T | P^T for a group of heads
+  size_t attn_scratch_bytes;
+  float* attn_stat;           // [heads * Lq128] float4 row statistics
   size_t colsum_bytes;
   float inv; float* inv_vec; long long inv_n;
 };
@@ -130,6 +132,17 @@ void DitEngine::ensure_transposed_weights(cudaStream_t s) {
   w16t_valid = true;
 }
 
+// scratch of the attention adjoint (see attention_backward): every head of one item when that stays under 8 GB
+// (0.4 GB at L = 1560), else as many heads as 16 GB hold, at least one (15 GB at L = 32 760)
+static size_t attn_scratch_bytes(int L, int TL, int heads) {
+  const size_t Lq128 = ((size_t)L + 127) & ~size_t(127);
+  const size_t Lk = L > TL ? L : TL, Lk128 = (Lk + 127) & ~size_t(127);
+  const size_t per_head = Lq128 * ((Lk + 3) & ~size_t(3)) * 8 + Lq128 * r8(Lk) * 2 + Lk128 * r8(L) * 4;
+  size_t n = heads;
+  while (n > 1 && n * per_head > (size_t(8) << 30)) --n;
+  return n * per_head + 4096;
+}
+
 void DitEngine::ensure_bwd_workspace(int B, int L) {
   if (bws_buf && B <= bws_B && L <= bws_L) return;
   B2_CUDA(cudaDeviceSynchronize());
@@ -145,7 +158,8 @@ void DitEngine::ensure_bwd_workspace(int B, int L) {
   bytes += Cr * d * 2 * 8 + Cr * d * 4 * 4;
   bytes += 2 * d * Tp * 2 + (M + Cr) * 4 * 8;
   bytes += (3 * d > f ? 3 * d : f) * Tp * 2 + (f > (size_t)cfg.text_dim ? f : (size_t)cfg.text_dim) * Tp * 2 + 3 * d * Tp * 2;
-  bytes += Lq * Lk * (4 * 2 + 2 * 3) + 64 * 4096;
+  bytes += attn_scratch_bytes(bws_L, (int)TL, cfg.num_heads) + (size_t)cfg.num_heads * (Lq + 128) * 16 + 64 * 4096;
+  (void)Lk;
   bytes += (size_t)cfg.num_layers * bws_B * 6 * d * 4 + bws_B * 16 * d * 4 + M * 64 * 8 + M * cfg.in_dim * 4 * 4 + M * 16;
   bytes += bw_colsum_scratch_bytes(bws_B, bws_L > (int)TL ? bws_L : (int)TL, (int)(f > 3 * d ? f : 3 * d)) * 2;
   bytes += 256 * 128;
@@ -238,22 +252,56 @@ void attention_backward(const Ctx& c, const AttnBwdGeom& a, DitEngine::BwdWorksp
   launch_transpose_h(a.q, a.ldq, k.qT, Mqp, Mq, a.dim, c.s);
   launch_transpose_h(a.k, a.ldk, k.kT, Mkp, Mk, a.dim, c.s);
   launch_transpose_h(a.dO, a.dim, k.dOT, Mqp, Mq, a.dim, c.s);
+  const int Lq128 = (a.Lq + 127) & ~127, Lk128 = (a.Lk + 127) & ~127;
   const long long lds = (a.Lk + 3) & ~3, ldk8 = r8(a.Lk), ldq8 = r8(a.Lq);
+  // heads per round: as many as the scratch holds (all 12 at L = 1560; one at a time at L = 32 760)
+  const size_t per_head = (size_t)Lq128 * lds * 8 + (size_t)Lq128 * ldk8 * 2 + (size_t)Lk128 * ldq8 * 4;
+  int hb = (int)(k.attn_scratch_bytes / per_head);
+  B2_CHECK(hb >= 1, "attention backward: scratch holds no head (%zu bytes needed)", per_head);
+  if (hb > a.heads) hb = a.heads;
+  float* S = k.S;
+  float* dP = S + (size_t)hb * Lq128 * lds;
+  __half* dS = reinterpret_cast<__half*>(dP + (size_t)hb * Lq128 * lds);
+  __half* dST = dS + (size_t)hb * Lq128 * ldk8;
+  __half* PT = dST + (size_t)hb * Lk128 * ldq8;
+  const long long wide = (long long)a.heads * 128;
   for (int it = 0; it < a.items; ++it)
-    for (int h = 0; h < a.heads; ++h) {
-      const __half* qh = a.q + (size_t)it * a.Lq * a.ldq + h * 128;
-      const __half* kh = a.k + (size_t)it * a.Lk * a.ldk + h * 128;
-      const __half* vh = a.v + (size_t)it * a.Lk * a.ldv + h * 128;
-      const __half* oh = a.dO + (size_t)it * a.Lq * a.dim + h * 128;
-      gemm_f32(qh, a.ldq, kh, a.ldk, a.Lq, a.Lk, 128, k.S, lds, nullptr, false, c.num_sms, c.s);
-      gemm_f32(oh, a.dim, vh, a.ldv, a.Lq, a.Lk, 128, k.dP, lds, nullptr, false, c.num_sms, c.s);
-      bw_attn_softmax_bwd(k.S, k.dP, lds, a.Lq, a.Lk, a.klen[it], a.scale, k.dS, ldk8, k.dST, k.PT, ldq8, c.s);
-      gemm_f32(k.dS, ldk8, k.kT + (size_t)h * 128 * Mkp + (size_t)it * a.Lk, Mkp, a.Lq, 128, a.Lk,
-               a.dq + (size_t)it * a.Lq * a.dim + h * 128, a.dim, nullptr, false, c.num_sms, c.s);
-      gemm_f32(k.dST, ldq8, k.qT + (size_t)h * 128 * Mqp + (size_t)it * a.Lq, Mqp, a.Lk, 128, a.Lq,
-               a.dk + (size_t)it * a.Lk * a.dim + h * 128, a.dim, nullptr, false, c.num_sms, c.s);
-      gemm_f16(k.PT, ldq8, k.dOT + (size_t)h * 128 * Mqp + (size_t)it * a.Lq, Mqp, a.Lk, 128, a.Lq,
-               a.dv + (size_t)it * a.Lk * a.lddv + h * 128, a.lddv, nullptr, c.num_sms, c.s);
+    for (int h0 = 0; h0 < a.heads; h0 += hb) {
+      const int nh = a.heads - h0 < hb ? a.heads - h0 : hb;
+      const __half* qi = a.q + (size_t)it * a.Lq * a.ldq + h0 * 128;
+      const __half* ki = a.k + (size_t)it * a.Lk * a.ldk + h0 * 128;
+      const __half* vi = a.v + (size_t)it * a.Lk * a.ldv + h0 * 128;
+      const __half* oi = a.dO + (size_t)it * a.Lq * a.dim + h0 * 128;
+      {   // S_h = q_h k_h^T and dP_h = dO_h v_h^T, fp32 [nh][Lq128][lds]
+        GemmParams p{};
+        p.M = a.Lq; p.N = a.Lk; p.K = 128; p.batches = nh; p.a_k0 = 128; p.b_k0 = 128; p.o_r0 = Lq128;
+        p.o_rows = (long long)nh * Lq128; p.o_cols = a.Lk; p.ld_f = lds;
+        p.out_f = S;
+        gemm_batched(EPI_F32, qi, a.ldq, a.Lq, wide - h0 * 128, ki, a.ldk, a.Lk, wide - h0 * 128, p, c.num_sms, c.s);
+        p.out_f = dP;
+        gemm_batched(EPI_F32, oi, a.dim, a.Lq, wide - h0 * 128, vi, a.ldv, a.Lk, wide - h0 * 128, p, c.num_sms, c.s);
+      }
+      bw_attn_softmax_bwd(S, dP, lds, nh, a.Lq, Lq128, a.Lk, Lk128, a.klen[it], a.scale, k.attn_stat, dS, ldk8, dST, PT, ldq8, c.s);
+      {   // dQ_h = dS_h k_h : W operand = rows [h 128, h 128 + 128) of k^T, columns of this item
+        GemmParams p{};
+        p.M = a.Lq; p.N = 128; p.K = a.Lk; p.batches = nh; p.a_m0 = Lq128; p.b_n0 = 128; p.o_c0 = 128;
+        p.o_rows = a.Lq; p.o_cols = (long long)nh * 128; p.ld_f = a.dim;
+        p.out_f = a.dq + (size_t)it * a.Lq * a.dim + h0 * 128;
+        gemm_batched(EPI_F32, dS, ldk8, (long long)nh * Lq128, a.Lk, k.kT + (size_t)h0 * 128 * Mkp + (size_t)it * a.Lk, Mkp,
+                     (long long)nh * 128, a.Lk, p, c.num_sms, c.s);
+      }
+      {   // dK_h = dS_h^T q_h,  dV_h = P_h^T dO_h
+        GemmParams p{};
+        p.M = a.Lk; p.N = 128; p.K = a.Lq; p.batches = nh; p.a_m0 = Lk128; p.b_n0 = 128; p.o_c0 = 128;
+        p.o_rows = a.Lk; p.o_cols = (long long)nh * 128; p.ld_f = a.dim;
+        p.out_f = a.dk + (size_t)it * a.Lk * a.dim + h0 * 128;
+        gemm_batched(EPI_F32, dST, ldq8, (long long)nh * Lk128, a.Lq, k.qT + (size_t)h0 * 128 * Mqp + (size_t)it * a.Lq, Mqp,
+                     (long long)nh * 128, a.Lq, p, c.num_sms, c.s);
+        p.out_f = nullptr; p.ld_f = 0;
+        p.out_h = a.dv + (size_t)it * a.Lk * a.lddv + h0 * 128; p.ld_h = a.lddv;
+        gemm_batched(EPI_F16, PT, ldq8, (long long)nh * Lk128, a.Lq, k.dOT + (size_t)h0 * 128 * Mqp + (size_t)it * a.Lq, Mqp,
+                     (long long)nh * 128, a.Lq, p, c.num_sms, c.s);
+      }
     }
 }
 }  // namespace
@@ -414,9 +462,9 @@ void DitEngine::backward(const float* const* dout, float loss_scale, int ffn_gra
     const size_t tb_rows = (size_t)(f > cfg.text_dim ? f : cfg.text_dim);
     k.tA = carve<__half>(p, ta_rows * k.Tp); k.tB = carve<__half>(p, (tb_rows > (size_t)d ? tb_rows : (size_t)d) * k.Tp);
     k.qT = carve<__half>(p, (size_t)d * k.Tp); k.kT = carve<__half>(p, (size_t)d * k.Tp); k.dOT = carve<__half>(p, (size_t)d * k.Tp);
-    const size_t Lq8 = r8(L), Lk8 = r8(L > TL ? L : TL);
-    k.S = carve<float>(p, Lq8 * Lk8); k.dP = carve<float>(p, Lq8 * Lk8);
-    k.dS = carve<__half>(p, Lq8 * Lk8); k.dST = carve<__half>(p, Lq8 * Lk8); k.PT = carve<__half>(p, Lq8 * Lk8);
+    k.attn_scratch_bytes = attn_scratch_bytes(L, TL, cfg.num_heads);
+    k.S = carve<float>(p, k.attn_scratch_bytes / 4);
+    k.attn_stat = carve<float>(p, (size_t)cfg.num_heads * ((L + 127) & ~127) * 4);
     const int widest = f > 3 * d ? f : 3 * d;
     k.colsum_bytes = bw_colsum_scratch_bytes(B, L > TL ? L : TL, widest);
     const size_t one = bw_colsum_scratch_bytes(1, M > k.Cr ? M : k.Cr, widest);

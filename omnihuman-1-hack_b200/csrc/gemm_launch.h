@@ -49,7 +49,7 @@ CUtensorMap make_out_map(const GemmParams& p, bool f32, uint32_t cw) {
   const uint64_t ncols = (!f32 && p.vt != nullptr) ? (uint64_t)p.vt_col0 : (uint64_t)p.N;   // QKV: q|k part only
   B2_CHECK(base != nullptr, "GEMM output pointer missing");
   if (!p.cv.enabled) {
-    uint64_t dims[2] = {ncols, (uint64_t)p.M};
+    uint64_t dims[2] = {p.o_cols > 0 ? (uint64_t)p.o_cols : ncols, p.o_rows > 0 ? (uint64_t)p.o_rows : (uint64_t)p.M};
     uint64_t str[1] = {ld * esz};
     uint32_t box[2] = {cw, 32};
     return make_tmap(base, f32, 2, dims, str, box, (int)(cw * esz));
@@ -92,7 +92,8 @@ void launch_one(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int 
   }
   constexpr bool OUT_F32 = (EPI == EPI_RESID_F32 || EPI == EPI_F32);
   const int tiles_m = (p.M + 127) / 128, tiles_n = (p.N + BN - 1) / BN;
-  const int units = ((tiles_m + CL - 1) / CL) * tiles_n;
+  const int units = ((tiles_m + CL - 1) / CL) * tiles_n * (p.batches > 1 ? p.batches : 1);
+  B2_CHECK(p.batches <= 1 || (CL == 1 && !p.cv.enabled && EPI != EPI_QKV), "batched GEMM: plain single-CTA epilogues only");
   const int KB = (p.K + 63) / 64;
   if (units <= 0 || KB <= 0) return;
   const int Gmax = max_ctas / CL;
@@ -128,7 +129,7 @@ void launch_one(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, int 
     tv = make_tmap(p.vt, false, 2, dims, str, box, 0);
   }
   const double rows = p.cv.enabled ? (double)p.cv.T * p.cv.H * p.cv.W : (double)p.M;
-  ProfScope prof(p.cv.enabled ? PC_CONV : PC_GEMM, 2.0 * rows * p.N * p.K, 0.0, stream);
+  ProfScope prof(p.cv.enabled ? PC_CONV : PC_GEMM, 2.0 * rows * p.N * p.K * (p.batches > 1 ? p.batches : 1), 0.0, stream);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(G * CL); cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;

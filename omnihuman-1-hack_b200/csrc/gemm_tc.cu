@@ -75,6 +75,21 @@ void gemm_linear(int epi, const __half* A, long long lda, const __half* W, long 
   launch_gemm(epi, bn, cl, ta, tb, p, num_sms, stream);
 }
 
+// `p.batches` independent products D_b[M,N] = A_b[M,K] W_b[N,K]^T in one launch (see GemmParams: batch b reads and
+// writes at per-batch origin offsets of the same buffers).  a_rows x a_cols / w_rows x w_cols: extents of the operand
+// tensor maps over all batches (TMA zero-fills beyond them: they are what clips a batch's last K slice and rows).
+void gemm_batched(int epi, const __half* A, long long lda, long long a_rows, long long a_cols, const __half* W,
+                  long long ldw, long long w_rows, long long w_cols, GemmParams p, int num_sms, cudaStream_t stream) {
+  p.cv.enabled = 0;
+  B2_CHECK(p.batches >= 1 && p.o_rows > 0 && p.o_cols > 0, "gemm_batched: batch count / output extents missing");
+  const int bn = pick_bn(p.M, p.N, num_sms, 0);
+  B2_CHECK(p.batches == 1 || p.o_c0 == 0 || p.o_c0 % bn == 0, "gemm_batched: column stride %d of the output is not a "
+           "multiple of the tile width %d", p.o_c0, bn);
+  CUtensorMap ta = make_tmap_2d(A, a_rows, a_cols, lda, 128);
+  CUtensorMap tb = make_tmap_2d(W, w_rows, w_cols, ldw, bn);
+  launch_gemm(epi, bn, 1, ta, tb, p, num_sms, stream);
+}
+
 // Causal / spatial convolution as an implicit GEMM over an NDHWC fp16 volume (vae.py:17-36):
 //   in   [Tbuf, H, W, Cin]   with the kt-1 history frames physically in front of the chunk
 //   w    [Cout, taps * cpad] K index = ((dt*kh + dh)*kw + dw) * cpad + c,  cpad = ceil(Cin/64)*64

@@ -79,6 +79,14 @@ struct GemmParams {
                           // its first tiles may be requested before the programmatic-dependency wait
   int dbg;                // diagnosis only (B200_GEMM_DBG): 1 = skip the epilogue's global stores, 2 = no operand
                           // loads (MMAs run on whatever is in shared memory), 4 = loads but no MMAs
+  // Batched mode (batches > 1; plain matrix epilogues, single-CTA tiles): `batches` independent M x N x K problems in
+  // one launch, e.g. the per-head products of the attention backward.  Batch b reads A at (row + b a_m0, k + b a_k0),
+  // W at (row + b b_n0, k + b b_k0) of the SAME tensor maps and stores at (row + b o_r0, column + b o_c0); the
+  // host sizes the maps over all batches (o_rows x o_cols for the output) and keeps tiles of one batch from
+  // spilling into the next (padded batch strides, or exact multiples of the tile).
+  int batches;
+  int a_m0, a_k0, b_n0, b_k0, o_r0, o_c0;
+  long long o_rows, o_cols;
 };
 
 constexpr int WARP_TMA = 8, WARP_MMA = 9;
@@ -191,7 +199,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int tiles_m = (p.M + C::BLOCK_M - 1) / C::BLOCK_M;
-  const int units = ((tiles_m + CL - 1) / CL) * tiles_n;       // one unit = CL vertically adjacent tiles
+  const int units_pb = ((tiles_m + CL - 1) / CL) * tiles_n;    // one unit = CL vertically adjacent tiles
+  const int units = units_pb * (p.batches > 1 ? p.batches : 1);
   const int num_kb = (p.K + C::BLOCK_K - 1) / C::BLOCK_K;
   const int G = gridDim.x / CL, cid = blockIdx.x / CL;
 
@@ -218,7 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == WARP_TMA) {
     // ------------------------------------------------------------------ TMA producer
     int pre = 0;                                           // stages whose W tile was requested early
-    if (lane == 0 && p.w_static && !(p.dbg & 2) && !PAIR && !p.cv.enabled) {
+    if (lane == 0 && p.w_static && !(p.dbg & 2) && !PAIR && !p.cv.enabled && p.batches <= 1) {
       TileSched s0(units, num_kb, G, cid, p.sk);
       int unit, kb0, kb1, n_contrib;
       if (s0.next(unit, kb0, kb1, n_contrib)) {
@@ -236,7 +245,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int unit, kb0, kb1, n_contrib;
       int issued = 0;                                      // k-slices issued so far by this CTA
       while (sched.next(unit, kb0, kb1, n_contrib)) {
-        const int m_blk = (unit / tiles_n) * CL + rank, n_blk = unit % tiles_n;
+        const int bt = unit / units_pb, ub = unit - bt * units_pb;
+        const int m_blk = (ub / tiles_n) * CL + rank, n_blk = ub % tiles_n;
+        const int a_row = m_blk * C::BLOCK_M + bt * p.a_m0, a_col = bt * p.a_k0;
+        const int b_row = n_blk * BLOCK_N + bt * p.b_n0, b_col = bt * p.b_k0;
         int ct = 0, ch0 = 0, cw0 = 0;
         if (p.cv.enabled) {
           const int per_frame = p.cv.tiles_h * p.cv.tiles_w;
@@ -266,9 +278,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int dw = tap % p.cv.kw, dh = (tap / p.cv.kw) % p.cv.kh, dt = tap / (p.cv.kw * p.cv.kh);
             tma_load_4d(sa, &tmap_a, &full[stage], cb * 64, cw0 + dw, ch0 + dh, ct + dt);
           } else {
-            tma_load_2d(sa, &tmap_a, &full[stage], kb * C::BLOCK_K, m_blk * C::BLOCK_M);
+            tma_load_2d(sa, &tmap_a, &full[stage], kb * C::BLOCK_K + a_col, a_row);
           }
-          if (!w_done) tma_load_2d(sb, &tmap_b, &full[stage], kb * C::BLOCK_K, n_blk * BLOCK_N);
+          if (!w_done) tma_load_2d(sb, &tmap_b, &full[stage], kb * C::BLOCK_K + b_col, b_row);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -337,7 +349,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int acc = seg & 1;
       const uint32_t acc_phase = (seg >> 1) & 1;
       ++seg;
-      const int m_blk = (unit / tiles_n) * CL + rank, n_blk = unit % tiles_n;
+      const int bt = unit / units_pb, ub = unit - bt * units_pb;
+      const int m_blk = (ub / tiles_n) * CL + rank, n_blk = ub % tiles_n;
       const uint32_t t_acc = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N;
 
       if (kb0 > 0) {
@@ -526,8 +539,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_4d(&tmap_o, stg, col0, cw, ch, ct);
             else tma_store_4d(&tmap_o, stg, col0, cw, ch, ct);
           } else {
-            if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_2d(&tmap_o, stg, col0, row0);
-            else tma_store_2d(&tmap_o, stg, col0, row0);
+            if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_2d(&tmap_o, stg, col0 + bt * p.o_c0, row0 + bt * p.o_r0);
+            else tma_store_2d(&tmap_o, stg, col0 + bt * p.o_c0, row0 + bt * p.o_r0);
           }
           tma_store_commit();
         }

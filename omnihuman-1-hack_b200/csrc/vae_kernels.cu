@@ -123,19 +123,30 @@ __global__ void __launch_bounds__(256) vae_softmax_kernel(const float* __restric
     o[i] = __float2half_rn(i < n ? __expf((r[i] - m) * scale) * inv : 0.f);
 }
 
-__global__ void transpose_h_kernel(const __half* __restrict__ in, long long ld, __half* __restrict__ out, long long ldo,
-                                   int R, int C, int write_cols) {
-  __shared__ __half tile[32][33];
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int i = ty; i < 32; i += 8) {
-    const int r = r0 + i, c = c0 + tx;
-    tile[i][tx] = (r < R && c < C) ? in[(long long)r * ld + c] : __float2half(0.f);
+// 64 x 64 tiles, 4-byte accesses on both sides (ld, ldo and the base pointers are even: every caller's are)
+__global__ void __launch_bounds__(256) transpose_h_kernel(const __half* __restrict__ in, long long ld, __half* __restrict__ out,
+                                                          long long ldo, int R, int C, int write_cols) {
+  __shared__ __half tile[64][66];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const __half zero = __float2half(0.f);
+  for (int i = wy; i < 64; i += 8) {
+    const int r = r0 + i, c = c0 + 2 * lane;
+    __half2 v = __halves2half2(zero, zero);
+    if (r < R) {
+      if (c + 1 < C) v = *reinterpret_cast<const __half2*>(in + (long long)r * ld + c);
+      else if (c < C) v = __halves2half2(in[(long long)r * ld + c], zero);
+    }
+    tile[i][2 * lane] = __low2half(v); tile[i][2 * lane + 1] = __high2half(v);
   }
   __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + tx;
-    if (c < C && r < write_cols) out[(long long)c * ldo + r] = tile[tx][i];
+  for (int i = wy; i < 64; i += 8) {
+    const int c = c0 + i, r = r0 + 2 * lane;
+    if (c >= C) continue;
+    const __half2 v = __halves2half2(tile[2 * lane][i], tile[2 * lane + 1][i]);
+    __half* o = out + (long long)c * ldo + r;
+    if (r + 1 < write_cols) *reinterpret_cast<__half2*>(o) = v;
+    else if (r < write_cols) *o = __low2half(v);
   }
 }
 
@@ -295,7 +306,9 @@ void launch_vae_softmax(const float* sc, long long ld_in, __half* out, long long
 void launch_transpose_h(const __half* in, long long ld, __half* out, long long ldo, int R, int C, cudaStream_t s,
                         int write_cols) {
   if (write_cols <= 0) write_cols = (int)ldo;
-  transpose_h_kernel<<<dim3((unsigned)((write_cols + 31) / 32), (C + 31) / 32), 256, 0, s>>>(in, ld, out, ldo, R, C,
+  B2_CHECK(ld % 2 == 0 && ldo % 2 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 3) == 0,
+           "transpose: leading dimensions and base pointers must be even");
+  transpose_h_kernel<<<dim3((unsigned)((write_cols + 63) / 64), (C + 63) / 64), 256, 0, s>>>(in, ld, out, ldo, R, C,
                                                                                           write_cols);
   B2_CUDA(cudaGetLastError());
   count_launch();
