@@ -204,9 +204,58 @@ def make_grad_golden():
     torch.save(rec, os.path.join(OUT, "dit_grad_tiny.pt"))
 
 
+DEEP = dict(dim=128, ffn_dim=256, num_heads=1, num_layers=13, text_dim=32, in_dim=16, seed=21)
+
+
+def make_grad_deep_golden():
+    """The shipped WanModel evaluates the FFN of every block with block_idx > 10 under torch.no_grad() on the CPU
+    (model.py:318-325): 13 blocks are the smallest model in which that shows.  Gradients of the same APT stage-1 loss
+    through the UNMODIFIED WanModel (13 blocks, dim 128; weights regenerate from the seed): d loss / d x, the gradient
+    norm of every parameter (None for the detached FFNs) and a few tensors in full."""
+    M, _ = ref_loader.load_reference_modules()
+    cfg = dict(DEEP)
+    sd = O.make_synthetic_weights(cfg["dim"], cfg["ffn_dim"], cfg["num_heads"], cfg["num_layers"], in_dim=cfg["in_dim"],
+                                  text_dim=cfg["text_dim"], seed=cfg["seed"])
+    m = M.WanModel(model_type="t2v", in_dim=cfg["in_dim"], dim=cfg["dim"], ffn_dim=cfg["ffn_dim"],
+                   num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], text_dim=cfg["text_dim"],
+                   use_checkpoint=False).train()
+    m.load_state_dict({k: v.float() for k, v in sd.items()}, strict=True)
+    gen = torch.Generator().manual_seed(77)
+    x0 = [torch.randn(16, 1, 8, 16, generator=gen)]
+    ctx = [torch.randn(29, 32, generator=gen)]
+    vt = [torch.randn(16, 1, 8, 16, generator=gen)]
+    t = torch.tensor([1000.0])
+    x = [u.clone().requires_grad_(True) for u in x0]
+    out = m(x, t, ctx, seq_len=32)
+    loss = sum(torch.nn.functional.mse_loss(o.float(), v) for o, v in zip(out, vt))
+    loss.backward()
+    params = dict(m.named_parameters())
+    keys = ["blocks.12.modulation", "blocks.12.self_attn.q.weight", "blocks.11.cross_attn.o.weight",
+            "blocks.10.ffn.0.weight", "blocks.3.ffn.2.weight", "blocks.0.self_attn.v.weight", "time_projection.1.bias"]
+    no_grad = sorted(k for k, p in params.items() if p.grad is None)
+    assert no_grad == sorted(f"blocks.{i}.ffn.{j}.{w}" for i in (11, 12) for j in (0, 2) for w in ("weight", "bias")), no_grad
+    rec = dict(cfg=cfg, x=x0, context=ctx, v_teacher=vt, t=t, seq_len=32, loss=loss.detach().clone(),
+               out=[o.detach().clone() for o in out], dx=[u.grad.clone() for u in x],
+               grads={k: params[k].grad.clone() for k in keys}, no_grad=no_grad,
+               grad_norms={k: float(p.grad.norm()) for k, p in params.items() if p.grad is not None})
+    sd_o = {k: v.float().clone().requires_grad_(True) for k, v in sd.items() if k != "freqs"}
+    x_o = [u.clone().requires_grad_(True) for u in x0]
+    out_o = O.dit_forward(sd_o, x_o, t, ctx, 32, num_heads=1, ffn_no_grad_from=11)
+    loss_o = sum(torch.nn.functional.mse_loss(o, v) for o, v in zip(out_o, vt))
+    loss_o.backward()
+    worst = max(float((sd_o[k].grad - rec["grads"][k]).norm() / rec["grads"][k].norm()) for k in keys)
+    assert all(sd_o[k].grad is None for k in no_grad)
+    print(f"deep grad golden: loss {float(loss):.6f} (oracle {float(loss_o):.6f}), worst rel-L2 {worst:.2e}, "
+          f"dx {float((x_o[0].grad - rec['dx'][0]).norm() / rec['dx'][0].norm()):.2e}, no grad: {len(no_grad)} tensors")
+    assert worst < 1e-4
+    torch.save(rec, os.path.join(OUT, "dit_grad_deep.pt"))
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "grads":
         return make_grad_golden()
+    if len(sys.argv) > 1 and sys.argv[1] == "grads_deep":
+        return make_grad_deep_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "omni":
         return make_omni_golden()
     if len(sys.argv) > 1 and sys.argv[1] == "disc":

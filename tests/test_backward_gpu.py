@@ -50,6 +50,33 @@ def test_grad_golden_tiny():
         assert abs(got - n) <= 5e-3 * n + 1e-7, (k, got, n)
 
 
+def test_grad_golden_deep_detached_ffns():
+    """13 blocks from the unmodified reference: blocks 11 and 12 run their FFN under no_grad (model.py:318-325), so
+    their FFN weights get NO gradient and nothing flows back through them -- `ffn_grad_blocks=11`, the shim's default."""
+    import b200dit
+    from b200dit import autograd as A
+    from oracle import dit_oracle as O
+    r = _load("dit_grad_deep.pt")
+    c = r["cfg"]
+    sd = O.make_synthetic_weights(c["dim"], c["ffn_dim"], c["num_heads"], c["num_layers"], in_dim=c["in_dim"],
+                                  text_dim=c["text_dim"], seed=c["seed"])
+    eng = b200dit.DitEngine.from_state_dict(sd, num_heads=1)
+    named = _params(sd, eng.device)
+    x = [u.to(eng.device).requires_grad_(True) for u in r["x"]]
+    out = A.dit_forward(eng, named, x, r["t"], r["context"], r["seq_len"], ffn_grad_blocks=11)
+    assert rel_l2(out[0].detach().cpu(), r["out"][0]) < 1e-3
+    loss = sum(torch.nn.functional.mse_loss(o, v.to(eng.device)) for o, v in zip(out, r["v_teacher"]))
+    loss.backward()
+    assert rel_l2(x[0].grad.cpu(), r["dx"][0]) < TOL
+    params = dict(named)
+    for k, ref in r["grads"].items():
+        assert rel_l2(params[k].grad.cpu().reshape(ref.shape), ref) < TOL, k
+    for k in r["no_grad"]:
+        assert float(params[k].grad.abs().max()) == 0.0, k          # the engine hands back exact zeros
+    for k, n in r["grad_norms"].items():
+        assert abs(float(params[k].grad.norm()) - n) <= 5e-3 * n + 1e-7, (k, float(params[k].grad.norm()), n)
+
+
 def _oracle_grads(sd, xs, t, ctx, seq_len, v_teacher, heads, detach_from=None):
     from oracle import dit_oracle as O
     sd_o = {k: v.clone().float().requires_grad_(True) for k, v in sd.items() if k != "freqs"}

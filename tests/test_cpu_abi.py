@@ -52,6 +52,17 @@ def test_no_cpu_fallback(built):
     assert lib.b200_kernel_launches() == 0
 
 
+def test_hard_limits_fail_loudly_on_the_host(built):
+    """Limits of the engine that the reference does not have are refused with a message, not mis-computed:
+    head_dim must be 128 (attention.py:54 allows up to 256), text_len a multiple of 8, freq_dim a multiple of 4.
+    b200dit_weight_names runs the same configuration check as b200dit_create and needs no GPU."""
+    for bad, needle in ((dict(dim=1536, num_heads=16), "head_dim"), (dict(dim=1536, num_heads=11), "divisible"),
+                        (dict(text_len=500), "text_len"), (dict(freq_dim=254), "freq_dim")):
+        with pytest.raises(built.B200Error) as e:
+            built.DitEngine.expected_weight_names(**bad)
+        assert needle in str(e.value), (bad, str(e.value))
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "omnihuman-1-hack_b200")
     for dp, _, fs in os.walk(pkg):

@@ -179,6 +179,27 @@ def test_dit_oracle_gradients_vs_golden():
         assert abs(float(sd[k].grad.norm()) - n) <= 1e-4 * max(n, 1e-6) + 1e-9, k
 
 
+def test_dit_oracle_gradients_deep_model_detached_ffns():
+    """13 blocks: the shipped WanModel runs the FFN of blocks 11 and 12 under no_grad (model.py:318-325).  The oracle's
+    `ffn_no_grad_from=11` against the gradients of the UNMODIFIED reference (oracle/make_golden.py grads_deep)."""
+    r = torch.load(os.path.join(GOLDEN, "dit_grad_deep.pt"))
+    c = r["cfg"]
+    sd = O.make_synthetic_weights(c["dim"], c["ffn_dim"], c["num_heads"], c["num_layers"], in_dim=c["in_dim"],
+                                  text_dim=c["text_dim"], seed=c["seed"])
+    sd = {k: v.float().clone().requires_grad_(True) for k, v in sd.items() if k != "freqs"}
+    x = [u.clone().requires_grad_(True) for u in r["x"]]
+    out = O.dit_forward(sd, x, r["t"], r["context"], r["seq_len"], num_heads=1, ffn_no_grad_from=11)
+    loss = sum(torch.nn.functional.mse_loss(o, v) for o, v in zip(out, r["v_teacher"]))
+    loss.backward()
+    assert rel_l2(out[0].detach(), r["out"][0]) < 1e-5 and abs(float(loss) - float(r["loss"])) < 1e-5
+    assert rel_l2(x[0].grad, r["dx"][0]) < 1e-4
+    for k, ref in r["grads"].items():
+        assert rel_l2(sd[k].grad, ref) < 1e-4, k
+    assert sorted(k for k, v in sd.items() if v.grad is None) == r["no_grad"]
+    for k, n in r["grad_norms"].items():
+        assert abs(float(sd[k].grad.norm()) - n) <= 1e-4 * max(n, 1e-6) + 1e-9, k
+
+
 def test_omni_audio_oracle_vs_golden_and_live_reference():
     """oracle/omni_oracle.process_audio vs the fixture made by the unmodified OmniConditionsModule
     (Omnihuman/omnihuman_wan_t2v.py:13-60) and, where the tree is mounted, vs the live class."""

@@ -214,6 +214,29 @@ def test_shim_reloads_after_in_place_weight_update():
     assert rel_l2(b[0].cpu(), fresh[0].cpu()) < 1e-6 and bias is not None
 
 
+def test_more_items_than_one_launch_holds():
+    """MAX_ITEMS = 16 items per launch (per-item scalars ride in kernel parameters): the C entry point refuses 17 with
+    a message; the Python host side splits 17 items over two launches and returns what 17 single calls return."""
+    import ctypes as C
+    import b200dit
+    from b200dit import _lib
+    g = _load("dit_t2v_tiny.pt")
+    eng = b200dit.DitEngine.from_state_dict({k: v.float() for k, v in g["sd"].items()}, num_heads=1)
+    n = _lib.MAX_ITEMS + 1
+    x = [g["x"][0].float().cuda() * (1 + 0.01 * i) for i in range(n)]
+    ctx = [g["context"][0].float().cuda()] * n
+    t = torch.full((n,), 500.0)
+    out = eng.forward(x, t, ctx, g["seq_len"])
+    one = eng.forward(x[-1:], t[-1:], ctx[-1:], g["seq_len"])
+    assert len(out) == n and rel_l2(out[-1].cpu(), one[0].cpu()) < 1e-5
+    tt = t.cuda()
+    o = [torch.empty_like(out[0]) for _ in range(n)]
+    rc = _lib.lib().b200dit_forward(eng._h, n, _lib.ptr_array([u.data_ptr() for u in x]), None, 0, C.c_void_p(tt.data_ptr()),
+                                    _lib.ptr_array([c.data_ptr() for c in ctx]), _lib.int_array([c.shape[0] for c in ctx]),
+                                    _lib.DTYPE_F32, None, 2, 8, 12, 60, _lib.ptr_array([u.data_ptr() for u in o]), None)
+    assert rc != 0 and b"items in one call" in _lib.lib().b200_last_error()
+
+
 def test_overflow_guard_counts_nonfinite_rows():
     """b200dit_nonfinite_rows: 0 on a healthy forward; an FFN whose hidden activations exceed the fp16 range
     (65504) poisons the residual stream and every later LayerNorm counts the rows."""
