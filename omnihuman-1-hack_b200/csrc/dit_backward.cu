@@ -22,6 +22,7 @@
 // Not covered: the i2v hooks (y / clip_fea) and gradients with respect to the text contexts -- the trainer feeds
 // neither (distilled_trainer.py:262-278); the Python side falls through to the reference for those.
 #include <cmath>
+#include <cstdlib>
 
 #include "backward.h"
 #include "dit_engine.h"
@@ -201,14 +202,21 @@ struct Ctx {
   const float* inv_vec;  // the same value as a vector (the reduce-add epilogue's per-column factor)
 };
 
-// dW[N, K] += dY[M, N]^T X[M, K]   (both operands transposed so that the token axis is the K-major reduction)
+// dW[N, K] += dY[M, N]^T X[M, K]: the token axis is the reduction.  Default: both row-major operands are read as
+// MN-major tiles by the GEMM (GemmParams::tn).  B200_WGRAD_TN=0: transposed copies made by an HBM-bound pass first
+// (the K-major path), kept for A/B runs.
 void wgrad(const Ctx& c, const __half* dY, long long ldy, const __half* X, long long ldx, int M, int N, int K, float* dW) {
+  static const int use_tn = std::getenv("B200_WGRAD_TN") ? std::atoi(std::getenv("B200_WGRAD_TN")) : 1;
+  GemmParams p{};
+  p.M = N; p.N = K; p.K = M; p.out_f = dW; p.ld_f = K; p.gate = c.inv_vec; p.gate_stride = 0; p.rows_per_item = 0;
+  if (use_tn && ldy % 8 == 0 && ldx % 8 == 0) {
+    gemm_tn(EPI_RESID_F32, dY, ldy, X, ldx, p, c.num_sms, c.s);
+    return;
+  }
   const int Mp = (int)r8(M);
   B2_CHECK(Mp <= c.Tp, "wgrad: transpose scratch too small");
   launch_transpose_h(dY, ldy, c.tA, Mp, M, N, c.s);
   launch_transpose_h(X, ldx, c.tB, Mp, M, K, c.s);
-  GemmParams p{};
-  p.M = N; p.N = K; p.K = M; p.out_f = dW; p.ld_f = K; p.gate = c.inv_vec; p.gate_stride = 0; p.rows_per_item = 0;
   gemm_linear(EPI_RESID_F32, c.tA, Mp, c.tB, Mp, p, c.num_sms, c.s);
 }
 // db[N] += column sums of dY[M, N]

@@ -75,6 +75,18 @@ void gemm_linear(int epi, const __half* A, long long lda, const __half* W, long 
   launch_gemm(epi, bn, cl, ta, tb, p, num_sms, stream);
 }
 
+// D[M,N] (+)= A^T W for row-major A [K, M] and W [K, N] (GemmParams::tn): no transposed copies of the operands.
+void gemm_tn(int epi, const __half* A, long long lda, const __half* W, long long ldw, GemmParams p, int num_sms,
+             cudaStream_t stream) {
+  p.cv.enabled = 0; p.tn = 1; p.w_static = 0;
+  int bn = pick_bn(p.M, p.N, num_sms, kUseSplit ? p.K : 0);
+  if (bn % 64 != 0) bn = 128;
+  B2_CHECK(lda % 8 == 0 && ldw % 8 == 0, "gemm_tn: leading dimensions must be multiples of 8");
+  CUtensorMap ta = make_tmap_2d(A, p.K, p.M, lda, 64);
+  CUtensorMap tb = make_tmap_2d(W, p.K, p.N, ldw, 64);
+  launch_gemm(epi, bn, 1, ta, tb, p, num_sms, stream);
+}
+
 // `p.batches` independent products D_b[M,N] = A_b[M,K] W_b[N,K]^T in one launch (see GemmParams: batch b reads and
 // writes at per-batch origin offsets of the same buffers).  a_rows x a_cols / w_rows x w_cols: extents of the operand
 // tensor maps over all batches (TMA zero-fills beyond them: they are what clips a batch's last K slice and rows).

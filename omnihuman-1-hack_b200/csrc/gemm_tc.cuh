@@ -86,6 +86,10 @@ struct GemmParams {
   // spilling into the next (padded batch strides, or exact multiples of the tile).
   int batches;
   int a_m0, a_k0, b_n0, b_k0, o_r0, o_c0;
+  // tn = 1: D[M,N] = A^T W with A stored [K, M] and W stored [K, N] row-major (both operands MN-major): the weight
+  // gradient dW = dY^T X straight from the row-major dY [tokens, N_out] and X [tokens, K_in].  The operand maps carry
+  // 64 x 64 boxes; a stage holds the tile as 64-column chunks of [64 K rows x 128 B].  BLOCK_N must be a multiple of 64.
+  int tn;
   long long o_rows, o_cols;
 };
 
@@ -227,7 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == WARP_TMA) {
     // ------------------------------------------------------------------ TMA producer
     int pre = 0;                                           // stages whose W tile was requested early
-    if (lane == 0 && p.w_static && !(p.dbg & 2) && !PAIR && !p.cv.enabled && p.batches <= 1) {
+    if (lane == 0 && p.w_static && !(p.dbg & 2) && !PAIR && !p.cv.enabled && p.batches <= 1 && !p.tn) {
       TileSched s0(units, num_kb, G, cid, p.sk);
       int unit, kb0, kb1, n_contrib;
       if (s0.next(unit, kb0, kb1, n_contrib)) {
@@ -273,6 +277,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const bool w_done = issued < pre;                // this stage's W tile is already in flight
           ++issued;
           if (!w_done) mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          if (p.tn) {
+            if constexpr (BLOCK_N % 64 == 0) {
+#pragma unroll
+              for (int c = 0; c < 2; ++c) tma_load_2d(sa + c * 8192, &tmap_a, &full[stage], a_row + c * 64, kb * C::BLOCK_K);
+#pragma unroll
+              for (int c = 0; c < BLOCK_N / 64; ++c) tma_load_2d(sb + c * 8192, &tmap_b, &full[stage], b_row + c * 64, kb * C::BLOCK_K);
+            }
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (p.cv.enabled) {
             const int tap = kb / p.cv.cblocks, cb = kb % p.cv.cblocks;
             const int dw = tap % p.cv.kw, dh = (tap / p.cv.kw) % p.cv.kh, dt = tap / (p.cv.kw * p.cv.kh);
@@ -287,7 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == WARP_MMA && (!PAIR || rank == 0)) {
     // ------------------------------------------------------------------ MMA issuer (pair mode: the leader only)
-    constexpr uint32_t idesc = umma_idesc_f16(C::BLOCK_M * CL, BLOCK_N);
+    const uint32_t idesc = umma_idesc_f16(C::BLOCK_M * CL, BLOCK_N) | (p.tn ? (UMMA_A_MN | UMMA_B_MN) : 0u);
     int stage = 0; uint32_t phase = 0;
     int seg = 0;
     TileSched sched(units, num_kb, G, cid, p.sk);
@@ -311,6 +325,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if constexpr (PAIR)
               umma_f16_pair(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc,
                             (kb > kb0 || k > 0) ? 1u : 0u);
+            else if (p.tn)     // 16 K rows per instruction = two 8-row groups = 2048 B; 64-column chunks 8192 B apart
+              umma_f16(d_tmem, umma_desc_mn_sw128(sa + k * 2048, 8192), umma_desc_mn_sw128(sb + k * 2048, 8192), idesc,
+                       (kb > kb0 || k > 0) ? 1u : 0u);
             else
               umma_f16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc,
                        (kb > kb0 || k > 0) ? 1u : 0u);

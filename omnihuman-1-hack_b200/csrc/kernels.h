@@ -34,6 +34,8 @@ void launch_gemm(int epi, int block_n, int cluster, const CUtensorMap& ta, const
 int gemm_cluster_size(int block_n, long long M, long long N, long long K, int num_sms, bool conv);
 void gemm_linear(int epi, const __half* A, long long lda, const __half* W, long long ldw, GemmParams p, int num_sms,
                  cudaStream_t stream, int force_bn = 0);
+void gemm_tn(int epi, const __half* A, long long lda, const __half* W, long long ldw, GemmParams p, int num_sms,
+             cudaStream_t stream);
 void gemm_batched(int epi, const __half* A, long long lda, long long a_rows, long long a_cols, const __half* W,
                   long long ldw, long long w_rows, long long w_cols, GemmParams p, int num_sms, cudaStream_t stream);
 void conv_gemm(int epi, const __half* in, int Tbuf, int H, int W, int Cin, const __half* w, int Cout, int kt, int kh,

@@ -299,6 +299,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// The same tile read as an MN-major operand (the M / N index is the contiguous one): rows are K indices, every row
+// holds 64 consecutive M / N elements (128 B, swizzled exactly as TMA writes them), groups of 8 K rows are 1024 B
+// apart (SBO) and the next 64 M / N elements start `lbo_bytes` further (LBO) -- canonical layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.  Pair with UMMA_A_MN / UMMA_B_MN in the instruction descriptor.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+constexpr uint32_t UMMA_A_MN = 1u << 15, UMMA_B_MN = 1u << 16;
 // Instruction descriptor, kind::f16: fp16 A/B (format 0) or bf16 (1), fp32 accumulate, K-major A and B.
 //   [4,6) D fmt (1=f32) | [7,10) A fmt | [10,13) B fmt | [15] A major | [16] B major | [17,23) N>>3 | [24,29) M>>4
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int ab_fmt = 0) {
