@@ -332,6 +332,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (q_in_item < p.Lq) *reinterpret_cast<float2*>(wml) = make_float2(m_ref * c, l_sum);
     } else {
     const float inv_l = 1.0f / l_sum;
+    if (p.lse != nullptr && q_in_item < p.Lq)
+      p.lse[((long long)item * p.heads + head) * p.Lq + q_in_item] = m_ref * c + log2f(l_sum);
     __half* o = p.out + ((long long)item * p.Lq + q_in_item) * p.ldo + head * 128;
 #pragma unroll
     for (int cidx = 0; cidx < 4; ++cidx) {
@@ -344,6 +346,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(t[i + e]) * inv_l;
+          if (p.out32 != nullptr) {
+            float* o32 = p.out32 + ((long long)item * p.Lq + q_in_item) * p.ldo32 + head * 128 + cidx * 32 + i;
+            *reinterpret_cast<float4*>(o32) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(o32 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
           uint4* dst = reinterpret_cast<uint4*>(o + cidx * 32 + i);
           if (p.accumulate) {
             const uint4 old = *dst;
@@ -1047,6 +1054,7 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
     const double waves2 = (double)((n2 + sms - 1) / sms);
     use_pair = p.Lq >= 2048 && min_keys >= 2048 && waves2 / 1.1 < waves1;
   }
+  if (p.lse != nullptr) use_pair = false;
   if (use_pair) {
     bool& configured3 = configured3_dev[dev & 63];
     if (!configured3) {
@@ -1073,7 +1081,7 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
   const int min_steps = steps_env ? std::max(1, std::atoi(steps_env)) : (persist ? 1 : 2);
   pd.split_tiles = 0; pd.split_parts = 1;
   const int rem = n_tiles % slots;
-  if (p.split_ws != nullptr && split_mode && rem > 0) {
+  if (p.split_ws != nullptr && split_mode && rem > 0 && p.lse == nullptr) {
     int min_kv = 1 << 30;
     for (int i = 0; i < p.items; ++i) min_kv = std::min(min_kv, (p.klen[i] + v2::KT - 1) / v2::KT);
     int parts = std::min(std::min(slots / rem, max_parts), min_kv / min_steps);
@@ -1081,7 +1089,7 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
     if (parts >= 2) { pd.split_tiles = rem; pd.split_parts = parts; }
   }
   pd.n_units = n_tiles - pd.split_tiles + pd.split_tiles * pd.split_parts;
-  if (persist) {
+  if (persist && p.lse == nullptr) {
     bool& configured4 = configured4_dev[dev & 63];
     if (!configured4) {
       B2_CUDA(cudaFuncSetAttribute(v4::attn_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM));

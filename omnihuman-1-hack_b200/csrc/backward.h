@@ -40,4 +40,22 @@ void bw_modtab_bwd(const float* dtab, int layers, int B, int dim, float* de0, fl
 void bw_headtab_bwd(const float* dscale, const float* dshift, int B, int dim, float* dhead_mod, float* de, float wscale,
                     cudaStream_t s);
 
+// ---- attn_bwd_tc.cu : fused FlashAttention backward (tcgen05 / TMEM), head_dim 128
+struct AttnBwdParams {
+  const __half* q; long long ldq;        // [items * Lq, ldq]   queries as the forward saw them, head h at columns h * 128
+  const __half* k; long long ldk;        // [items * Lk, ldk]
+  const __half* v; long long ldv;        // [items * Lk, ldv]   row-major values
+  const float* O; long long ldo;         // fp32 [items * Lq, ldo]   the forward's output rows (AttnParams::out32)
+  const __half* dO; long long lddo;      // [items * Lq, lddo]
+  const float* lse;                      // [items][heads][Lq]  log2-domain row statistic of the forward (AttnParams::lse)
+  float* dsum;                           // [items][heads][Lq]  scratch: rowsum(dO o O)
+  float* dq; long long lddq;             // fp32 [items * Lq, lddq]   (zeroed and accumulated here)
+  float* dk; long long lddk;             // fp32 [items * Lk, lddk]
+  __half* dv; long long lddv;            // fp16 [items * Lk, lddv]
+  int items, heads, Lq, Lk;
+  int klen[MAX_ITEMS];
+  float scale;
+};
+void launch_attention_backward(const AttnBwdParams& p, cudaStream_t stream);
+
 }  // namespace b2

@@ -23,6 +23,7 @@
 // neither (distilled_trainer.py:262-278); the Python side falls through to the reference for those.
 #include <cmath>
 #include <cstdlib>
+#include <string>
 
 #include "backward.h"
 #include "dit_engine.h"
@@ -67,6 +68,9 @@ struct DitEngine::BwdWorkspace {
   float *S;                   // scratch of the attention adjoint: S | dP | dS | dS^T | P^T for a group of heads
   size_t attn_scratch_bytes;
   float* attn_stat;           // [heads * Lq128] float4 row statistics
+  float *lse_self, *lse_cross, *dsum;   // [items][heads][L]: the recompute's softmax statistics, rowsum(dO o O)
+  float *o32_self, *o32_cross;          // [M, dim] fp32 attention outputs of the recompute
+  bool fused_attn;
   size_t colsum_bytes;
   float inv; float* inv_vec; long long inv_n;
 };
@@ -155,10 +159,11 @@ void DitEngine::ensure_bwd_workspace(int B, int L) {
   const size_t M = (size_t)bws_B * bws_L, Mp = r8(M), Cr = (size_t)bws_B * TL, Tp = Mp > Cr ? Mp : Cr;
   const size_t Lq = r8(bws_L), Lk = Lq > TL ? Lq : TL;
   size_t bytes = 0;
-  bytes += M * d * 2 * 12 + M * 3 * d * 2 * 2 + M * f * 2 * 4 + M * d * 4 * 12;
+  bytes += M * d * 2 * 12 + M * 3 * d * 2 * 2 + M * f * 2 * 4 + M * d * 4 * 14;
   bytes += Cr * d * 2 * 8 + Cr * d * 4 * 4;
   bytes += 2 * d * Tp * 2 + (M + Cr) * 4 * 8;
   bytes += (3 * d > f ? 3 * d : f) * Tp * 2 + (f > (size_t)cfg.text_dim ? f : (size_t)cfg.text_dim) * Tp * 2 + 3 * d * Tp * 2;
+  bytes += 3 * ((size_t)bws_B * cfg.num_heads * bws_L * 4 + 256);
   bytes += attn_scratch_bytes(bws_L, (int)TL, cfg.num_heads) + (size_t)cfg.num_heads * (Lq + 128) * 16 + 64 * 4096;
   (void)Lk;
   bytes += (size_t)cfg.num_layers * bws_B * 6 * d * 4 + bws_B * 16 * d * 4 + M * 64 * 8 + M * cfg.in_dim * 4 * 4 + M * 16;
@@ -333,6 +338,7 @@ void DitEngine::block_recompute(int l, BwdWorkspace& k, cudaStream_t s) {
   a.items = B; a.heads = Hn; a.Lq = L; a.Lk_rows = L; a.scale = 1.0f / std::sqrt(128.0f);
   a.split_ws = attn_split.as<float>();
   for (int i = 0; i < B; ++i) a.klen[i] = k.Ltok;
+  if (k.fused_attn) { a.lse = k.lse_self; a.out32 = k.o32_self; a.ldo32 = d; }
   launch_attention(a, s);
   gemm_f32(k.att, d, b.o_w, d, M, d, d, k.y1, d, b.o_b, false, num_sms, s, true);
   bw_axpy_gate(x, k.y1, mod + 2 * d, 6 * d, L, k.x1, M, d, s);
@@ -346,6 +352,7 @@ void DitEngine::block_recompute(int l, BwdWorkspace& k, cudaStream_t s) {
   AttnParams cx = a;
   cx.q = k.cqn; cx.ldq = d; cx.k = k.ckn; cx.ldk = d; cx.vt = k.vtc; cx.ldvt = k.Crp; cx.out = k.catt; cx.Lk_rows = TL;
   for (int i = 0; i < B; ++i) cx.klen[i] = tg.ctx_rows[i] < TL ? tg.ctx_rows[i] : TL;
+  if (k.fused_attn) { cx.lse = k.lse_cross; cx.out32 = k.o32_cross; cx.ldo32 = d; }
   launch_attention(cx, s);
   gemm_f32(k.catt, d, b.co_w, d, M, d, d, k.y3, d, b.co_b, false, num_sms, s, true);
   bw_axpy_gate(k.x1, k.y3, nullptr, 0, L, k.x2, M, d, s);
@@ -389,8 +396,17 @@ void DitEngine::block_backward(int l, BwdWorkspace& k, bool ffn_grad, cudaStream
   {
     int klen[MAX_ITEMS];
     for (int i = 0; i < B; ++i) klen[i] = tg.ctx_rows[i] < TL ? tg.ctx_rows[i] : TL;
-    AttnBwdGeom a{k.cqn, d, k.ckn, d, k.ckv_raw + d, 2 * d, k.datt, B, Hn, L, TL, d, klen, scale, k.dq, k.dk, k.dkv + d, 2 * d};
-    attention_backward(c, a, k);
+    if (k.fused_attn) {
+      AttnBwdParams f{};
+      f.q = k.cqn; f.ldq = d; f.k = k.ckn; f.ldk = d; f.v = k.ckv_raw + d; f.ldv = 2 * d; f.O = k.o32_cross; f.ldo = d;
+      f.dO = k.datt; f.lddo = d; f.lse = k.lse_cross; f.dsum = k.dsum; f.dq = k.dq; f.lddq = d; f.dk = k.dk; f.lddk = d;
+      f.dv = k.dkv + d; f.lddv = 2 * d; f.items = B; f.heads = Hn; f.Lq = L; f.Lk = TL; f.scale = scale;
+      for (int i = 0; i < B; ++i) f.klen[i] = klen[i];
+      launch_attention_backward(f, s);
+    } else {
+      AttnBwdGeom a{k.cqn, d, k.ckn, d, k.ckv_raw + d, 2 * d, k.datt, B, Hn, L, TL, d, klen, scale, k.dq, k.dk, k.dkv + d, 2 * d};
+      attention_backward(c, a, k);
+    }
   }
   bw_rms_rope_bwd(k.dq, k.cq_raw, d, k.rcq, b.cnorm_q, nullptr, L, k.dun, k.dy, d, M, d, s);
   bw_colsum(k.dun, DT_F32, d, k.cq_raw, DT_F16, d, k.rcq, 1, M, d, grad_of(b.cnorm_q), 0, c.inv, true, k.colsum_ws, s);
@@ -414,9 +430,18 @@ void DitEngine::block_backward(int l, BwdWorkspace& k, bool ffn_grad, cudaStream
   {
     int klen[MAX_ITEMS];
     for (int i = 0; i < B; ++i) klen[i] = k.Ltok;
-    AttnBwdGeom a{k.qn, 2 * d, k.qn + d, 2 * d, k.qkv_raw + 2 * d, 3 * d, k.datt, B, Hn, L, L, d, klen, scale, k.dq, k.dk,
-                  k.dqkv + 2 * d, 3 * d};
-    attention_backward(c, a, k);
+    if (k.fused_attn) {
+      AttnBwdParams f{};
+      f.q = k.qn; f.ldq = 2 * d; f.k = k.qn + d; f.ldk = 2 * d; f.v = k.qkv_raw + 2 * d; f.ldv = 3 * d; f.O = k.o32_self; f.ldo = d;
+      f.dO = k.datt; f.lddo = d; f.lse = k.lse_self; f.dsum = k.dsum; f.dq = k.dq; f.lddq = d; f.dk = k.dk; f.lddk = d;
+      f.dv = k.dqkv + 2 * d; f.lddv = 3 * d; f.items = B; f.heads = Hn; f.Lq = L; f.Lk = L; f.scale = scale;
+      for (int i = 0; i < B; ++i) f.klen[i] = klen[i];
+      launch_attention_backward(f, s);
+    } else {
+      AttnBwdGeom a{k.qn, 2 * d, k.qn + d, 2 * d, k.qkv_raw + 2 * d, 3 * d, k.datt, B, Hn, L, L, d, klen, scale, k.dq, k.dk,
+                    k.dqkv + 2 * d, 3 * d};
+      attention_backward(c, a, k);
+    }
   }
   bw_rms_rope_bwd(k.dq, k.qkv_raw, 3 * d, k.rq, b.norm_q, k.cs, L, k.dun, k.dqkv, 3 * d, M, d, s);
   bw_colsum(k.dun, DT_F32, d, k.qkv_raw, DT_F16, 3 * d, k.rq, 1, M, d, grad_of(b.norm_q), 0, c.inv, true, k.colsum_ws, s);
@@ -473,6 +498,13 @@ void DitEngine::backward(const float* const* dout, float loss_scale, int ffn_gra
     k.attn_scratch_bytes = attn_scratch_bytes(L, TL, cfg.num_heads);
     k.S = carve<float>(p, k.attn_scratch_bytes / 4);
     k.attn_stat = carve<float>(p, (size_t)cfg.num_heads * ((L + 127) & ~127) * 4);
+    k.lse_self = carve<float>(p, (size_t)B * cfg.num_heads * L); k.lse_cross = carve<float>(p, (size_t)B * cfg.num_heads * L);
+    k.dsum = carve<float>(p, (size_t)B * cfg.num_heads * L);
+    k.o32_self = carve<float>(p, Md); k.o32_cross = carve<float>(p, Md);
+    // B200_ATTN_BWD=gemm: the attention adjoint as batched GEMMs over materialised S / dP (the first implementation,
+    // kept for A/B runs); default: the fused tcgen05 kernel of attn_bwd_tc.cu
+    static const bool use_gemm = std::getenv("B200_ATTN_BWD") && std::string(std::getenv("B200_ATTN_BWD")) == "gemm";
+    k.fused_attn = !use_gemm;
     const int widest = f > 3 * d ? f : 3 * d;
     k.colsum_bytes = bw_colsum_scratch_bytes(B, L > TL ? L : TL, widest);
     const size_t one = bw_colsum_scratch_bytes(1, M > k.Cr ? M : k.Cr, widest);

@@ -142,6 +142,10 @@ struct AttnParams {
   float* split_ws;
   int split_tiles, split_parts;        // set by launch_attention
   int n_units;                         // set by launch_attention: whole tiles + parts (= the v2 grid; the persistent kernel's work list)
+  // optional (the backward's recompute): lse[(item * heads + head) * Lq + q] = log2 of the row's sum of
+  // exp2(logit * scale * log2 e), i.e. P = exp2(s c - lse).  Selects the one-CTA-per-tile kernel without the key split.
+  float* lse;
+  float* out32; long long ldo32;       // with lse: the output rows in fp32 too (the backward forms rowsum(dO o O) from them)
 };
 constexpr long long ATTN_SPLIT_WS_BYTES = 512ll * (128 * 128 + 2 * 128) * 4;    // up to 512 partial tiles
 void launch_attention(const AttnParams& p, cudaStream_t stream);
