@@ -225,6 +225,13 @@ B200_API int b200disc_forward(b200disc_engine* e, const float* const* taps, int3
  * softmax_scale <= 0 selects 1/sqrt(128). */
 B200_API int b200_flash_attention(const void* q, const void* k, const void* v, const int32_t* k_lens, int32_t B,
                                   int32_t Lq, int32_t Lk, int32_t H, float softmax_scale, void* out, void* stream);
+/* The adjoint of the same operator -- what autograd reaches through flash_attention (attention.py:24-130) in the
+ * student's training step (distilled_trainer.py:301): q, k, v, dout as above (fp16 device; dout = d loss / d out),
+ * dq [B, Lq, H, 128] and dk [B, Lk, H, 128] fp32, dv [B, Lk, H, 128] fp16.  Runs the forward once more for its row
+ * statistics, then the fused tcgen05 backward kernel (csrc/attn_bwd_tc.cu).  Keys >= k_lens[b] get zero gradients. */
+B200_API int b200_flash_attention_backward(const void* q, const void* k, const void* v, const void* dout,
+                                           const int32_t* k_lens, int32_t B, int32_t Lq, int32_t Lk, int32_t H,
+                                           float softmax_scale, float* dq, float* dk, void* dv, void* stream);
 /* nn.Linear: out[M,N] = epilogue(A[M,K] W[N,K]^T + bias).  A, W fp16 device (row-major, leading
  * dimensions lda / ldw in elements), bias fp32 or NULL.  epilogue 0: fp16 store, 1: GELU(tanh) + fp16
  * store, 4: fp32 store.  block_n 0 = automatic, else 128, 144, 192 or 256 (single-CTA 128 x N tiles) or

@@ -8,7 +8,7 @@ the `b200dit` alias module at the repository root:
     eng = b200dit.DitEngine.from_module(wan_model)      # or b200dit.install(wan_model)
 """
 from ._lib import B200Error, LIB_PATH, MAX_ITEMS  # noqa: F401
-from .engine import (DitEngine, VaeEngine, flash_attention, kernel_launches, linear, profile_collect,  # noqa: F401
+from .engine import (DitEngine, VaeEngine, flash_attention, flash_attention_backward, kernel_launches, linear, profile_collect,  # noqa: F401
                      profile_enable)
 from . import discriminator, flops, omni, parallel, pipelines, solvers, synthetic  # noqa: F401
 from .omni import AudioProcessor  # noqa: F401

@@ -65,6 +65,7 @@ SIGNATURES = {
     "b200disc_forward": (_I, [_P, _PP, _I, _I, _P, _P, _P]),
     "b200omni_audio_tokens": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _L, _P]),
     "b200_flash_attention": (_I, [_P, _P, _P, _IP, _I, _I, _I, _I, _F, _P, _P]),
+    "b200_flash_attention_backward": (_I, [_P, _P, _P, _P, _IP, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
     "b200_linear": (_I, [_P, _L, _P, _L, _P, _I, _I, _I, _I, _P, _L, _I, _P]),
     "b200_solver_lincomb": (_I, [_I, _PP, _I, _PP, C.POINTER(C.c_float), _L, _P]),
     "b200_last_error": (C.c_char_p, []),

@@ -4,6 +4,7 @@
 #include <string>
 
 #include "../../include/b200dit.h"
+#include "backward.h"
 #include "dit_engine.h"
 #include "disc_engine.h"
 #include "vae_engine.h"
@@ -247,6 +248,45 @@ int b200_flash_attention(const void* q, const void* k, const void* v, const int3
     b2::launch_attention(p, s);
     B2_CUDA(cudaFreeAsync(split, s));
     B2_CUDA(cudaFreeAsync(vt, s));
+  });
+}
+
+int b200_flash_attention_backward(const void* q, const void* k, const void* v, const void* dout, const int32_t* k_lens,
+                                  int32_t B, int32_t Lq, int32_t Lk, int32_t H, float softmax_scale, float* dq, float* dk,
+                                  void* dv, void* stream) {
+  return guarded([&] {
+    B2_CHECK(q && k && v && dout && dq && dk && dv, "null argument");
+    B2_CHECK(B >= 1 && B <= b2::MAX_ITEMS && Lq >= 1 && Lk >= 1 && H >= 1, "bad attention shape");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long wide = (long long)H * 128;
+    const int Lkp = (Lk + 7) & ~7, Lp = B * Lkp;
+    // the forward again, for its row statistics and fp32 rows (what a training framework would have saved)
+    void *vt = nullptr, *o16 = nullptr, *o32 = nullptr, *lse = nullptr, *dsum = nullptr;
+    B2_CUDA(cudaMallocAsync(&vt, (size_t)wide * Lp * 2, s));
+    B2_CUDA(cudaMallocAsync(&o16, (size_t)B * Lq * wide * 2, s));
+    B2_CUDA(cudaMallocAsync(&o32, (size_t)B * Lq * wide * 4, s));
+    B2_CUDA(cudaMallocAsync(&lse, (size_t)B * H * Lq * 4, s));
+    B2_CUDA(cudaMallocAsync(&dsum, (size_t)B * H * Lq * 4, s));
+    for (int b = 0; b < B; ++b)
+      b2::launch_transpose_h(static_cast<const __half*>(v) + (size_t)b * Lk * wide, wide,
+                             static_cast<__half*>(vt) + (size_t)b * Lkp, Lp, Lk, (int)wide, s, Lkp);
+    b2::AttnParams p{};
+    p.q = static_cast<const __half*>(q); p.ldq = wide; p.k = static_cast<const __half*>(k); p.ldk = wide;
+    p.vt = static_cast<const __half*>(vt); p.ldvt = Lp; p.out = static_cast<__half*>(o16); p.ldo = wide;
+    p.items = B; p.heads = H; p.Lq = Lq; p.Lk_rows = Lk; p.vt_stride = Lkp;
+    p.scale = softmax_scale > 0.f ? softmax_scale : 0.08838834764831845f;
+    for (int i = 0; i < B; ++i) p.klen[i] = k_lens ? (k_lens[i] < Lk ? k_lens[i] : Lk) : Lk;
+    p.lse = static_cast<float*>(lse); p.out32 = static_cast<float*>(o32); p.ldo32 = wide;
+    b2::launch_attention(p, s);
+    b2::AttnBwdParams f{};
+    f.q = p.q; f.ldq = wide; f.k = p.k; f.ldk = wide; f.v = static_cast<const __half*>(v); f.ldv = wide;
+    f.O = static_cast<const float*>(o32); f.ldo = wide; f.dO = static_cast<const __half*>(dout); f.lddo = wide;
+    f.lse = static_cast<const float*>(lse); f.dsum = static_cast<float*>(dsum);
+    f.dq = dq; f.lddq = wide; f.dk = dk; f.lddk = wide; f.dv = static_cast<__half*>(dv); f.lddv = wide;
+    f.items = B; f.heads = H; f.Lq = Lq; f.Lk = Lk; f.scale = p.scale;
+    for (int i = 0; i < B; ++i) f.klen[i] = p.klen[i];
+    b2::launch_attention_backward(f, s);
+    for (void* ptr : {vt, o16, o32, lse, dsum}) B2_CUDA(cudaFreeAsync(ptr, s));
   });
 }
 

@@ -467,6 +467,27 @@ def flash_attention(q, k, v, q_lens=None, k_lens=None, dropout_p=0., softmax_sca
     return out.to(out_dtype)
 
 
+def flash_attention_backward(q, k, v, dout, k_lens=None, softmax_scale=None):
+    """Adjoint of `flash_attention` (b200_flash_attention_backward): q, dout [B,Lq,N,128], k / v [B,Lk,N,128] ->
+    (dq fp32, dk fp32, dv fp16), the gradients autograd would hand back through attention.py:24-130."""
+    assert q.is_cuda and q.size(-1) == 128
+    b, lq, n, _ = q.shape
+    lk = k.shape[1]
+    qh, kh, vh, dh = (u.to(torch.float16).contiguous() for u in (q, k, v, dout))
+    dq = torch.empty((b, lq, n, 128), dtype=torch.float32, device=q.device)
+    dk = torch.empty((b, lk, n, 128), dtype=torch.float32, device=q.device)
+    dv = torch.empty((b, lk, n, 128), dtype=torch.float16, device=q.device)
+    kl = None
+    if k_lens is not None:
+        kl = int_array([int(u) for u in (k_lens.tolist() if torch.is_tensor(k_lens) else k_lens)])
+    with torch.cuda.device(q.device):
+        check(lib().b200_flash_attention_backward(
+            C.c_void_p(qh.data_ptr()), C.c_void_p(kh.data_ptr()), C.c_void_p(vh.data_ptr()), C.c_void_p(dh.data_ptr()), kl,
+            b, lq, lk, n, float(softmax_scale or 0.0), C.c_void_p(dq.data_ptr()), C.c_void_p(dk.data_ptr()),
+            C.c_void_p(dv.data_ptr()), _stream_ptr()))
+    return dq, dk, dv
+
+
 def linear(a, w, bias=None, epilogue="f16", block_n=0):
     """nn.Linear on the tcgen05 GEMM: a [M,K] fp16, w [N,K] fp16 -> [M,N] (fp16, gelu fp16 or fp32)."""
     epi = {"f16": 0, "gelu": 1, "f32": 4}[epilogue]
