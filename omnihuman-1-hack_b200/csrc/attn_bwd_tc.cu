@@ -12,8 +12,8 @@
 //     operands, with the SAME shared-memory tiles of dO and Q read as MN-major B operands (no transposed copies),
 //   * dQ^T = K^T dS^T takes the K tile as an MN-major A operand and dS from a small shared-memory tile.
 // Nothing of size Lq x Lk ever exists in HBM.
-//   warps 0..3  softmax adjoint (thread = key row), warps 4..7 dQ epilogue (thread = channel row of dQ^T),
-//   warp 8 TMA producer, warp 9 MMA issuer
+//   warps 0..7  softmax adjoint (thread = key row x 32 of the step's 64 queries) and dQ epilogue (thread = channel row
+//               of dQ^T x the same 32 queries), warp 8 TMA producer, warp 9 MMA issuer
 //   TMEM columns: S^T / P^T [0,64)  dP^T / dS^T [64,128)  dV [128,256)  dK [256,384)  dQ^T [384,448)
 #include <cmath>
 #include <cstdlib>
@@ -33,7 +33,7 @@ constexpr int OFF_K = 0;
 constexpr int OFF_V = OFF_K + K_BYTES;
 constexpr int OFF_Q = OFF_V + K_BYTES;          // [2 stages][Q | dO]
 constexpr int OFF_DS = OFF_Q + 2 * 2 * Q_BYTES; // dS [64 queries x 128 keys] fp16: two [64 x 64] SW128 halves
-constexpr int OFF_STG = OFF_DS + 2 * 64 * 128;  // dQ staging: four [64 queries x 32 d] fp32 boxes
+constexpr int OFF_STG = OFF_DS + 2 * 64 * 128;  // dQ staging: eight [32 queries x 32 d] fp32 boxes, one per warp
 constexpr int OFF_STAT = OFF_STG + 64 * 128 * 4;   // [2][2][64] floats: LSE | D of the step's queries
 constexpr int OFF_BAR = OFF_STAT + 2 * 2 * 64 * 4;
 constexpr int SMEM = OFF_BAR + 256;
@@ -87,7 +87,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tma_prefetch_desc(&tmap_dq);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-    mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(dq_full, 1); mbar_init(dq_empty, 4); mbar_init(acc_done, 1);
+    mbar_init(s_full, 1); mbar_init(p_ready, 8); mbar_init(dq_full, 1); mbar_init(dq_empty, 8); mbar_init(acc_done, 1);
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
@@ -141,9 +141,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < QT / 16; ++kk) {   // over the 64 queries, 16 per instruction (two 8-row groups = 2048 B)
-          umma_f16_ts(tmem + T_DV, tmem + T_ST + kk * 8, umma_desc_mn_sw128(sdo + kk * 2048, Q_BYTES / 2), id_acc,
+          // queries [32 h, 32 h + 32) sit as fp16 pairs in the first 16 columns of the h-th 32-column half
+          const uint32_t ta = (kk >> 1) * 32 + (kk & 1) * 8;
+          umma_f16_ts(tmem + T_DV, tmem + T_ST + ta, umma_desc_mn_sw128(sdo + kk * 2048, Q_BYTES / 2), id_acc,
                       (i > 0 || kk > 0));
-          umma_f16_ts(tmem + T_DK, tmem + T_DP + kk * 8, umma_desc_mn_sw128(sq + kk * 2048, Q_BYTES / 2), id_acc,
+          umma_f16_ts(tmem + T_DK, tmem + T_DP + ta, umma_desc_mn_sw128(sq + kk * 2048, Q_BYTES / 2), id_acc,
                       (i > 0 || kk > 0));
         }
 #pragma unroll
@@ -156,10 +158,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       umma_commit(acc_done);
     }
     __syncwarp();
-  } else if (warp < 4) {
-    // ---- softmax adjoint: thread r owns key row r of the tile and the 64 queries of the step
-    const int r = warp * 32 + lane;
-    const uint32_t lane_sel = uint32_t(warp * 32) << 16;
+  } else {
+    // ---- warps 0..7.  Softmax adjoint: warp w owns key rows (w & 3) * 32 + lane (its TMEM lane quadrant) and the
+    // query columns [(w >> 2) * 32, + 32) of the step -- two warps per quadrant, so the step's 128 x 64 logits cost each
+    // thread 32 exponentials.  dQ epilogue (of the PREVIOUS step, while S^T of this one is being formed): the same
+    // warp owns channels (w & 3) * 32 + lane of dQ^T and the same 32 query columns; it stages its [32 queries x 32 d]
+    // fp32 box and reduce-adds it on its own (no cross-warp synchronisation).
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_sel = uint32_t(quad * 32) << 16;
     const int key = kt * KT + r;
     const bool key_ok = key < klen;
     const float c = p.scale * 1.4426950408889634f;
@@ -167,61 +174,84 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const float* dd_g = p.dsum + ((long long)item * p.heads + head) * p.Lq;
     uint8_t* sds = smem + OFF_DS + (r >> 6) * 8192;            // this key's half of the dS tile
     const int kc = r & 63;                                     // key column inside the half
+    float* stg = reinterpret_cast<float*>(smem + OFF_STG) + warp * (32 * 32);   // [32 queries][32 d]
+    const int tid = threadIdx.x;
+    auto dq_epilogue = [&](int i) {
+      mbar_wait_w(dq_full, i & 1, lane);
+      tc_fence_after();
+      uint32_t a[32];
+      tmem_ld32(tmem + lane_sel + T_DQ + half * 32, a);
+      tmem_wait_ld();
+      tc_fence_before();
+      if (lane == 0) tma_store_wait_read0();                   // this warp's previous reduce has read its staging box
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);                    // dQ^T may be overwritten by the next step
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stg[j * 32 + lane] = __uint_as_float(a[j]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(&tmap_dq, stg, head * 128 + quad * 32, item * p.Lq + i * QT + half * 32);
+        tma_store_commit();
+      }
+    };
     for (int i = 0; i < n_it; ++i) {
       float* st = stat + (i & 1) * 128;
-      {
-        const int q = i * QT + (r & 63);
+      if (tid < 128) {
+        const int q = i * QT + (tid & 63);
         float v;
-        if (r < 64) v = q < p.Lq ? lse_g[q] : INFINITY;        // P = exp2(.. - inf) = 0 for the rows past the item
+        if (tid < 64) v = q < p.Lq ? lse_g[q] : INFINITY;      // P = exp2(.. - inf) = 0 for the rows past the item
         else v = q < p.Lq ? dd_g[q] : 0.f;
-        st[r] = v;
+        st[tid] = v;
       }
-      named_bar(1, 128);
+      named_bar(1, 256);
+      if (i > 0) dq_epilogue(i - 1);
       mbar_wait_w(s_full, i & 1, lane);
       tc_fence_after();
-      uint32_t pk[32], dk[32];
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
+      uint32_t pk[16], dk[16];
+      {
         uint32_t s[32], dp[32];
-        tmem_ld32(tmem + lane_sel + T_ST + ch * 32, s);
-        tmem_ld32(tmem + lane_sel + T_DP + ch * 32, dp);
+        tmem_ld32(tmem + lane_sel + T_ST + half * 32, s);
+        tmem_ld32(tmem + lane_sel + T_DP + half * 32, dp);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const float2 l2 = *reinterpret_cast<const float2*>(st + ch * 32 + j);
-          const float2 d2 = *reinterpret_cast<const float2*>(st + 64 + ch * 32 + j);
+          const float2 l2 = *reinterpret_cast<const float2*>(st + half * 32 + j);
+          const float2 d2 = *reinterpret_cast<const float2*>(st + 64 + half * 32 + j);
           float p0 = key_ok ? ex2f(fmaf(__uint_as_float(s[j]), c, -l2.x)) : 0.f;
           float p1 = key_ok ? ex2f(fmaf(__uint_as_float(s[j + 1]), c, -l2.y)) : 0.f;
           const float e0 = p.scale * p0 * (__uint_as_float(dp[j]) - d2.x);
           const float e1 = p.scale * p1 * (__uint_as_float(dp[j + 1]) - d2.y);
-          pk[ch * 16 + (j >> 1)] = pack2(p0, p1);
-          dk[ch * 16 + (j >> 1)] = pack2(e0, e1);
+          pk[j >> 1] = pack2(p0, p1);
+          dk[j >> 1] = pack2(e0, e1);
           // dS [query][key] for dQ: neighbouring key rows pair up, so every lane stores one 4-byte word --
           // even lanes the pair (key, key + 1) of query j, odd lanes the pair (key - 1, key) of query j + 1
           const float o0 = __shfl_xor_sync(0xffffffffu, e0, 1), o1 = __shfl_xor_sync(0xffffffffu, e1, 1);
-          const int qq = ch * 32 + j + (lane & 1);
+          const int qq = half * 32 + j + (lane & 1);
           const uint32_t w = (lane & 1) ? pack2(o1, e1) : pack2(e0, o0);
           *reinterpret_cast<uint32_t*>(sds + sw128_offset(qq, kc >> 3) + ((kc & 6) << 1)) = w;
         }
       }
-      tmem_st32(tmem + lane_sel + T_ST, pk);                   // P^T over its own logits (fp16 pairs)
-      tmem_st32(tmem + lane_sel + T_DP, dk);                   // dS^T likewise
+      // P^T / dS^T (fp16 pairs) go back over the first 16 of this warp's OWN 32 logit columns
+      tmem_st16(tmem + lane_sel + T_ST + half * 32, pk);
+      tmem_st16(tmem + lane_sel + T_DP + half * 32, dk);
       tmem_wait_st();
       tc_fence_before();
       fence_proxy_async_smem();                                // the dS tile is read by the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
     }
-    // ---- dV, dK of this key tile
+    dq_epilogue(n_it - 1);
+    // ---- dV, dK of this key tile: this warp's 32 key rows x channels [half * 64, + 64)
     mbar_wait_w(acc_done, 0, lane);
     tc_fence_after();
     const bool store = key < p.Lk;
-    __half* dv = p.dv + ((long long)item * p.Lk + key) * p.lddv + head * 128;
-    float* dkp = p.dk + ((long long)item * p.Lk + key) * p.lddk + head * 128;
+    __half* dv = p.dv + ((long long)item * p.Lk + key) * p.lddv + head * 128 + half * 64;
+    float* dkp = p.dk + ((long long)item * p.Lk + key) * p.lddk + head * 128 + half * 64;
 #pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
+    for (int ch = 0; ch < 2; ++ch) {
       uint32_t t[32];
-      tmem_ld32(tmem + lane_sel + T_DV + ch * 32, t);
+      tmem_ld32(tmem + lane_sel + T_DV + half * 64 + ch * 32, t);
       tmem_wait_ld();
       if (store) {
 #pragma unroll
@@ -230,7 +260,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               make_uint4(pack2(__uint_as_float(t[j]), __uint_as_float(t[j + 1])), pack2(__uint_as_float(t[j + 2]), __uint_as_float(t[j + 3])),
                          pack2(__uint_as_float(t[j + 4]), __uint_as_float(t[j + 5])), pack2(__uint_as_float(t[j + 6]), __uint_as_float(t[j + 7])));
       }
-      tmem_ld32(tmem + lane_sel + T_DK + ch * 32, t);
+      tmem_ld32(tmem + lane_sel + T_DK + half * 64 + ch * 32, t);
       tmem_wait_ld();
       if (store) {
 #pragma unroll
@@ -239,36 +269,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
     tc_fence_before();
-  } else if (warp < 8) {
-    // ---- dQ epilogue: thread d owns channel d of dQ^T [128 d x 64 queries]; staged as [query][d] and reduce-added
-    const int w = warp - 4, d = w * 32 + lane;
-    const uint32_t lane_sel = uint32_t(w * 32) << 16;
-    float* stg = reinterpret_cast<float*>(smem + OFF_STG) + (d >> 5) * (64 * 32) + (d & 31);
-    for (int i = 0; i < n_it; ++i) {
-      mbar_wait_w(dq_full, i & 1, lane);
-      tc_fence_after();
-      uint32_t a[32], b[32];
-      tmem_ld32(tmem + lane_sel + T_DQ, a);
-      tmem_ld32(tmem + lane_sel + T_DQ + 32, b);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dq_empty);                    // dQ^T may be overwritten by the next step
-      if (threadIdx.x == 128) tma_store_wait_read0();          // the previous step's reduce has read the staging tile
-      named_bar(2, 128);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) { stg[j * 32] = __uint_as_float(a[j]); stg[(32 + j) * 32] = __uint_as_float(b[j]); }
-      fence_proxy_async_smem();
-      named_bar(2, 128);
-      if (threadIdx.x == 128) {
-        const int q_row0 = item * p.Lq + i * QT;
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb)
-          tma_reduce_add_2d(&tmap_dq, smem + OFF_STG + cb * (64 * 32 * 4), head * 128 + cb * 32, q_row0);
-        tma_store_commit();
-      }
-    }
-    if (threadIdx.x == 128) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();                       // bulk reduces read shared memory asynchronously
   }
 
   __syncthreads();
@@ -322,7 +323,7 @@ void launch_attention_backward(const AttnBwdParams& p, cudaStream_t stream) {
   CUtensorMap tv = make_tmap_2d(p.v, Mk, wide, p.ldv, 128);
   uint64_t dims[2] = {wide, (uint64_t)Mq};
   uint64_t str[1] = {(uint64_t)p.lddq * 4};
-  uint32_t box[2] = {32, 64};
+  uint32_t box[2] = {32, 32};
   CUtensorMap tdq = make_tmap(p.dq, true, 2, dims, str, box, 0);
   const int n_kt = (p.Lk + KT - 1) / KT;
   attn_bwd_kernel<<<n_kt * p.heads * p.items, 320, SMEM, stream>>>(tq, tk, tv, tdo, tdq, p);

@@ -56,9 +56,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x
 
 // ---------------------------------------------------------------- column sums, two stages, fixed order
 // part[(item * chunks + chunk) * dim + c] = sum over the chunk's rows of A[r, c] * B[r, c] * rs[r]
-// One thread per column PAIR (4- or 8-byte loads), CS_ROWS rows per block (short, fully unrolled: at M = 1560 the
-// pass is latency-bound, ncu: 12 % occupancy with 32 rows per block), four independent accumulators.
-constexpr int CS_ROWS = 8;
+// One thread per column PAIR (4- or 8-byte loads), a short run of rows per block (at M = 1560 the pass is
+// latency-bound: ncu showed 12 % occupancy with 32 rows per block), four independent accumulators.
+constexpr int CS_MIN_ROWS = 8, CS_MAX_CHUNKS = 128;
+inline int cs_rows(int rows_per_item) {            // rows per stage-1 block: at most 128 partial rows per item for stage 2
+  const int r = (rows_per_item + CS_MAX_CHUNKS - 1) / CS_MAX_CHUNKS;
+  return r < CS_MIN_ROWS ? CS_MIN_ROWS : r;
+}
 template <class TA>
 __device__ __forceinline__ float2 ld2(const TA* p, long long i);
 template <>
@@ -70,16 +74,15 @@ __device__ __forceinline__ float2 ld2<__half>(const __half* p, long long i) {
 template <class TA, class TB, bool HAS_B>
 __global__ void __launch_bounds__(128) colsum_stage1_kernel(const TA* __restrict__ A, long long lda, const TB* __restrict__ B,
                                                             long long ldb, const float* __restrict__ rs, int rows_per_item,
-                                                            int dim, float* __restrict__ part, int chunks) {
+                                                            int dim, float* __restrict__ part, int chunks, int rows_per_chunk) {
   const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
   if (c >= dim) return;
   const int chunk = blockIdx.y, item = blockIdx.z;
-  const int r0 = chunk * CS_ROWS, r1 = min(r0 + CS_ROWS, rows_per_item);
+  const int r0 = chunk * rows_per_chunk, r1 = min(r0 + rows_per_chunk, rows_per_item);
   float2 acc[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
   const long long base = (long long)item * rows_per_item;
-#pragma unroll
-  for (int r = r0; r < r0 + CS_ROWS; ++r) {
-    if (r >= r1) break;
+#pragma unroll 8
+  for (int r = r0; r < r1; ++r) {
     const long long row = base + r;
     float2 v = ld2<TA>(A, row * lda + c);
     if (HAS_B) { const float2 w = ld2<TB>(B, row * ldb + c); v.x *= w.x; v.y *= w.y; }
@@ -432,17 +435,17 @@ void bw_colsum(const void* A, int a_dt, long long lda, const void* B, int b_dt, 
                int rows_per_item, int dim, float* out, long long out_item_stride, float scale, bool accumulate, float* scratch,
                cudaStream_t s) {
   B2_CHECK(dim % 2 == 0 && lda % 2 == 0 && (B == nullptr || ldb % 2 == 0), "column sums work on column pairs");
-  const int chunks = (rows_per_item + CS_ROWS - 1) / CS_ROWS;
+  const int rpc = cs_rows(rows_per_item), chunks = (rows_per_item + rpc - 1) / rpc;
   const dim3 grid((dim / 2 + 127) / 128, chunks, items);
   const float* Af = reinterpret_cast<const float*>(A); const __half* Ah = reinterpret_cast<const __half*>(A);
   const float* Bf = reinterpret_cast<const float*>(B); const __half* Bh = reinterpret_cast<const __half*>(B);
   if (B == nullptr) {
-    if (a_dt == DT_F32) colsum_stage1_kernel<float, float, false><<<grid, 128, 0, s>>>(Af, lda, nullptr, 0, rs, rows_per_item, dim, scratch, chunks);
-    else colsum_stage1_kernel<__half, float, false><<<grid, 128, 0, s>>>(Ah, lda, nullptr, 0, rs, rows_per_item, dim, scratch, chunks);
+    if (a_dt == DT_F32) colsum_stage1_kernel<float, float, false><<<grid, 128, 0, s>>>(Af, lda, nullptr, 0, rs, rows_per_item, dim, scratch, chunks, rpc);
+    else colsum_stage1_kernel<__half, float, false><<<grid, 128, 0, s>>>(Ah, lda, nullptr, 0, rs, rows_per_item, dim, scratch, chunks, rpc);
   } else if (a_dt == DT_F32 && b_dt == DT_F32) {
-    colsum_stage1_kernel<float, float, true><<<grid, 128, 0, s>>>(Af, lda, Bf, ldb, rs, rows_per_item, dim, scratch, chunks);
+    colsum_stage1_kernel<float, float, true><<<grid, 128, 0, s>>>(Af, lda, Bf, ldb, rs, rows_per_item, dim, scratch, chunks, rpc);
   } else if (a_dt == DT_F32 && b_dt == DT_F16) {
-    colsum_stage1_kernel<float, __half, true><<<grid, 128, 0, s>>>(Af, lda, Bh, ldb, rs, rows_per_item, dim, scratch, chunks);
+    colsum_stage1_kernel<float, __half, true><<<grid, 128, 0, s>>>(Af, lda, Bh, ldb, rs, rows_per_item, dim, scratch, chunks, rpc);
   } else {
     fail("bw_colsum: unsupported operand types %d x %d", a_dt, b_dt);
   }
@@ -452,7 +455,7 @@ void bw_colsum(const void* A, int a_dt, long long lda, const void* B, int b_dt, 
   B2_AFTER();
 }
 size_t bw_colsum_scratch_bytes(int items, int rows_per_item, int dim) {
-  return (size_t)items * ((rows_per_item + CS_ROWS - 1) / CS_ROWS) * dim * sizeof(float);
+  return (size_t)items * ((rows_per_item + CS_MIN_ROWS - 1) / CS_MIN_ROWS) * dim * sizeof(float);
 }
 
 void bw_axpy_gate(const float* xin, const float* y, const float* g, long long g_item_stride, int rows_per_item, float* xout,
