@@ -70,9 +70,17 @@ PAIR_WORKER = r'''
 import os, sys, torch
 sys.path.insert(0, os.environ["B200_ROOT"])
 import b200dit
-from b200dit import parallel as par, pipelines as P
+from b200dit import parallel as par, pipelines as P, solvers as PS
 rank, world = par.init("gloo")
 assert world == 2
+
+
+def cpu_lincomb(inputs, coeffs, like):          # host-logic stand-in for the fused CUDA combine (tests only)
+    ins = [t if t is not None else like for t in inputs]
+    return [sum(c * t for c, t in zip(row, ins)) for row in coeffs]
+
+
+PS._lincomb = cpu_lincomb
 
 
 class FakeEngine:
