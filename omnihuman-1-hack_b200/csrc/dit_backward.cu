@@ -148,6 +148,13 @@ static size_t attn_scratch_bytes(int L, int TL, int heads) {
   return n * per_head + 4096;
 }
 
+static bool attn_bwd_gemm_path() {
+  // B200_ATTN_BWD=gemm: the attention adjoint as batched GEMMs over materialised S / dP (the first implementation,
+  // kept for A/B runs); default: the fused tcgen05 kernel of attn_bwd_tc.cu, which needs no Lq x Lk scratch
+  static const bool v = std::getenv("B200_ATTN_BWD") && std::string(std::getenv("B200_ATTN_BWD")) == "gemm";
+  return v;
+}
+
 void DitEngine::ensure_bwd_workspace(int B, int L) {
   if (bws_buf && B <= bws_B && L <= bws_L) return;
   B2_CUDA(cudaDeviceSynchronize());
@@ -164,7 +171,8 @@ void DitEngine::ensure_bwd_workspace(int B, int L) {
   bytes += 2 * d * Tp * 2 + (M + Cr) * 4 * 8;
   bytes += (3 * d > f ? 3 * d : f) * Tp * 2 + (f > (size_t)cfg.text_dim ? f : (size_t)cfg.text_dim) * Tp * 2 + 3 * d * Tp * 2;
   bytes += 3 * ((size_t)bws_B * cfg.num_heads * bws_L * 4 + 256);
-  bytes += attn_scratch_bytes(bws_L, (int)TL, cfg.num_heads) + (size_t)cfg.num_heads * (Lq + 128) * 16 + 64 * 4096;
+  bytes += (attn_bwd_gemm_path() ? attn_scratch_bytes(bws_L, (int)TL, cfg.num_heads) : 4096) +
+           (size_t)cfg.num_heads * (Lq + 128) * 16 + 64 * 4096;
   (void)Lk;
   bytes += (size_t)cfg.num_layers * bws_B * 6 * d * 4 + bws_B * 16 * d * 4 + M * 64 * 8 + M * cfg.in_dim * 4 * 4 + M * 16;
   bytes += bw_colsum_scratch_bytes(bws_B, bws_L > (int)TL ? bws_L : (int)TL, (int)(f > 3 * d ? f : 3 * d)) * 2;
@@ -495,16 +503,13 @@ void DitEngine::backward(const float* const* dout, float loss_scale, int ffn_gra
     const size_t tb_rows = (size_t)(f > cfg.text_dim ? f : cfg.text_dim);
     k.tA = carve<__half>(p, ta_rows * k.Tp); k.tB = carve<__half>(p, (tb_rows > (size_t)d ? tb_rows : (size_t)d) * k.Tp);
     k.qT = carve<__half>(p, (size_t)d * k.Tp); k.kT = carve<__half>(p, (size_t)d * k.Tp); k.dOT = carve<__half>(p, (size_t)d * k.Tp);
-    k.attn_scratch_bytes = attn_scratch_bytes(L, TL, cfg.num_heads);
+    k.attn_scratch_bytes = attn_bwd_gemm_path() ? attn_scratch_bytes(L, TL, cfg.num_heads) : 4096;
     k.S = carve<float>(p, k.attn_scratch_bytes / 4);
     k.attn_stat = carve<float>(p, (size_t)cfg.num_heads * ((L + 127) & ~127) * 4);
     k.lse_self = carve<float>(p, (size_t)B * cfg.num_heads * L); k.lse_cross = carve<float>(p, (size_t)B * cfg.num_heads * L);
     k.dsum = carve<float>(p, (size_t)B * cfg.num_heads * L);
     k.o32_self = carve<float>(p, Md); k.o32_cross = carve<float>(p, Md);
-    // B200_ATTN_BWD=gemm: the attention adjoint as batched GEMMs over materialised S / dP (the first implementation,
-    // kept for A/B runs); default: the fused tcgen05 kernel of attn_bwd_tc.cu
-    static const bool use_gemm = std::getenv("B200_ATTN_BWD") && std::string(std::getenv("B200_ATTN_BWD")) == "gemm";
-    k.fused_attn = !use_gemm;
+    k.fused_attn = !attn_bwd_gemm_path();
     const int widest = f > 3 * d ? f : 3 * d;
     k.colsum_bytes = bw_colsum_scratch_bytes(B, L > TL ? L : TL, widest);
     const size_t one = bw_colsum_scratch_bytes(1, M > k.Cr ? M : k.Cr, widest);

@@ -209,6 +209,17 @@ void load_into_slot(Slot& s, const char* name, const void* data, int dtype, int 
   B2_CHECK(n == s.numel, "weight %s has %lld elements, expected %lld", name, n, s.numel);
   const size_t esz = dtype == DT_F32 ? 4 : 2;
   B2_CHECK(dtype == DT_F32 || dtype == DT_F16 || dtype == DT_BF16, "weight %s: unsupported dtype %d", name, dtype);
+  // A device-resident source (the live parameters of a module being trained: the shim reloads after every optimizer
+  // step) is converted in place on the default stream, nothing staged, nothing synchronised per tensor -- finalize()
+  // synchronises once.  Host sources are staged through a device buffer.
+  cudaPointerAttributes at{};
+  const bool on_device = cudaPointerGetAttributes(&at, data) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+  if (!on_device) cudaGetLastError();
+  if (on_device && s.tr_rows == 0) {
+    launch_convert(data, dtype, s.dst, s.dst_dtype, n, 0);
+    s.loaded = true;
+    return;
+  }
   DevBuf stage;
   stage.ensure(n * esz);
   B2_CUDA(cudaMemcpy(stage.p, data, n * esz, cudaMemcpyDefault));

@@ -46,7 +46,7 @@ class AptDiscriminator:
         with torch.cuda.device(self.device):
             check(lib().b200disc_create(self.dim, backbone.cfg["num_heads"], int(bool(qk_norm)),
                                         float(backbone.cfg["eps"]), C.byref(self._h)))
-            _load_state(lib().b200disc_load_weight, self._h, state_dict, lambda n: not n.startswith("backbone."))
+            keep = _load_state(lib().b200disc_load_weight, self._h, state_dict, lambda n: not n.startswith("backbone."))
             check(lib().b200disc_finalize(self._h))
         self._taps, self._rows = None, 0
 

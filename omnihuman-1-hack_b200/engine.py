@@ -20,6 +20,9 @@ def _stream_ptr():
 
 
 def _load_state(load_fn, handle, sd, accept):
+    """One load call per state_dict entry.  Device-resident sources are converted asynchronously (the engine
+    synchronises once in *_finalize), so every tensor handed over is returned and must stay referenced until then."""
+    keep = []
     for name, tensor in sd.items():
         if not accept(name):
             continue
@@ -27,8 +30,10 @@ def _load_state(load_fn, handle, sd, accept):
         if t.dtype not in _DT:
             t = t.float()
         t = t.contiguous()
+        keep.append(t)
         shape = (C.c_int64 * max(t.dim(), 1))(*(list(t.shape) or [1]))
         check(load_fn(handle, name.encode(), C.c_void_p(t.data_ptr()), _DT[t.dtype], max(t.dim(), 1), shape))
+    return keep
 
 
 class DitEngine:
@@ -101,8 +106,9 @@ class DitEngine:
     def load_state_dict(self, sd):
         self._ctx_key = None              # cached cross-attention K / V belong to the old weights
         with torch.cuda.device(self.device):
-            _load_state(lib().b200dit_load_weight, self._h, sd, lambda n: n != "freqs")
+            keep = _load_state(lib().b200dit_load_weight, self._h, sd, lambda n: n != "freqs")
             check(lib().b200dit_finalize(self._h))
+            del keep
 
     def set_pad_to_seq_len(self, enabled):
         """Carry the reference's seq_len - L zero-padded rows of every item through the blocks (model.py:522), so that
