@@ -43,6 +43,9 @@ def main():
     ap.add_argument("--train", action="store_true",
                     help="config 4: the student training step (forward + backward on the engine, distilled_trainer.py:241-301)")
     ap.add_argument("--batch", type=int, default=1, help="config 4 --train: items per training step (reference: 1)")
+    ap.add_argument("--shim", action="store_true",
+                    help="config 4 --train: the whole trainer-visible step through wan_shim.install on a module with live "
+                         "parameters: forward, loss.backward() (engine), AdamW step, weight reload on the next call")
     ap.add_argument("--pair-split", action="store_true",
                     help="config 4: teacher cond / uncond of one item on a rank pair (one send per item)")
     a = ap.parse_args()
@@ -72,6 +75,52 @@ def main():
                 f"{a.steps} DPM++ steps, cfg 7.5 annealed", "n_gpus": world, "ms": ms,
                 "denoise_steps_per_s": a.steps / (ms / 1e3), "tflops": 2 * a.steps * (eng.last_flops / 2) / (ms / 1e3) / 1e12,
                 "finite": bool(torch.isfinite(out[0]).all())}
+    elif a.config == 4 and a.train and a.shim:
+        # distilled_trainer.py:241-316 as the trainer sees it: the module's parameters are the source of truth, the
+        # engine holds a snapshot that the shim refreshes after every optimizer step
+        sd = make_device_weights(cfg, 0, dev)
+
+        class Student(torch.nn.Module):              # attribute surface of WanModel (model.py:445-460)
+            def __init__(self):
+                super().__init__()
+                self.model_type, self.dim, self.ffn_dim, self.num_heads, self.num_layers = "t2v", 1536, 8960, 12, a.layers
+                self.in_dim, self.out_dim, self.text_dim, self.text_len, self.freq_dim, self.eps = 16, 16, 4096, 512, 256, 1e-6
+                self._keys = list(sd)
+                self.ps = torch.nn.ParameterList([torch.nn.Parameter(sd[k].float()) for k in self._keys])
+
+            def named_parameters(self, *aa, **kw):
+                return iter(zip(self._keys, self.ps))
+
+            def state_dict(self, *aa, **kw):
+                return {k: p.detach() for k, p in zip(self._keys, self.ps)}
+
+            def forward(self, *aa, **kw):
+                raise AssertionError("the original forward must not run")
+
+        m = Student()
+        eng = b200dit.install(m)
+        opt = torch.optim.AdamW(list(m.ps), lr=1e-6)
+        gi = torch.Generator().manual_seed(7)
+        noises = [torch.randn(16, 1, 60, 104, generator=gi).to(dev) for _ in range(a.items)]
+        ctxs = [torch.randn(512, 4096, generator=gi).to(dev) for _ in range(a.items)]
+        vts = [torch.randn(16, 1, 60, 104, generator=gi).to(dev) for _ in range(a.items)]
+        t1000 = torch.full((a.batch,), 1000.0, device=dev)
+
+        def step(i0):
+            idx = list(range(i0, min(i0 + a.batch, a.items)))
+            opt.zero_grad(set_to_none=True)
+            out = m([noises[i] for i in idx], t=t1000[:len(idx)], context=[ctxs[i] for i in idx], seq_len=1560)
+            loss = sum(torch.nn.functional.mse_loss(o, vts[i]) for o, i in zip(out, idx)) / len(idx)
+            loss.backward()
+            opt.step()
+            return loss.detach()
+        step(0); step(0)                                       # warm-up: workspaces, AdamW state, transposed weights
+        ls, ms = timed(lambda: torch.stack([step(i0) for i0 in range(0, a.items, a.batch)]))
+        line = {"config": 4, "workload": f"{a.items} APT stage-1 training items through wan_shim.install on a module with live "
+                f"fp32 parameters ({a.batch} item(s) per step): engine forward + backward, param.grad read-back, AdamW step, "
+                "engine weight reload before the next forward", "n_gpus": world, "ms": ms,
+                "items_per_s": a.items / (ms / 1e3), "ms_per_step": ms / ((a.items + a.batch - 1) // a.batch),
+                "reloads": getattr(m, "_b200_reloads", 0), "mean_loss": float(ls.mean()), "finite": bool(torch.isfinite(ls).all())}
     elif a.config == 4 and a.train:
         # the student's training step: items i % world == rank, forward + backward per step of `batch` items;
         # gradients accumulate in the engine (DDP's all-reduce of the 5.7 GB fp32 gradient is the trainer's, not timed)
