@@ -141,8 +141,27 @@ class CpuStep:
         with self.torch.no_grad():
             c = O.dit_forward(self.sd, self.x, self.t, self.ctx, self.L, num_layers=nl)[0]
             u = O.dit_forward(self.sd, self.x, self.t, self.ctx0, self.L, num_layers=nl)[0]
-            O.cfg_combine(c, u, GUIDE)
+            v = O.cfg_combine(c, u, GUIDE)
+        if nl == self.layers:
+            self.last = (c, u, v)                            # the checker's outputs of the whole step (parity leg)
         return time.perf_counter() - t0
+
+    def parity(self, dev):
+        """The engine on exactly the sample the CPU leg just computed (same weights, inputs, t, guide scale):
+        rel-L2 of one forward and of the CFG-combined step against the fp32 oracle.  The checker, not the product."""
+        import b200dit
+        torch = self.torch
+        eng = b200dit.DitEngine.from_state_dict(self.sd, num_heads=CFG_13B["num_heads"], device=dev)
+        with torch.no_grad():
+            c = eng.forward(self.x, self.t, self.ctx, self.L)[0].cpu()
+            v = eng.forward_cfg(self.x, self.t, self.ctx, self.ctx0, self.L, GUIDE)[0].cpu()
+        rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+        out = {"forward_rel_l2": rel(c, self.last[0]), "cfg_step_rel_l2": rel(v, self.last[2]), "guide_scale": GUIDE,
+               "layers": self.layers, "L": self.L, "tolerance": "1e-3 per forward (BASELINE.json north_star); the CFG step "
+               "multiplies the cond - uncond difference by the guide scale",
+               "checker": "oracle/dit_oracle.py (fp32 CPU) on the cpu_baseline sample: same weights, inputs, t"}
+        eng.close()
+        return out
 
 
 def cpu_baseline(frames, layers=None, full_steps=1):
@@ -165,7 +184,8 @@ def cpu_baseline(frames, layers=None, full_steps=1):
         step_s = t1 + max(t2 - t1, 1e-9) * (layers - 1)
         sample = (f"2 of {layers} blocks x 2 CFG branches + embeddings/head at L={L}, fp32 CPU oracle, block cost "
                   f"scaled to {layers} layers (a whole step at T={frames} is minutes of CPU work)")
-    return {"value": 1.0 / step_s, "unit": "denoise-steps/s", "cores": st.cores, "kind": "port", "sample": sample}, step_s
+    info = {"value": 1.0 / step_s, "unit": "denoise-steps/s", "cores": st.cores, "kind": "port", "sample": sample}
+    return info, (st if frames == 1 else None)
 
 
 def run_reference(args):
@@ -555,7 +575,9 @@ def main():
         if world == 1 and not args.no_block_table:
             line["block_table"] = block_table(dev, burst, sustained)
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"], _ = cpu_baseline(T)
+            line["cpu_baseline"], cpu_step = cpu_baseline(T)
+            if cpu_step is not None and hasattr(cpu_step, "last"):
+                line["parity"] = cpu_step.parity(dev)           # live, at the full 30-block size
         elif world > 1:
             line["cpu_baseline"] = {"value": None, "unit": "denoise-steps/s", "cores": 0, "kind": "port",
                                     "sample": "measured at N=1 only"}
