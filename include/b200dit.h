@@ -155,6 +155,11 @@ B200_API int b200dit_backward(b200dit_engine* e, const float* const* dout, float
                               float* const* dx, void* stream);
 /* optimizer.zero_grad() (distilled_trainer.py:305). */
 B200_API int b200dit_zero_grad(b200dit_engine* e, void* stream);
+/* Data-parallel training (accelerate's DDP around the student, distilled_trainer.py:79): the engine keeps ALL parameter
+ * gradients in two contiguous device fp32 buffers (one mirrors the fp16-packed GEMM weights, one the fp32 parameters).
+ * A trainer with one process per GPU all-reduces exactly these two buffers between b200dit_backward and its
+ * optimizer step -- two large NCCL calls instead of one per parameter.  The pointers stay valid for the engine's life. */
+B200_API int b200dit_grad_buffers(b200dit_engine* e, float** g16, int64_t* n16, float** g32, int64_t* n32);
 /* `param.grad` of the parameter stored under the reference state_dict key `name`: dst (device fp32, numel elements)
  * = scale * gradient, or += when accumulate != 0. */
 B200_API int b200dit_read_grad(b200dit_engine* e, const char* name, float* dst, int64_t numel, float scale,

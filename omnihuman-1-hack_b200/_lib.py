@@ -47,6 +47,7 @@ SIGNATURES = {
     "b200dit_train_forward": (_I, [_P, _I, _PP, _P, _PP, _IP, _I, _I, _I, _I, _I, _PP, _P]),
     "b200dit_backward": (_I, [_P, _PP, _F, _I, _PP, _P]),
     "b200dit_zero_grad": (_I, [_P, _P]),
+    "b200dit_grad_buffers": (_I, [_P, _PP, C.POINTER(C.c_int64), _PP, C.POINTER(C.c_int64)]),
     "b200dit_read_grad": (_I, [_P, C.c_char_p, _P, _L, _F, _I, _P]),
     "b200vae_create": (_I, [_I, _I, _PP]),
     "b200vae_destroy": (None, [_P]),

@@ -164,6 +164,13 @@ int b200dit_read_grad(b200dit_engine* e, const char* name, float* dst, int64_t n
   });
 }
 
+int b200dit_grad_buffers(b200dit_engine* e, float** g16, int64_t* n16, float** g32, int64_t* n32) {
+  return guarded([&] {
+    B2_CHECK(e && g16 && n16 && g32 && n32, "null argument");
+    e->impl.grad_buffers(g16, n16, g32, n32);
+  });
+}
+
 int b200vae_create(int32_t dim, int32_t z_dim, b200vae_engine** out) {
   return guarded([&] {
     B2_CHECK(out != nullptr, "null argument");

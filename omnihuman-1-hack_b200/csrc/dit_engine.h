@@ -99,6 +99,12 @@ class DitEngine {
   void zero_grad(cudaStream_t stream);
   // dst (+)= scale * gradient of the parameter stored under the reference key `name` (fp32, numel elements)
   void read_grad(const char* name, float* dst, long long numel, float scale, bool accumulate, cudaStream_t stream);
+  // the two fp32 gradient stores (mirrors of the fp16-packed and of the fp32 parameters): what a data-parallel trainer
+  // all-reduces between backward and the optimizer step (accelerate's DDP, distilled_trainer.py:79)
+  void grad_buffers(float** p16, int64_t* n16, float** p32, int64_t* n32) {
+    ensure_grads();
+    *p16 = g16->as<float>(); *n16 = (int64_t)w16_elems; *p32 = g32->as<float>(); *n32 = (int64_t)w32_elems;
+  }
   struct BwdWorkspace;                   // per-block intermediates of the backward (dit_backward.cu)
 
   b200dit_config cfg;

@@ -322,6 +322,20 @@ class DitEngine:
         with torch.cuda.device(self.device):
             check(lib().b200dit_zero_grad(self._h, _stream_ptr()))
 
+    def grad_buffers(self):
+        """The engine's two gradient stores as zero-copy fp32 CUDA tensors (b200dit_grad_buffers): what a
+        data-parallel trainer all-reduces between `backward` and its optimizer step (`parallel.all_reduce_gradients`)."""
+        p16, p32, n16, n32 = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+        with torch.cuda.device(self.device):
+            check(lib().b200dit_grad_buffers(self._h, C.byref(p16), C.byref(n16), C.byref(p32), C.byref(n32)))
+
+        class _Raw:                                   # __cuda_array_interface__: borrowed device memory, no copy
+            def __init__(s, ptr, n):
+                s.__cuda_array_interface__ = dict(shape=(int(n),), typestr="<f4", data=(int(ptr), False), version=3)
+
+        return [torch.as_tensor(_Raw(p16.value, n16.value), device=self.device),
+                torch.as_tensor(_Raw(p32.value, n32.value), device=self.device)]
+
     def read_grad(self, name, shape, out=None, accumulate=False):
         """Gradient of the parameter stored under the reference key `name` (fp32), b200dit_read_grad."""
         scale = 1.0

@@ -150,6 +150,24 @@ def gather_from_ranks(local, counts, group=None):
     return [[out[r][j] for j in range(counts[r])] for r in range(w)]
 
 
+def all_reduce_gradients(engine, group=None, average=True):
+    """Data-parallel training step (the DDP that accelerate wraps around the student, distilled_trainer.py:79):
+    every rank ran `backward` on its own items; the gradients -- two contiguous fp32 buffers inside the engine
+    (`DitEngine.grad_buffers`) -- are summed over the ranks in place (NCCL all_reduce over NVLink on the B200 box) and
+    divided by the world size, so `read_grad` / `param.grad` then hold the mean gradient on every rank."""
+    if world_size() == 1:
+        return
+    w = dist.get_world_size(group)
+    nccl = dist.get_backend(group) == "nccl"
+    for buf in engine.grad_buffers():
+        if average and nccl:
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=group)      # averaged inside the collective
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                buf.mul_(1.0 / w)
+
+
 def pipeline_schedule(T, world, chunk_frames):
     """Chunk schedule of the multi-GPU time-chunked VAE decode (b200vae_decode_pipelined): chunk 0 is latent frame
     0 alone (one output frame), chunk k >= 1 holds up to `chunk_frames` latent frames (four output frames each);

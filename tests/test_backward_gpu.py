@@ -180,6 +180,13 @@ def test_backward_needs_its_forward_and_accumulates():
     eng.backward(d, want_dx=False)                      # same forward, second backward: accumulates
     b = eng.read_grad("blocks.0.ffn.0.weight", (256, 128))
     assert rel_l2(b.cpu(), 2 * a.cpu()) < 1e-6
+    # the two contiguous gradient stores a data-parallel trainer all-reduces hold exactly the per-parameter gradients
+    bufs = eng.grad_buffers()
+    total = sum(float(u.double().pow(2).sum()) for u in bufs)
+    per_param = sum(float(eng.read_grad(k, v.shape).double().pow(2).sum()) for k, v in sd.items() if k != "freqs")
+    assert abs(total - per_param) <= 1e-9 * per_param and total > 0
+    bufs[0].zero_(); bufs[1].zero_()                    # zero-copy views: clearing them clears the engine's gradients
+    assert float(eng.read_grad("blocks.0.ffn.0.weight", (256, 128)).abs().max()) == 0.0
     eng.forward(x, r["t"][:1], c, g["seq_len"])
     with pytest.raises(b200dit.B200Error):
         eng.backward(d, want_dx=False)

@@ -66,6 +66,49 @@ def test_gloo_world2_shard_and_gather(tmp_path):
         assert f"ok {r}" in out
 
 
+GRAD_WORKER = r'''
+import os, sys, torch
+sys.path.insert(0, os.environ["B200_ROOT"])
+import b200dit
+from b200dit import parallel as par
+rank, world = par.init("gloo")
+
+
+class FakeEngine:                      # DitEngine.grad_buffers: two contiguous fp32 gradient stores
+    def __init__(self):
+        self.b = [torch.full((1000,), float(rank + 1)), torch.arange(7, dtype=torch.float32) * (rank + 1)]
+
+    def grad_buffers(self):
+        return self.b
+
+
+e = FakeEngine()
+par.all_reduce_gradients(e)
+assert torch.allclose(e.b[0], torch.full((1000,), 1.5)) and torch.allclose(e.b[1], torch.arange(7, dtype=torch.float32) * 1.5)
+print("ok", rank)
+'''
+
+
+def test_gloo_world2_gradient_all_reduce(tmp_path):
+    """Data-parallel training step (DDP around the student, distilled_trainer.py:79): the engine's gradient stores are
+    averaged over the ranks in place."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "grad_worker.py"
+    script.write_text(GRAD_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), B200_ROOT=ROOT, CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for r, p in enumerate(procs):
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
+        assert f"ok {r}" in out
+
+
 PAIR_WORKER = r'''
 import os, sys, torch
 sys.path.insert(0, os.environ["B200_ROOT"])

@@ -143,11 +143,15 @@ def main():
         with torch.no_grad():
             _, ms_f = timed(lambda: [eng.forward([noises[i]], torch.tensor([1000.0], device=dev), [ctxs[i]], 1560) for i in mine])
         ls, ms = timed(lambda: run(mine))
+        _, ms_ar = timed(lambda: parallel.all_reduce_gradients(eng))      # DDP's exchange: once per optimizer step
         gn = float(eng.read_grad("blocks.0.self_attn.q.weight", (1536, 1536)).norm())
         line = {"config": 4, "workload": f"{a.items} APT stage-1 student training steps (forward at t=1000 + MSE + backward, "
                 f"{a.batch} item(s) per step) on [16,1,60,104], FFN of blocks > 10 detached as in model.py:318-325, "
                 "items i % world == rank", "n_gpus": world, "ms": ms, "items_per_s": a.items / (ms / 1e3),
-                "forward_only_ms": ms_f, "fwd_bwd_over_fwd": ms / ms_f, "mean_loss": float(ls.mean()),
+                "forward_only_ms": ms_f, "fwd_bwd_over_fwd": ms / ms_f, "grad_all_reduce_ms": ms_ar,
+                "grad_all_reduce": "two NCCL all_reduce (AVG) calls over the engine's contiguous fp32 gradient stores "
+                                   f"({sum(b.numel() for b in eng.grad_buffers()) * 4 / 1e9:.2f} GB), once per optimizer step",
+                "mean_loss": float(ls.mean()),
                 "grad_norm_blocks0_q": gn, "finite": bool(torch.isfinite(ls).all())}
     elif a.config == 4:
         eng = b200dit.DitEngine(**cfg, device=dev)
