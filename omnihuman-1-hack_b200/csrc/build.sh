@@ -7,7 +7,7 @@ OBJ="${HERE}/../build"
 mkdir -p "${OBJ}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden)
-SRCS=(gemm_tc gemm_tc_pair attn_tc attn_bwd_tc elementwise backward_kernels profile dit_engine dit_backward vae_engine vae_kernels disc_engine capi)
+SRCS=(gemm_tc gemm_tc_pair conv_tc attn_tc attn_bwd_tc elementwise backward_kernels profile dit_engine dit_backward vae_engine vae_kernels disc_engine capi)
 pids=()
 for s in "${SRCS[@]}"; do
   [ -f "${HERE}/${s}.cu" ] || continue

@@ -1,0 +1,479 @@
+// Halo convolution on tcgen05: the 3x3 spatial taps of a causal (kt x 3 x 3) convolution read ONE shared-memory
+// copy of the input tile (vae.py:17-36 CausalConv3d, :186-220 ResidualBlock, :101-141 Resample).
+//
+// Why: as an implicit GEMM with one TMA window per filter tap (gemm_tc.cuh, conv mode) the narrow decoder stages
+// (96 / 192 channels at 480x832 / 240x416) re-read every input pixel 27 times and every weight once per 128 pixels from
+// L2: ncu measured 10-13 TB/s of L2 traffic with the tensor pipe 25 % (96 channels) / 50 % (192) active
+// (profiles/r2_vae_launches_T5.txt) -- L2-bound.  Here
+//   * a unit is a column of P sub-tiles of 16 rows x 8 pixels (M = 128 each, P accumulators in TMEM);
+//   * per (frame tap dt, channel chunk) the producer loads the (16 P + 2) x 10 pixel halo ONCE (4-D TMA box, zero
+//     fill outside the image = the conv's zero padding); tap (dh, dw) of sub-tile p is the operand view that starts
+//     at pixel row ((16 p + dh) * 10 + dw) of that slab with 8-row groups 10 rows apart.  The tcgen05 shared-memory
+//     descriptor takes any start row and any group stride because the 128B / 64B swizzle is a function of the absolute
+//     shared-memory address (measured: tools/probe_umma_desc.cu, profiles/r2_probe_umma_desc.txt);
+//   * the weight tile of a (tap, chunk) is loaded once per unit and used by the P sub-tiles.
+// L2 bytes per 128 output pixels at 96 channels: 995 KB -> 227 KB (P = 5); at 192 channels 3.3 MB -> 1.2 MB (P = 2).
+// Channel chunks are 64 wide (128B swizzle) or 32 wide (64B swizzle: 96 channels = 3 chunks, no K padding).
+//
+// Epilogue (8 warps; warp (quad, half) owns TMEM lanes [32 quad, +32) of the sub-tiles p = half, half + 2, ...):
+// bias, optional residual read, fp32 store / reduce-add through TMA (image borders clipped by the tensor map) and,
+// when the tile holds all output channels of a pixel, the following RMS_norm (+ SiLU) (vae.py:40-54) written as the
+// fp16 operand of the next convolution -- the separate normalisation pass and its fp32 round trip disappear.
+#include <cmath>
+
+#include "host_util.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace b2 {
+namespace {
+
+enum HaloEpi : int { HE_RESID = 1, HE_STORE = 2, HE_NORM = 4, HE_REDUCE = 8 };
+
+struct HaloParams {
+  int T, H, W;                 // output frames / height / width
+  int kt, nchunks, cpad;       // frame taps, channel chunks of CK, K stride of one tap in the weight matrix
+  int N, tiles_n;
+  int P, subrows, bands, cols; // sub-tiles per unit; ceil(H / 16); ceil(subrows / P); ceil(W / 8)
+  int nbuf;                    // accumulator sets in TMEM (2 when 2 P BN <= 512)
+  int nb;                      // weight ring depth
+  int a_slab;                  // bytes between the two halo slabs (1024-aligned)
+  long long units;
+  const float* bias;
+  const float* gamma; float norm_scale; int silu;
+  const float* resid; long long ld_r;
+  int dbg;                     // diagnosis only (B200_HALO_DBG): 1 no weight loads, 2 no halo loads, 4 no stores, 8 no MMAs
+};
+
+constexpr int W_A = 8, W_B = 9, W_MMA = 10, HALO_THREADS = 352;
+constexpr int HALO_STAGING = 8 * 4096;
+
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int ROW_BYTES>
+__device__ __forceinline__ uint32_t halo_stage_offset(int r, int k) {
+  if constexpr (ROW_BYTES == 128) return r * 128 + ((k ^ (r & 7)) << 4);
+  else if constexpr (ROW_BYTES == 64) return r * 64 + ((k ^ ((r >> 1) & 3)) << 4);
+  else return r * 32 + ((k ^ ((r >> 2) & 1)) << 4);
+}
+
+template <int CW>
+__device__ __forceinline__ void halo_ld(uint32_t taddr, uint32_t (&r)[CW]) {
+  if constexpr (CW == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+}
+template <int CW>
+__device__ __forceinline__ void halo_st(uint32_t taddr, uint32_t (&r)[CW]) {
+  if constexpr (CW == 32) tmem_st32(taddr, r); else tmem_st16(taddr, r);
+}
+
+struct HaloUnit { int t, h0, w0, n0, np; };
+__device__ __forceinline__ HaloUnit halo_unit(const HaloParams& p, long long u, int BN) {
+  HaloUnit q;
+  const int nb = (int)(u % p.tiles_n); u /= p.tiles_n;
+  const int col = (int)(u % p.cols); u /= p.cols;
+  const int band = (int)(u % p.bands);
+  q.t = (int)(u / p.bands);
+  q.h0 = band * 16 * p.P;
+  q.w0 = col * 8;
+  q.n0 = nb * BN;
+  q.np = min(p.P, p.subrows - band * p.P);
+  return q;
+}
+
+template <int BN, int CK, int EPI>
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_h,
+                 const HaloParams p) {
+  constexpr int RB = CK * 2;                         // bytes of one pixel's channel chunk = one operand row
+  constexpr int B_SLOT = BN * RB;
+  constexpr int CW = (BN % 32 == 0) ? 32 : 16;
+  constexpr int NCH = BN / CW;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + 2 * p.a_slab;
+  uint8_t* staging = sb + p.nb * B_SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + HALO_STAGING);
+  uint64_t* a_full = bars;            // [2]
+  uint64_t* a_empty = bars + 2;       // [2]
+  uint64_t* b_full = bars + 4;        // [8]
+  uint64_t* b_empty = bars + 12;      // [8]
+  uint64_t* acc_full = bars + 20;     // [2]
+  uint64_t* acc_empty = bars + 22;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  float* s_bias = reinterpret_cast<float*>(staging + HALO_STAGING + 256);     // [BN * tiles_n <= 512]
+  float* s_gamma = s_bias + 512;
+
+  const int warp = warp_id(), lane = lane_id();
+  pdl_launch();
+  if (warp == W_A && lane == 0) {
+    tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); tma_prefetch_desc(&tmap_o); tma_prefetch_desc(&tmap_h);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
+    }
+    for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < 512; i += HALO_THREADS) {       // model constants: safe before the dependency wait
+    s_bias[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.f;
+    s_gamma[i] = (p.gamma != nullptr && i < p.N) ? __ldg(p.gamma + i) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nslabs = p.kt * p.nchunks;
+  const uint32_t a_bytes = 10u * (16 * p.P + 2) * RB;
+
+  if (warp == W_B) {
+    // ------------------------------------------------------------ weight producer (constants: no dependency wait)
+    if (lane == 0) {
+      uint32_t ib = 0;
+      for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const HaloUnit q = halo_unit(p, u, BN);
+        for (int s = 0; s < nslabs; ++s) {
+          const int dt = s / p.nchunks, ch = s - dt * p.nchunks;
+          for (int tap = 0; tap < 9; ++tap, ++ib) {
+            const int slot = ib % p.nb; const uint32_t ph = (ib / p.nb) & 1;
+            mbar_wait(&b_empty[slot], ph ^ 1);
+            if (p.dbg & 1) { mbar_arrive(&b_full[slot]); continue; }
+            mbar_expect_tx(&b_full[slot], B_SLOT);
+            tma_load_2d(sb + slot * B_SLOT, &tmap_b, &b_full[slot], (dt * 9 + tap) * p.cpad + ch * CK, q.n0);
+          }
+        }
+      }
+    }
+  } else if (warp == W_A) {
+    // ------------------------------------------------------------ halo producer
+    pdl_wait();
+    if (lane == 0) {
+      uint32_t ia = 0;
+      for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const HaloUnit q = halo_unit(p, u, BN);
+        for (int s = 0; s < nslabs; ++s, ++ia) {
+          const int dt = s / p.nchunks, ch = s - dt * p.nchunks;
+          const int slot = ia & 1; const uint32_t ph = (ia >> 1) & 1;
+          mbar_wait(&a_empty[slot], ph ^ 1);
+          if (p.dbg & 2) { mbar_arrive(&a_full[slot]); continue; }
+          mbar_expect_tx(&a_full[slot], a_bytes);
+          tma_load_4d(sa + slot * p.a_slab, &tmap_a, &a_full[slot], ch * CK, q.w0 - 1, q.h0 - 1, q.t + dt);
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+    constexpr int PMAX = 512 / BN > 5 ? 5 : 512 / BN;
+    // high words of the operand descriptors: group stride (10 pixel rows for the halo views, 8 for the weights),
+    // descriptor version, swizzle mode
+    constexpr uint32_t SWZ = (CK == 64 ? 2u : 4u) << 29;
+    constexpr uint32_t A_HI = ((10 * RB) >> 4) | (1u << 14) | SWZ;
+    constexpr uint32_t B_HI = ((8 * RB) >> 4) | (1u << 14) | SWZ;
+    uint32_t ia = 0, ib = 0, iu = 0;
+    for (long long u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
+      const HaloUnit q = halo_unit(p, u, BN);
+      const int buf = iu % p.nbuf; const uint32_t aph = (iu / p.nbuf) & 1;
+      mbar_wait(&acc_empty[buf], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + buf * p.P * BN;
+      for (int s = 0; s < nslabs; ++s, ++ia) {
+        const int aslot = ia & 1;
+        mbar_wait(&a_full[aslot], (ia >> 1) & 1);
+        const uint32_t slab = smem_u32(sa + aslot * p.a_slab);
+        for (int tap = 0; tap < 9; ++tap, ++ib) {
+          const int bslot = ib % p.nb;
+          mbar_wait(&b_full[bslot], (ib / p.nb) & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            // descriptors differ in their start-address field only: one add per instruction
+            const int dh = tap / 3, dw = tap - dh * 3;
+            const uint32_t b_lo = (1u << 16) | ((smem_u32(sb + bslot * B_SLOT) & 0x3FFFFu) >> 4);
+            const uint32_t a_lo = (1u << 16) | (((slab + (dh * 10 + dw) * RB) & 0x3FFFFu) >> 4);
+            const uint32_t first = (s > 0 || tap > 0) ? 1u : 0u;
+            if (!(p.dbg & 8)) {
+#pragma unroll
+              for (int k = 0; k < CK / 16; ++k) {
+#pragma unroll
+                for (int sp = 0; sp < PMAX; ++sp)
+                  if (sp < q.np)
+                    umma_f16_lohi(d0 + sp * BN, a_lo + sp * (10 * RB) + 2 * k, A_HI, b_lo + 2 * k, B_HI, idesc,
+                                  k > 0 ? 1u : first);
+              }
+            }
+            umma_commit(&b_empty[bslot]);
+            if (tap == 8) {
+              umma_commit(&a_empty[aslot]);
+              if (s == nslabs - 1) umma_commit(&acc_full[buf]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 0..7)
+    pdl_wait();
+    const int quad = warp & 3, half = warp >> 2;
+    uint8_t* stg_base = staging + warp * 4096;
+    int n_store = 0;
+    uint32_t iu = 0;
+    const uint32_t lane_sel = uint32_t(quad * 32) << 16;
+    for (long long u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
+      const HaloUnit q = halo_unit(p, u, BN);
+      const int buf = iu % p.nbuf; const uint32_t aph = (iu / p.nbuf) & 1;
+      mbar_wait(&acc_full[buf], aph);
+      tc_fence_after();
+      for (int sp = half; sp < q.np; sp += 2) {
+        const uint32_t t_acc = tmem_base + lane_sel + buf * p.P * BN + sp * BN;
+        const int hrow = q.h0 + 16 * sp + 4 * quad;            // first image row of this warp's 4 x 8 pixels
+        const int my_h = hrow + (lane >> 3), my_w = q.w0 + (lane & 7);
+        const bool in_img = my_h < p.H && my_w < p.W;
+        float ssq = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          const int col0 = q.n0 + c * CW;
+          uint32_t r[CW];
+          halo_ld<CW>(t_acc + c * CW, r);
+          tmem_wait_ld();
+          float v[CW];
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + col0);
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j) {
+            const float4 b = b4[j];
+            v[4 * j] = __uint_as_float(r[4 * j]) + b.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+          }
+          if constexpr ((EPI & HE_RESID) != 0) {
+            if (in_img) {
+              const float4* x4 = reinterpret_cast<const float4*>(
+                  p.resid + (((long long)q.t * p.H + my_h) * p.W + my_w) * p.ld_r + col0);
+#pragma unroll
+              for (int j = 0; j < CW / 4; ++j) {
+                const float4 x = __ldg(x4 + j);
+                v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+              }
+            }
+            if constexpr ((EPI & HE_NORM) != 0) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) r[j] = __float_as_uint(v[j]);
+              halo_st<CW>(t_acc + c * CW, r);                  // pass 2 re-reads the updated row
+            }
+          }
+          if constexpr ((EPI & HE_NORM) != 0) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) ssq = fmaf(v[j], v[j], ssq);
+          }
+          if constexpr ((EPI & (HE_STORE | HE_REDUCE)) != 0) {
+            constexpr int ROW_BYTES = CW * 4;
+            constexpr int BOX = 32 * ROW_BYTES;
+            constexpr int NBUF = BOX >= 4096 ? 1 : 2;
+            uint8_t* stg = stg_base + (NBUF == 1 ? 0 : (n_store & 1) * BOX);
+            ++n_store;
+            if (lane == 0) { if (NBUF == 1) tma_store_wait_read0(); else tma_store_wait_read1(); }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < CW / 4; ++k)
+              *reinterpret_cast<float4*>(stg + halo_stage_offset<ROW_BYTES>(lane, k)) =
+                  make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (!(p.dbg & 4)) {
+                if constexpr ((EPI & HE_REDUCE) != 0) tma_reduce_add_4d(&tmap_o, stg, col0, q.w0, hrow, q.t);
+                else tma_store_4d(&tmap_o, stg, col0, q.w0, hrow, q.t);
+              }
+              tma_store_commit();
+            }
+          }
+        }
+        if constexpr ((EPI & HE_NORM) != 0) {
+          if constexpr ((EPI & HE_RESID) != 0) tmem_wait_st();
+          const float inv = p.norm_scale / fmaxf(sqrtf(ssq), 1e-12f);       // F.normalize eps (vae.py:51-54)
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c) {
+            const int col0 = q.n0 + c * CW;
+            uint32_t r[CW];
+            halo_ld<CW>(t_acc + c * CW, r);
+            tmem_wait_ld();
+            float v[CW];
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+              float x = __uint_as_float(r[j]);
+              if constexpr ((EPI & HE_RESID) == 0) x += s_bias[col0 + j];
+              float y = x * inv * s_gamma[col0 + j];
+              if (p.silu) y = y / (1.f + __expf(-y));
+              v[j] = y;
+            }
+            constexpr int ROW_BYTES = CW * 2;
+            constexpr int BOX = 32 * ROW_BYTES;
+            uint8_t* stg = stg_base + (n_store & 1) * 2048;
+            ++n_store;
+            if (lane == 0) tma_store_wait_read1();
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < CW / 8; ++k)
+              *reinterpret_cast<uint4*>(stg + halo_stage_offset<ROW_BYTES>(lane, k)) =
+                  make_uint4(pack_h2(v[8 * k], v[8 * k + 1]), pack_h2(v[8 * k + 2], v[8 * k + 3]),
+                             pack_h2(v[8 * k + 4], v[8 * k + 5]), pack_h2(v[8 * k + 6], v[8 * k + 7]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (!(p.dbg & 4)) tma_store_4d(&tmap_h, stg, col0, q.w0, hrow, q.t);
+              tma_store_commit();
+            }
+            static_assert(BOX <= 2048, "fp16 staging boxes alternate inside the warp's 4 KB");
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int BN, int CK, int EPI>
+void launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& th,
+                 const HaloParams& p, int smem_bytes, int grid, cudaStream_t stream) {
+  static bool configured_dev[64] = {false};
+  int dev = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  auto kern = conv_halo_kernel<BN, CK, EPI>;
+  if (!configured_dev[dev & 63]) {
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured_dev[dev & 63] = true;
+  }
+  launch_pdl(kern, dim3(grid), dim3(HALO_THREADS), smem_bytes, stream, ta, tb, to, th, p);
+  count_launch();
+}
+
+template <int BN, int CK>
+void launch_halo_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& th,
+                     const HaloParams& p, int smem_bytes, int grid, cudaStream_t s) {
+  switch (epi) {
+    case HE_STORE: launch_halo<BN, CK, HE_STORE>(ta, tb, to, th, p, smem_bytes, grid, s); break;
+    case HE_REDUCE: launch_halo<BN, CK, HE_REDUCE>(ta, tb, to, th, p, smem_bytes, grid, s); break;
+    case HE_NORM: launch_halo<BN, CK, HE_NORM>(ta, tb, to, th, p, smem_bytes, grid, s); break;
+    case HE_STORE | HE_NORM: launch_halo<BN, CK, HE_STORE | HE_NORM>(ta, tb, to, th, p, smem_bytes, grid, s); break;
+    case HE_RESID | HE_STORE: launch_halo<BN, CK, HE_RESID | HE_STORE>(ta, tb, to, th, p, smem_bytes, grid, s); break;
+    case HE_RESID | HE_STORE | HE_NORM:
+      launch_halo<BN, CK, HE_RESID | HE_STORE | HE_NORM>(ta, tb, to, th, p, smem_bytes, grid, s); break;
+    default: fail("conv_halo: unsupported epilogue combination %d", epi);
+  }
+}
+
+int halo_tile_width(int Cout) { return Cout % 192 == 0 ? 192 : Cout == 96 ? 96 : Cout <= 16 ? 16 : 0; }
+
+}  // namespace
+
+bool conv_halo_supported(int Cin, int Cout, int kt, int kh, int kw) {
+  static const int enabled = std::getenv("B200_CONV_HALO") ? std::atoi(std::getenv("B200_CONV_HALO")) : 1;
+  return enabled && kh == 3 && kw == 3 && (kt == 1 || kt == 3) && Cin % 32 == 0 && halo_tile_width(Cout) != 0 &&
+         Cout <= 512;
+}
+
+void conv_halo(const ConvHaloArgs& a, int num_sms, cudaStream_t stream) {
+  B2_CHECK(conv_halo_supported(a.Cin, a.Cout, a.kt, 3, 3), "conv_halo: unsupported shape %d -> %d (kt %d)", a.Cin, a.Cout, a.kt);
+  B2_CHECK(a.Tbuf == a.T_out + a.kt - 1, "conv buffer has %d frames, expected %d", a.Tbuf, a.T_out + a.kt - 1);
+  const int BN = halo_tile_width(a.Cout);
+  const int CK = a.Cin % 64 == 0 ? 64 : 32;
+  const int RB = CK * 2;
+  HaloParams p{};
+  p.T = a.T_out; p.H = a.H; p.W = a.W; p.kt = a.kt; p.nchunks = a.Cin / CK; p.cpad = a.cpad;
+  p.N = a.Cout; p.tiles_n = (a.Cout + BN - 1) / BN;
+  p.subrows = (a.H + 15) / 16; p.cols = (a.W + 7) / 8;
+  const int B_SLOT = BN * RB;
+  const int tail = HALO_STAGING + 256 + 2 * 512 * 4;
+  // sub-tiles per unit: as many accumulators as TMEM holds (<= 5), while two halo slabs and >= 4 weight slots fit
+  int P = 512 / BN;
+  if (P > 5) P = 5;
+  if (P > p.subrows) P = p.subrows;
+  auto slab = [&](int P_) { return ((10 * (16 * P_ + 2) * RB + 1023) / 1024) * 1024; };
+  while (P > 1 && 2 * slab(P) + 4 * B_SLOT + tail > 227 * 1024) --P;
+  p.P = P; p.a_slab = slab(P);
+  p.bands = (p.subrows + P - 1) / P;
+  p.nbuf = 2 * P * BN <= 512 ? 2 : 1;
+  int nb = (227 * 1024 - tail - 2 * p.a_slab) / B_SLOT;
+  if (nb > 8) nb = 8;
+  B2_CHECK(nb >= 2, "conv_halo: shared memory does not hold the weight ring (%d -> %d)", a.Cin, a.Cout);
+  p.nb = nb;
+  p.units = (long long)a.T_out * p.bands * p.cols * p.tiles_n;
+  p.bias = a.bias; p.gamma = a.gamma; p.norm_scale = std::sqrt((float)a.Cout); p.silu = a.silu;
+  p.resid = a.resid; p.ld_r = a.ld_r;
+  static const int dbg = std::getenv("B200_HALO_DBG") ? std::atoi(std::getenv("B200_HALO_DBG")) : 0;
+  p.dbg = dbg;
+  const int smem_bytes = 2 * p.a_slab + nb * B_SLOT + tail;
+
+  int epi = 0;
+  if (a.out_h != nullptr) {
+    B2_CHECK(p.tiles_n == 1 && a.gamma != nullptr, "conv_halo: the fused RMS_norm needs all %d channels in one tile", a.Cout);
+    epi |= HE_NORM;
+  }
+  if (a.resid != nullptr) {
+    B2_CHECK(a.out_f != nullptr && !a.accumulate, "conv_halo: residual read needs a plain fp32 store");
+    epi |= HE_RESID | HE_STORE;
+  } else if (a.out_f != nullptr) {
+    epi |= a.accumulate ? HE_REDUCE : HE_STORE;
+  }
+  B2_CHECK(epi != 0, "conv_halo: no output");
+  B2_CHECK(!(epi & HE_REDUCE) || !(epi & HE_NORM), "conv_halo: reduce-add cannot feed the fused norm (pass resid)");
+
+  uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.Tbuf};
+  uint64_t str[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2, (uint64_t)a.H * a.W * a.Cin * 2};
+  uint32_t box[4] = {(uint32_t)CK, 10, (uint32_t)(16 * P + 2), 1};
+  const CUtensorMap ta = make_tmap(a.in, false, 4, dims, str, box, RB);
+  const long long Ktot = (long long)a.kt * 9 * a.cpad;
+  uint64_t wd[2] = {(uint64_t)Ktot, (uint64_t)a.Cout};
+  uint64_t ws[1] = {(uint64_t)Ktot * 2};
+  uint32_t wb[2] = {(uint32_t)CK, (uint32_t)BN};
+  const CUtensorMap tb = make_tmap(a.w, false, 2, wd, ws, wb, RB);
+  const uint32_t cw = BN % 32 == 0 ? 32 : 16;
+  CUtensorMap to = tb, th = tb;
+  if (a.out_f != nullptr) {
+    uint64_t od[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.T_out};
+    uint64_t os[3] = {(uint64_t)a.ld_f * 4, (uint64_t)a.W * a.ld_f * 4, (uint64_t)a.H * a.W * a.ld_f * 4};
+    uint32_t ob[4] = {cw, 8, 4, 1};
+    to = make_tmap(a.out_f, true, 4, od, os, ob, (int)cw * 4);
+  }
+  if (a.out_h != nullptr) {
+    uint64_t od[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.T_out};
+    uint64_t os[3] = {(uint64_t)a.Cout * 2, (uint64_t)a.W * a.Cout * 2, (uint64_t)a.H * a.W * a.Cout * 2};
+    uint32_t ob[4] = {cw, 8, 4, 1};
+    th = make_tmap(a.out_h, false, 4, od, os, ob, (int)cw * 2);
+  }
+  const int grid = (int)(p.units < num_sms ? p.units : num_sms);
+  const double flops = 2.0 * a.T_out * a.H * a.W * (double)a.Cout * a.kt * 9 * a.Cin;
+  ProfScope prof(PC_CONV, flops, 0.0, stream);
+  const int key = BN * 100 + CK;
+  switch (key) {
+    case 19264: launch_halo_epi<192, 64>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    case 19232: launch_halo_epi<192, 32>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    case 9664: launch_halo_epi<96, 64>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    case 9632: launch_halo_epi<96, 32>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    case 1664: launch_halo_epi<16, 64>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    case 1632: launch_halo_epi<16, 32>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    default: fail("conv_halo: no kernel for tile width %d / chunk %d", BN, CK);
+  }
+}
+
+}  // namespace b2

@@ -41,6 +41,20 @@ void gemm_batched(int epi, const __half* A, long long lda, long long a_rows, lon
 void conv_gemm(int epi, const __half* in, int Tbuf, int H, int W, int Cin, const __half* w, int Cout, int kt, int kh,
                int kw, int T_out, GemmParams p, int num_sms, cudaStream_t stream, int pad_h = -1, int pad_w = -1);
 
+// ---- conv_tc.cu : kt x 3 x 3 convolution whose spatial taps share one shared-memory halo tile (see the file header)
+struct ConvHaloArgs {
+  const __half* in; int Tbuf, H, W, Cin;      // fp16 volume [Tbuf, H, W, Cin], the kt - 1 history frames in front
+  const __half* w; int Cout, kt, cpad;        // fp16 weights [Cout, kt * 9 * cpad] (launch_repack_conv_weight)
+  int T_out;
+  const float* bias;
+  float* out_f; long long ld_f;               // fp32 [T_out, H, W, ld_f]: stored, or reduced into when `accumulate`
+  int accumulate;
+  const float* resid; long long ld_r;         // optional: out_f = resid + conv (read in the epilogue; may alias out_f)
+  __half* out_h; const float* gamma; int silu; // optional: RMS_norm(out) * gamma (+ SiLU) as fp16 [T_out, H, W, Cout]
+};
+bool conv_halo_supported(int Cin, int Cout, int kt, int kh, int kw);
+void conv_halo(const ConvHaloArgs& a, int num_sms, cudaStream_t stream);
+
 // ---- vae_kernels.cu : HBM-bound passes of the VAE decode (channels-last volumes [T, H, W, C])
 // z fp32 [C, T, h, w] -> (z * std + mean) -> fp16 [T*h*w, C]               (vae.py:547-551)
 void launch_vae_prep_latent(const float* z, const float* mean, const float* stdv, __half* out, int C, int T, int hw,

@@ -285,6 +285,14 @@ struct VaeEngine::Impl {
   // out = conv(in) + bias, or out += conv(in) + bias when `accumulate` (the residual add, in place)
   void run_conv(const std::string& name, const __half* in, int Tc, int H, int W, float* out, bool accumulate) {
     const ConvW& c = convs.at(name);
+    if (!c.s2d && conv_halo_supported(c.cin_act, c.cout, c.kt, c.kh, c.kw)) {
+      ConvHaloArgs a{};
+      a.in = in; a.Tbuf = Tc + c.kt - 1; a.H = H; a.W = W; a.Cin = c.cin_act;
+      a.w = c.w->as<__half>(); a.Cout = c.cout; a.kt = c.kt; a.cpad = c.cpad; a.T_out = Tc;
+      a.bias = c.b->as<float>(); a.out_f = out; a.ld_f = (c.cout + 3) & ~3; a.accumulate = accumulate ? 1 : 0;
+      conv_halo(a, num_sms, s);
+      return;
+    }
     GemmParams p{};
     p.bias = c.b->as<float>(); p.out_f = out; p.ld_f = (c.cout + 3) & ~3;      // TMA rows are 16-byte multiples
     conv_gemm(accumulate ? EPI_RESID_F32 : EPI_F32, in, Tc + c.kt - 1, H, W, c.cin_act, c.w->as<__half>(), c.cout, c.kt,

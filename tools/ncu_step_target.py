@@ -1,6 +1,6 @@
 """ncu target (developer tool): ONE eager pass of a hot path between cudaProfilerStart/Stop, after a warm-up pass.
   dit   two-sample CFG forward of a 2-block 1.3B-width model (M = 6240: every per-block kernel of the bench step)
-  vae   WanVAE decode of a [16,2,60,104] latent (frame 0 alone + one full-resolution chunk)
+  vae [T]  WanVAE decode of a [16,T,60,104] latent (default T = 2: frame 0 alone + one full-resolution chunk)
   bwd   one student training step (forward + backward), one item, 2 blocks
 usage: ncu --profile-from-start off ... python tools/ncu_step_target.py dit"""
 import os
@@ -19,7 +19,7 @@ g = torch.Generator().manual_seed(7)
 rn = lambda *s: torch.randn(*s, generator=g).to(dev)
 if what == "vae":
     vae = b200dit.VaeEngine.from_state_dict(synthetic.vae_decoder_weights(dim=96, seed=0), device=dev)
-    z = [rn(16, 2, 60, 104)]
+    z = [rn(16, int(sys.argv[2]) if len(sys.argv) > 2 else 2, 60, 104)]
     run = lambda: vae.decode(z)
 else:
     cfg = dict(CFG_13B, num_layers=2)
