@@ -48,15 +48,39 @@ struct HaloParams {
 constexpr int W_A = 8, W_B = 9, W_MMA = 10, HALO_THREADS = 352;
 constexpr int HALO_STAGING = 8 * 4096;
 
+// tcgen05.mma / commit guarded by a per-thread predicate (`elected` = lane 0) instead of a branch: the issuing warp
+// stays converged, so the descriptor arithmetic runs on the uniform datapath and lands in the uniform registers the
+// instruction takes -- inside `if (lane == 0)` every operand went through R2UR (about 20 instructions and ~100
+// clocks per MMA, more than a 128 x 96 x 16 MMA takes to execute).
 __device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                              uint32_t idesc, uint32_t accumulate) {
+                                              uint32_t idesc, uint32_t accumulate, uint32_t elected) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
       "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 e, %7, 0;\n\t"
       "mov.b64 da, {%1, %2};\n\t"
       "mov.b64 db, {%3, %4};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
-      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+// spin without the out-of-line timeout path of mbar_wait: a call inside the issue loop keeps every loop-carried value
+// out of the uniform registers.  Used by the MMA warp only -- the producers and the epilogue bound their waits and
+// trap, which ends the whole grid, so this spin cannot outlive a protocol error.
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar, uint32_t elected) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "setp.ne.b32 e, %1, 0;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+      ::"r"(smem_u32(bar)), "r"(elected)
       : "memory");
 }
 
@@ -185,18 +209,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (long long u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
       const HaloUnit q = halo_unit(p, u, BN);
       const int buf = iu % p.nbuf; const uint32_t aph = (iu / p.nbuf) & 1;
-      mbar_wait(&acc_empty[buf], aph ^ 1);
+      mbar_spin(&acc_empty[buf], aph ^ 1);
       tc_fence_after();
       const uint32_t d0 = tmem_base + buf * p.P * BN;
       for (int s = 0; s < nslabs; ++s, ++ia) {
         const int aslot = ia & 1;
-        mbar_wait(&a_full[aslot], (ia >> 1) & 1);
+        mbar_spin(&a_full[aslot], (ia >> 1) & 1);
         const uint32_t slab = smem_u32(sa + aslot * p.a_slab);
         for (int tap = 0; tap < 9; ++tap, ++ib) {
           const int bslot = ib % p.nb;
-          mbar_wait(&b_full[bslot], (ib / p.nb) & 1);
+          mbar_spin(&b_full[bslot], (ib / p.nb) & 1);
           tc_fence_after();
-          if (lane == 0) {
+          __syncwarp();
+          const uint32_t elected = elect_one();
+          {
             // descriptors differ in their start-address field only: one add per instruction
             const int dh = tap / 3, dw = tap - dh * 3;
             const uint32_t b_lo = (1u << 16) | ((smem_u32(sb + bslot * B_SLOT) & 0x3FFFFu) >> 4);
@@ -209,13 +235,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int sp = 0; sp < PMAX; ++sp)
                   if (sp < q.np)
                     umma_f16_lohi(d0 + sp * BN, a_lo + sp * (10 * RB) + 2 * k, A_HI, b_lo + 2 * k, B_HI, idesc,
-                                  k > 0 ? 1u : first);
+                                  k > 0 ? 1u : first, elected);
               }
             }
-            umma_commit(&b_empty[bslot]);
+            umma_commit_elect(&b_empty[bslot], elected);
             if (tap == 8) {
-              umma_commit(&a_empty[aslot]);
-              if (s == nslabs - 1) umma_commit(&acc_full[buf]);
+              umma_commit_elect(&a_empty[aslot], elected);
+              if (s == nslabs - 1) umma_commit_elect(&acc_full[buf], elected);
             }
           }
           __syncwarp();
