@@ -48,42 +48,6 @@ struct HaloParams {
 constexpr int W_A = 8, W_B = 9, W_MMA = 10, HALO_THREADS = 352;
 constexpr int HALO_STAGING = 8 * 4096;
 
-// tcgen05.mma / commit guarded by a per-thread predicate (`elected` = lane 0) instead of a branch: the issuing warp
-// stays converged, so the descriptor arithmetic runs on the uniform datapath and lands in the uniform registers the
-// instruction takes -- inside `if (lane == 0)` every operand went through R2UR (about 20 instructions and ~100
-// clocks per MMA, more than a 128 x 96 x 16 MMA takes to execute).
-__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                              uint32_t idesc, uint32_t accumulate, uint32_t elected) {
-  asm volatile(
-      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "setp.ne.b32 e, %7, 0;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
-      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(elected)
-      : "memory");
-}
-// spin without the out-of-line timeout path of mbar_wait: a call inside the issue loop keeps every loop-carried value
-// out of the uniform registers.  Used by the MMA warp only -- the producers and the epilogue bound their waits and
-// trap, which ends the whole grid, so this spin cannot outlive a protocol error.
-__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
-  return pred;
-}
-__device__ __forceinline__ void umma_commit_elect(uint64_t* bar, uint32_t elected) {
-  asm volatile(
-      "{\n\t.reg .pred e;\n\t"
-      "setp.ne.b32 e, %1, 0;\n\t"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
-      ::"r"(smem_u32(bar)), "r"(elected)
-      : "memory");
-}
-
 template <int ROW_BYTES>
 __device__ __forceinline__ uint32_t halo_stage_offset(int r, int k) {
   if constexpr (ROW_BYTES == 128) return r * 128 + ((k ^ (r & 7)) << 4);
@@ -238,10 +202,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                   k > 0 ? 1u : first, elected);
               }
             }
-            umma_commit_elect(&b_empty[bslot], elected);
+            umma_commit_e(&b_empty[bslot], elected);
             if (tap == 8) {
-              umma_commit_elect(&a_empty[aslot], elected);
-              if (s == nslabs - 1) umma_commit_elect(&acc_full[buf], elected);
+              umma_commit_e(&a_empty[aslot], elected);
+              if (s == nslabs - 1) umma_commit_e(&acc_full[buf], elected);
             }
           }
           __syncwarp();

@@ -310,38 +310,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int acc = seg & 1;
       const uint32_t acc_phase = (seg >> 1) & 1;
       ++seg;
-      mbar_wait(&acc_empty[acc], acc_phase ^ 1);       // epilogue drained this accumulator
+      mbar_spin(&acc_empty[acc], acc_phase ^ 1);       // epilogue drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
       for (int kb = kb0; kb < kb1; ++kb) {
-        if (!(p.dbg & 2)) mbar_wait(&full[stage], phase);
+        if (!(p.dbg & 2)) mbar_spin(&full[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        // the warp stays converged: uniform descriptor arithmetic, instructions guarded by the elected lane (ptx.cuh)
+        const uint32_t el = elect_one();
+        {
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
 #pragma unroll
           for (int k = 0; k < C::BLOCK_K / C::UMMA_K; ++k) {
             if (p.dbg & 4) break;
             if constexpr (PAIR)
-              umma_f16_pair(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc,
-                            (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_f16_pair_e(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc,
+                              (kb > kb0 || k > 0) ? 1u : 0u, el);
             else if (p.tn)     // 16 K rows per instruction = two 8-row groups = 2048 B; 64-column chunks 8192 B apart
-              umma_f16(d_tmem, umma_desc_mn_sw128(sa + k * 2048, 8192), umma_desc_mn_sw128(sb + k * 2048, 8192), idesc,
-                       (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_f16_e(d_tmem, umma_desc_mn_sw128(sa + k * 2048, 8192), umma_desc_mn_sw128(sb + k * 2048, 8192), idesc,
+                         (kb > kb0 || k > 0) ? 1u : 0u, el);
             else
-              umma_f16(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc,
-                       (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_f16_e(d_tmem, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sb + k * 32), idesc,
+                         (kb > kb0 || k > 0) ? 1u : 0u, el);
           }
           // the smem slot (of both CTAs in pair mode) is reusable once these MMAs retire
           if constexpr (PAIR) {
-            umma_commit_pair(&empty[stage], 3);
-            if (kb == kb1 - 1) umma_commit_pair(&acc_full[acc], 3);
+            umma_commit_pair_e(&empty[stage], 3, el);
+            if (kb == kb1 - 1) umma_commit_pair_e(&acc_full[acc], 3, el);
           } else {
-            umma_commit(&empty[stage]);
-            if (kb == kb1 - 1) umma_commit(&acc_full[acc]);
+            umma_commit_e(&empty[stage], el);
+            if (kb == kb1 - 1) umma_commit_e(&acc_full[acc], el);
           }
         }
-        __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }

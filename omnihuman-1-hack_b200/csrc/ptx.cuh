@@ -249,6 +249,72 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ----------------------------------------------------------------------------- single-thread issue on the uniform datapath
+// tcgen05.mma / commit take their operands from uniform registers.  When the issuing warp's loop contains a call
+// (mbar_wait's out-of-line timeout path) or the issue sits inside `if (lane == 0)`, ptxas keeps the loop-carried
+// addresses in vector registers and moves every operand over with R2UR.BROADCAST: about 20 instructions and
+// ~100 clocks per MMA (cuobjdump -sass), more than a narrow MMA takes to execute.  The issuing warps therefore
+// (1) spin on their barriers inline -- the other roles keep the bounded waits and trap, which ends the whole grid,
+// so the spin cannot outlive a protocol error -- and (2) stay converged: every lane computes the (uniform)
+// descriptors and the instruction itself is guarded by the elect.sync predicate.
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_f16_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate, uint32_t elected) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 e, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t elected) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 e, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+// descriptors as (low, high) words: the low word carries the start address, so a tap / K step is one 32-bit add
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate, uint32_t elected) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 e, %7, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint64_t* bar, uint32_t elected) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "setp.ne.b32 e, %1, 0;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+      ::"r"(smem_u32(bar)), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_e(uint64_t* bar, uint16_t cta_mask, uint32_t elected) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "setp.ne.b32 e, %2, 0;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n"
+      ::"r"(smem_u32(bar)), "h"(cta_mask), "r"(elected)
+      : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (thread i <-> lane base+i).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
