@@ -116,48 +116,50 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   } else if (warp == W_MMA) {
-    if (lane == 0) {
+    // converged issuing warp, inline spins, elect-guarded instructions: see ptx.cuh ("single-thread issue ...")
+    {
       constexpr uint32_t id_s = umma_idesc_f16(128, QT);                        // S^T, dP^T: 128 keys x 64 queries
       constexpr uint32_t id_acc = umma_idesc_f16(128, 128) | UMMA_B_MN;         // dV, dK: B = dO / Q read MN-major
       constexpr uint32_t id_dq = umma_idesc_f16(128, QT) | UMMA_A_MN;           // dQ^T: A = K read MN-major
       const uint32_t sk = smem_u32(smem + OFF_K), sv = smem_u32(smem + OFF_V), sds = smem_u32(smem + OFF_DS);
-      mbar_wait(kv_full, 0);
+      mbar_spin(kv_full, 0);
       for (int i = 0; i < n_it; ++i) {
         const int st = i & 1;
         const uint32_t sq = smem_u32(smem + OFF_Q + st * 2 * Q_BYTES), sdo = sq + Q_BYTES;
-        mbar_wait(&qdo_full[st], (i >> 1) & 1);
+        mbar_spin(&qdo_full[st], (i >> 1) & 1);
         tc_fence_after();
+        uint32_t el = elect_one();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)       // S^T = K Q^T over d
-          umma_f16(tmem + T_ST, umma_desc_sw128(sk + (kk >> 2) * (K_BYTES / 2) + (kk & 3) * 32),
-                   umma_desc_sw128(sq + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32), id_s, kk > 0);
+          umma_f16_e(tmem + T_ST, umma_desc_sw128(sk + (kk >> 2) * (K_BYTES / 2) + (kk & 3) * 32),
+                     umma_desc_sw128(sq + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32), id_s, kk > 0, el);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)       // dP^T = V dO^T over d
-          umma_f16(tmem + T_DP, umma_desc_sw128(sv + (kk >> 2) * (K_BYTES / 2) + (kk & 3) * 32),
-                   umma_desc_sw128(sdo + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32), id_s, kk > 0);
-        umma_commit(s_full);
-        mbar_wait(p_ready, i & 1);
-        if (i > 0) mbar_wait(dq_empty, (i - 1) & 1);
+          umma_f16_e(tmem + T_DP, umma_desc_sw128(sv + (kk >> 2) * (K_BYTES / 2) + (kk & 3) * 32),
+                     umma_desc_sw128(sdo + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32), id_s, kk > 0, el);
+        umma_commit_e(s_full, el);
+        mbar_spin(p_ready, i & 1);
+        if (i > 0) mbar_spin(dq_empty, (i - 1) & 1);
         tc_fence_after();
+        el = elect_one();
 #pragma unroll
         for (int kk = 0; kk < QT / 16; ++kk) {   // over the 64 queries, 16 per instruction (two 8-row groups = 2048 B)
           // queries [32 h, 32 h + 32) sit as fp16 pairs in the first 16 columns of the h-th 32-column half
           const uint32_t ta = (kk >> 1) * 32 + (kk & 1) * 8;
-          umma_f16_ts(tmem + T_DV, tmem + T_ST + ta, umma_desc_mn_sw128(sdo + kk * 2048, Q_BYTES / 2), id_acc,
-                      (i > 0 || kk > 0));
-          umma_f16_ts(tmem + T_DK, tmem + T_DP + ta, umma_desc_mn_sw128(sq + kk * 2048, Q_BYTES / 2), id_acc,
-                      (i > 0 || kk > 0));
+          umma_f16_ts_e(tmem + T_DV, tmem + T_ST + ta, umma_desc_mn_sw128(sdo + kk * 2048, Q_BYTES / 2), id_acc,
+                        (i > 0 || kk > 0), el);
+          umma_f16_ts_e(tmem + T_DK, tmem + T_DP + ta, umma_desc_mn_sw128(sq + kk * 2048, Q_BYTES / 2), id_acc,
+                        (i > 0 || kk > 0), el);
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)       // dQ^T = K^T dS^T over the 128 keys
-          umma_f16(tmem + T_DQ, umma_desc_mn_sw128(sk + kk * 2048, K_BYTES / 2),
-                   umma_desc_sw128(sds + (kk >> 2) * 8192 + (kk & 3) * 32), id_dq, kk > 0);
-        umma_commit(&qdo_empty[st]);
-        umma_commit(dq_full);
+          umma_f16_e(tmem + T_DQ, umma_desc_mn_sw128(sk + kk * 2048, K_BYTES / 2),
+                     umma_desc_sw128(sds + (kk >> 2) * 8192 + (kk & 3) * 32), id_dq, kk > 0, el);
+        umma_commit_e(&qdo_empty[st], el);
+        umma_commit_e(dq_full, el);
       }
-      umma_commit(acc_done);
+      umma_commit_e(acc_done, elect_one());
     }
-    __syncwarp();
   } else {
     // ---- warps 0..7.  Softmax adjoint: warp w owns key rows (w & 3) * 32 + lane (its TMEM lane quadrant) and the
     // query columns [(w >> 2) * 32, + 32) of the step -- two warps per quadrant, so the step's 128 x 64 logits cost each

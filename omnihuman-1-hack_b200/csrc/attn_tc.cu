@@ -154,51 +154,48 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     constexpr uint32_t idesc_qk = umma_idesc_f16(128, KT);
     constexpr uint32_t idesc_pv = umma_idesc_f16(128, 128);
     const uint32_t sq = smem_u32(smem + OFF_Q);
+    // converged issuing warp, inline spins, elect-guarded instructions: see ptx.cuh ("single-thread issue ...")
     auto issue_qk = [&](int i) {
       const int st = i % KSTAGES; const uint32_t kph = (i / KSTAGES) & 1;
       const int sb = i & 1; const uint32_t sph = (i >> 1) & 1;
-      if (lane == 0) {
-        mbar_wait(&k_full[st], kph);
-        mbar_wait(&s_empty[sb], sph ^ 1);
-        tc_fence_after();
-        const uint32_t sk = smem_u32(smem + OFF_K + st * K_BYTES);
+      mbar_spin(&k_full[st], kph);
+      mbar_spin(&s_empty[sb], sph ^ 1);
+      tc_fence_after();
+      const uint32_t el = elect_one();
+      const uint32_t sk = smem_u32(smem + OFF_K + st * K_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          if (p.dbg & 16) break;                             // diagnosis: no Q.K^T MMAs
-          if (p.dbg & 64)                                    // diagnosis: Q as a TMEM operand (reads O's columns:
-            umma_f16_ts(tmem_base + sb * KT, tmem_o + kk * 8,   // wrong values, right traffic -- no Q re-read from smem)
-                        umma_desc_sw128(sk + (kk >> 2) * KSUB + (kk & 3) * 32), idesc_qk, kk > 0);
-          else
-          umma_f16(tmem_base + sb * KT, umma_desc_sw128(sq + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32),
-                   umma_desc_sw128(sk + (kk >> 2) * KSUB + (kk & 3) * 32), idesc_qk, kk > 0);
-        }
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[sb]);
+      for (int kk = 0; kk < 8; ++kk) {
+        if (p.dbg & 16) break;                             // diagnosis: no Q.K^T MMAs
+        if (p.dbg & 64)                                    // diagnosis: Q as a TMEM operand (reads O's columns:
+          umma_f16_ts_e(tmem_base + sb * KT, tmem_o + kk * 8,   // wrong values, right traffic -- no Q re-read from smem)
+                        umma_desc_sw128(sk + (kk >> 2) * KSUB + (kk & 3) * 32), idesc_qk, kk > 0, el);
+        else
+          umma_f16_e(tmem_base + sb * KT, umma_desc_sw128(sq + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32),
+                     umma_desc_sw128(sk + (kk >> 2) * KSUB + (kk & 3) * 32), idesc_qk, kk > 0, el);
       }
-      __syncwarp();
+      umma_commit_e(&k_empty[st], el);
+      umma_commit_e(&s_full[sb], el);
     };
-    mbar_wait_warp(q_full, 0, lane);
+    mbar_spin(q_full, 0);
     issue_qk(0);
     for (int j = 0; j < n_kv; ++j) {
       // S_{j+1} overwrites the buffer that held S_{j-1} / P_{j-1}: issued after P.V of step j-1 (program
       // order; the tensor pipe executes in issue order), and only once the softmax has read S_{j-1}
       if (j + 1 < n_kv) issue_qk(j + 1);
       const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
-      if (lane == 0) {
-        mbar_wait(&v_full[st], ph);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        const uint32_t sv = smem_u32(smem + OFF_V + st * V_BYTES);
-        const uint32_t tp = tmem_base + st * KT;          // P_j: fp16 pairs in the first 32 columns of S_j's buffer
+      mbar_spin(&v_full[st], ph);
+      mbar_spin(p_full, j & 1);
+      tc_fence_after();
+      const uint32_t el = elect_one();
+      const uint32_t sv = smem_u32(smem + OFF_V + st * V_BYTES);
+      const uint32_t tp = tmem_base + st * KT;          // P_j: fp16 pairs in the first 32 columns of S_j's buffer
 #pragma unroll
-        for (int kk = 0; kk < KT / 16; ++kk) {
-          if (p.dbg & 32) break;                             // diagnosis: no P.V MMAs
-          umma_f16_ts(tmem_o, tp + kk * 8, umma_desc_sw128(sv + kk * 32), idesc_pv, (j > 0 || kk > 0));
-        }
-        umma_commit(&v_empty[st]);
-        umma_commit(pv_done);
+      for (int kk = 0; kk < KT / 16; ++kk) {
+        if (p.dbg & 32) break;                             // diagnosis: no P.V MMAs
+        umma_f16_ts_e(tmem_o, tp + kk * 8, umma_desc_sw128(sv + kk * 32), idesc_pv, (j > 0 || kk > 0), el);
       }
-      __syncwarp();
+      umma_commit_e(&v_empty[st], el);
+      umma_commit_e(pv_done, el);
     }
   } else {
     // ---- softmax: thread r owns query row r of the tile and all 64 keys of the step
@@ -548,45 +545,44 @@ attn_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     constexpr uint32_t idesc_qk = umma_idesc_f16(128, KT);
     constexpr uint32_t idesc_pv = umma_idesc_f16(128, 128);
     const uint32_t sq = smem_u32(smem + OFF_Q);
+    // The issuing warp stays converged and spins inline (ptx.cuh, "single-thread issue on the uniform datapath"):
+    // with the issue under `if (lane == 0)` and mbar_wait's out-of-line path every operand of the 12 MMAs of a key
+    // step went through R2UR -- the step was issue-bound (tensor pipe 42 % active, r2_ncu_attn_full_raw.csv).
     auto issue_qk = [&](uint32_t g, bool last_of_unit) {
       const int st = g % KSTAGES; const uint32_t kph = (g / KSTAGES) & 1;
       const int sb = g & 1; const uint32_t sph = (g >> 1) & 1;
-      if (lane == 0) {
-        mbar_wait(&k_full[st], kph);
-        mbar_wait(&s_empty[sb], sph ^ 1);
-        tc_fence_after();
-        const uint32_t sk = smem_u32(smem + OFF_K + st * K_BYTES);
+      mbar_spin(&k_full[st], kph);
+      mbar_spin(&s_empty[sb], sph ^ 1);
+      tc_fence_after();
+      const uint32_t el = elect_one();
+      const uint32_t sk = smem_u32(smem + OFF_K + st * K_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem_base + sb * KT, umma_desc_sw128(sq + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32),
-                   umma_desc_sw128(sk + (kk >> 2) * KSUB + (kk & 3) * 32), idesc_qk, kk > 0);
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[sb]);
-        if (last_of_unit) umma_commit(q_empty);
-      }
-      __syncwarp();
+      for (int kk = 0; kk < 8; ++kk)
+        umma_f16_e(tmem_base + sb * KT, umma_desc_sw128(sq + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32),
+                   umma_desc_sw128(sk + (kk >> 2) * KSUB + (kk & 3) * 32), idesc_qk, kk > 0, el);
+      umma_commit_e(&k_empty[st], el);
+      umma_commit_e(&s_full[sb], el);
+      if (last_of_unit) umma_commit_e(q_empty, el);
     };
     uint32_t g = 0;                                          // key steps issued so far, over all units
     int ui = 0;
     for (UnitIter it(p); it.next(p, w); ++ui) {
-      mbar_wait_warp(q_full, ui & 1, lane);
+      mbar_spin(q_full, ui & 1);
       issue_qk(g, w.n_kv == 1);
       for (int j = 0; j < w.n_kv; ++j, ++g) {
         if (j + 1 < w.n_kv) issue_qk(g + 1, j + 2 == w.n_kv);
         const int st = g & 1; const uint32_t ph = (g >> 1) & 1;
-        if (lane == 0) {
-          mbar_wait(&v_full[st], ph);
-          mbar_wait(p_full, g & 1);
-          tc_fence_after();
-          const uint32_t sv = smem_u32(smem + OFF_V + st * V_BYTES);
-          const uint32_t tp = tmem_base + st * KT;
+        mbar_spin(&v_full[st], ph);
+        mbar_spin(p_full, g & 1);
+        tc_fence_after();
+        const uint32_t el = elect_one();
+        const uint32_t sv = smem_u32(smem + OFF_V + st * V_BYTES);
+        const uint32_t tp = tmem_base + st * KT;
 #pragma unroll
-          for (int kk = 0; kk < KT / 16; ++kk)
-            umma_f16_ts(tmem_o, tp + kk * 8, umma_desc_sw128(sv + kk * 32), idesc_pv, (j > 0 || kk > 0));
-          umma_commit(&v_empty[st]);
-          umma_commit(pv_done);
-        }
-        __syncwarp();
+        for (int kk = 0; kk < KT / 16; ++kk)
+          umma_f16_ts_e(tmem_o, tp + kk * 8, umma_desc_sw128(sv + kk * 32), idesc_pv, (j > 0 || kk > 0), el);
+        umma_commit_e(&v_empty[st], el);
+        umma_commit_e(pv_done, el);
       }
     }
   } else {
@@ -848,41 +844,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     constexpr uint32_t idesc_qk = umma_idesc_f16(128, KT);
     constexpr uint32_t idesc_pv = umma_idesc_f16(128, 128);
     const uint32_t sq = smem_u32(smem + OFF_Q + t * Q_BYTES);
+    // converged issuing warps, inline spins, elect-guarded instructions: see ptx.cuh ("single-thread issue ...")
     auto issue_qk = [&](int i) {
       const int st = i % KSTAGES; const uint32_t kph = (i / KSTAGES) & 1;
       const int sb = i & 1; const uint32_t sph = (i >> 1) & 1;
-      if (lane == 0) {
-        mbar_wait(&k_full[st], kph);
-        mbar_wait(&s_empty[t * 2 + sb], sph ^ 1);
-        tc_fence_after();
-        const uint32_t sk = smem_u32(smem + OFF_K + st * K_BYTES);
+      mbar_spin(&k_full[st], kph);
+      mbar_spin(&s_empty[t * 2 + sb], sph ^ 1);
+      tc_fence_after();
+      const uint32_t el = elect_one();
+      const uint32_t sk = smem_u32(smem + OFF_K + st * K_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem_base + sb * KT, umma_desc_sw128(sq + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32),
-                   umma_desc_sw128(sk + (kk >> 2) * KSUB + (kk & 3) * 32), idesc_qk, kk > 0);
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[t * 2 + sb]);
-      }
-      __syncwarp();
+      for (int kk = 0; kk < 8; ++kk)
+        umma_f16_e(tmem_base + sb * KT, umma_desc_sw128(sq + (kk >> 2) * (Q_BYTES / 2) + (kk & 3) * 32),
+                   umma_desc_sw128(sk + (kk >> 2) * KSUB + (kk & 3) * 32), idesc_qk, kk > 0, el);
+      umma_commit_e(&k_empty[st], el);
+      umma_commit_e(&s_full[t * 2 + sb], el);
     };
-    mbar_wait_warp(q_full, 0, lane);
+    mbar_spin(q_full, 0);
     issue_qk(0);
     for (int j = 0; j < n_kv; ++j) {
       if (j + 1 < n_kv) issue_qk(j + 1);
       const int st = j % VSTAGES; const uint32_t ph = (j / VSTAGES) & 1;
-      if (lane == 0) {
-        mbar_wait(&v_full[st], ph);
-        mbar_wait(&p_full[t], j & 1);
-        tc_fence_after();
-        const uint32_t sv = smem_u32(smem + OFF_V + st * V_BYTES);
-        const uint32_t tp = tmem_base + (j & 1) * KT;
+      mbar_spin(&v_full[st], ph);
+      mbar_spin(&p_full[t], j & 1);
+      tc_fence_after();
+      const uint32_t el = elect_one();
+      const uint32_t sv = smem_u32(smem + OFF_V + st * V_BYTES);
+      const uint32_t tp = tmem_base + (j & 1) * KT;
 #pragma unroll
-        for (int kk = 0; kk < KT / 16; ++kk)
-          umma_f16_ts(tmem_o, tp + kk * 8, umma_desc_sw128(sv + kk * 32), idesc_pv, (j > 0 || kk > 0));
-        umma_commit(&v_empty[st]);
-        umma_commit(&pv_done[t]);
-      }
-      __syncwarp();
+      for (int kk = 0; kk < KT / 16; ++kk)
+        umma_f16_ts_e(tmem_o, tp + kk * 8, umma_desc_sw128(sv + kk * 32), idesc_pv, (j > 0 || kk > 0), el);
+      umma_commit_e(&v_empty[st], el);
+      umma_commit_e(&pv_done[t], el);
     }
   } else {
     // ---- softmax of tile t: thread = one query row, all 64 keys of the step (the v2 loop)
