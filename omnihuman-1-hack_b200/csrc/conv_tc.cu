@@ -223,13 +223,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (long long u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
       const HaloUnit q = halo_unit(p, u, BN);
       const int buf = iu % p.nbuf; const uint32_t aph = (iu / p.nbuf) & 1;
+      // residual rows of this thread's pixel: fetched one chunk ahead (the first one while the MMAs still run)
+      float4 xr[CW / 4];
+      auto load_resid = [&](int sp, int c) {
+        const int h = q.h0 + 16 * sp + 4 * quad + (lane >> 3), w = q.w0 + (lane & 7);
+        if (sp < q.np && h < p.H && w < p.W) {
+          const float4* x4 = reinterpret_cast<const float4*>(
+              p.resid + (((long long)q.t * p.H + h) * p.W + w) * p.ld_r + q.n0 + c * CW);
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j) xr[j] = __ldg(x4 + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j) xr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      if constexpr ((EPI & HE_RESID) != 0) load_resid(half, 0);
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
       for (int sp = half; sp < q.np; sp += 2) {
         const uint32_t t_acc = tmem_base + lane_sel + buf * p.P * BN + sp * BN;
         const int hrow = q.h0 + 16 * sp + 4 * quad;            // first image row of this warp's 4 x 8 pixels
-        const int my_h = hrow + (lane >> 3), my_w = q.w0 + (lane & 7);
-        const bool in_img = my_h < p.H && my_w < p.W;
         float ssq = 0.f;
 #pragma unroll 1
         for (int c = 0; c < NCH; ++c) {
@@ -246,15 +259,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
           }
           if constexpr ((EPI & HE_RESID) != 0) {
-            if (in_img) {
-              const float4* x4 = reinterpret_cast<const float4*>(
-                  p.resid + (((long long)q.t * p.H + my_h) * p.W + my_w) * p.ld_r + col0);
 #pragma unroll
-              for (int j = 0; j < CW / 4; ++j) {
-                const float4 x = __ldg(x4 + j);
-                v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
-              }
+            for (int j = 0; j < CW / 4; ++j) {
+              const float4 x = xr[j];
+              v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
             }
+            if (c + 1 < NCH) load_resid(sp, c + 1); else load_resid(sp + 2, 0);
             if constexpr ((EPI & HE_NORM) != 0) {
 #pragma unroll
               for (int j = 0; j < CW; ++j) r[j] = __float_as_uint(v[j]);
@@ -298,13 +308,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             halo_ld<CW>(t_acc + c * CW, r);
             tmem_wait_ld();
             float v[CW];
+            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + col0);
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + col0);
 #pragma unroll
-            for (int j = 0; j < CW; ++j) {
-              float x = __uint_as_float(r[j]);
-              if constexpr ((EPI & HE_RESID) == 0) x += s_bias[col0 + j];
-              float y = x * inv * s_gamma[col0 + j];
-              if (p.silu) y = y / (1.f + __expf(-y));
-              v[j] = y;
+            for (int j = 0; j < CW / 4; ++j) {
+              const float4 g = g4[j];
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if constexpr ((EPI & HE_RESID) == 0) b = b4[j];
+              v[4 * j] = (__uint_as_float(r[4 * j]) + b.x) * inv * g.x;
+              v[4 * j + 1] = (__uint_as_float(r[4 * j + 1]) + b.y) * inv * g.y;
+              v[4 * j + 2] = (__uint_as_float(r[4 * j + 2]) + b.z) * inv * g.z;
+              v[4 * j + 3] = (__uint_as_float(r[4 * j + 3]) + b.w) * inv * g.w;
+            }
+            if (p.silu) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
             }
             constexpr int ROW_BYTES = CW * 2;
             constexpr int BOX = 32 * ROW_BYTES;
@@ -380,6 +398,10 @@ bool conv_halo_supported(int Cin, int Cout, int kt, int kh, int kw) {
   static const int enabled = std::getenv("B200_CONV_HALO") ? std::atoi(std::getenv("B200_CONV_HALO")) : 1;
   return enabled && kh == 3 && kw == 3 && (kt == 1 || kt == 3) && Cin % 32 == 0 && halo_tile_width(Cout) != 0 &&
          Cout <= 512;
+}
+
+bool conv_halo_fusable(int Cin, int Cout, int kt, int kh, int kw) {
+  return conv_halo_supported(Cin, Cout, kt, kh, kw) && halo_tile_width(Cout) == Cout;
 }
 
 void conv_halo(const ConvHaloArgs& a, int num_sms, cudaStream_t stream) {

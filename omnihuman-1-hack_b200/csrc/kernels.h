@@ -53,6 +53,7 @@ struct ConvHaloArgs {
   __half* out_h; const float* gamma; int silu; // optional: RMS_norm(out) * gamma (+ SiLU) as fp16 [T_out, H, W, Cout]
 };
 bool conv_halo_supported(int Cin, int Cout, int kt, int kh, int kw);
+bool conv_halo_fusable(int Cin, int Cout, int kt, int kh, int kw);   // the tile holds every output channel of a pixel
 void conv_halo(const ConvHaloArgs& a, int num_sms, cudaStream_t stream);
 
 // ---- vae_kernels.cu : HBM-bound passes of the VAE decode (channels-last volumes [T, H, W, C])

@@ -68,13 +68,19 @@ struct VaeEngine::Impl {
 
   int dim, zdim, c0, num_sms = 148;
   int chunk_frames = 4;
+  const bool fuse_norms = std::getenv("B200_VAE_FUSE") ? std::atoi(std::getenv("B200_VAE_FUSE")) != 0 : true;
   std::vector<PlanItem> plan, eplan;
   bool has_encoder = false;
   std::unordered_map<std::string, ConvW> convs;
   std::unordered_map<std::string, std::unique_ptr<DevBuf>> gammas;
   std::unordered_map<std::string, bool> gamma_loaded;
   std::unordered_map<std::string, std::unique_ptr<DevBuf>> hist;
-  DevBuf F[3], A0, A1, Z16, X0, attn_ws, consts;
+  DevBuf F[3], A0, A1, A2, Z16, X0, attn_ws, consts;
+  // Causal operand buffers: a conv reads op(cur); a conv whose epilogue also produces the NEXT conv's operand (fused
+  // RMS_norm + SiLU, conv_tc.cu) writes it into op(cur ^ 1) and flips `cur`.
+  int cur = 0;
+  DevBuf& op(int i) { return i ? A2 : A0; }
+  struct Next { std::string conv, gamma; int C; };          // the conv / norm weight that consumes a block's output
   bool finalized = false;
   cudaStream_t s = nullptr;
 
@@ -231,8 +237,9 @@ struct VaeEngine::Impl {
 
   // ---- conv plumbing --------------------------------------------------------------------------
   // Returns where the producer must write the chunk's Tc frames; history (2 frames) is placed in front.
-  __half* begin_causal(const std::string& name, int Tc, int H, int W, int C) {
+  __half* begin_causal(const std::string& name, int Tc, int H, int W, int C, int bi = -1) {
     const size_t frame = (size_t)H * W * C;
+    DevBuf& A0 = op(bi < 0 ? cur : bi);
     if (pipe.active) {
       // chunk c continues from the history that chunk c - 1 -- on the previous rank -- left in this rank's arena.
       // Chunk 0 starts from the causal zero padding, and so do the time_convs of chunk 1 (chunk 0 skips them,
@@ -267,8 +274,9 @@ struct VaeEngine::Impl {
     B2_CUDA(cudaMemcpyAsync(A0.p, hb->p, 2 * frame * 2, cudaMemcpyDeviceToDevice, s));
     return A0.as<__half>() + 2 * frame;
   }
-  void end_causal(const std::string& name, int Tc, int H, int W, int C) {
+  void end_causal(const std::string& name, int Tc, int H, int W, int C, int bi = -1) {
     const size_t frame = (size_t)H * W * C;
+    DevBuf& A0 = op(bi < 0 ? cur : bi);
     if (pipe.active) {
       if (pipe.chunk + 1 >= pipe.n_chunks) return;             // nobody continues from the last chunk
       const auto& sl = pipe.slot.at(name);
@@ -284,15 +292,28 @@ struct VaeEngine::Impl {
   }
   // out = conv(in) + bias, or out += conv(in) + bias when `accumulate` (the residual add, in place)
   void run_conv(const std::string& name, const __half* in, int Tc, int H, int W, float* out, bool accumulate) {
+    run_conv_fused(name, in, Tc, H, W, out, accumulate, nullptr, nullptr, nullptr);
+  }
+  // The tile of the halo kernel holds every output channel of a pixel: its epilogue can also apply the RMS_norm +
+  // SiLU that follows the conv (vae.py:186-220) and emit the next conv's fp16 operand.
+  bool fusable(const std::string& name) const {
+    const ConvW& c = convs.at(name);
+    return !c.s2d && conv_halo_fusable(c.cin_act, c.cout, c.kt, c.kh, c.kw);
+  }
+  // out (fp32, optional) = [resid +] conv(in) + bias; norm_out (fp16, optional) = silu(RMS_norm(that) * gamma)
+  void run_conv_fused(const std::string& name, const __half* in, int Tc, int H, int W, float* out, bool accumulate,
+                      const float* resid, __half* norm_out, const float* gamma) {
     const ConvW& c = convs.at(name);
     if (!c.s2d && conv_halo_supported(c.cin_act, c.cout, c.kt, c.kh, c.kw)) {
       ConvHaloArgs a{};
       a.in = in; a.Tbuf = Tc + c.kt - 1; a.H = H; a.W = W; a.Cin = c.cin_act;
       a.w = c.w->as<__half>(); a.Cout = c.cout; a.kt = c.kt; a.cpad = c.cpad; a.T_out = Tc;
       a.bias = c.b->as<float>(); a.out_f = out; a.ld_f = (c.cout + 3) & ~3; a.accumulate = accumulate ? 1 : 0;
+      a.resid = resid; a.ld_r = a.ld_f; a.out_h = norm_out; a.gamma = gamma; a.silu = 1;
       conv_halo(a, num_sms, s);
       return;
     }
+    B2_CHECK(resid == nullptr && norm_out == nullptr, "fused conv epilogue requested for %s on the plain path", name.c_str());
     GemmParams p{};
     p.bias = c.b->as<float>(); p.out_f = out; p.ld_f = (c.cout + 3) & ~3;      // TMA rows are 16-byte multiples
     conv_gemm(accumulate ? EPI_RESID_F32 : EPI_F32, in, Tc + c.kt - 1, H, W, c.cin_act, c.w->as<__half>(), c.cout, c.kt,
@@ -307,24 +328,48 @@ struct VaeEngine::Impl {
     gemm_linear(epi, in, c.cin, c.w->as<__half>(), c.cin, p, num_sms, s);
   }
 
-  // ResidualBlock (vae.py:186-220): x (fp32, buffer xi) -> returns index of the buffer holding the result
-  int res_block(const std::string& p, int xi, int Tc, int H, int W, int cin, int cout) {
+  // ResidualBlock (vae.py:186-220): x (fp32, buffer xi) -> returns index of the buffer holding the result.
+  // pre: the operand of residual.2 (norm + SiLU of x, history in front) already sits in op(cur), written by the
+  // epilogue of the conv that produced x.  next: the conv / norm that consumes this block's output; when the halo
+  // kernel runs residual.6, its epilogue adds the shortcut, stores x and writes that operand too (returns *fused).
+  int res_block(const std::string& p, int xi, int Tc, int H, int W, int cin, int cout, bool pre = false,
+                const Next* next = nullptr, bool* fused = nullptr) {
     const long long P = (long long)Tc * H * W;
     const int yi = (xi + 1) % 3, si = (xi + 2) % 3;
-    __half* a = begin_causal(p + "residual.2", Tc, H, W, cin);
-    launch_vae_norm(F[xi].as<float>(), gammas.at(p + "residual.0.gamma")->as<float>(), a, P, cin, 1, s);
-    end_causal(p + "residual.2", Tc, H, W, cin);
-    run_conv(p + "residual.2", A0.as<__half>(), Tc, H, W, F[yi].as<float>(), false);
+    if (fused) *fused = false;
+    if (!pre) {
+      __half* a = begin_causal(p + "residual.2", Tc, H, W, cin);
+      launch_vae_norm(F[xi].as<float>(), gammas.at(p + "residual.0.gamma")->as<float>(), a, P, cin, 1, s);
+      end_causal(p + "residual.2", Tc, H, W, cin);
+    }
+    if (fuse_norms && fusable(p + "residual.2")) {
+      __half* a = begin_causal(p + "residual.6", Tc, H, W, cout, cur ^ 1);
+      run_conv_fused(p + "residual.2", op(cur).as<__half>(), Tc, H, W, nullptr, false, nullptr, a,
+                     gammas.at(p + "residual.3.gamma")->as<float>());
+      end_causal(p + "residual.6", Tc, H, W, cout, cur ^ 1);
+      cur ^= 1;
+    } else {
+      run_conv(p + "residual.2", op(cur).as<__half>(), Tc, H, W, F[yi].as<float>(), false);
+      __half* a = begin_causal(p + "residual.6", Tc, H, W, cout);
+      launch_vae_norm(F[yi].as<float>(), gammas.at(p + "residual.3.gamma")->as<float>(), a, P, cout, 1, s);
+      end_causal(p + "residual.6", Tc, H, W, cout);
+    }
     int out = xi;
     if (cin != cout) {
       launch_vae_cast(F[xi].as<float>(), A1.as<__half>(), P * cin, s);
       linear_1x1(p + "shortcut", A1.as<__half>(), P, EPI_F32, F[si].as<float>(), false);
       out = si;
     }
-    a = begin_causal(p + "residual.6", Tc, H, W, cout);
-    launch_vae_norm(F[yi].as<float>(), gammas.at(p + "residual.3.gamma")->as<float>(), a, P, cout, 1, s);
-    end_causal(p + "residual.6", Tc, H, W, cout);
-    run_conv(p + "residual.6", A0.as<__half>(), Tc, H, W, F[out].as<float>(), true);   // += onto the shortcut, in place
+    if (fuse_norms && next != nullptr && next->C == cout && fusable(p + "residual.6")) {
+      __half* a = begin_causal(next->conv, Tc, H, W, cout, cur ^ 1);
+      run_conv_fused(p + "residual.6", op(cur).as<__half>(), Tc, H, W, F[out].as<float>(), false, F[out].as<float>(), a,
+                     gammas.at(next->gamma)->as<float>());
+      end_causal(next->conv, Tc, H, W, cout, cur ^ 1);
+      cur ^= 1;
+      if (fused) *fused = true;
+    } else {
+      run_conv(p + "residual.6", op(cur).as<__half>(), Tc, H, W, F[out].as<float>(), true);   // += onto the shortcut, in place
+    }
     return out;
   }
 
@@ -363,7 +408,9 @@ struct VaeEngine::Impl {
   }
 
   // Resample upsample2d / upsample3d (vae.py:101-141)
-  int up_block(const std::string& p, int xi, int& Tc, int& H, int& W, int cin, int cout, bool temporal, bool first) {
+  int up_block(const std::string& p, int xi, int& Tc, int& H, int& W, int cin, int cout, bool temporal, bool first,
+               const Next* next = nullptr, bool* fused = nullptr) {
+    if (fused) *fused = false;
     const int yi = (xi + 1) % 3;
     int src = xi, interleave = 0;
     if (temporal && !first) {
@@ -371,14 +418,23 @@ struct VaeEngine::Impl {
       __half* a = begin_causal(p + "time_conv", Tc, H, W, cin);
       launch_vae_cast(F[xi].as<float>(), a, P * cin, s);
       end_causal(p + "time_conv", Tc, H, W, cin);
-      run_conv(p + "time_conv", A0.as<__half>(), Tc, H, W, F[yi].as<float>(), false);      // [Tc,H,W,2cin]
+      run_conv(p + "time_conv", op(cur).as<__half>(), Tc, H, W, F[yi].as<float>(), false);      // [Tc,H,W,2cin]
       src = yi; interleave = 1;
     }
     launch_vae_upsample(F[src].as<float>(), A1.as<__half>(), Tc, H, W, cin, interleave, s);
     if (interleave) Tc *= 2;
     H *= 2; W *= 2;
     const int oi = (src + 1) % 3;
-    run_conv(p + "resample.1", A1.as<__half>(), Tc, H, W, F[oi].as<float>(), false);
+    if (fuse_norms && next != nullptr && next->C == cout && fusable(p + "resample.1")) {
+      __half* a = begin_causal(next->conv, Tc, H, W, cout, cur ^ 1);
+      run_conv_fused(p + "resample.1", A1.as<__half>(), Tc, H, W, F[oi].as<float>(), false, nullptr, a,
+                     gammas.at(next->gamma)->as<float>());
+      end_causal(next->conv, Tc, H, W, cout, cur ^ 1);
+      cur ^= 1;
+      if (fused) *fused = true;
+    } else {
+      run_conv(p + "resample.1", A1.as<__half>(), Tc, H, W, F[oi].as<float>(), false);
+    }
     return oi;
   }
 
@@ -405,12 +461,12 @@ struct VaeEngine::Impl {
       return yi;
     }
     B2_CHECK(Tc % 2 == 0, "temporal downsample needs an even number of frames per chunk (got %d)", Tc);
-    B2_CUDA(cudaMemcpyAsync(A0.p, hb->p, frame * 2, cudaMemcpyDeviceToDevice, s));
-    launch_vae_cast(F[yi].as<float>(), A0.as<__half>() + frame, (long long)Tc * frame, s);
-    B2_CUDA(cudaMemcpyAsync(hb->p, A0.as<__half>() + (size_t)Tc * frame, frame * 2, cudaMemcpyDeviceToDevice, s));
+    B2_CUDA(cudaMemcpyAsync(op(cur).p, hb->p, frame * 2, cudaMemcpyDeviceToDevice, s));
+    launch_vae_cast(F[yi].as<float>(), op(cur).as<__half>() + frame, (long long)Tc * frame, s);
+    B2_CUDA(cudaMemcpyAsync(hb->p, op(cur).as<__half>() + (size_t)Tc * frame, frame * 2, cudaMemcpyDeviceToDevice, s));
     const int zi = (yi + 1) % 3;
     for (int k = 0; k < Tc / 2; ++k)          // output frame k = taps over frames 2k, 2k+1, 2k+2 of [last | chunk]
-      run_conv(name, A0.as<__half>() + (size_t)2 * k * frame, 1, H, W, F[zi].as<float>() + (size_t)k * frame, false);
+      run_conv(name, op(cur).as<__half>() + (size_t)2 * k * frame, 1, H, W, F[zi].as<float>() + (size_t)k * frame, false);
     Tc /= 2;
     return zi;
   }
@@ -438,6 +494,7 @@ struct VaeEngine::Impl {
     upd(f32_max, (size_t)T_lat * H * W * 2 * zdim);
     for (int i = 0; i < 3; ++i) F[i].ensure(f32_max * 4 + 256);
     A0.ensure(a0_max * 2 + 256);
+    A2.ensure(a0_max * 2 + 256);
     A1.ensure(a1_max * 2 + 256);
   }
 
@@ -460,7 +517,7 @@ struct VaeEngine::Impl {
       __half* a = begin_causal("encoder.conv1", Tc, H, W, 8);
       launch_vae_prep_video(video, a, T, t0, Tc, (long long)H * W, s);
       end_causal("encoder.conv1", Tc, H, W, 8);
-      run_conv("encoder.conv1", A0.as<__half>(), Tc, H, W, F[0].as<float>(), false);
+      run_conv("encoder.conv1", op(cur).as<__half>(), Tc, H, W, F[0].as<float>(), false);
       int xi = 0;
       for (size_t i = 0; i < eplan.size(); ++i) {
         const std::string p = "encoder.downsamples." + std::to_string(i) + ".";
@@ -474,7 +531,7 @@ struct VaeEngine::Impl {
       launch_vae_norm(F[xi].as<float>(), gammas.at("encoder.head.0.gamma")->as<float>(), a, (long long)Tc * H * W, c0, 1, s);
       end_causal("encoder.head.2", Tc, H, W, c0);
       const int oi = (xi + 1) % 3, mi = (xi + 2) % 3;
-      run_conv("encoder.head.2", A0.as<__half>(), Tc, H, W, F[oi].as<float>(), false);        // [Tc, h, w, 2 zdim]
+      run_conv("encoder.head.2", op(cur).as<__half>(), Tc, H, W, F[oi].as<float>(), false);        // [Tc, h, w, 2 zdim]
       const long long P = (long long)Tc * H * W;
       launch_vae_cast(F[oi].as<float>(), A1.as<__half>(), P * 2 * zdim, s);
       linear_1x1("conv1", A1.as<__half>(), P, EPI_F32, F[mi].p, false);                        // vae.py:533
@@ -508,6 +565,7 @@ struct VaeEngine::Impl {
     upd(a0_max, (size_t)(Tc + 2) * H * W * dim);
     for (int i = 0; i < 3; ++i) F[i].ensure(f32_max * 4 + 256);
     A0.ensure(a0_max * 2 + 256);
+    A2.ensure(a0_max * 2 + 256);
     A1.ensure(a1_max * 2 + 256);
     Z16.ensure((size_t)T * h * w * zdim * 2 + 256);
     X0.ensure((size_t)T * h * w * zdim * 4 + 256);
@@ -609,21 +667,36 @@ struct VaeEngine::Impl {
       __half* a = begin_causal("decoder.conv1", Tc, H, W, zdim);
       launch_vae_cast(X0.as<float>() + (size_t)t0 * hw * zdim, a, (long long)Tc * hw * zdim, s);
       end_causal("decoder.conv1", Tc, H, W, zdim);
-      run_conv("decoder.conv1", A0.as<__half>(), Tc, H, W, F[0].as<float>(), false);
+      run_conv("decoder.conv1", op(cur).as<__half>(), Tc, H, W, F[0].as<float>(), false);
       int xi = res_block("decoder.middle.0.", 0, Tc, H, W, c0, c0);
       attn_block("decoder.middle.1.", xi, Tc, H, W, c0);
       xi = res_block("decoder.middle.2.", xi, Tc, H, W, c0, c0);
+      bool pre = false;                                     // the next res block's first operand is already written
       for (size_t i = 0; i < plan.size(); ++i) {
         const std::string p = "decoder.upsamples." + std::to_string(i) + ".";
-        if (plan[i].kind == 0) xi = res_block(p, xi, Tc, H, W, plan[i].cin, plan[i].cout);
-        else xi = up_block(p, xi, Tc, H, W, plan[i].cin, plan[i].cout, plan[i].kind == 1, first);
+        // what consumes this item's output: the next res block's first norm, or the head's
+        Next nx, *np = nullptr;
+        if (i + 1 < plan.size() && plan[i + 1].kind == 0) {
+          const std::string q = "decoder.upsamples." + std::to_string(i + 1) + ".";
+          nx = {q + "residual.2", q + "residual.0.gamma", plan[i + 1].cin};
+          np = &nx;
+        } else if (i + 1 == plan.size()) {
+          nx = {"decoder.head.2", "decoder.head.0.gamma", dim};
+          np = &nx;
+        }
+        bool fused = false;
+        if (plan[i].kind == 0) xi = res_block(p, xi, Tc, H, W, plan[i].cin, plan[i].cout, pre, np, &fused);
+        else xi = up_block(p, xi, Tc, H, W, plan[i].cin, plan[i].cout, plan[i].kind == 1, first, np, &fused);
+        pre = fused;
       }
       // head (vae.py:455-471)
-      a = begin_causal("decoder.head.2", Tc, H, W, dim);
-      launch_vae_norm(F[xi].as<float>(), gammas.at("decoder.head.0.gamma")->as<float>(), a, (long long)Tc * H * W, dim, 1, s);
-      end_causal("decoder.head.2", Tc, H, W, dim);
+      if (!pre) {
+        a = begin_causal("decoder.head.2", Tc, H, W, dim);
+        launch_vae_norm(F[xi].as<float>(), gammas.at("decoder.head.0.gamma")->as<float>(), a, (long long)Tc * H * W, dim, 1, s);
+        end_causal("decoder.head.2", Tc, H, W, dim);
+      }
       const int oi = (xi + 1) % 3;
-      run_conv("decoder.head.2", A0.as<__half>(), Tc, H, W, F[oi].as<float>(), false);     // [.., 4]: 3 channels, pitch 4
+      run_conv("decoder.head.2", op(cur).as<__half>(), Tc, H, W, F[oi].as<float>(), false);     // [.., 4]: 3 channels, pitch 4
       launch_vae_store_rgb(F[oi].as<float>(), out, Tc, (long long)H * W, f_out, T_total, s);
       f_out += Tc;
       t0 += Tl;
