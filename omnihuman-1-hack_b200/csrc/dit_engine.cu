@@ -432,8 +432,15 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
   for (int i = 0; i < B; ++i) cimg.klen[i] = IMG_TOK;
 
   // tile widths (the QKV-style epilogues route columns per chunk, so tiles may straddle the q | k | v boundaries)
-  const int bn_qkv = pick_bn(M, 3 * d, num_sms, d), bn_cq = pick_bn(M, d, num_sms, d);
-  const int bn_ckv = pick_bn(B * TL, 2 * d, num_sms, d), bn_img = pick_bn(B * IMG_PAD, 2 * d, num_sms, d);
+  // (width, or width + 1000 for CTA-pair tiles: gemm_linear's force_bn)
+  static const bool plan = std::getenv("B200_GEMM_PLAN") == nullptr || std::atoi(std::getenv("B200_GEMM_PLAN")) != 0;
+  auto pick = [&](long long m, long long n) {
+    if (!plan) return pick_bn(m, n, num_sms, d);
+    const GemmPlan g = gemm_plan(m, n, d, num_sms);
+    return g.bn + (g.cl == 2 ? 1000 : 0);
+  };
+  const int fb_qkv = pick(M, 3 * d), fb_cq = pick(M, d), fb_ckv = pick(B * TL, 2 * d), fb_img = pick(B * IMG_PAD, 2 * d);
+  const int bn_qkv = fb_qkv % 1000, bn_cq = fb_cq % 1000, bn_ckv = fb_ckv % 1000, bn_img = fb_img % 1000;
   auto ssq_tiles = [](int cols, int bn) { return (cols + bn - 1) / bn; };
   if (fuse_qk_norm) { self.q_ssq = w.ssq; self.q_ssq_ld = 4 * ssq_tiles(2 * d, bn_qkv); self.q_ssq_n = 2 * ssq_tiles(2 * d, bn_qkv); }
   cross.q_ssq = w.ssq; cross.q_ssq_ld = 4 * ssq_tiles(d, bn_cq); cross.q_ssq_n = 2 * ssq_tiles(d, bn_cq);
@@ -453,7 +460,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
       if (fuse_qk_norm) {             // q / k leave the epilogue weighted and rotated (model.py:144-146,151-152)
         p.gamma_a = b.norm_q; p.gamma_b = b.norm_k; p.rope_cs = reinterpret_cast<const float2*>(cs);
       }
-      gemm_linear(EPI_QKV, w.u, d, b.qkv_w, d, p, num_sms, s, bn_qkv);
+      gemm_linear(EPI_QKV, w.u, d, b.qkv_w, d, p, num_sms, s, fb_qkv);
     }
     // what is left of the two RMSNorms is one scalar per row: the key's is applied in place here (half the bytes
     // of the former norm + rotation pass), the query's rides in the softmax scale of its row (self.q_ssq)
@@ -475,7 +482,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
       GemmParams p{}; p.w_static = 1; p.M = M; p.N = d; p.K = d; p.bias = b.cq_b; p.out_h = w.qk; p.ld_h = d;
       p.ssq = w.ssq; p.ssq_cols = d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(d, bn_cq); p.vt_col0 = d;
       p.rows_per_item = L;
-      gemm_linear(EPI_QKV, w.u, d, b.cq_w, d, p, num_sms, s, bn_cq);
+      gemm_linear(EPI_QKV, w.u, d, b.cq_w, d, p, num_sms, s, fb_cq);
     }
     __half* kc_l = w.kc + (size_t)l * w.kv_stride;
     __half* vtc_l = w.vtc + (size_t)l * ((size_t)Hn * 128 * B * TL);
@@ -483,7 +490,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
       GemmParams p{}; p.w_static = 1; p.M = B * TL; p.N = 2 * d; p.K = d; p.bias = b.ckv_b; p.out_h = kc_l; p.ld_h = d;
       p.ssq = w.ssq_c; p.ssq_cols = d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(d, bn_ckv); p.vt = vtc_l;
       p.vt_col0 = d; p.vt_ld = B * TL; p.vt_rows = d; p.rows_per_item = TL;
-      gemm_linear(EPI_QKV, w.ctx_e, d, b.ckv_w, d, p, num_sms, s, bn_ckv);
+      gemm_linear(EPI_QKV, w.ctx_e, d, b.ckv_w, d, p, num_sms, s, fb_ckv);
       launch_rms_rope(kc_l, d, d, 1, w.ssq_c, 4 * ssq_tiles(d, bn_ckv), 2 * ssq_tiles(d, bn_ckv), b.cnorm_k, nullptr,
                       nullptr, B * TL, TL, eps, s, b.cnorm_q);
     }
@@ -496,7 +503,7 @@ void DitEngine::enqueue(const FwdInputs& in, cudaStream_t s) {
         GemmParams p{}; p.w_static = 1; p.M = B * IMG_PAD; p.N = 2 * d; p.K = d; p.bias = b.ckv_img_b; p.out_h = ki_l; p.ld_h = d;
         p.ssq = w.ssq_i; p.ssq_cols = d; p.ssq_split = d; p.ssq_ld = 4 * ssq_tiles(d, bn_img); p.vt = vti_l;
         p.vt_col0 = d; p.vt_ld = B * IMG_PAD; p.vt_rows = d; p.rows_per_item = IMG_PAD;
-        gemm_linear(EPI_QKV, w.ctx_img, d, b.ckv_img_w, d, p, num_sms, s, bn_img);
+        gemm_linear(EPI_QKV, w.ctx_img, d, b.ckv_img_w, d, p, num_sms, s, fb_img);
         launch_rms_rope(ki_l, d, d, 1, w.ssq_i, 4 * ssq_tiles(d, bn_img), 2 * ssq_tiles(d, bn_img), b.cnorm_k_img,
                         nullptr, nullptr, B * IMG_PAD, IMG_PAD, eps, s, b.cnorm_q);
       }

@@ -10,6 +10,7 @@ void launch_gemm_pair(int epi, int block_n, const CUtensorMap& ta, const CUtenso
 namespace {
 
 const int kPairMode = env_flag("B200_GEMM_PAIR", -1);       // -1 automatic, 0 never, 1 whenever instantiated
+const int kPlan = env_flag("B200_GEMM_PLAN", 1);            // 1: joint width / pair choice (gemm_plan), 0: the round-1 rules
 
 template <int BN>
 void launch_narrow(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms,
@@ -66,8 +67,14 @@ void gemm_linear(int epi, const __half* A, long long lda, const __half* W, long 
                  cudaStream_t stream, int force_bn) {
   p.cv.enabled = 0;
   int bn = force_bn % 1000;                            // force_bn >= 1000: CTA-pair kernel of width force_bn - 1000
-  if (bn == 0) bn = pick_bn(p.M, p.N, num_sms, kUseSplit ? p.K : 0);
-  int cl = gemm_cluster_size(bn, p.M, p.N, p.K, num_sms, false);
+  int cl;
+  if (bn == 0 && kPlan && kPairMode < 0 && p.batches <= 1) {
+    const GemmPlan g = gemm_plan(p.M, p.N, p.K, num_sms);
+    bn = g.bn; cl = g.cl;
+  } else {
+    if (bn == 0) bn = pick_bn(p.M, p.N, num_sms, kUseSplit ? p.K : 0);
+    cl = gemm_cluster_size(bn, p.M, p.N, p.K, num_sms, false);
+  }
   if (force_bn >= 1000) { B2_CHECK(gemm_pair_width(bn), "no CTA-pair kernel of width %d", bn); cl = 2; }
   else if (force_bn > 0) cl = 1;
   CUtensorMap ta = make_tmap_2d(A, p.M, p.K, lda, 128);

@@ -132,6 +132,44 @@ inline int pick_bn(long long M, long long N, int num_sms, long long K = 0) {
   return best;
 }
 
+// Joint choice of tile width and single-CTA / CTA-pair tiles for a plain linear layer.  Measured per-wave times at
+// M = 6240 (ncu, profiles/r2_dit_launches_uniform.txt): 128 x 256 single-CTA tiles at K = 1536 run L2-bound
+// (13.4 TB/s, tensor pipe 62 %: 13.9 us per wave), 256 x 256 pair tiles move half the weight bytes per SM and reach
+// 89 % (9.8 us per wave); at K = 8960 single tiles are within 7 % of that (the fill / epilogue of a tile is
+// amortised over 140 K slices).  cost = waves x width x (per-column cost of the width) x (mode factor).
+struct GemmPlan { int bn, cl; };
+inline GemmPlan gemm_plan(long long M, long long N, long long K, int num_sms) {
+  const long long tm = (M + 127) / 128;
+  const int KB = (int)((K + 63) / 64);
+  GemmPlan best{128, 1};
+  if (N <= 128) return best;
+  double best_cost = 1e30;
+  for (int cl = 1; cl <= 2; ++cl) {
+    if (cl == 2 && tm < 8) continue;                       // small problems: not worth a cluster launch
+    for (int i = 0; i < 3; ++i) {
+      const int bn = kGemmWidths[i];
+      const long long tn = (N + bn - 1) / bn;
+      double waves, f;
+      if (cl == 1) {
+        const long long tiles = tm * tn;
+        waves = (double)((tiles + num_sms - 1) / num_sms);
+        if (KB >= 64 && tiles % num_sms != 0) {
+          const int S = gemm_tail_split(tiles, num_sms, KB);
+          if (S > 1) waves = (double)(tiles / num_sms) + 1.0 / S + 24.0 / KB;
+        }
+        f = KB >= 64 ? 1.07 : 1.42;
+      } else {
+        const long long units = ((tm + 1) / 2) * tn, pairs = num_sms / 2;
+        waves = (double)((units + pairs - 1) / pairs);
+        f = 1.0;
+      }
+      const double cost = waves * bn * gemm_width_factor(bn) * f;
+      if (cost < best_cost) { best_cost = cost; best = {bn, cl}; }
+    }
+  }
+  return best;
+}
+
 // ---- attn_tc.cu : softmax(Q K^T / sqrt(128)) V, head_dim 128, non-causal, keys >= klen masked
 struct AttnParams {
   const __half* q; long long ldq;      // [items*Lq, ldq], head h at columns h*128
