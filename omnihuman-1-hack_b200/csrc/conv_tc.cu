@@ -301,6 +301,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if constexpr ((EPI & HE_NORM) != 0) {
           if constexpr ((EPI & HE_RESID) != 0) tmem_wait_st();
           const float inv = p.norm_scale / fmaxf(sqrtf(ssq), 1e-12f);       // F.normalize eps (vae.py:51-54)
+          if constexpr ((EPI & (HE_STORE | HE_REDUCE)) != 0) {
+            // the fp32 boxes of pass 1 use the whole staging area: the last one must have been read before the
+            // fp16 boxes (which alternate between its halves and only wait for the store before last) overwrite it
+            if (lane == 0) tma_store_wait_read0();
+            __syncwarp();
+          }
 #pragma unroll 1
           for (int c = 0; c < NCH; ++c) {
             const int col0 = q.n0 + c * CW;
@@ -419,6 +425,8 @@ void conv_halo(const ConvHaloArgs& a, int num_sms, cudaStream_t stream) {
   // sub-tiles per unit: as many accumulators as TMEM holds (<= 5), while two halo slabs and >= 4 weight slots fit
   int P = 512 / BN;
   if (P > 5) P = 5;
+  static const int p_env = std::getenv("B200_HALO_P") ? std::atoi(std::getenv("B200_HALO_P")) : 0;
+  if (p_env > 0 && BN == 96 && p_env < P) P = p_env;   // experiment: fewer accumulators per set, double-buffered
   if (P > p.subrows) P = p.subrows;
   auto slab = [&](int P_) { return ((10 * (16 * P_ + 2) * RB + 1023) / 1024) * 1024; };
   while (P > 1 && 2 * slab(P) + 4 * B_SLOT + tail > 227 * 1024) --P;

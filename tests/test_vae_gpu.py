@@ -56,6 +56,25 @@ def test_vae_decode_full_resolution_60x104():
     _check(pix, ref)
 
 
+def test_vae_halo_conv_partial_tiles_and_determinism():
+    """The halo convolution (csrc/conv_tc.cu) tiles a frame into columns of 16 x 8 pixel sub-tiles: a 7 x 9 latent
+    gives 56 x 72 pixels at the last stage (a half-empty last sub-tile row, bands of 5 + a short band) and odd
+    sizes at every earlier stage; T = 3 crosses the chunk boundary with the fused norm epilogues writing the
+    next conv's causal operand.  Against the CPU oracle (vae.py:544-568), and twice: the result must not depend
+    on the timing of the asynchronous staging stores."""
+    import b200dit
+    from oracle import vae_oracle as VO
+    sd = VO.make_synthetic_vae_weights(dim=96, seed=5)
+    eng = b200dit.VaeEngine.from_state_dict(sd)
+    z = torch.randn(16, 3, 7, 9, generator=torch.Generator().manual_seed(3))
+    pix = eng.decode([z])[0].cpu()
+    with torch.no_grad():
+        ref = VO.vae_decode(sd, z)
+    _check(pix, ref)
+    for _ in range(3):
+        assert torch.equal(eng.decode([z])[0].cpu(), pix)
+
+
 def test_install_vae_shim():
     import b200dit
     from oracle import vae_oracle as VO
