@@ -42,7 +42,7 @@ struct HaloParams {
   const float* bias;
   const float* gamma; float norm_scale; int silu;
   const float* resid; long long ld_r;
-  int dbg;                     // diagnosis only (B200_HALO_DBG): 1 no weight loads, 2 no halo loads, 4 no stores, 8 no MMAs
+  int dbg;                     // diagnosis only (B200_HALO_DBG): 1 no weight loads, 2 no halo loads, 4 no stores, 8 no MMAs, 16 no SiLU
 };
 
 constexpr int W_A = 8, W_B = 9, W_MMA = 10, HALO_THREADS = 352;
@@ -326,7 +326,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               v[4 * j + 2] = (__uint_as_float(r[4 * j + 2]) + b.z) * inv * g.z;
               v[4 * j + 3] = (__uint_as_float(r[4 * j + 3]) + b.w) * inv * g.w;
             }
-            if (p.silu) {
+            if (p.silu && !(p.dbg & 16)) {
 #pragma unroll
               for (int j = 0; j < CW; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
             }
