@@ -45,7 +45,8 @@ __device__ __forceinline__ float ex2_fma(float x) {
 // element i of a step's 64 logits: MUFU, or the FMA path for one in EX2_FMA_EVERY
 template <int I>
 __device__ __forceinline__ float ex2_mixed(float x) {
-  if constexpr (EX2_FMA_EVERY > 0 && (I % EX2_FMA_EVERY) == EX2_FMA_EVERY - 1) return ex2_fma(x);
+  constexpr int every = EX2_FMA_EVERY > 0 ? EX2_FMA_EVERY : 1;
+  if constexpr (EX2_FMA_EVERY > 0 && (I % every) == every - 1) return ex2_fma(x);
   else return ex2(x);
 }
 

@@ -37,7 +37,8 @@ struct HaloParams {
   int P, subrows, bands, cols; // sub-tiles per unit; ceil(H / 16); ceil(subrows / P); ceil(W / 8)
   int nbuf;                    // accumulator sets in TMEM (2 when 2 P BN <= 512)
   int nb;                      // weight ring depth
-  int a_slab;                  // bytes between the two halo slabs (1024-aligned)
+  int na;                      // halo slab ring depth (2..4)
+  int a_slab;                  // bytes between two halo slabs (1024-aligned)
   long long units;
   const float* bias;
   const float* gamma; float norm_scale; int silu;
@@ -47,6 +48,9 @@ struct HaloParams {
 
 constexpr int W_A = 8, W_B = 9, W_MMA = 10, HALO_THREADS = 352;
 constexpr int HALO_STAGING = 8 * 4096;
+constexpr int HALO_MAX_NB = 32;                           // weight ring slots (a pair unit at 96 channels uses a 3 KB
+                                                          // tile in ~200 clocks: the ring must cover a TMA round trip)
+constexpr int HALO_BARS = 1024;                           // barrier block: (16 + 2 * HALO_MAX_NB) * 8 bytes
 
 template <int ROW_BYTES>
 __device__ __forceinline__ uint32_t halo_stage_offset(int r, int k) {
@@ -65,61 +69,73 @@ __device__ __forceinline__ void halo_st(uint32_t taddr, uint32_t (&r)[CW]) {
 }
 
 struct HaloUnit { int t, h0, w0, n0, np; };
-__device__ __forceinline__ HaloUnit halo_unit(const HaloParams& p, long long u, int BN) {
+// cl CTAs of a cluster take horizontally adjacent 8-pixel columns of the same band (cl = 1: p.cols columns)
+__device__ __forceinline__ HaloUnit halo_unit(const HaloParams& p, long long u, int BN, int cl, int rank) {
   HaloUnit q;
+  const int ucols = (p.cols + cl - 1) / cl;
   const int nb = (int)(u % p.tiles_n); u /= p.tiles_n;
-  const int col = (int)(u % p.cols); u /= p.cols;
+  const int col = (int)(u % ucols); u /= ucols;
   const int band = (int)(u % p.bands);
   q.t = (int)(u / p.bands);
   q.h0 = band * 16 * p.P;
-  q.w0 = col * 8;
+  q.w0 = (col * cl + rank) * 8;
   q.n0 = nb * BN;
   q.np = min(p.P, p.subrows - band * p.P);
   return q;
 }
 
-template <int BN, int CK, int EPI>
+// CL = 2: CTA pairs (tcgen05 cta_group::2).  The two CTAs of a cluster run the units of two adjacent pixel columns
+// in lockstep: every MMA is one M = 256 instruction issued by the leader over both CTAs' halo slabs and accumulators,
+// each CTA holds HALF of the weight tile (rows [rank BN / 2, + BN / 2)).  Per 128 pixels that halves the weight
+// bytes from L2 and the weight reads of the MMA from shared memory (N = 96: 4 KB of A + 1.5 KB of B per 48-clock
+// instruction instead of 4 + 3 KB = 149 B/clk against the port's 128) -- which pays for TWO accumulator sets
+// (2 x 2 x 96 or 2 x 1 x 192 columns): the epilogue of a unit runs under the MMAs of the next one.
+template <int BN, int CK, int EPI, int CL>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_h,
                  const HaloParams p) {
   constexpr int RB = CK * 2;                         // bytes of one pixel's channel chunk = one operand row
-  constexpr int B_SLOT = BN * RB;
+  constexpr bool PAIR = CL == 2;
+  constexpr int B_ROWS = BN / CL;                    // weight-tile rows held by one CTA
+  constexpr int B_SLOT = B_ROWS * RB;
   constexpr int CW = (BN % 32 == 0) ? 32 : 16;
   constexpr int NCH = BN / CW;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sa = smem;
-  uint8_t* sb = smem + 2 * p.a_slab;
+  uint8_t* sb = smem + p.na * p.a_slab;
   uint8_t* staging = sb + p.nb * B_SLOT;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + HALO_STAGING);
-  uint64_t* a_full = bars;            // [2]
-  uint64_t* a_empty = bars + 2;       // [2]
-  uint64_t* b_full = bars + 4;        // [8]
-  uint64_t* b_empty = bars + 12;      // [8]
-  uint64_t* acc_full = bars + 20;     // [2]
-  uint64_t* acc_empty = bars + 22;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-  float* s_bias = reinterpret_cast<float*>(staging + HALO_STAGING + 256);     // [BN * tiles_n <= 512]
+  // pair mode: a_full / b_full / acc_empty are used in the leader only (it collects both CTAs' loads and epilogue
+  // arrivals); a_empty / b_empty / acc_full exist in both CTAs and are fed by the leader's multicast commits
+  uint64_t* a_full = bars;            // [4]
+  uint64_t* a_empty = bars + 4;       // [4]
+  uint64_t* acc_full = bars + 8;      // [2]
+  uint64_t* acc_empty = bars + 10;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* b_full = bars + 16;       // [HALO_MAX_NB]
+  uint64_t* b_empty = bars + 16 + HALO_MAX_NB;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const long long u0 = blockIdx.x / CL, ustep = gridDim.x / CL;
+  float* s_bias = reinterpret_cast<float*>(staging + HALO_STAGING + HALO_BARS);     // [BN * tiles_n <= 512]
   float* s_gamma = s_bias + 512;
 
   const int warp = warp_id(), lane = lane_id();
   pdl_launch();
   if (warp == W_A && lane == 0) {
     tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); tma_prefetch_desc(&tmap_o); tma_prefetch_desc(&tmap_h);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
-      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
-    }
-    for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8 * CL); }
+    for (int i = 0; i < HALO_MAX_NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     fence_barrier_init();
   }
-  if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
+  if (warp == W_MMA) { if (PAIR) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
   for (int i = threadIdx.x; i < 512; i += HALO_THREADS) {       // model constants: safe before the dependency wait
     s_bias[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.f;
     s_gamma[i] = (p.gamma != nullptr && i < p.N) ? __ldg(p.gamma + i) : 0.f;
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int nslabs = p.kt * p.nchunks;
@@ -129,16 +145,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------ weight producer (constants: no dependency wait)
     if (lane == 0) {
       uint32_t ib = 0;
-      for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
-        const HaloUnit q = halo_unit(p, u, BN);
+      for (long long u = u0; u < p.units; u += ustep) {
+        const HaloUnit q = halo_unit(p, u, BN, CL, rank);
         for (int s = 0; s < nslabs; ++s) {
           const int dt = s / p.nchunks, ch = s - dt * p.nchunks;
           for (int tap = 0; tap < 9; ++tap, ++ib) {
             const int slot = ib % p.nb; const uint32_t ph = (ib / p.nb) & 1;
             mbar_wait(&b_empty[slot], ph ^ 1);
-            if (p.dbg & 1) { mbar_arrive(&b_full[slot]); continue; }
-            mbar_expect_tx(&b_full[slot], B_SLOT);
-            tma_load_2d(sb + slot * B_SLOT, &tmap_b, &b_full[slot], (dt * 9 + tap) * p.cpad + ch * CK, q.n0);
+            if constexpr (PAIR) {
+              const uint32_t bar = map_to_cta(&b_full[slot], 0);
+              if (p.dbg & 1) { if (rank == 0) mbar_arrive(&b_full[slot]); continue; }
+              if (rank == 0) mbar_expect_tx(&b_full[slot], 2 * B_SLOT);
+              tma_load_2d_pair(sb + slot * B_SLOT, &tmap_b, bar, (dt * 9 + tap) * p.cpad + ch * CK, q.n0 + rank * B_ROWS);
+            } else {
+              if (p.dbg & 1) { mbar_arrive(&b_full[slot]); continue; }
+              mbar_expect_tx(&b_full[slot], B_SLOT);
+              tma_load_2d(sb + slot * B_SLOT, &tmap_b, &b_full[slot], (dt * 9 + tap) * p.cpad + ch * CK, q.n0);
+            }
           }
         }
       }
@@ -148,21 +171,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     pdl_wait();
     if (lane == 0) {
       uint32_t ia = 0;
-      for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
-        const HaloUnit q = halo_unit(p, u, BN);
+      for (long long u = u0; u < p.units; u += ustep) {
+        const HaloUnit q = halo_unit(p, u, BN, CL, rank);
         for (int s = 0; s < nslabs; ++s, ++ia) {
           const int dt = s / p.nchunks, ch = s - dt * p.nchunks;
-          const int slot = ia & 1; const uint32_t ph = (ia >> 1) & 1;
+          const int slot = ia % p.na; const uint32_t ph = (ia / p.na) & 1;
           mbar_wait(&a_empty[slot], ph ^ 1);
-          if (p.dbg & 2) { mbar_arrive(&a_full[slot]); continue; }
-          mbar_expect_tx(&a_full[slot], a_bytes);
-          tma_load_4d(sa + slot * p.a_slab, &tmap_a, &a_full[slot], ch * CK, q.w0 - 1, q.h0 - 1, q.t + dt);
+          if constexpr (PAIR) {
+            const uint32_t bar = map_to_cta(&a_full[slot], 0);
+            if (p.dbg & 2) { if (rank == 0) mbar_arrive(&a_full[slot]); continue; }
+            if (rank == 0) mbar_expect_tx(&a_full[slot], 2 * a_bytes);
+            tma_load_4d_pair(sa + slot * p.a_slab, &tmap_a, bar, ch * CK, q.w0 - 1, q.h0 - 1, q.t + dt);
+          } else {
+            if (p.dbg & 2) { mbar_arrive(&a_full[slot]); continue; }
+            mbar_expect_tx(&a_full[slot], a_bytes);
+            tma_load_4d(sa + slot * p.a_slab, &tmap_a, &a_full[slot], ch * CK, q.w0 - 1, q.h0 - 1, q.t + dt);
+          }
         }
       }
     }
-  } else if (warp == W_MMA) {
-    // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+  } else if (warp == W_MMA && rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (pair mode: the leader only)
+    constexpr uint32_t idesc = umma_idesc_f16(128 * CL, BN);
     constexpr int PMAX = 512 / BN > 5 ? 5 : 512 / BN;
     // high words of the operand descriptors: group stride (10 pixel rows for the halo views, 8 for the weights),
     // descriptor version, swizzle mode
@@ -170,15 +200,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     constexpr uint32_t A_HI = ((10 * RB) >> 4) | (1u << 14) | SWZ;
     constexpr uint32_t B_HI = ((8 * RB) >> 4) | (1u << 14) | SWZ;
     uint32_t ia = 0, ib = 0, iu = 0;
-    for (long long u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
-      const HaloUnit q = halo_unit(p, u, BN);
+    for (long long u = u0; u < p.units; u += ustep, ++iu) {
+      const HaloUnit q = halo_unit(p, u, BN, CL, rank);
       const int buf = iu % p.nbuf; const uint32_t aph = (iu / p.nbuf) & 1;
       mbar_spin(&acc_empty[buf], aph ^ 1);
       tc_fence_after();
       const uint32_t d0 = tmem_base + buf * p.P * BN;
       for (int s = 0; s < nslabs; ++s, ++ia) {
-        const int aslot = ia & 1;
-        mbar_spin(&a_full[aslot], (ia >> 1) & 1);
+        const int aslot = ia % p.na;
+        mbar_spin(&a_full[aslot], (ia / p.na) & 1);
         const uint32_t slab = smem_u32(sa + aslot * p.a_slab);
         for (int tap = 0; tap < 9; ++tap, ++ib) {
           const int bslot = ib % p.nb;
@@ -197,21 +227,36 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int k = 0; k < CK / 16; ++k) {
 #pragma unroll
                 for (int sp = 0; sp < PMAX; ++sp)
-                  if (sp < q.np)
-                    umma_f16_lohi(d0 + sp * BN, a_lo + sp * (10 * RB) + 2 * k, A_HI, b_lo + 2 * k, B_HI, idesc,
-                                  k > 0 ? 1u : first, elected);
+                  if (sp < q.np) {
+                    if constexpr (PAIR)
+                      umma_f16_lohi_pair(d0 + sp * BN, a_lo + sp * (10 * RB) + 2 * k, A_HI, b_lo + 2 * k, B_HI, idesc,
+                                         k > 0 ? 1u : first, elected);
+                    else
+                      umma_f16_lohi(d0 + sp * BN, a_lo + sp * (10 * RB) + 2 * k, A_HI, b_lo + 2 * k, B_HI, idesc,
+                                    k > 0 ? 1u : first, elected);
+                  }
               }
             }
-            umma_commit_e(&b_empty[bslot], elected);
-            if (tap == 8) {
-              umma_commit_e(&a_empty[aslot], elected);
-              if (s == nslabs - 1) umma_commit_e(&acc_full[buf], elected);
+            if constexpr (PAIR) {
+              umma_commit_pair_e(&b_empty[bslot], 3, elected);
+              if (tap == 8) {
+                umma_commit_pair_e(&a_empty[aslot], 3, elected);
+                if (s == nslabs - 1) umma_commit_pair_e(&acc_full[buf], 3, elected);
+              }
+            } else {
+              umma_commit_e(&b_empty[bslot], elected);
+              if (tap == 8) {
+                umma_commit_e(&a_empty[aslot], elected);
+                if (s == nslabs - 1) umma_commit_e(&acc_full[buf], elected);
+              }
             }
           }
           __syncwarp();
         }
       }
     }
+  } else if (warp == W_MMA) {
+    // the peer's MMA warp has nothing to issue
   } else {
     // ------------------------------------------------------------ epilogue (warps 0..7)
     pdl_wait();
@@ -220,8 +265,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int n_store = 0;
     uint32_t iu = 0;
     const uint32_t lane_sel = uint32_t(quad * 32) << 16;
-    for (long long u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
-      const HaloUnit q = halo_unit(p, u, BN);
+    for (long long u = u0; u < p.units; u += ustep, ++iu) {
+      const HaloUnit q = halo_unit(p, u, BN, CL, rank);
       const int buf = iu % p.nbuf; const uint32_t aph = (iu / p.nbuf) & 1;
       // residual rows of this thread's pixel: fetched one chunk ahead (the first one while the MMAs still run)
       float4 xr[CW / 4];
@@ -353,45 +398,79 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) {
+        if (PAIR && rank != 0) mbar_arrive_cluster(map_to_cta(&acc_empty[buf], 0));   // the leader's MMA warp waits
+        else mbar_arrive(&acc_empty[buf]);
+      }
     }
     if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync(); else __syncthreads();
   if (warp == W_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <int BN, int CK, int EPI>
+template <int BN, int CK, int EPI, int CL>
 void launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& th,
                  const HaloParams& p, int smem_bytes, int grid, cudaStream_t stream) {
   static bool configured_dev[64] = {false};
+  static int max_clusters_dev[64] = {0};
   int dev = 0;
   B2_CUDA(cudaGetDevice(&dev));
-  auto kern = conv_halo_kernel<BN, CK, EPI>;
+  auto kern = conv_halo_kernel<BN, CK, EPI, CL>;
   if (!configured_dev[dev & 63]) {
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (CL > 1) {                                   // clusters that can be co-resident (GPCs with an odd SM count lose one)
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(grid); q.blockDim = dim3(HALO_THREADS); q.dynamicSmemBytes = 227 * 1024;
+      cudaLaunchAttribute at{};
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      q.attrs = &at; q.numAttrs = 1;
+      int n = 0;
+      B2_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &q));
+      B2_CHECK(n >= 1, "no cluster of %d CTAs fits on this device", CL);
+      max_clusters_dev[dev & 63] = n;
+    }
     configured_dev[dev & 63] = true;
   }
-  launch_pdl(kern, dim3(grid), dim3(HALO_THREADS), smem_bytes, stream, ta, tb, to, th, p);
+  if (CL > 1 && grid > max_clusters_dev[dev & 63] * CL) grid = max_clusters_dev[dev & 63] * CL;
+  if (CL == 1) {
+    launch_pdl(kern, dim3(grid), dim3(HALO_THREADS), smem_bytes, stream, ta, tb, to, th, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(HALO_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = CL; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+    if (pdl_enabled()) {
+      at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
+    B2_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, th, p));
+  }
   count_launch();
 }
 
-template <int BN, int CK>
+template <int BN, int CK, int CL>
 void launch_halo_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& th,
                      const HaloParams& p, int smem_bytes, int grid, cudaStream_t s) {
   switch (epi) {
-    case HE_STORE: launch_halo<BN, CK, HE_STORE>(ta, tb, to, th, p, smem_bytes, grid, s); break;
-    case HE_REDUCE: launch_halo<BN, CK, HE_REDUCE>(ta, tb, to, th, p, smem_bytes, grid, s); break;
-    case HE_NORM: launch_halo<BN, CK, HE_NORM>(ta, tb, to, th, p, smem_bytes, grid, s); break;
-    case HE_STORE | HE_NORM: launch_halo<BN, CK, HE_STORE | HE_NORM>(ta, tb, to, th, p, smem_bytes, grid, s); break;
-    case HE_RESID | HE_STORE: launch_halo<BN, CK, HE_RESID | HE_STORE>(ta, tb, to, th, p, smem_bytes, grid, s); break;
+    case HE_STORE: launch_halo<BN, CK, HE_STORE, CL>(ta, tb, to, th, p, smem_bytes, grid, s); break;
+    case HE_REDUCE: launch_halo<BN, CK, HE_REDUCE, CL>(ta, tb, to, th, p, smem_bytes, grid, s); break;
+    case HE_NORM: launch_halo<BN, CK, HE_NORM, CL>(ta, tb, to, th, p, smem_bytes, grid, s); break;
+    case HE_STORE | HE_NORM: launch_halo<BN, CK, HE_STORE | HE_NORM, CL>(ta, tb, to, th, p, smem_bytes, grid, s); break;
+    case HE_RESID | HE_STORE: launch_halo<BN, CK, HE_RESID | HE_STORE, CL>(ta, tb, to, th, p, smem_bytes, grid, s); break;
     case HE_RESID | HE_STORE | HE_NORM:
-      launch_halo<BN, CK, HE_RESID | HE_STORE | HE_NORM>(ta, tb, to, th, p, smem_bytes, grid, s); break;
+      launch_halo<BN, CK, HE_RESID | HE_STORE | HE_NORM, CL>(ta, tb, to, th, p, smem_bytes, grid, s); break;
     default: fail("conv_halo: unsupported epilogue combination %d", epi);
   }
 }
@@ -420,10 +499,15 @@ void conv_halo(const ConvHaloArgs& a, int num_sms, cudaStream_t stream) {
   p.T = a.T_out; p.H = a.H; p.W = a.W; p.kt = a.kt; p.nchunks = a.Cin / CK; p.cpad = a.cpad;
   p.N = a.Cout; p.tiles_n = (a.Cout + BN - 1) / BN;
   p.subrows = (a.H + 15) / 16; p.cols = (a.W + 7) / 8;
-  const int B_SLOT = BN * RB;
-  const int tail = HALO_STAGING + 256 + 2 * 512 * 4;
+  // CTA pairs (see the kernel): two accumulator sets of 512 / (2 BN) sub-tiles per CTA, half a weight tile per CTA
+  // MEASURED slower (81-frame decode 363 against 312 ms): with P = 2 the weight tiles are fetched 2.5x as often and
+  // the TMA row rate, not the tensor pipe, paces the unit; off unless B200_HALO_PAIR=1
+  static const int pair_env = std::getenv("B200_HALO_PAIR") ? std::atoi(std::getenv("B200_HALO_PAIR")) : 0;
+  const int CL = (pair_env && (BN == 96 || BN == 192) && p.cols >= 2 && num_sms >= 2) ? 2 : 1;
+  const int B_SLOT = (BN / CL) * RB;
+  const int tail = HALO_STAGING + HALO_BARS + 2 * 512 * 4;
   // sub-tiles per unit: as many accumulators as TMEM holds (<= 5), while two halo slabs and >= 4 weight slots fit
-  int P = 512 / BN;
+  int P = CL == 2 ? 512 / (2 * BN) : 512 / BN;
   if (P > 5) P = 5;
   static const int p_env = std::getenv("B200_HALO_P") ? std::atoi(std::getenv("B200_HALO_P")) : 0;
   if (p_env > 0 && BN == 96 && p_env < P) P = p_env;   // experiment: fewer accumulators per set, double-buffered
@@ -433,16 +517,20 @@ void conv_halo(const ConvHaloArgs& a, int num_sms, cudaStream_t stream) {
   p.P = P; p.a_slab = slab(P);
   p.bands = (p.subrows + P - 1) / P;
   p.nbuf = 2 * P * BN <= 512 ? 2 : 1;
-  int nb = (227 * 1024 - tail - 2 * p.a_slab) / B_SLOT;
-  if (nb > 8) nb = 8;
+  // halo ring: 2 slabs, up to 4 when the weight ring still gets >= 16 slots (a slab of a pair unit is consumed in
+  // ~1.7k clocks, about one TMA round trip); weight ring: what is left, up to HALO_MAX_NB slots
+  int na = 2;
+  while (na < 4 && (227 * 1024 - tail - (na + 1) * p.a_slab) / B_SLOT >= 16) ++na;
+  int nb = (227 * 1024 - tail - na * p.a_slab) / B_SLOT;
+  if (nb > HALO_MAX_NB) nb = HALO_MAX_NB;
   B2_CHECK(nb >= 2, "conv_halo: shared memory does not hold the weight ring (%d -> %d)", a.Cin, a.Cout);
-  p.nb = nb;
-  p.units = (long long)a.T_out * p.bands * p.cols * p.tiles_n;
+  p.nb = nb; p.na = na;
+  p.units = (long long)a.T_out * p.bands * ((p.cols + CL - 1) / CL) * p.tiles_n;
   p.bias = a.bias; p.gamma = a.gamma; p.norm_scale = std::sqrt((float)a.Cout); p.silu = a.silu;
   p.resid = a.resid; p.ld_r = a.ld_r;
   static const int dbg = std::getenv("B200_HALO_DBG") ? std::atoi(std::getenv("B200_HALO_DBG")) : 0;
   p.dbg = dbg;
-  const int smem_bytes = 2 * p.a_slab + nb * B_SLOT + tail;
+  const int smem_bytes = na * p.a_slab + nb * B_SLOT + tail;
 
   int epi = 0;
   if (a.out_h != nullptr) {
@@ -465,7 +553,7 @@ void conv_halo(const ConvHaloArgs& a, int num_sms, cudaStream_t stream) {
   const long long Ktot = (long long)a.kt * 9 * a.cpad;
   uint64_t wd[2] = {(uint64_t)Ktot, (uint64_t)a.Cout};
   uint64_t ws[1] = {(uint64_t)Ktot * 2};
-  uint32_t wb[2] = {(uint32_t)CK, (uint32_t)BN};
+  uint32_t wb[2] = {(uint32_t)CK, (uint32_t)(BN / CL)};
   const CUtensorMap tb = make_tmap(a.w, false, 2, wd, ws, wb, RB);
   const uint32_t cw = BN % 32 == 0 ? 32 : 16;
   CUtensorMap to = tb, th = tb;
@@ -481,18 +569,23 @@ void conv_halo(const ConvHaloArgs& a, int num_sms, cudaStream_t stream) {
     uint32_t ob[4] = {cw, 8, 4, 1};
     th = make_tmap(a.out_h, false, 4, od, os, ob, (int)cw * 2);
   }
-  const int grid = (int)(p.units < num_sms ? p.units : num_sms);
+  const long long slots = num_sms / CL;
+  const int grid = (int)(p.units < slots ? p.units : slots) * CL;
   const double flops = 2.0 * a.T_out * a.H * a.W * (double)a.Cout * a.kt * 9 * a.Cin;
   ProfScope prof(PC_CONV, flops, 0.0, stream);
-  const int key = BN * 100 + CK;
+  const int key = (BN * 100 + CK) * 10 + CL;
   switch (key) {
-    case 19264: launch_halo_epi<192, 64>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
-    case 19232: launch_halo_epi<192, 32>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
-    case 9664: launch_halo_epi<96, 64>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
-    case 9632: launch_halo_epi<96, 32>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
-    case 1664: launch_halo_epi<16, 64>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
-    case 1632: launch_halo_epi<16, 32>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
-    default: fail("conv_halo: no kernel for tile width %d / chunk %d", BN, CK);
+    case 192641: launch_halo_epi<192, 64, 1>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    case 192321: launch_halo_epi<192, 32, 1>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    case 96641: launch_halo_epi<96, 64, 1>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    case 96321: launch_halo_epi<96, 32, 1>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    case 16641: launch_halo_epi<16, 64, 1>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    case 16321: launch_halo_epi<16, 32, 1>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    case 192642: launch_halo_epi<192, 64, 2>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    case 192322: launch_halo_epi<192, 32, 2>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    case 96642: launch_halo_epi<96, 64, 2>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    case 96322: launch_halo_epi<96, 32, 2>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
+    default: fail("conv_halo: no kernel for tile width %d / chunk %d / cluster %d", BN, CK, CL);
   }
 }
 
