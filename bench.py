@@ -231,6 +231,30 @@ BLOCK_SHAPES = [("1 x L=6240 (one sequence, latent [16,4,60,104])", 1, 4), ("4 x
                 ("1 x L=1560", 1, 1), ("1 x L=32760 (T=21)", 1, 21)]
 
 
+def vae_leg(dev, burst):
+    """SURVEY 8(a) A14-A15 / 8(d) config 5's decode leg: WanVAE decode of one 81-frame latent [16,21,60,104] ->
+    [3,81,480,832] on this GPU (synthetic weights of the reference's widths), device-timed; TFLOP/s of the
+    reference's convolution FLOPs (no padding counted)."""
+    import b200dit
+    eng = b200dit.VaeEngine.from_state_dict(b200dit.synthetic.vae_decoder_weights(dim=96, seed=0), device=dev)
+    z = torch.randn(16, 21, 60, 104, generator=torch.Generator().manual_seed(21)).to(dev)
+    for _ in range(2):
+        out = eng.decode([z])[0]
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 3
+    e0.record()
+    for _ in range(n):
+        out = eng.decode([z])[0]
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    fl = b200dit.flops.vae_decode_flops(21)
+    return {"workload": "WanVAE decode [16,21,60,104] -> [3,81,480,832], one GPU, weights and latent resident in HBM",
+            "ms": ms, "frames_per_s": 81 / (ms / 1e3), "tflops": fl / (ms / 1e3) / 1e12,
+            "frac_of_burst": fl / (ms / 1e3) / 1e12 / burst, "finite": bool(torch.isfinite(out).all())}
+
+
 def block_table(dev, burst, sustained, shapes=BLOCK_SHAPES):
     """SURVEY 8(d) fused-block micro-benchmark: ONE WanAttentionBlock (LayerNorm+modulation -> QKV -> RMSNorm/RoPE ->
     self-attention -> o -> norm3 -> cross-attention -> FFN, context K/V cached) at the four shapes.  Block time =
@@ -574,6 +598,7 @@ def main():
         line.update(legs)
         if world == 1 and not args.no_block_table:
             line["block_table"] = block_table(dev, burst, sustained)
+            line["vae_decode"] = vae_leg(dev, burst)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"], cpu_step = cpu_baseline(T)
             if cpu_step is not None and hasattr(cpu_step, "last"):

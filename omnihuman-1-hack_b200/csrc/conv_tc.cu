@@ -43,7 +43,11 @@ struct HaloParams {
   const float* bias;
   const float* gamma; float norm_scale; int silu;
   const float* resid; long long ld_r;
-  int dbg;                     // diagnosis only (B200_HALO_DBG): 1 no weight loads, 2 no halo loads, 4 no stores, 8 no MMAs, 16 no SiLU
+  float* out_f; long long ld_f;   // fp32 output rows (cooperative stores); the tensor map serves the reduce-add path
+  __half* out_h;                  // fp16 norm output [T, H, W, N]
+  long long* trace;            // diagnosis only (B200_HALO_TRACE=<launch index>): CTA 0 records, per unit, clock64 at
+                               // [0] MMA warp past acc_empty, [1] last MMA issued, [2] epilogue sees acc_full, [3] epilogue done
+  int dbg;                     // diagnosis only (B200_HALO_DBG): 1 no weight loads, 2 no halo loads, 4 no stores, 8 no MMAs, 16 no SiLU, 32 no shortcut loads, 64 no TMEM write-back
 };
 
 constexpr int W_A = 8, W_B = 9, W_MMA = 10, HALO_THREADS = 352;
@@ -205,6 +209,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int buf = iu % p.nbuf; const uint32_t aph = (iu / p.nbuf) & 1;
       mbar_spin(&acc_empty[buf], aph ^ 1);
       tc_fence_after();
+      if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && iu < 64) p.trace[iu * 4 + 0] = clock64();
       const uint32_t d0 = tmem_base + buf * p.P * BN;
       for (int s = 0; s < nslabs; ++s, ++ia) {
         const int aslot = ia % p.na;
@@ -254,6 +259,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
         }
       }
+      if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && iu < 64) p.trace[iu * 4 + 1] = clock64();
     }
   } else if (warp == W_MMA) {
     // the peer's MMA warp has nothing to issue
@@ -269,22 +275,39 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const HaloUnit q = halo_unit(p, u, BN, CL, rank);
       const int buf = iu % p.nbuf; const uint32_t aph = (iu / p.nbuf) & 1;
       // residual rows of this thread's pixel: fetched one chunk ahead (the first one while the MMAs still run)
+      // The loads are COOPERATIVE (lane l fetches 16-byte piece l % 8 of pixel 4 i + l / 8: one full line per 8 lanes)
+      // and reach their owner through the staging area: per-thread row loads are 32 L1 wavefronts per instruction,
+      // 15k wavefronts per unit -- they, not the stores, made the shortcut epilogue 39k clocks against 17k.
       float4 xr[CW / 4];
       auto load_resid = [&](int sp, int c) {
-        const int h = q.h0 + 16 * sp + 4 * quad + (lane >> 3), w = q.w0 + (lane & 7);
-        if (sp < q.np && h < p.H && w < p.W) {
-          const float4* x4 = reinterpret_cast<const float4*>(
-              p.resid + (((long long)q.t * p.H + h) * p.W + w) * p.ld_r + q.n0 + c * CW);
 #pragma unroll
-          for (int j = 0; j < CW / 4; ++j) xr[j] = __ldg(x4 + j);
-        } else {
-#pragma unroll
-          for (int j = 0; j < CW / 4; ++j) xr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < CW / 4; ++i) {
+          const int px = 4 * i + (lane >> 3), k = lane & 7;
+          const int h = q.h0 + 16 * sp + 4 * quad + (px >> 3), w = q.w0 + (px & 7);
+          if (sp < q.np && h < p.H && w < p.W && !(p.dbg & 32))
+            xr[i] = __ldg(reinterpret_cast<const float4*>(
+                p.resid + (((long long)q.t * p.H + h) * p.W + w) * p.ld_r + q.n0 + c * CW + 4 * k));
+          else
+            xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
-      if constexpr ((EPI & HE_RESID) != 0) load_resid(half, 0);
+      if constexpr ((EPI & HE_RESID) != 0) {
+        load_resid(half, 0);
+        // the shortcut rows come from HBM (a 16-frame stage is GBs): pull this warp's rows of the unit into L2 while
+        // the MMAs run, so that the chunk-ahead loads of the epilogue pay L2 latency
+        for (int sp = half; sp < q.np; sp += 2) {
+          const int h = q.h0 + 16 * sp + 4 * quad + (lane >> 3), w = q.w0 + (lane & 7);
+          if (h < p.H && w < p.W) {
+            const float* row = p.resid + (((long long)q.t * p.H + h) * p.W + w) * p.ld_r + q.n0;
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(row + c * 32));
+          }
+        }
+      }
       mbar_wait(&acc_full[buf], aph);
       tc_fence_after();
+      if (p.trace != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0 && iu < 64) p.trace[iu * 4 + 2] = clock64();
       for (int sp = half; sp < q.np; sp += 2) {
         const uint32_t t_acc = tmem_base + lane_sel + buf * p.P * BN + sp * BN;
         const int hrow = q.h0 + 16 * sp + 4 * quad;            // first image row of this warp's 4 x 8 pixels
@@ -303,55 +326,79 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             v[4 * j] = __uint_as_float(r[4 * j]) + b.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
             v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
           }
-          if constexpr ((EPI & HE_RESID) != 0) {
+          if constexpr ((EPI & HE_RESID) != 0 && CW == 32) {
+            // pieces -> staging (row = pixel, swizzled) -> every thread reads its own pixel's 128 bytes
 #pragma unroll
-            for (int j = 0; j < CW / 4; ++j) {
-              const float4 x = xr[j];
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(stg_base + halo_stage_offset<128>(4 * i + (lane >> 3), lane & 7)) = xr[i];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x = *reinterpret_cast<const float4*>(stg_base + halo_stage_offset<128>(lane, j));
               v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
             }
             if (c + 1 < NCH) load_resid(sp, c + 1); else load_resid(sp + 2, 0);
+            __syncwarp();                                        // the staging area is rewritten by the stores below
             if constexpr ((EPI & HE_NORM) != 0) {
 #pragma unroll
               for (int j = 0; j < CW; ++j) r[j] = __float_as_uint(v[j]);
-              halo_st<CW>(t_acc + c * CW, r);                  // pass 2 re-reads the updated row
+              if (!(p.dbg & 64)) halo_st<CW>(t_acc + c * CW, r);   // pass 2 re-reads the updated row
             }
           }
           if constexpr ((EPI & HE_NORM) != 0) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) ssq = fmaf(v[j], v[j], ssq);
           }
-          if constexpr ((EPI & (HE_STORE | HE_REDUCE)) != 0) {
-            constexpr int ROW_BYTES = CW * 4;
-            constexpr int BOX = 32 * ROW_BYTES;
-            constexpr int NBUF = BOX >= 4096 ? 1 : 2;
-            uint8_t* stg = stg_base + (NBUF == 1 ? 0 : (n_store & 1) * BOX);
-            ++n_store;
-            if (lane == 0) { if (NBUF == 1) tma_store_wait_read0(); else tma_store_wait_read1(); }
-            __syncwarp();
+          if constexpr ((EPI & HE_STORE) != 0 && CW == 32) {
+            // fp32 rows: own row -> swizzled staging -> the warp stores its 4 x 8 pixels cooperatively, one full
+            // 128-byte line per 8 lanes.  (Through TMA boxes the bulk-store engine paced the epilogue at 7-9 clocks
+            // per 64-byte row: 39k clocks per unit with the shortcut add against 17k without, B200_HALO_TRACE.)
 #pragma unroll
-            for (int k = 0; k < CW / 4; ++k)
-              *reinterpret_cast<float4*>(stg + halo_stage_offset<ROW_BYTES>(lane, k)) =
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<float4*>(stg_base + halo_stage_offset<128>(lane, k)) =
                   make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-            fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-              if (!(p.dbg & 4)) {
-                if constexpr ((EPI & HE_REDUCE) != 0) tma_reduce_add_4d(&tmap_o, stg, col0, q.w0, hrow, q.t);
-                else tma_store_4d(&tmap_o, stg, col0, q.w0, hrow, q.t);
+            if (!(p.dbg & 4)) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int px = 4 * i + (lane >> 3), k = lane & 7;
+                const int h = hrow + (px >> 3), w = q.w0 + (px & 7);
+                const float4 val = *reinterpret_cast<const float4*>(stg_base + halo_stage_offset<128>(px, k));
+                if (h < p.H && w < p.W)
+                  *reinterpret_cast<float4*>(p.out_f + (((long long)q.t * p.H + h) * p.W + w) * p.ld_f + col0 + 4 * k) = val;
               }
-              tma_store_commit();
+            }
+            __syncwarp();
+          } else if constexpr ((EPI & (HE_STORE | HE_REDUCE)) != 0) {
+            // reduce-add (and the 16-column head tile, whose rows are clipped by the tensor map): 2 KB boxes that
+            // alternate between the halves of the warp's staging area
+#pragma unroll
+            for (int hh = 0; hh < CW / 16; ++hh) {
+              uint8_t* stg = stg_base + (n_store & 1) * 2048;
+              ++n_store;
+              if (lane == 0) tma_store_wait_read1();
+              __syncwarp();
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<float4*>(stg + halo_stage_offset<64>(lane, k)) =
+                    make_float4(v[hh * 16 + 4 * k], v[hh * 16 + 4 * k + 1], v[hh * 16 + 4 * k + 2], v[hh * 16 + 4 * k + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (!(p.dbg & 4)) {
+                  if constexpr ((EPI & HE_REDUCE) != 0) tma_reduce_add_4d(&tmap_o, stg, col0 + hh * 16, q.w0, hrow, q.t);
+                  else tma_store_4d(&tmap_o, stg, col0 + hh * 16, q.w0, hrow, q.t);
+                }
+                tma_store_commit();
+              }
             }
           }
         }
-        if constexpr ((EPI & HE_NORM) != 0) {
+        if constexpr ((EPI & HE_NORM) != 0 && CW == 32) {      // (the 16-column head tile never carries a fused norm)
           if constexpr ((EPI & HE_RESID) != 0) tmem_wait_st();
           const float inv = p.norm_scale / fmaxf(sqrtf(ssq), 1e-12f);       // F.normalize eps (vae.py:51-54)
-          if constexpr ((EPI & (HE_STORE | HE_REDUCE)) != 0) {
-            // the fp32 boxes of pass 1 use the whole staging area: the last one must have been read before the
-            // fp16 boxes (which alternate between its halves and only wait for the store before last) overwrite it
-            if (lane == 0) tma_store_wait_read0();
-            __syncwarp();
-          }
+          // (every box, fp32 or fp16, is 2 KB and takes the half of the staging area given by the parity of n_store:
+          // waiting for all but the latest bulk group before writing a half is enough on every path)
 #pragma unroll 1
           for (int c = 0; c < NCH; ++c) {
             const int col0 = q.n0 + c * CW;
@@ -375,29 +422,30 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
               for (int j = 0; j < CW; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
             }
-            constexpr int ROW_BYTES = CW * 2;
-            constexpr int BOX = 32 * ROW_BYTES;
-            uint8_t* stg = stg_base + (n_store & 1) * 2048;
-            ++n_store;
-            if (lane == 0) tma_store_wait_read1();
-            __syncwarp();
+            // fp16 rows (64 bytes per pixel and chunk): staged like a 64B-swizzled box, stored 8 pixels per instruction
 #pragma unroll
-            for (int k = 0; k < CW / 8; ++k)
-              *reinterpret_cast<uint4*>(stg + halo_stage_offset<ROW_BYTES>(lane, k)) =
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<uint4*>(stg_base + halo_stage_offset<64>(lane, k)) =
                   make_uint4(pack_h2(v[8 * k], v[8 * k + 1]), pack_h2(v[8 * k + 2], v[8 * k + 3]),
                              pack_h2(v[8 * k + 4], v[8 * k + 5]), pack_h2(v[8 * k + 6], v[8 * k + 7]));
-            fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-              if (!(p.dbg & 4)) tma_store_4d(&tmap_h, stg, col0, q.w0, hrow, q.t);
-              tma_store_commit();
+            if (!(p.dbg & 4)) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int px = 8 * i + (lane >> 2), k = lane & 3;
+                const int h = hrow + (px >> 3), w = q.w0 + (px & 7);
+                const uint4 val = *reinterpret_cast<const uint4*>(stg_base + halo_stage_offset<64>(px, k));
+                if (h < p.H && w < p.W)
+                  *reinterpret_cast<uint4*>(p.out_h + (((long long)q.t * p.H + h) * p.W + w) * p.N + col0 + 8 * k) = val;
+              }
             }
-            static_assert(BOX <= 2048, "fp16 staging boxes alternate inside the warp's 4 KB");
+            __syncwarp();
           }
         }
       }
       tc_fence_before();
       __syncwarp();
+      if (p.trace != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0 && iu < 64) p.trace[iu * 4 + 3] = clock64();
       if (lane == 0) {
         if (PAIR && rank != 0) mbar_arrive_cluster(map_to_cta(&acc_empty[buf], 0));   // the leader's MMA warp waits
         else mbar_arrive(&acc_empty[buf]);
@@ -486,7 +534,7 @@ bool conv_halo_supported(int Cin, int Cout, int kt, int kh, int kw) {
 }
 
 bool conv_halo_fusable(int Cin, int Cout, int kt, int kh, int kw) {
-  return conv_halo_supported(Cin, Cout, kt, kh, kw) && halo_tile_width(Cout) == Cout;
+  return conv_halo_supported(Cin, Cout, kt, kh, kw) && halo_tile_width(Cout) == Cout && Cout % 32 == 0;
 }
 
 void conv_halo(const ConvHaloArgs& a, int num_sms, cudaStream_t stream) {
@@ -528,8 +576,18 @@ void conv_halo(const ConvHaloArgs& a, int num_sms, cudaStream_t stream) {
   p.units = (long long)a.T_out * p.bands * ((p.cols + CL - 1) / CL) * p.tiles_n;
   p.bias = a.bias; p.gamma = a.gamma; p.norm_scale = std::sqrt((float)a.Cout); p.silu = a.silu;
   p.resid = a.resid; p.ld_r = a.ld_r;
+  p.out_f = a.out_f; p.ld_f = a.ld_f; p.out_h = a.out_h;
   static const int dbg = std::getenv("B200_HALO_DBG") ? std::atoi(std::getenv("B200_HALO_DBG")) : 0;
   p.dbg = dbg;
+  static const int trace_launch = std::getenv("B200_HALO_TRACE") ? std::atoi(std::getenv("B200_HALO_TRACE")) : -1;
+  static int launch_index = 0;
+  static long long* trace_buf = nullptr;
+  const bool tracing = trace_launch >= 0 && launch_index++ == trace_launch;
+  if (tracing) {
+    if (trace_buf == nullptr) B2_CUDA(cudaMalloc(&trace_buf, 64 * 4 * sizeof(long long)));
+    B2_CUDA(cudaMemset(trace_buf, 0, 64 * 4 * sizeof(long long)));
+    p.trace = trace_buf;
+  }
   const int smem_bytes = na * p.a_slab + nb * B_SLOT + tail;
 
   int epi = 0;
@@ -560,8 +618,8 @@ void conv_halo(const ConvHaloArgs& a, int num_sms, cudaStream_t stream) {
   if (a.out_f != nullptr) {
     uint64_t od[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.T_out};
     uint64_t os[3] = {(uint64_t)a.ld_f * 4, (uint64_t)a.W * a.ld_f * 4, (uint64_t)a.H * a.W * a.ld_f * 4};
-    uint32_t ob[4] = {cw, 8, 4, 1};
-    to = make_tmap(a.out_f, true, 4, od, os, ob, (int)cw * 4);
+    uint32_t ob[4] = {16, 8, 4, 1};
+    to = make_tmap(a.out_f, true, 4, od, os, ob, 64);
   }
   if (a.out_h != nullptr) {
     uint64_t od[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.T_out};
@@ -586,6 +644,17 @@ void conv_halo(const ConvHaloArgs& a, int num_sms, cudaStream_t stream) {
     case 96642: launch_halo_epi<96, 64, 2>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
     case 96322: launch_halo_epi<96, 32, 2>(epi, ta, tb, to, th, p, smem_bytes, grid, stream); break;
     default: fail("conv_halo: no kernel for tile width %d / chunk %d / cluster %d", BN, CK, CL);
+  }
+  if (tracing) {
+    B2_CUDA(cudaStreamSynchronize(stream));
+    long long h[64 * 4];
+    B2_CUDA(cudaMemcpy(h, trace_buf, sizeof h, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "conv_halo trace: %d -> %d channels, %d x %d x %d, BN %d CK %d P %d CL %d epi %d; CTA 0, clocks\n", a.Cin, a.Cout,
+            a.T_out, a.H, a.W, BN, CK, p.P, CL, epi);
+    for (int i = 0; i + 1 < 64 && h[(i + 1) * 4 + 3] != 0; ++i)
+      fprintf(stderr, "  unit %2d: MMA issue %6lld  | issue end -> acc_full seen %6lld | epilogue %6lld | epilogue end -> next MMA start %6lld | unit %6lld\n",
+              i, h[i * 4 + 1] - h[i * 4 + 0], h[i * 4 + 2] - h[i * 4 + 1], h[i * 4 + 3] - h[i * 4 + 2], h[(i + 1) * 4 + 0] - h[i * 4 + 3],
+              h[(i + 1) * 4 + 0] - h[i * 4 + 0]);
   }
 }
 
