@@ -235,6 +235,7 @@ def vae_leg(dev, burst):
     """SURVEY 8(a) A14-A15 / 8(d) config 5's decode leg: WanVAE decode of one 81-frame latent [16,21,60,104] ->
     [3,81,480,832] on this GPU (synthetic weights of the reference's widths), device-timed; TFLOP/s of the
     reference's convolution FLOPs (no padding counted)."""
+    import torch
     import b200dit
     eng = b200dit.VaeEngine.from_state_dict(b200dit.synthetic.vae_decoder_weights(dim=96, seed=0), device=dev)
     z = torch.randn(16, 21, 60, 104, generator=torch.Generator().manual_seed(21)).to(dev)
@@ -597,8 +598,14 @@ def main():
                 "roofline": roof, "single_sample": single}
         line.update(legs)
         if world == 1 and not args.no_block_table:
-            line["block_table"] = block_table(dev, burst, sustained)
-            line["vae_decode"] = vae_leg(dev, burst)
+            # extra legs: a failure in one of them is reported in its key and never costs the headline line
+            for key, leg in (("block_table", lambda: block_table(dev, burst, sustained)),
+                             ("vae_decode", lambda: vae_leg(dev, burst))):
+                try:
+                    line[key] = leg()
+                except Exception as exc:  # noqa: BLE001
+                    line[key] = {"error": f"{type(exc).__name__}: {exc}"}
+                    print(f"bench: leg {key} failed: {exc!r}", file=sys.stderr)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"], cpu_step = cpu_baseline(T)
             if cpu_step is not None and hasattr(cpu_step, "last"):
