@@ -1124,7 +1124,7 @@ void launch_attention(const AttnParams& p, cudaStream_t stream) {
     launch_pdl(v2::attn_fwd_kernel, dim3(pd.n_units), dim3(192), v2::SMEM, stream, tq, tk, tv, pd);
   }
   count_launch();
-  if (pd.split_tiles > 0) {
+  if (pd.split_tiles > 0 && !(diag_skip() & 4)) {
     launch_pdl(v2::attn_combine_kernel, dim3(pd.split_tiles, TILE / 8), dim3(256), 0, stream, pd, n_tiles - pd.split_tiles);
     count_launch();
   }

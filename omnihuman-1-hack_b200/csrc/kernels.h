@@ -202,6 +202,7 @@ struct AttnParams {
 };
 constexpr long long ATTN_SPLIT_WS_BYTES = 512ll * (128 * 128 + 2 * 128) * 4;    // up to 512 partial tiles
 void launch_attention(const AttnParams& p, cudaStream_t stream);
+int diag_skip();                       // B200_DIAG_SKIP bits (elementwise.cu): timing diagnosis only
 
 // ---- elementwise.cu
 struct ItemPtrs { const float* p[MAX_ITEMS]; };
