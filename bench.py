@@ -474,22 +474,32 @@ def main():
         gm = prof["gemm"]
         tot_ms = sum(p["ms"] for p in prof.values())
         ach = gm["flops"] / (gm["ms"] / 1e3) / 1e12 if gm["ms"] > 0 else 0.0
-        # DRAM traffic per launch of the same kernel family from the committed `ncu --set full` capture
-        # (profiles/r1_ncu_traffic.json: one capture per GEMM shape of a block at M = 6240), averaged with the
-        # per-block launch mix qkv x1, o / cross-q / cross-o x3, ffn.0 x1, ffn.2 x1
-        traffic, tsrc = None, None
-        tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+        # DRAM traffic per launch of the same kernel family from the committed `ncu --set full` capture at HEAD
+        # (profiles/r2_ncu_traffic.json: the six GEMM launches of one block at M = 6240, cold caches), averaged
+        # over the launches of a block; the compulsory bytes beside it (operands + outputs once, fp32 residual
+        # read + written by the reduce-add epilogues)
+        traffic, tsrc, compulsory = None, None, None
+        tp = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
         if os.path.isfile(tp) and S == 2 and T == 1:
             tj = json.load(open(tp))
-            mb = lambda key: sum(v["dram_read_mb"] + v["dram_write_mb"] for k, v in tj.items() if k.startswith(key))
-            traffic = 1e6 * (mb("qkv") + 3 * mb("o-shaped") + mb("ffn.0") + mb("ffn.2")) / 6.0
-            tsrc = "profiles/r1_ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
+            per = [v["dram_read_mb"] + v["dram_write_mb"] for k, v in tj.items()
+                   if isinstance(v, dict) and not k.startswith("patch")]
+            traffic = 1e6 * sum(per) / len(per)
+            tsrc = ("profiles/r2_ncu_traffic.json (ncu --set full at round-2 HEAD, dram__bytes_read.sum + "
+                    "dram__bytes_write.sum, mean over the six GEMM launches of a block)")
+            Mr, d_, f_ = 2 * S * L, cfg["dim"], cfg["ffn_dim"]
+            comp = [Mr * d_ * 2 + 3 * d_ * d_ * 2 + Mr * 3 * d_ * 2,            # qkv: A + W + fp16 out
+                    3 * (Mr * d_ * 2 + d_ * d_ * 2) + 2 * (2 * Mr * d_ * 4) + Mr * d_ * 2,   # o, cross-o (fp32 RMW), cross-q
+                    Mr * d_ * 2 + d_ * f_ * 2 + Mr * f_ * 2,                    # ffn.0
+                    Mr * f_ * 2 + d_ * f_ * 2 + 2 * Mr * d_ * 4]                # ffn.2
+            compulsory = sum(comp) / 6.0
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 128xN / 256xN tiles, fused epilogues)",
                 "achieved": ach, "peak": burst, "peak_sustained": sustained, "unit": "TFLOP/s", "frac": ach / burst,
                 "frac_of_sustained": ach / sustained,
                 "peak_source": src + " MEASURED_PEAKS.json: `peak` = cuBLAS bf16 burst (BASELINE.md section 2's primary "
                                "denominator), `peak_sustained` = the seconds-long figure under the power cap",
-                "traffic": traffic, "traffic_source": tsrc, "launches_per_step": gm["launches"] // 2,
+                "traffic": traffic, "traffic_source": tsrc, "compulsory_bytes_per_launch": compulsory,
+                "launches_per_step": gm["launches"] // 2,
                 "avg_launch_us": 1e3 * gm["ms"] / max(gm["launches"], 1),
                 "flops_per_launch": gm["flops"] / max(gm["launches"], 1),
                 "share_of_step": gm["ms"] / tot_ms if tot_ms else None,
