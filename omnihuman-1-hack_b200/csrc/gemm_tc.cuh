@@ -430,14 +430,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       // acc_full of this segment implies every epilogue warp is done with the segment two back, the
-      // previous user of this parity's bias slot; the 4 warps of a column half write identical values
+      // previous user of this parity's bias slot.  The slot of a column half is written by the half's first warp
+      // and read by all four after a named barrier (ids 1 / 2, 128 threads): earlier every warp of the half
+      // wrote the same values and synchronised only with itself -- harmless, but a write / read race between
+      // warps that compute-sanitizer's racecheck reports (profiles/r2_sanitizer.txt).
       float* bias_w = bias_all + (half * 2 + acc) * 128;
       if (p.bias != nullptr) {
-        if (lane < CW) {
+        if (quad == 0 && lane < CW) {
 #pragma unroll
           for (int ci = 0; ci < C_SPLIT; ++ci) bias_w[ci * CW + lane] = bv[ci];
         }
-        __syncwarp();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
       }
       float ssq_a = 0.f, ssq_b = 0.f;                     // EPI_QKV: sums of squares of slice 0 / slice 1
       bool fused = false;                                 // EPI_QKV: norm weight + rotation applied here
