@@ -160,6 +160,16 @@ class CpuStep:
                "layers": self.layers, "L": self.L, "tolerance": "1e-3 per forward (BASELINE.json north_star); the CFG step "
                "multiplies the cond - uncond difference by the guide scale",
                "checker": "oracle/dit_oracle.py (fp32 CPU) on the cpu_baseline sample: same weights, inputs, t"}
+        # yardstick (SURVEY 7 hard part 1): how far the reference's own GPU path (cuBLAS fp16 autocast + flash_attn +
+        # eager elementwise under the caller's bf16 autocast) lands from the engine on a CFG step of this workload --
+        # measured on a B200 by tools/library_baseline.py, committed under profiles/
+        yp = os.path.join(ROOT, "profiles", "r2_library_baseline.jsonl")
+        if os.path.isfile(yp):
+            for ln in open(yp):
+                rec = json.loads(ln)
+                if "rel_l2_vs_engine" in rec and rec.get("pattern", "").startswith("co-batched"):
+                    out["library_gpu_path_cfg_step_rel_l2_vs_engine"] = rec["rel_l2_vs_engine"]
+                    out["library_gpu_path_source"] = "profiles/r2_library_baseline.jsonl (tools/library_baseline.py, same guide scale)"
         eng.close()
         return out
 
