@@ -629,7 +629,11 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"], cpu_step = cpu_baseline(T)
             if cpu_step is not None and hasattr(cpu_step, "last"):
-                line["parity"] = cpu_step.parity(dev)           # live, at the full 30-block size
+                try:
+                    line["parity"] = cpu_step.parity(dev)       # live, at the full 30-block size
+                except Exception as exc:  # noqa: BLE001
+                    line["parity"] = {"error": f"{type(exc).__name__}: {exc}"}
+                    print(f"bench: parity leg failed: {exc!r}", file=sys.stderr)
         elif world > 1:
             line["cpu_baseline"] = {"value": None, "unit": "denoise-steps/s", "cores": 0, "kind": "port",
                                     "sample": "measured at N=1 only"}
