@@ -32,7 +32,10 @@ __device__ __forceinline__ float ex2(float x) {
 // 76.5, cross 36.9 / 35.8, Lk = 6240 244 / 249 -- no gain, the step is paced by the MMA / TMA side, so it
 // stays off (0) and every exponential is MUFU ex2.approx.  x <= 8 by the rescale threshold; masked logits (-inf)
 // clamp to 2^-120, fp16 zero.
-constexpr int EX2_FMA_EVERY = 0;
+#ifndef B200_EX2_FMA_EVERY
+#define B200_EX2_FMA_EVERY 0
+#endif
+constexpr int EX2_FMA_EVERY = B200_EX2_FMA_EVERY;      // -DB200_EX2_FMA_EVERY=n: A/B builds (tools/_bin)
 __device__ __forceinline__ float ex2_fma(float x) {
   x = fmaxf(x, -120.f);
   const float xr = x + 12582912.f;                  // 1.5 * 2^23: round(x) sits in the low mantissa bits
